@@ -1,0 +1,76 @@
+"""Load the UNMODIFIED reference functions from /root/reference (build container only).
+
+TEST INFRASTRUCTURE.  `tools/eval_mm_protocol.py` cannot be imported as-is: its
+`from datasets.dataset import MultiModalDataset` (eval_mm_protocol.py:29) resolves to the
+HuggingFace `datasets` package and `models.model` (eval_mm_protocol.py:30) pulls CLIP weights.
+Neither is needed for the feature-level math, so both are stubbed before exec.
+"""
+import importlib.util
+import io
+import contextlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("REID_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "tools", "eval_mm_protocol.py"))
+
+
+_cache = {}
+
+
+def load_reference_eval():
+    """Returns the reference module object for tools/eval_mm_protocol.py."""
+    if "eval" in _cache:
+        return _cache["eval"]
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    saved = {k: sys.modules.get(k) for k in ("datasets", "datasets.dataset", "models.model", "configs", "configs.config")}
+    try:
+        ds = types.ModuleType("datasets"); ds.__path__ = []
+        dsd = types.ModuleType("datasets.dataset")
+        dsd.MultiModalDataset = type("MultiModalDataset", (), {})
+        mm = types.ModuleType("models.model")
+        mm.CLIPBasedMultiModalReIDModel = type("CLIPBasedMultiModalReIDModel", (), {})
+        cc = types.ModuleType("configs"); cc.__path__ = []
+        ccc = types.ModuleType("configs.config")
+        ccc.TrainingConfig = type("TrainingConfig", (), {})
+        sys.modules.update({"datasets": ds, "datasets.dataset": dsd, "models.model": mm,
+                            "configs": cc, "configs.config": ccc})
+        spec = importlib.util.spec_from_file_location(
+            "ref_eval_mm_protocol", os.path.join(REFERENCE_ROOT, "tools", "eval_mm_protocol.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    # silence tqdm progress bars of the reference loop
+    mod.tqdm = lambda it, **kw: it
+    _cache["eval"] = mod
+    return mod
+
+
+def load_reference_sdm():
+    """Returns the reference `sdm_loss_stable` (models/sdm_loss.py:13), stdout silenced by caller."""
+    if "sdm" in _cache:
+        return _cache["sdm"]
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    spec = importlib.util.spec_from_file_location(
+        "ref_sdm_loss", os.path.join(REFERENCE_ROOT, "models", "sdm_loss.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _cache["sdm"] = mod
+    return mod
+
+
+def quiet(fn, *a, **kw):
+    """Call fn with stdout swallowed (the reference prints warnings / debug lines)."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **kw)

@@ -1,0 +1,172 @@
+"""Seeded synthetic "CLIP-shaped" 512-d features for the retrieval path and the SDM loss.
+
+Recipe: feature = c_id + b_modality + sigma_modality * N(0, I), NOT
+pre-normalised, so the normalise / fuse kernels do real work.  Noise levels are frozen here so
+that MM-k mAP sits in an informative range (neither 0 nor 1).  Modality names follow the
+reference evaluator (tools/eval_mm_protocol.py:35): ir, cpencil, sketch, text; gallery = rgb.
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+FEAT_DIM = 512
+# reference order ALL_NON_RGB = ["ir", "cpencil", "sketch", "text"] (eval_mm_protocol.py:35)
+MODALITIES = ("ir", "cpencil", "sketch", "text")
+MOD_ID = {m: i for i, m in enumerate(MODALITIES)}
+# default weight_cfg of run_eval (eval_mm_protocol.py:504)
+DEFAULT_WEIGHTS = {"ir": 1.0, "cpencil": 1.0, "sketch": 1.0, "text": 1.2}
+
+SIGMA_RGB = 4.0
+SIGMA = {"ir": 5.0, "cpencil": 5.0, "sketch": 6.0, "text": 7.0}
+BIAS_SCALE = 0.3
+
+# MM-k modality combinations in the order build_queries emits them (sorted tuples of
+# itertools.combinations over ALL_NON_RGB, eval_mm_protocol.py:243-244)
+def mm_combos(k: int) -> List[tuple]:
+    from itertools import combinations
+    return [tuple(sorted(c)) for c in combinations(MODALITIES, k)]
+
+
+@dataclass
+class RetrievalCase:
+    """Tensor view of one evaluation job."""
+    gallery_raw: torch.Tensor      # [G, D] fp32, un-normalised rgb features
+    g_pid: torch.Tensor            # [G] int64
+    query_raw: torch.Tensor        # [Q, k, D] fp32, un-normalised per-modality features
+    mod_id: torch.Tensor           # [Q, k] int32 index into MODALITIES
+    q_pid: torch.Tensor            # [Q] int64
+    excl: torch.Tensor             # [Q, E] int32 gallery indices to mask (same image), -1 pad
+    k: int
+
+    @property
+    def Q(self):
+        return self.query_raw.shape[0]
+
+    @property
+    def G(self):
+        return self.gallery_raw.shape[0]
+
+
+def make_retrieval_case(seed: int, n_ids: int, gal_per_id: int, k: int, queries_per_id: int,
+                        excl_frac: float = 0.01, n_excl: int = 2, device="cpu",
+                        dim: int = FEAT_DIM, chunk: int = 1 << 16) -> RetrievalCase:
+    """Generate a case.  Identity centres are regenerated per chunk from the seed so the
+    1M-gallery configuration never needs more than a chunk of scratch."""
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    centres = torch.randn(n_ids, dim, generator=gen, device=dev)
+    bias = {m: BIAS_SCALE * torch.randn(dim, generator=gen, device=dev) for m in ("rgb",) + MODALITIES}
+
+    G = n_ids * gal_per_id
+    g_pid = torch.arange(G, device=dev, dtype=torch.int64) // gal_per_id
+    gallery = torch.empty(G, dim, device=dev)
+    for s in range(0, G, chunk):
+        e = min(G, s + chunk)
+        noise = torch.randn(e - s, dim, generator=gen, device=dev)
+        gallery[s:e] = centres[g_pid[s:e]] + bias["rgb"] + SIGMA_RGB * noise
+
+    combos = mm_combos(k)
+    Q = n_ids * queries_per_id
+    q_pid = torch.arange(Q, device=dev, dtype=torch.int64) // queries_per_id
+    # query j of an identity uses combination j % len(combos) (mirrors the C(4,k) combos per id)
+    combo_of_q = (torch.arange(Q, device=dev) % queries_per_id) % len(combos)
+    combo_tab = torch.tensor([[MOD_ID[m] for m in c] for c in combos], device=dev, dtype=torch.int32)
+    mod_id = combo_tab[combo_of_q]                       # [Q, k]
+    sig_tab = torch.tensor([SIGMA[m] for m in MODALITIES], device=dev)
+    bias_tab = torch.stack([bias[m] for m in MODALITIES])  # [4, D]
+    query = torch.empty(Q, k, dim, device=dev)
+    for s in range(0, Q, chunk):
+        e = min(Q, s + chunk)
+        noise = torch.randn(e - s, k, dim, generator=gen, device=dev)
+        mid = mod_id[s:e].long()
+        query[s:e] = centres[q_pid[s:e]][:, None, :] + bias_tab[mid] + sig_tab[mid][..., None] * noise
+
+    # same-image exclusions: a seeded fraction of queries masks n_excl gallery rows of its own id
+    excl = torch.full((Q, max(1, n_excl)), -1, device=dev, dtype=torch.int32)
+    if excl_frac > 0 and n_excl > 0:
+        pick = torch.rand(Q, generator=gen, device=dev) < excl_frac
+        idx = torch.nonzero(pick).flatten()
+        for j in range(n_excl):
+            off = torch.randint(0, gal_per_id, (idx.numel(),), generator=gen, device=dev)
+            excl[idx, j] = (q_pid[idx] * gal_per_id + off).to(torch.int32)
+    return RetrievalCase(gallery, g_pid, query, mod_id, q_pid, excl, k)
+
+
+def weights_tensor(weight_cfg: Optional[Dict[str, float]] = None, device="cpu") -> torch.Tensor:
+    cfg = DEFAULT_WEIGHTS if weight_cfg is None else weight_cfg
+    return torch.tensor([float(cfg.get(m, 1.0)) for m in MODALITIES], dtype=torch.float32, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# Bridging a RetrievalCase to the reference's list-of-dicts interface (used by tests, the
+# oracle and the drop-in demo): a fake extractor that serves pre-extracted features.
+# ---------------------------------------------------------------------------------------------
+class TensorExtractor:
+    """Duck-typed stand-in for eval_mm_protocol.FeatureExtractor (eval_mm_protocol.py:133-219).
+
+    `encode_*` return the stored raw feature for a key; `fuse_features_if_any` reproduces the
+    reference's EFFECTIVE behaviour: single feature -> returned as is, several -> None because
+    FeatureFusion raises on 1-D inputs and the exception is swallowed.
+    """
+
+    def __init__(self, table: Dict[str, torch.Tensor]):
+        self.table = table
+
+    def _get(self, key):
+        return self.table[key]
+
+    encode_ir = encode_cpencil = encode_sketch = encode_text = encode_rgb = _get
+
+    def fuse_features_if_any(self, modal_feats, modalities):
+        if len(modal_feats) <= 1:
+            return modal_feats[0] if modal_feats else None
+        return None
+
+
+def case_to_reference_inputs(case: RetrievalCase):
+    """-> (queries, gallery_meta, extractor) in the reference's own formats
+    (eval_mm_protocol.py:270-274, 314-318)."""
+    G, Q = case.G, case.Q
+    gallery_meta = [{"img_id": "g%d" % i, "pid": int(p), "camid": None}
+                    for i, p in enumerate(case.g_pid.tolist())]
+    table = {}
+    queries = []
+    excl = case.excl.tolist()
+    mod = case.mod_id.tolist()
+    qp = case.q_pid.tolist()
+    qr = case.query_raw.cpu()
+    for qi in range(Q):
+        samples = {}
+        ex = [e for e in excl[qi] if e >= 0]
+        for j, mi in enumerate(mod[qi]):
+            m = MODALITIES[mi]
+            key = "q%d_%s" % (qi, m)
+            table[key] = qr[qi, j]
+            # the j-th sample carries the img_id of the j-th excluded gallery row (same image)
+            img_id = ("g%d" % ex[j]) if j < len(ex) else ("x%d_%s" % (qi, m))
+            if m == "text":
+                samples[m] = {"text": key, "img_id": img_id}
+            else:
+                samples[m] = {"img_path": key, "img_id": img_id}
+        queries.append({"pid": qp[qi], "modalities": tuple(MODALITIES[mi] for mi in mod[qi]),
+                        "samples": samples})
+    return queries, gallery_meta, TensorExtractor(table)
+
+
+# ---------------------------------------------------------------------------------------------
+# SDM batches
+# ---------------------------------------------------------------------------------------------
+def make_sdm_batch(seed: int, P: int, K: int, n_modalities: int = 5, dim: int = FEAT_DIM,
+                   dtype=torch.float32, device="cpu"):
+    """P identities x K samples, one feature matrix per modality; modality 0 is `vis`."""
+    gen = torch.Generator(device=torch.device(device))
+    gen.manual_seed(seed)
+    labels = torch.arange(P, device=device).repeat_interleave(K)
+    centres = torch.randn(P, dim, generator=gen, device=device)
+    feats = []
+    for _ in range(n_modalities):
+        f = centres[labels] + 1.5 * torch.randn(P * K, dim, generator=gen, device=device)
+        feats.append(f.to(dtype))
+    return feats, labels

@@ -1,0 +1,112 @@
+"""The oracle restatements against the golden fixtures produced by the unmodified reference
+(and, when /root/reference is present, against the live reference functions)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval as orc
+from oracle import sdm as osdm
+from oracle import ref_loader
+from prcv2025reid_b200 import synth
+from tests import _golden
+
+
+@pytest.mark.parametrize("name", _golden.RETRIEVAL_NAMES)
+def test_retrieval_oracle_matches_reference_golden(name):
+    case, z = _golden.load_retrieval(name)
+    w = synth.weights_tensor()
+    g = orc.l2n(case.gallery_raw)
+    q = orc.fuse_queries(case.query_raw, case.mod_id, w)
+    if "q_fused" in z:
+        assert np.array_equal(q.numpy(), z["q_fused"])          # bit-exact vs extract_query_feat
+        assert np.array_equal(g.numpy(), z["g_norm"])
+    else:
+        assert np.array_equal(q.numpy()[::7], z["q_fused_s"])
+        assert np.array_equal(g.numpy()[::13], z["g_norm_s"])
+    loop = orc.rank_and_metrics_loop(q, g, case.q_pid, case.g_pid, case.excl, return_per_query=True)
+    gold = z["metrics"]
+    assert [loop["mAP"], loop["R@1"], loop["R@5"], loop["R@10"], loop["num_queries"]] == list(gold)
+    assert np.array_equal(loop["_top_idx"], z["top10"])
+    nomask = orc.rank_and_metrics_loop(q, g, case.q_pid, case.g_pid, None)
+    assert [nomask["mAP"], nomask["R@1"], nomask["R@5"], nomask["R@10"], nomask["num_queries"]] == list(z["metrics_nomask"])
+    cnt = orc.rank_and_metrics_counting(q, g, case.q_pid, case.g_pid, case.excl)
+    assert cnt["num_queries"] == loop["num_queries"]
+    assert abs(cnt["mAP"] - loop["mAP"]) < 1e-9
+    for k in ("R@1", "R@5", "R@10"):
+        assert cnt[k] == loop[k]
+    sub = orc.submission_ranking(q, g, top_k=20)
+    assert np.array_equal(sub, z["submission"])
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_retrieval_oracle_matches_live_reference():
+    ref = ref_loader.load_reference_eval()
+    case = synth.make_retrieval_case(77, 25, 5, 3, 4, excl_frac=0.2, n_excl=2)
+    queries, gmeta, ext = synth.case_to_reference_inputs(case)
+    w = synth.weights_tensor()
+    g = ref.l2n(case.gallery_raw)
+    m = ref_loader.quiet(ref.rank_and_metrics, queries, g, gmeta, ext, dict(synth.DEFAULT_WEIGHTS))
+    q = orc.fuse_queries(case.query_raw, case.mod_id, w)
+    o = orc.rank_and_metrics_loop(q, orc.l2n(case.gallery_raw), case.q_pid, case.g_pid, case.excl)
+    assert m == o
+
+
+def test_query_without_positive_is_skipped():
+    case = synth.make_retrieval_case(5, 10, 3, 2, 2, excl_frac=0.0)
+    q_pid = case.q_pid.clone(); q_pid[:4] = 10_000     # ids absent from the gallery
+    w = synth.weights_tensor()
+    q = orc.fuse_queries(case.query_raw, case.mod_id, w); g = orc.l2n(case.gallery_raw)
+    out = orc.rank_and_metrics_loop(q, g, q_pid, case.g_pid, case.excl)
+    assert out["num_queries"] == case.Q - 4
+    out2 = orc.rank_and_metrics_counting(q, g, q_pid, case.g_pid, case.excl)
+    assert out2["num_queries"] == case.Q - 4
+
+
+def test_zero_row_normalises_to_zero():
+    x = torch.zeros(3, 512); x[1] = 1.0
+    y = orc.l2n(x)
+    assert torch.all(y[0] == 0) and torch.all(y[2] == 0)
+    assert abs(float(y[1].norm()) - 1.0) < 1e-6
+
+
+SDM_NAMES = ["p4k2_tau02", "p4k2_tau01", "p3k2", "ragged", "no_pos", "nan_feat", "quick_check",
+             "p64k8_fp32", "p64k8_bf16", "p4k2_bf16"]
+
+
+@pytest.mark.parametrize("name", SDM_NAMES)
+def test_sdm_oracle_matches_reference_golden(name):
+    c = _golden.load_sdm()[name]
+    q, v, y = _golden.sdm_inputs(c)
+    q = q.clone().requires_grad_(True); v = v.clone().requires_grad_(True)
+    loss = osdm.sdm_loss_oracle(q, v, y, tau=float(c["tau"]))
+    assert float(loss.detach()) == float(c["loss"])
+    assert bool(loss.requires_grad) == bool(c["differentiable"])
+    if loss.requires_grad:
+        loss.backward()
+        dq, dv = q.grad.float().numpy(), v.grad.float().numpy()
+        if "dq" in c:
+            assert np.array_equal(dq, c["dq"]) and np.array_equal(dv, c["dv"])
+        else:
+            assert np.array_equal(dq[::16], c["dq_s"]) and np.array_equal(dv[::16], c["dv_s"])
+
+
+@pytest.mark.parametrize("name", ["p4k2_tau02", "p4k2_tau01", "p3k2", "ragged", "quick_check"])
+def test_sdm_closed_form_matches_reference_autograd(name):
+    c = _golden.load_sdm()[name]
+    q, v, y = _golden.sdm_inputs(c)
+    loss, dq, dv = osdm.sdm_fwd_bwd_f64(q, v, y, tau=float(c["tau"]))
+    assert abs(loss - float(c["loss"])) < 1e-5 * max(1.0, abs(loss))
+    assert np.abs(dq - c["dq"]).max() < 1e-5 * np.abs(c["dq"]).max() + 1e-9
+    assert np.abs(dv - c["dv"]).max() < 1e-5 * np.abs(c["dv"]).max() + 1e-9
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_sdm_oracle_matches_live_reference():
+    sdm = ref_loader.load_reference_sdm().sdm_loss_stable
+    g = torch.Generator().manual_seed(123)
+    q = torch.randn(24, 512, generator=g); v = torch.randn(20, 512, generator=g)
+    lq = torch.randint(0, 6, (24,), generator=g); lv = torch.randint(0, 7, (20,), generator=g)
+    y = (lq[:, None] == lv[None, :]).float()
+    a = ref_loader.quiet(sdm, q, v, y, tau=0.3)
+    b = osdm.sdm_loss_oracle(q, v, y, tau=0.3)
+    assert float(a) == float(b)
