@@ -1,0 +1,154 @@
+/* reid_b200.h -- C ABI of libreid_b200.so: B200 (sm_100a) kernels for the PRCV2025REID hot path.
+ *
+ * The reference (LingmaFuture/PRCV2025REID) has no FFI layer; its boundary for this path is a
+ * set of Python functions.  Each entry point below names the reference
+ * code it replaces (file:line under the reference tree).  Conventions:
+ *   - C linkage, POD arguments only, caller-owned DEVICE memory on the current CUDA device;
+ *   - every launch is ordered on the passed stream (a cudaStream_t as void*), no host sync,
+ *     no hidden allocation -- scratch comes from the caller (`workspace`), sized by
+ *     reid_workspace_bytes();
+ *   - return 0 = OK, negative = REID_E_* (see reid_strerror); never throws.
+ *   - gallery / query feature rows are dense row-major, row stride = d elements, d % 8 == 0.
+ */
+#ifndef REID_B200_H
+#define REID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REID_OK 0
+#define REID_E_INVALID -1    /* bad argument (null pointer, unsupported d / k / topk ...) */
+#define REID_E_CUDA -2       /* a CUDA runtime / driver call failed (cudaGetLastError kept) */
+#define REID_E_WORKSPACE -3  /* workspace too small */
+#define REID_E_UNSUPPORTED -4
+
+#define REID_DTYPE_F32 0
+#define REID_DTYPE_BF16 1
+#define REID_DTYPE_F16 2
+
+/* fixed sizes of the fused retrieval path */
+#define REID_KLIST 32        /* per-(query, gallery-chunk) running top list; candidates are complete down to it */
+#define REID_RTOP 32         /* candidates re-scored in fp32 per query and shard */
+
+const char* reid_strerror(int code);
+int reid_abi_version(void);
+
+/* ---- K1: eval_mm_protocol.py:46-48 `l2n` (F.normalize(x, dim=-1)): out = x / max(||x||2, eps).
+ * out_f32 and/or out_f16 may be NULL.  out_f16 is the tensor-core operand copy. */
+int reid_l2norm_rows(const float* x, float* out_f32, void* out_f16, int64_t rows, int d, float eps,
+                     void* stream);
+
+/* ---- K2: eval_mm_protocol.py:328-365 `extract_query_feat` on pre-extracted features:
+ * out[q] = l2n( sum_j w[mod_id[q,j]] * l2n(feats[q,j,:]) ), slots with mod_id < 0 are skipped;
+ * k == 1 (single modality) reproduces l2n(l2n(f)) without the weight (:209-210, :359). */
+int reid_mm_fuse_normalize(const float* feats, const int32_t* mod_id, const float* w, int n_mod,
+                           float* out_f32, void* out_f16, int64_t Q, int k, int d, void* stream);
+
+/* ---- K3: eval_mm_protocol.py:50-53 `cosine_sim` (a @ b.T) as a TMA-fed tcgen05 GEMM on fp16
+ * operands with fp32 accumulation in TMEM; S is [Q, ldS] fp32 row-major, ldS >= G. */
+int reid_sim_gemm(const void* q_f16, const void* g_f16, float* S, int64_t Q, int64_t G, int d,
+                  int64_t ldS, void* stream);
+
+/* ---- gallery identity index (replaces the per-query `(g_pids == pid)` scans of
+ * eval_mm_protocol.py:390,427).  sorted_pid/order: gallery rows sorted by pid (stable).
+ * max_run (device int32[1]) = largest number of gallery rows sharing one pid (= Pmax bound). */
+int reid_pid_index_build(const int64_t* g_pid, int64_t G, int64_t* sorted_pid, int32_t* order,
+                         int32_t* max_run, void* workspace, size_t workspace_bytes, void* stream);
+/* code[i] = first position of pids[i] in sorted_pid, or -1 when absent; count[i] = run length. */
+int reid_pid_lookup(const int64_t* sorted_pid, int64_t G, const int64_t* pids, int64_t n,
+                    int32_t* code, int32_t* count, void* stream);
+
+/* ---- exact fp32 scores of every query's positives (eval_mm_protocol.py:427 `is_pos`),
+ * slot j of query q is gallery row order[q_code[q] + j].  Rows outside the local shard
+ * [g_offset, g_offset + G_local), masked rows (excl) and slots >= q_count[q] get -inf.
+ * excl: [Q, E] global gallery indices masked for the query (same-image rule :408-418), -1 pad. */
+int reid_pos_scores(const float* q_f32, const float* g_f32, const int32_t* order,
+                    const int32_t* q_code, const int32_t* q_count, const int32_t* excl, int E,
+                    int64_t Q, int64_t G_local, int64_t g_offset, int d, int Pmax,
+                    float* pos_score, void* stream);
+/* sort each row of pos_score descending in place; n_pos[q] = number of finite entries. */
+int reid_pos_sort(float* pos_score, int32_t* n_pos, int64_t Q, int Pmax, void* stream);
+
+/* ---- K3+K4 fused: eval_mm_protocol.py:401-455 for one gallery shard without materialising
+ * S or an argsort.  tcgen05 GEMM (fp16 in, fp32 TMEM accumulators) whose epilogue
+ *   (a) counts, for every positive threshold pos_thr[q,j] (sorted desc), the local gallery rows
+ *       that are neither positives of q nor masked and score above it  -> pos_above[q,j] (+=)
+ *   (b) appends every row that beats the running REID_KLIST-th best of its (query, chunk) to
+ *       cand_score/cand_idx[q, chunk, :cand_cap] (local row index), count in cand_count[q,chunk].
+ * g_code / q_code: pid codes from reid_pid_lookup.  n_chunks = gallery chunks per query block
+ * (work decomposition; buffers are sized with it).  pos_above and cand_count must be zeroed. */
+int reid_retrieve_fused(const void* q_f16, const void* g_f16, const int32_t* q_code,
+                        const int32_t* g_code, const int32_t* excl, int E, const float* pos_thr,
+                        const int32_t* n_pos, int64_t Q, int64_t G_local, int64_t g_offset, int d,
+                        int Pmax, int n_chunks, int cand_cap, int32_t* pos_above,
+                        float* cand_score, int32_t* cand_idx, int32_t* cand_count,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- exact fp32 SIMT form of the same step (all scores in fp32, CUDA cores).  Used for the
+ * queries the fused path flags, for tiny problems, and as the in-library cross-check.
+ * q_sel: optional list of n_sel query indices to process (NULL = all Q). */
+int reid_retrieve_exact(const float* q_f32, const float* g_f32, const int32_t* q_code,
+                        const int32_t* g_code, const int32_t* excl, int E, const float* pos_thr,
+                        const int32_t* n_pos, const int32_t* q_sel, int64_t n_sel, int64_t Q,
+                        int64_t G_local, int64_t g_offset, int d, int Pmax, int n_chunks,
+                        int cand_cap, int32_t* pos_above, float* cand_score, int32_t* cand_idx,
+                        int32_t* cand_count, void* stream);
+
+/* ---- candidate re-scoring: gathers a query's candidates, keeps the REID_RTOP best by
+ * approximate score, re-scores them in fp32 (same dot routine as reid_pos_scores), sorts
+ * them (score desc, index asc) -> top_score/top_idx[q, REID_RTOP] (global gallery index, -1 pad).
+ * Positives whose threshold lies above the completeness cut-off (+eps) get their exact
+ * local count written to pos_above.  flag[q] != 0 when exactness of top-`topk` / CMC cannot be
+ * guaranteed within eps (or a candidate buffer overflowed): re-run those through
+ * reid_retrieve_exact.  eps = bound on |approx - exact| score error (0 for the exact path). */
+int reid_rescore_topk(const float* q_f32, const float* g_f32, const int32_t* q_code,
+                      const int32_t* g_code, const float* pos_thr, const int32_t* n_pos,
+                      const float* cand_score, const int32_t* cand_idx, const int32_t* cand_count,
+                      const int32_t* q_sel, int64_t n_sel, int64_t Q, int64_t G_local,
+                      int64_t g_offset, int d, int Pmax, int n_chunks, int cand_cap, int topk,
+                      float eps, int32_t* pos_above, float* top_score, int32_t* top_idx,
+                      int32_t* flag, void* stream);
+
+/* merge n_lists per-shard top lists [n_lists, Q, REID_RTOP] into out[Q, topk] (score desc, idx asc) */
+int reid_merge_topk(const float* scores, const int32_t* idx, int n_lists, int64_t Q, int topk,
+                    float* out_score, int32_t* out_idx, void* stream);
+
+/* ---- metrics: eval_mm_protocol.py:435-469.  rank_j = 1 + pos_above[q,j] + j;
+ * AP = (1/P) sum_j (j+1)/rank_j in float64; hit@k = rank_0 <= k; queries with n_pos == 0 are
+ * skipped (:430-432).  out[5] = {mAP, R@1, R@5, R@10, num_valid}; ap_per_query optional [Q]. */
+int reid_metrics_reduce(const int32_t* pos_above, const int32_t* n_pos, int64_t Q, int Pmax,
+                        double* out, double* ap_per_query, void* stream);
+
+/* ---- SDM loss: models/sdm_loss.py:13-149 `sdm_loss_stable`, batched over modality pairs.
+ * One launch computes every pair; pair p uses qry[p] [N_p, d], gal[p] [M_p, d] (dtype F32 or
+ * BF16), y[p] [N_p, M_p] float {0,1}.  loss[p] (fp32), status[p] (bit0: returned the reference's
+ * non-differentiable zero; bit1: non-finite feature; bit2: non-finite S; bit3: no positives).
+ * saved[p]: fp32 scratch of reid_sdm_saved_floats(N,M) floats kept for the backward. */
+typedef struct {
+  const void* qry; const void* gal; const float* y;
+  int32_t N; int32_t M;
+  float* loss; int32_t* status; float* saved;
+  const float* grad_out;   /* backward only: upstream scalar gradient */
+  void* dqry; void* dgal;  /* backward only: gradients in the input dtype */
+} reid_sdm_pair;
+#define REID_SDM_MAX_PAIRS 16
+size_t reid_sdm_saved_floats(int N, int M, int d);
+int reid_sdm_fwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps,
+                 void* stream);
+int reid_sdm_bwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps,
+                 void* stream);
+
+/* scratch sizes.  which: 0 = reid_pid_index_build(G), 1 = reid_retrieve_fused */
+size_t reid_workspace_bytes(int which, int64_t Q, int64_t G, int d);
+
+/* device properties the host side sizes grids with */
+int reid_device_sm_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,95 @@
+"""ctypes binding of libreid_b200.so (include/reid_b200.h).  No CPU fallback: importing the
+kernels without the built library raises."""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p, POINTER, Structure
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libreid_b200.so")
+
+KLIST = 32
+RTOP = 32
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+SDM_MAX_PAIRS = 16
+
+
+class ReidError(RuntimeError):
+    pass
+
+
+class SdmPair(Structure):
+    _fields_ = [("qry", c_void_p), ("gal", c_void_p), ("y", c_void_p), ("N", c_int32), ("M", c_int32),
+                ("loss", c_void_p), ("status", c_void_p), ("saved", c_void_p), ("grad_out", c_void_p),
+                ("dqry", c_void_p), ("dgal", c_void_p)]
+
+
+_SIGS = {
+    "reid_strerror": (c_char_p, [c_int]),
+    "reid_abi_version": (c_int, []),
+    "reid_device_sm_count": (c_int, []),
+    "reid_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64, c_int]),
+    "reid_l2norm_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
+    "reid_mm_fuse_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "reid_sim_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_void_p]),
+    "reid_pid_index_build": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "reid_pid_lookup": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "reid_pos_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
+                                c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "reid_pos_sort": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "reid_retrieve_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "reid_retrieve_exact": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "reid_rescore_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
+                                  c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "reid_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "reid_metrics_reduce": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "reid_sdm_saved_floats": (c_size_t, [c_int, c_int, c_int]),
+    "reid_sdm_fwd": (c_int, [POINTER(SdmPair), c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "reid_sdm_bwd": (c_int, [POINTER(SdmPair), c_int, c_int, c_int, c_float, c_float, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = sorted(_SIGS)
+_lib = None
+
+
+def lib():
+    """The loaded library; raises ReidError when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ReidError("libreid_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().reid_strerror(rc).decode()
+        extra = ""
+        if rc == -2:
+            try:
+                import torch
+                torch.cuda.synchronize()
+            except Exception as e:  # surface the CUDA error text
+                extra = " (%s)" % e
+        raise ReidError("%s failed: %s [%d]%s" % (what or "libreid_b200 call", msg, rc, extra))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,387 @@
+// rank.cu -- exact fp32 retrieval (SIMT), candidate re-scoring, shard merge, metrics.
+//
+// Replaces eval_mm_protocol.py:401-469 (sims, mask, argsort, CMC, AP) without an argsort:
+//   rank_j = 1 + #{valid non-positive g : s_g > s_pos_j} + j   (positives sorted descending)
+//   AP     = (1/P) sum_j (j+1) / rank_j          (== the reference's walk down the full ranking)
+//   hit@k  = rank_0 <= k
+// reid_retrieve_exact is the all-fp32 CUDA-core form (fallback for flagged queries, tiny
+// problems, in-library cross-check of the tcgen05 path); reid_rescore_topk turns per-chunk
+// candidate buffers into an exactly ordered top list; reid_metrics_reduce produces the dict.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// exact path: CTA = 8 warps, QT queries staged in smem, gallery chunk streamed by warps.
+// ------------------------------------------------------------------------------------------
+constexpr int XQT = 8;        // queries per CTA
+constexpr int XWARPS = 8;
+
+__global__ void __launch_bounds__(XWARPS * 32)
+retrieve_exact_kernel(const float* __restrict__ q_f32, const float* __restrict__ g_f32,
+                      const int32_t* __restrict__ q_code, const int32_t* __restrict__ g_code,
+                      const int32_t* __restrict__ excl, int E, const float* __restrict__ pos_thr,
+                      const int32_t* __restrict__ n_pos, const int32_t* __restrict__ q_sel, int64_t n_sel,
+                      int64_t G_local, int64_t g_offset, int d, int Pmax, int n_chunks, int cand_cap,
+                      int32_t* __restrict__ pos_above, float* __restrict__ cand_score,
+                      int32_t* __restrict__ cand_idx, int32_t* __restrict__ cand_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sq = reinterpret_cast<float*>(smem_raw);                  // [XQT][d]
+  float* sthr = sq + XQT * d;                                      // [XQT][Pmax]
+  int32_t* scnt = reinterpret_cast<int32_t*>(sthr + XQT * Pmax);   // [XQT][Pmax]
+  int32_t* sexcl = scnt + XQT * Pmax;                              // [XQT][max(E,1)]
+  __shared__ int s_qidx[XQT], s_code[XQT], s_npos[XQT];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunk = blockIdx.y;
+  const int64_t qt0 = (int64_t)blockIdx.x * XQT;
+  const int Ee = E > 0 ? E : 1;
+
+  if (threadIdx.x < XQT) {
+    const int64_t sel = qt0 + threadIdx.x;
+    int qi = -1;
+    if (sel < n_sel) qi = q_sel ? q_sel[sel] : (int)sel;
+    s_qidx[threadIdx.x] = qi;
+    s_code[threadIdx.x] = qi >= 0 ? q_code[qi] : -2;
+    s_npos[threadIdx.x] = qi >= 0 ? min(n_pos[qi], Pmax) : 0;
+  }
+  __syncthreads();
+  for (int t = 0; t < XQT; ++t) {
+    const int qi = s_qidx[t];
+    for (int c = threadIdx.x; c < d; c += blockDim.x) sq[t * d + c] = qi >= 0 ? q_f32[(int64_t)qi * d + c] : 0.f;
+    for (int p = threadIdx.x; p < Pmax; p += blockDim.x) {
+      sthr[t * Pmax + p] = qi >= 0 ? pos_thr[(int64_t)qi * Pmax + p] : INFINITY;
+      scnt[t * Pmax + p] = 0;
+    }
+    for (int e = threadIdx.x; e < Ee; e += blockDim.x)
+      sexcl[t * Ee + e] = (qi >= 0 && E > 0) ? excl[(int64_t)qi * E + e] : -1;
+  }
+  __syncthreads();
+
+  // per-warp running top list: lane i holds entry i of each query's list
+  // (all of s, lmin, nfill are warp-uniform; only lv / li differ per lane)
+  float lv[XQT]; int li[XQT]; float lmin[XQT]; int nfill[XQT];
+#pragma unroll
+  for (int t = 0; t < XQT; ++t) { lv[t] = REID_NEG_INF; li[t] = -1; lmin[t] = REID_NEG_INF; nfill[t] = 0; }
+
+  const int64_t rows_per_chunk = (G_local + n_chunks - 1) / n_chunks;
+  const int64_t r0 = chunk * rows_per_chunk;
+  const int64_t r1 = reid_min64(G_local, r0 + rows_per_chunk);
+  for (int64_t r = r0 + warp; r < r1; r += XWARPS) {
+    const float* grow = g_f32 + r * (int64_t)d;
+    const int gcode = g_code[r];
+    const int32_t gidx = (int32_t)(g_offset + r);
+#pragma unroll
+    for (int t = 0; t < XQT; ++t) {
+      if (s_qidx[t] < 0) continue;
+      const float s = warp_dot(sq + t * d, grow, d, lane);
+      bool masked = false;
+      for (int e = 0; e < Ee; ++e) masked |= (sexcl[t * Ee + e] == gidx);
+      if (masked) continue;                                     // sims_masked = -1e9 (:421-422)
+      const int np = s_npos[t];
+      if (gcode != s_code[t] && np > 0 && s > sthr[t * Pmax + np - 1]) {
+        for (int p = lane; p < np; p += 32)
+          if (s > sthr[t * Pmax + p]) atomicAdd(&scnt[t * Pmax + p], 1);
+      }
+      if (nfill[t] < 32) {                                      // list not full yet: fill lane by lane
+        if (lane == nfill[t]) { lv[t] = s; li[t] = (int)r; }
+        if (++nfill[t] == 32) lmin[t] = warp_min(lv[t]);
+      } else if (s > lmin[t]) {                                 // replace the current minimum entry
+        const unsigned holders = __ballot_sync(0xffffffffu, lv[t] == lmin[t]);
+        if (lane == __ffs(holders) - 1) { lv[t] = s; li[t] = (int)r; }
+        lmin[t] = warp_min(lv[t]);
+      }
+    }
+  }
+  __syncthreads();
+  // flush: counts and per-warp lists
+  for (int t = 0; t < XQT; ++t) {
+    const int qi = s_qidx[t];
+    if (qi < 0) continue;
+    for (int p = threadIdx.x; p < s_npos[t]; p += blockDim.x) {
+      const int c = scnt[t * Pmax + p];
+      if (c) atomicAdd(&pos_above[(int64_t)qi * Pmax + p], c);
+    }
+    const unsigned have = __ballot_sync(0xffffffffu, li[t] >= 0);
+    if (have) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&cand_count[(int64_t)qi * n_chunks + chunk], __popc(have));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (li[t] >= 0) {
+        const int slot = base + __popc(have & ((1u << lane) - 1));
+        if (slot < cand_cap) {
+          const int64_t o = ((int64_t)qi * n_chunks + chunk) * cand_cap + slot;
+          cand_score[o] = lv[t]; cand_idx[o] = li[t];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// re-scoring: one CTA (4 warps) per query
+// ------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 128;
+
+__device__ void block_bitonic_desc(float* key, int32_t* val, int n2) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float a = key[i], b = key[ixj];
+          const int ia = val[i], ib = val[ixj];
+          const bool first_block = ((i & k) == 0);
+          // descending overall: in a "first" block the better element goes to the lower index
+          const bool swap = first_block ? ranks_before(b, ib, a, ia) : ranks_before(a, ia, b, ib);
+          if (swap) { key[i] = b; key[ixj] = a; val[i] = ib; val[ixj] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g_f32,
+                    const int32_t* __restrict__ q_code, const int32_t* __restrict__ g_code,
+                    const float* __restrict__ pos_thr, const int32_t* __restrict__ n_pos,
+                    const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                    const int32_t* __restrict__ cand_count, const int32_t* __restrict__ q_sel,
+                    int64_t G_local, int64_t g_offset, int d, int Pmax, int n_chunks, int cand_cap, int topk,
+                    float eps, int n2, int32_t* __restrict__ pos_above, float* __restrict__ top_score,
+                    int32_t* __restrict__ top_idx, int32_t* __restrict__ flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* key = reinterpret_cast<float*>(smem_raw);        // [n2]
+  int32_t* val = reinterpret_cast<int32_t*>(key + n2);    // [n2]
+  __shared__ float ex_s[REID_RTOP];
+  __shared__ int32_t ex_i[REID_RTOP];
+  __shared__ int s_total, s_overflow, s_flag;
+
+  const int qi = q_sel ? q_sel[blockIdx.x] : (int)blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_total = 0; s_overflow = 0; s_flag = 0; }
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) { key[i] = REID_NEG_INF; val[i] = 0x7fffffff; }
+  __syncthreads();
+  // gather the chunk buffers (compact, order irrelevant: sorted next)
+  for (int c = 0; c < n_chunks; ++c) {
+    int cnt = cand_count[(int64_t)qi * n_chunks + c];
+    if (cnt > cand_cap) { cnt = cand_cap; if (threadIdx.x == 0) s_overflow = 1; }
+    __syncthreads();
+    const int base = s_total;
+    const int64_t o = ((int64_t)qi * n_chunks + c) * cand_cap;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) { key[base + i] = cand_score[o + i]; val[base + i] = cand_idx[o + i]; }
+    __syncthreads();
+    if (threadIdx.x == 0) s_total = base + cnt;
+  }
+  __syncthreads();
+  const int total = s_total;
+  int ns = 32;                       // sort only the occupied power-of-two prefix
+  while (ns < total) ns <<= 1;
+  block_bitonic_desc(key, val, ns);
+  const int R = min(total, REID_RTOP);
+  // completeness cut-off: every local row whose approximate score exceeds `cut` is a candidate
+  const float cut = (total >= REID_KLIST) ? key[REID_KLIST - 1] : REID_NEG_INF;
+  // exact fp32 re-score of the R best candidates (same dot routine as reid_pos_scores)
+  for (int r = warp; r < REID_RTOP; r += RS_THREADS / 32) {
+    float s = REID_NEG_INF; int gi = 0x7fffffff;
+    if (r < R) {
+      gi = val[r];
+      s = warp_dot(q_f32 + (int64_t)qi * d, g_f32 + (int64_t)gi * d, d, lane);
+    }
+    if (lane == 0) { ex_s[r] = s; ex_i[r] = gi; }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // warp bitonic over 32 entries (score desc, idx asc)
+    float s = ex_s[lane]; int gi = ex_i[lane];
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const float so = __shfl_xor_sync(0xffffffffu, s, j);
+        const int io = __shfl_xor_sync(0xffffffffu, gi, j);
+        const bool lower = (lane & j) == 0;
+        const bool first_block = (lane & k) == 0;
+        const bool other_better = ranks_before(so, io, s, gi);
+        // lower lane of a descending block keeps the better element
+        const bool take = (lower == first_block) ? other_better : !other_better;
+        if (take) { s = so; gi = io; }
+      }
+    }
+    ex_s[lane] = s; ex_i[lane] = gi;
+    top_score[(int64_t)qi * REID_RTOP + lane] = s;
+    top_idx[(int64_t)qi * REID_RTOP + lane] = (lane < R) ? (int32_t)(g_offset + gi) : -1;
+  }
+  __syncthreads();
+  // exact counts for positives above the cut-off; exactness flags
+  const int np = min(n_pos[qi], Pmax);
+  const int qcode = q_code[qi];
+  const float bound = cut + eps;   // no local non-candidate row can score above this
+  for (int j = threadIdx.x; j < np; j += blockDim.x) {
+    const float t = pos_thr[(int64_t)qi * Pmax + j];
+    int lb = 0;
+    for (int r = 0; r < R; ++r) lb += (g_code[ex_i[r]] != qcode && ex_s[r] > t) ? 1 : 0;
+    int32_t* dst = pos_above + (int64_t)qi * Pmax + j;
+    if (t > bound || cut == REID_NEG_INF) *dst = lb;       // exact local count
+    else {
+      if (*dst < lb) *dst = lb;                            // lb is a rigorous lower bound
+      if (j == 0 && lb < 10) s_flag = 1;                   // CMC@10 undecidable within eps
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (cut > REID_NEG_INF && R >= topk && ex_s[topk - 1] < bound) s_flag = 1;        // top-k undecidable
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flag[qi] = (s_flag || s_overflow) ? 1 : 0;
+}
+
+// merge per-shard top lists: one warp-multiple CTA per query, bitonic over n_lists*RTOP entries
+__global__ void __launch_bounds__(128)
+merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, int n_lists, int64_t Q,
+                  int topk, int n2, float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* key = reinterpret_cast<float*>(smem_raw);
+  int32_t* val = reinterpret_cast<int32_t*>(key + n2);
+  const int64_t q = blockIdx.x;
+  const int n = n_lists * REID_RTOP;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    float s = REID_NEG_INF; int gi = 0x7fffffff;
+    if (i < n) {
+      const int l = i / REID_RTOP, r = i % REID_RTOP;
+      const int64_t o = ((int64_t)l * Q + q) * REID_RTOP + r;
+      gi = idx[o]; s = scores[o];
+      if (gi < 0) { gi = 0x7fffffff; s = REID_NEG_INF; }
+    }
+    key[i] = s; val[i] = gi;
+  }
+  __syncthreads();
+  block_bitonic_desc(key, val, n2);
+  for (int i = threadIdx.x; i < topk; i += blockDim.x) {
+    const bool ok = (i < n2) && (val[i] != 0x7fffffff);
+    out_score[q * topk + i] = ok ? key[i] : REID_NEG_INF;
+    out_idx[q * topk + i] = ok ? val[i] : -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// metrics
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+metrics_kernel(const int32_t* __restrict__ pos_above, const int32_t* __restrict__ n_pos, int64_t Q, int Pmax,
+               double* __restrict__ acc /*[5]*/, double* __restrict__ ap_per_query) {
+  double ap_sum = 0.0, h1 = 0.0, h5 = 0.0, h10 = 0.0, nv = 0.0;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
+    const int np = min(n_pos[q], Pmax);
+    double ap = 0.0;
+    if (np > 0) {                                            // else: skipped (:430-432)
+      const int32_t* row = pos_above + q * (int64_t)Pmax;
+      for (int j = 0; j < np; ++j) ap += (double)(j + 1) / (double)(row[j] + j + 1);   // hit / rank_idx (:451)
+      ap /= (double)np;                                      // :455
+      const int first = row[0] + 1;
+      h1 += first <= 1; h5 += first <= 5; h10 += first <= 10;   // :436-438
+      ap_sum += ap; nv += 1.0;
+    }
+    if (ap_per_query) ap_per_query[q] = (np > 0) ? ap : -1.0;
+  }
+  __shared__ double red[5][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v[5] = {ap_sum, h1, h5, h10, nv};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) red[k][warp] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    atomicAdd(&acc[threadIdx.x], s);
+  }
+}
+
+__global__ void metrics_finalize_kernel(double* acc) {
+  const double n = acc[4];
+  for (int k = 0; k < 4; ++k) acc[k] = n > 0.0 ? acc[k] / n : 0.0;   // np.mean / empty -> 0.0 (:458-461)
+}
+
+}  // namespace
+
+extern "C" int reid_retrieve_exact(const float* q_f32, const float* g_f32, const int32_t* q_code,
+                                   const int32_t* g_code, const int32_t* excl, int E, const float* pos_thr,
+                                   const int32_t* n_pos, const int32_t* q_sel, int64_t n_sel, int64_t Q,
+                                   int64_t G_local, int64_t g_offset, int d, int Pmax, int n_chunks, int cand_cap,
+                                   int32_t* pos_above, float* cand_score, int32_t* cand_idx, int32_t* cand_count,
+                                   void* stream) {
+  if (!q_f32 || !g_f32 || !q_code || !g_code || !pos_thr || !n_pos || !pos_above || !cand_score || !cand_idx ||
+      !cand_count || d <= 0 || d % 4 != 0 || Pmax <= 0 || n_chunks <= 0 || (E > 0 && !excl))
+    return REID_E_INVALID;
+  if (cand_cap < XWARPS * 32) return REID_E_INVALID;   // every warp flushes up to 32 entries
+  if (!q_sel) n_sel = Q;
+  if (n_sel <= 0 || G_local <= 0) return REID_OK;
+  const size_t smem = (size_t)XQT * d * 4 + (size_t)XQT * Pmax * 8 + (size_t)XQT * (E > 0 ? E : 1) * 4;
+  if (smem > 200 * 1024) return REID_E_UNSUPPORTED;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(retrieve_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return REID_E_CUDA;
+  dim3 grid((unsigned)((n_sel + XQT - 1) / XQT), (unsigned)n_chunks);
+  retrieve_exact_kernel<<<grid, XWARPS * 32, smem, (cudaStream_t)stream>>>(
+      q_f32, g_f32, q_code, g_code, excl, E, pos_thr, n_pos, q_sel, n_sel, G_local, g_offset, d, Pmax, n_chunks,
+      cand_cap, pos_above, cand_score, cand_idx, cand_count);
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}
+
+extern "C" int reid_rescore_topk(const float* q_f32, const float* g_f32, const int32_t* q_code,
+                                 const int32_t* g_code, const float* pos_thr, const int32_t* n_pos,
+                                 const float* cand_score, const int32_t* cand_idx, const int32_t* cand_count,
+                                 const int32_t* q_sel, int64_t n_sel, int64_t Q, int64_t G_local, int64_t g_offset,
+                                 int d, int Pmax, int n_chunks, int cand_cap, int topk, float eps,
+                                 int32_t* pos_above, float* top_score, int32_t* top_idx, int32_t* flag,
+                                 void* stream) {
+  if (!q_f32 || !g_f32 || !q_code || !g_code || !pos_thr || !n_pos || !cand_score || !cand_idx || !cand_count ||
+      !pos_above || !top_score || !top_idx || !flag || d <= 0 || d % 4 != 0 || topk <= 0 || topk > REID_RTOP)
+    return REID_E_INVALID;
+  if (!q_sel) n_sel = Q;
+  if (n_sel <= 0) return REID_OK;
+  int n2 = 32;
+  while (n2 < n_chunks * cand_cap) n2 <<= 1;
+  const size_t smem = (size_t)n2 * 8;
+  if (smem > 200 * 1024) return REID_E_UNSUPPORTED;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(rescore_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return REID_E_CUDA;
+  rescore_topk_kernel<<<(unsigned)n_sel, RS_THREADS, smem, (cudaStream_t)stream>>>(
+      q_f32, g_f32, q_code, g_code, pos_thr, n_pos, cand_score, cand_idx, cand_count, q_sel, G_local, g_offset, d,
+      Pmax, n_chunks, cand_cap, topk, eps, n2, pos_above, top_score, top_idx, flag);
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}
+
+extern "C" int reid_merge_topk(const float* scores, const int32_t* idx, int n_lists, int64_t Q, int topk,
+                               float* out_score, int32_t* out_idx, void* stream) {
+  if (!scores || !idx || !out_score || !out_idx || n_lists <= 0 || topk <= 0 || n_lists * REID_RTOP > 8192)
+    return REID_E_INVALID;
+  if (Q <= 0) return REID_OK;
+  int n2 = 32;
+  while (n2 < n_lists * REID_RTOP) n2 <<= 1;
+  merge_topk_kernel<<<(unsigned)Q, 128, (size_t)n2 * 8, (cudaStream_t)stream>>>(scores, idx, n_lists, Q, topk, n2,
+                                                                                 out_score, out_idx);
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}
+
+extern "C" int reid_metrics_reduce(const int32_t* pos_above, const int32_t* n_pos, int64_t Q, int Pmax,
+                                   double* out, double* ap_per_query, void* stream) {
+  if (!pos_above || !n_pos || !out || Q < 0 || Pmax <= 0) return REID_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(out, 0, 5 * sizeof(double), st) != cudaSuccess) return REID_E_CUDA;
+  if (Q > 0) {
+    const int grid = (int)reid_min64((Q + 255) / 256, 148 * 4);
+    metrics_kernel<<<grid, 256, 0, st>>>(pos_above, n_pos, Q, Pmax, out, ap_per_query);
+  }
+  metrics_finalize_kernel<<<1, 1, 0, st>>>(out);
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}

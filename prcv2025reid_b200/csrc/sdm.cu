@@ -1,0 +1,388 @@
+// sdm.cu -- SDM cross-modal alignment loss, forward and backward, batched over modality pairs.
+//
+// Replaces models/sdm_loss.py:13-149 (`sdm_loss_stable`) and its autograd backward.
+// One launch per direction covers every (modality -> vis) pair of a training step: the reference
+// issues ~25 ATen ops and >= 10 host syncs per pair; here all guards
+// (non-finite features / similarities, rows without positives, negative result) are evaluated on
+// the device and reported in `status`, the loss is then the reference's zero.
+//
+//   S      = q^ g^T / tau_eff, clamp(+-20)                     (:28, :31-32, :86, :94)
+//   L      = 0.5 * [ mean_{i in R} (lse_i - mean_{pos} S_ij) + mean_{j in C} (lse_j - mean_{pos} S_ij) ]
+//   dL/dS  = 0.5 * [ 1_R (softmax_row - y/cnt_row)/|R| + 1_C (softmax_col - y/cnt_col)/|C| ]
+//   dq^ = dS g^ / tau, dg^ = dS^T q^ / tau, then the normalisation Jacobian.
+//
+// All arithmetic is fp32 on CUDA cores (bf16 inputs are first rounded exactly as the reference's
+// bf16 F.normalize rounds them); a grid of CTAs per pair cooperates through grid-wide barriers
+// (cooperative launch), a single CTA per pair is used when the pair is one tile (C2: N=M=8).
+// HBM roofline per pair, fwd+bwd: 3*(N+M)*d*s + 2*N*M*4 bytes.
+#include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int TB = 256;      // threads per CTA
+constexpr int TM = 64;       // tile rows
+constexpr int TN = 64;       // tile cols
+constexpr int KC = 16;       // k chunk
+
+struct SdmBatch {
+  reid_sdm_pair p[REID_SDM_MAX_PAIRS];
+  int n_pairs;
+};
+
+struct Saved {
+  float *den_q, *den_g, *lse_r, *lse_c, *cnt_r, *cnt_c, *ce_r, *ce_c, *hdr, *S, *dqn, *dgn;
+};
+__host__ __device__ inline size_t saved_floats(int N, int M, int d) {
+  return (size_t)4 * N + (size_t)4 * M + 8 + (size_t)N * M + (size_t)(N + M) * d;
+}
+__device__ inline Saved carve(float* base, int N, int M, int d) {
+  Saved s;
+  s.den_q = base; s.den_g = s.den_q + N;
+  s.lse_r = s.den_g + M; s.lse_c = s.lse_r + N;
+  s.cnt_r = s.lse_c + M; s.cnt_c = s.cnt_r + N;
+  s.ce_r = s.cnt_c + M; s.ce_c = s.ce_r + N;
+  s.hdr = s.ce_c + M;              // [0]=nR [1]=nC [2]=flags(as int bits) [3]=loss
+  s.S = s.hdr + 8;
+  s.dqn = s.S + (size_t)N * M;
+  s.dgn = s.dqn + (size_t)N * d;
+  return s;
+}
+
+template <bool BF16>
+__device__ __forceinline__ float ld_elem(const void* base, size_t i) {
+  if (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
+  return reinterpret_cast<const float*>(base)[i];
+}
+// normalised element exactly as the reference forms it: fp32: x / den ; bf16: round_bf16(x / den)
+template <bool BF16>
+__device__ __forceinline__ float norm_elem(const void* base, size_t i, float den) {
+  const float v = __fdiv_rn(ld_elem<BF16>(base, i), den);
+  if (BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  return v;
+}
+
+__device__ __forceinline__ void sync_all(bool multi) {
+  if (multi) cg::this_grid().sync(); else __syncthreads();
+}
+
+// 64x64 output tile, 256 threads, thread (ty,tx) owns rows ty*4.., cols tx*4..
+// la(r,k) / lb(k,c) are tile-local element functors returning 0 outside the matrix.
+template <bool A_KCONTIG, bool B_KCONTIG, class LA, class LB>
+__device__ __forceinline__ void tile_gemm(int K, LA la, LB lb, float (&acc)[4][4], float (*As)[TM + 4], float (*Bs)[TN + 4]) {
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    if (A_KCONTIG) { const int r = t >> 2, kq = (t & 3) * 4;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) As[kq + u][r] = (k0 + kq + u < K) ? la(r, k0 + kq + u) : 0.f;
+    } else { const int kk = t >> 4, r4 = (t & 15) * 4;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) As[kk][r4 + u] = (k0 + kk < K) ? la(r4 + u, k0 + kk) : 0.f;
+    }
+    if (B_KCONTIG) { const int c = t >> 2, kq = (t & 3) * 4;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Bs[kq + u][c] = (k0 + kq + u < K) ? lb(k0 + kq + u, c) : 0.f;
+    } else { const int kk = t >> 4, c4 = (t & 15) * 4;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Bs[kk][c4 + u] = (k0 + kk < K) ? lb(k0 + kk, c4 + u) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+
+// row denominators max(||x||, eps) in the reference's dtype path + non-finite detection
+template <bool BF16>
+__device__ void phase_norms(const void* x, int rows, int d, float eps, float* den, int* flags, int cta, int nctas) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = cta * (TB / 32) + warp; r < rows; r += nctas * (TB / 32)) {
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) { const float v = ld_elem<BF16>(x, (size_t)r * d + c); ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    float nrm = sqrtf(ss), e = eps;
+    if (BF16) { nrm = __bfloat162float(__float2bfloat16_rn(nrm)); e = __bfloat162float(__float2bfloat16_rn(eps)); }
+    const float dn = fmaxf(nrm, e);
+    bool bad = false;
+    for (int c = lane; c < d; c += 32) bad |= !isfinite(norm_elem<BF16>(x, (size_t)r * d + c, dn));
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 2);     // sdm_loss.py:79-81
+    if (lane == 0) den[r] = dn;
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(TB)
+sdm_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
+  __shared__ __align__(16) float As[KC][TM + 4];
+  __shared__ __align__(16) float Bs[KC][TN + 4];
+  __shared__ double red[TB / 32][4];
+  const bool multi = gridDim.x > 1;
+  const reid_sdm_pair& P = batch.p[blockIdx.y];
+  const int N = P.N, M = P.M, cta = blockIdx.x, nctas = gridDim.x;
+  Saved sv = carve(P.saved, N, M, d);
+  int* flags = reinterpret_cast<int*>(sv.hdr + 2);
+  if (cta == 0 && threadIdx.x == 0) *flags = 0;
+  sync_all(multi);
+  // ---- phase 0: denominators (:31-32) ----
+  phase_norms<BF16>(P.qry, N, d, eps, sv.den_q, flags, cta, nctas);
+  phase_norms<BF16>(P.gal, M, d, eps, sv.den_g, flags, cta, nctas);
+  sync_all(multi);
+  // ---- phase 1: S = q^ g^T / tau, clamp (:86, :94) ----
+  const int tiles_m = (N + TM - 1) / TM, tiles_n = (M + TN - 1) / TN;
+  for (int tile = cta; tile < tiles_m * tiles_n; tile += nctas) {
+    const int i0 = (tile / tiles_n) * TM, j0 = (tile % tiles_n) * TN;
+    float acc[4][4];
+    auto la = [&](int r, int k) { const int i = i0 + r; return i < N ? norm_elem<BF16>(P.qry, (size_t)i * d + k, sv.den_q[i]) : 0.f; };
+    auto lb = [&](int k, int c) { const int j = j0 + c; return j < M ? norm_elem<BF16>(P.gal, (size_t)j * d + k, sv.den_g[j]) : 0.f; };
+    tile_gemm<true, true>(d, la, lb, acc, As, Bs);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    bool bad = false;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = i0 + ty * 4 + a, j = j0 + tx * 4 + b;
+        if (i < N && j < M) {
+          const float s = __fdiv_rn(acc[a][b], tau_eff);
+          bad |= !isfinite(s);
+          sv.S[(size_t)i * M + j] = fminf(fmaxf(s, -20.f), 20.f);
+        }
+      }
+    if (bad) atomicOr(flags, 4);                                            // :89-91
+  }
+  sync_all(multi);
+  // ---- phase 2: per-row and per-column log-sum-exp and cross-entropy (:34-57) ----
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = cta * (TB / 32) + warp; i < N; i += nctas * (TB / 32)) {
+      float mx = -INFINITY;
+      for (int j = lane; j < M; j += 32) mx = fmaxf(mx, sv.S[(size_t)i * M + j]);
+      mx = warp_max(mx);
+      float se = 0.f, ps = 0.f, pc = 0.f;
+      for (int j = lane; j < M; j += 32) {
+        const float s = sv.S[(size_t)i * M + j];
+        se += expf(s - mx);
+        if (P.y[(size_t)i * M + j] > 0.f) { ps += s; pc += 1.f; }
+      }
+      se = warp_sum(se); ps = warp_sum(ps); pc = warp_sum(pc);
+      if (lane == 0) {
+        const float lse = mx + logf(se);
+        sv.lse_r[i] = lse; sv.cnt_r[i] = pc;
+        sv.ce_r[i] = pc > 0.f ? (lse - ps / pc) : 0.f;     // -(q * log_p).sum, q uniform over positives
+      }
+    }
+    // columns: warp handles one column; lanes stride over rows (S is L2 resident, N*M*4 bytes)
+    for (int j = cta * (TB / 32) + warp; j < M; j += nctas * (TB / 32)) {
+      float mx = -INFINITY;
+      for (int i = lane; i < N; i += 32) mx = fmaxf(mx, sv.S[(size_t)i * M + j]);
+      mx = warp_max(mx);
+      float se = 0.f, ps = 0.f, pc = 0.f;
+      for (int i = lane; i < N; i += 32) {
+        const float s = sv.S[(size_t)i * M + j];
+        se += expf(s - mx);
+        if (P.y[(size_t)i * M + j] > 0.f) { ps += s; pc += 1.f; }
+      }
+      se = warp_sum(se); ps = warp_sum(ps); pc = warp_sum(pc);
+      if (lane == 0) {
+        const float lse = mx + logf(se);
+        sv.lse_c[j] = lse; sv.cnt_c[j] = pc;
+        sv.ce_c[j] = pc > 0.f ? (lse - ps / pc) : 0.f;
+      }
+    }
+  }
+  sync_all(multi);
+  // ---- phase 3: means over valid rows / columns, guards (:60-68, :101-106, :121-123, :142-147) ----
+  if (cta == 0) {
+    double sr = 0.0, nr = 0.0, sc = 0.0, nc = 0.0;
+    for (int i = threadIdx.x; i < N; i += TB)
+      if (sv.cnt_r[i] > 0.f && isfinite(sv.ce_r[i])) { sr += sv.ce_r[i]; nr += 1.0; }
+    for (int j = threadIdx.x; j < M; j += TB)
+      if (sv.cnt_c[j] > 0.f && isfinite(sv.ce_c[j])) { sc += sv.ce_c[j]; nc += 1.0; }
+    double v[4] = {sr, nr, sc, nc};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      if (lane == 0) red[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t[4] = {0, 0, 0, 0};
+      for (int w = 0; w < TB / 32; ++w)
+        for (int k = 0; k < 4; ++k) t[k] += red[w][k];
+      int anypos = 0;
+      for (int i = 0; i < N && !anypos; ++i) anypos = sv.cnt_r[i] > 0.f;
+      int st = *flags;
+      if (!anypos) st |= 8;
+      const float lr = t[1] > 0 ? (float)(t[0] / t[1]) : 0.f;
+      const float lc = t[3] > 0 ? (float)(t[2] / t[3]) : 0.f;
+      float loss = 0.5f * (lr + lc);
+      if (!(st & (2 | 4 | 8)) && (isnan(loss) || isinf(loss) || loss < 0.f)) st |= 16;
+      if (st & (2 | 4 | 8 | 16)) { st |= 1; loss = 0.f; }
+      sv.hdr[0] = (float)t[1]; sv.hdr[1] = (float)t[3]; sv.hdr[3] = loss;
+      *flags = st;
+      *P.loss = loss;
+      *P.status = st;
+    }
+  }
+}
+
+template <bool BF16>
+__device__ __forceinline__ void st_out(void* base, size_t i, float v) {
+  if (BF16) reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(base)[i] = v;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(TB)
+sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
+  __shared__ __align__(16) float As[KC][TM + 4];
+  __shared__ __align__(16) float Bs[KC][TN + 4];
+  const bool multi = gridDim.x > 1;
+  const reid_sdm_pair& P = batch.p[blockIdx.y];
+  const int N = P.N, M = P.M, cta = blockIdx.x, nctas = gridDim.x;
+  Saved sv = carve(P.saved, N, M, d);
+  const int st = *reinterpret_cast<const int*>(sv.hdr + 2);
+  const float nR = sv.hdr[0], nC = sv.hdr[1];
+  const float gscale = (st & 1) ? 0.f : (*P.grad_out) * 0.5f / tau_eff;
+  const float wr = nR > 0.f ? gscale / nR : 0.f, wc = nC > 0.f ? gscale / nC : 0.f;
+  // dL/dS element (chain through clamp: zero where saturated)
+  auto dS = [&](int i, int j) -> float {
+    if (i >= N || j >= M) return 0.f;
+    const float s = sv.S[(size_t)i * M + j];
+    if (s >= 20.f || s <= -20.f) return 0.f;
+    const float pos = P.y[(size_t)i * M + j] > 0.f ? 1.f : 0.f;
+    float g = 0.f;
+    const float cr = sv.cnt_r[i], cc = sv.cnt_c[j];
+    if (cr > 0.f && isfinite(sv.ce_r[i])) g += wr * (expf(s - sv.lse_r[i]) - pos / cr);
+    if (cc > 0.f && isfinite(sv.ce_c[j])) g += wc * (expf(s - sv.lse_c[j]) - pos / cc);
+    return g;
+  };
+  const int tiles_d = (d + TN - 1) / TN;
+  const int tq = ((N + TM - 1) / TM) * tiles_d, tg = ((M + TM - 1) / TM) * tiles_d;
+  const bool dead = (st & 1) != 0;   // reference returned its non-differentiable zero: gradients are zero
+  for (int tile = cta; tile < tq + tg && !dead; tile += nctas) {
+    float acc[4][4];
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    if (tile < tq) {        // dq^[i][c] = sum_j dS[i][j] g^[j][c]
+      const int i0 = (tile / tiles_d) * TM, c0 = (tile % tiles_d) * TN;
+      auto la = [&](int r, int k) { return dS(i0 + r, k); };
+      auto lb = [&](int k, int c) { return (c0 + c < d) ? norm_elem<BF16>(P.gal, (size_t)k * d + c0 + c, sv.den_g[k]) : 0.f; };
+      tile_gemm<true, false>(M, la, lb, acc, As, Bs);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = i0 + ty * 4 + a, c = c0 + tx * 4 + b;
+          if (i < N && c < d) sv.dqn[(size_t)i * d + c] = acc[a][b];
+        }
+    } else {                // dg^[j][c] = sum_i dS[i][j] q^[i][c]
+      const int t2 = tile - tq;
+      const int j0 = (t2 / tiles_d) * TM, c0 = (t2 % tiles_d) * TN;
+      auto la = [&](int r, int k) { return dS(k, j0 + r); };
+      auto lb = [&](int k, int c) { return (c0 + c < d) ? norm_elem<BF16>(P.qry, (size_t)k * d + c0 + c, sv.den_q[k]) : 0.f; };
+      tile_gemm<false, false>(N, la, lb, acc, As, Bs);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int j = j0 + ty * 4 + a, c = c0 + tx * 4 + b;
+          if (j < M && c < d) sv.dgn[(size_t)j * d + c] = acc[a][b];
+        }
+    }
+  }
+  sync_all(multi);
+  // normalisation Jacobian: dx = (dxn - x^ (dxn . x^)) / den   (den = ||x|| unless clamped by eps)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = cta * (TB / 32) + warp; r < N + M; r += nctas * (TB / 32)) {
+    const bool isq = r < N;
+    const int row = isq ? r : r - N;
+    const void* x = isq ? P.qry : P.gal;
+    void* out = isq ? P.dqry : P.dgal;
+    const float den = isq ? sv.den_q[row] : sv.den_g[row];
+    const float* dxn = (isq ? sv.dqn : sv.dgn) + (size_t)row * d;
+    float e = eps;
+    if (BF16) e = __bfloat162float(__float2bfloat16_rn(eps));
+    const bool clamped = !(den > e);   // norm <= eps: denominator is the constant eps
+    if (dead) {
+      for (int c = lane; c < d; c += 32) st_out<BF16>(out, (size_t)row * d + c, 0.f);
+      continue;
+    }
+    float dot = 0.f;
+    for (int c = lane; c < d; c += 32) dot = fmaf(dxn[c], norm_elem<BF16>(x, (size_t)row * d + c, den), dot);
+    dot = warp_sum(dot);
+    if (clamped) dot = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float xn = norm_elem<BF16>(x, (size_t)row * d + c, den);
+      st_out<BF16>(out, (size_t)row * d + c, (dxn[c] - xn * dot) / den);
+    }
+  }
+}
+
+template <class K>
+int launch_sdm(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float eps, bool bwd, cudaStream_t st) {
+  if (!pairs || n_pairs <= 0 || n_pairs > REID_SDM_MAX_PAIRS || d <= 0) return REID_E_INVALID;
+  SdmBatch b;
+  b.n_pairs = n_pairs;
+  int max_tiles = 1;
+  for (int i = 0; i < n_pairs; ++i) {
+    const reid_sdm_pair& p = pairs[i];
+    if (!p.qry || !p.gal || !p.y || !p.loss || !p.status || !p.saved || p.N <= 0 || p.M <= 0) return REID_E_INVALID;
+    if (bwd && (!p.grad_out || !p.dqry || !p.dgal)) return REID_E_INVALID;
+    b.p[i] = p;
+    const int tm = (p.N + TM - 1) / TM, tn = (p.M + TN - 1) / TN, td = (d + TN - 1) / TN;
+    const int tiles = bwd ? (tm + tn) * td : tm * tn;
+    const int rows = (p.N + p.M + 7) / 8;
+    const int want = bwd ? tiles : (tiles > 1 ? (tiles > rows ? tiles : rows) : 1);
+    if (want > max_tiles) max_tiles = want;
+  }
+  const float tau_eff = fmaxf(0.15f, fminf(0.5f, tau));                    // sdm_loss.py:28
+  int per_sm = 0, sms = 0, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return REID_E_CUDA;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return REID_E_CUDA;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TB, 0) != cudaSuccess) return REID_E_CUDA;
+  int ctas = max_tiles;
+  const int cap = (per_sm * sms) / n_pairs;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  dim3 grid(ctas, n_pairs);
+  if (ctas == 1) {
+    kernel<<<grid, TB, 0, st>>>(b, d, tau_eff, eps);
+  } else {
+    void* args[] = {&b, &d, (void*)&tau_eff, &eps};
+    if (cudaLaunchCooperativeKernel((const void*)kernel, grid, dim3(TB), args, 0, st) != cudaSuccess) return REID_E_CUDA;
+  }
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}
+
+}  // namespace
+
+extern "C" size_t reid_sdm_saved_floats(int N, int M, int d) { return saved_floats(N, M, d); }
+
+extern "C" int reid_sdm_fwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps, void* stream) {
+  if (dtype == REID_DTYPE_F32) return launch_sdm(sdm_fwd_kernel<false>, pairs, n_pairs, d, tau, eps, false, (cudaStream_t)stream);
+  if (dtype == REID_DTYPE_BF16) return launch_sdm(sdm_fwd_kernel<true>, pairs, n_pairs, d, tau, eps, false, (cudaStream_t)stream);
+  return REID_E_UNSUPPORTED;
+}
+
+extern "C" int reid_sdm_bwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps, void* stream) {
+  if (dtype == REID_DTYPE_F32) return launch_sdm(sdm_bwd_kernel<false>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
+  if (dtype == REID_DTYPE_BF16) return launch_sdm(sdm_bwd_kernel<true>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
+  return REID_E_UNSUPPORTED;
+}

@@ -1,0 +1,246 @@
+"""Tensor-level host side of the retrieval + evaluation path (one gallery shard per process).
+
+Mirrors the math of tools/eval_mm_protocol.py (reference) on device tensors:
+    prepare_gallery   <- build_gallery / extract_gallery_feats cache + `g_feats = l2n(g_feats)` (:546)
+    fuse_queries      <- extract_query_feat (:328-365), batched
+    retrieve          <- the body of rank_and_metrics (:396-469) for a batch of queries
+PyTorch is used only for device memory, streams and (optionally) torch.distributed; every
+arithmetic step is a call into libreid_b200.so.  There is no CPU / eager fallback.
+"""
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import _cabi, sharding
+from ._cabi import check, ptr, stream_ptr
+
+# bound on |fp16 tensor-core score - fp32 score| for unit-norm rows: both operands are rounded to
+# fp16 (relative 2^-11 each), so |err| <= (2*2^-11 + 2^-22) * sum|q_i g_i| <= 2^-10 (Cauchy-Schwarz),
+# plus fp32 accumulation slack.  Queries whose top-k / CMC cannot be decided within this bound are
+# re-run through the all-fp32 kernel, so the bound only affects speed, never results.
+EPS_FP16 = 2.0 ** -10 + 2.0 ** -13
+
+
+def _f32c(t):
+    return t.detach().to(dtype=torch.float32).contiguous()
+
+
+@dataclass
+class GalleryShard:
+    g_f32: torch.Tensor        # [G_local, D] fp32, L2-normalised rows
+    g_f16: torch.Tensor        # [G_local, D] fp16 copy (tensor-core operand)
+    g_code: torch.Tensor       # [G_local] int32 pid code of every local row
+    sorted_pid: torch.Tensor   # [G_total] int64, gallery pids sorted
+    order: torch.Tensor        # [G_total] int32, gallery row of every sorted position
+    pmax: int                  # largest number of gallery rows sharing one pid
+    g_offset: int
+    G_total: int
+
+    @property
+    def G_local(self):
+        return self.g_f32.shape[0]
+
+    @property
+    def d(self):
+        return self.g_f32.shape[1]
+
+
+def l2norm_rows(x: torch.Tensor, want_f16: bool = False, eps: float = 1e-12):
+    """K1.  x [rows, D] fp32 cuda -> (fp32 normalised, fp16 copy or None)."""
+    x = _f32c(x)
+    rows, d = x.shape
+    out = torch.empty_like(x)
+    out16 = torch.empty(rows, d, dtype=torch.float16, device=x.device) if want_f16 else None
+    check(_cabi.lib().reid_l2norm_rows(ptr(x), ptr(out), ptr(out16), rows, d, eps, stream_ptr()), "reid_l2norm_rows")
+    return out, out16
+
+
+def fuse_queries(query_raw: torch.Tensor, mod_id: torch.Tensor, weights: torch.Tensor):
+    """K2.  query_raw [Q,k,D] fp32, mod_id [Q,k] int32 (index into weights, <0 = empty slot),
+    weights [n_mod] fp32 -> (q_f32 [Q,D], q_f16 [Q,D])."""
+    query_raw = _f32c(query_raw)
+    Q, k, d = query_raw.shape
+    mod_id = mod_id.to(device=query_raw.device, dtype=torch.int32).contiguous()
+    weights = weights.to(device=query_raw.device, dtype=torch.float32).contiguous()
+    q32 = torch.empty(Q, d, dtype=torch.float32, device=query_raw.device)
+    q16 = torch.empty(Q, d, dtype=torch.float16, device=query_raw.device)
+    check(_cabi.lib().reid_mm_fuse_normalize(ptr(query_raw), ptr(mod_id), ptr(weights), weights.numel(), ptr(q32),
+                                             ptr(q16), Q, k, d, stream_ptr()), "reid_mm_fuse_normalize")
+    return q32, q16
+
+
+def cosine_sim_f16(q_f16: torch.Tensor, g_f16: torch.Tensor) -> torch.Tensor:
+    """K3 (unfused).  [Q,D] x [G,D] fp16 -> S [Q,G] fp32 via the tcgen05 GEMM."""
+    Q, d = q_f16.shape
+    G = g_f16.shape[0]
+    S = torch.empty(Q, G, dtype=torch.float32, device=q_f16.device)
+    check(_cabi.lib().reid_sim_gemm(ptr(q_f16), ptr(g_f16), ptr(S), Q, G, d, G, stream_ptr()), "reid_sim_gemm")
+    return S
+
+
+def prepare_gallery(gallery: torch.Tensor, g_pid_all: torch.Tensor, g_offset: int = 0) -> GalleryShard:
+    """Normalise the local gallery rows and build the identity index over the WHOLE gallery's pids.
+
+    gallery [G_local, D] (cuda, any float dtype), g_pid_all [G_total] int64 (replicated on every rank).
+    """
+    L = _cabi.lib()
+    dev = gallery.device
+    g32, g16 = l2norm_rows(gallery, want_f16=True)
+    g_pid_all = g_pid_all.to(device=dev, dtype=torch.int64).contiguous()
+    G_total = g_pid_all.numel()
+    sorted_pid = torch.empty_like(g_pid_all)
+    order = torch.empty(G_total, dtype=torch.int32, device=dev)
+    max_run = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = L.reid_workspace_bytes(0, 0, G_total, 0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(L.reid_pid_index_build(ptr(g_pid_all), G_total, ptr(sorted_pid), ptr(order), ptr(max_run), ptr(ws),
+                                 ws_bytes, stream_ptr()), "reid_pid_index_build")
+    G_local = g32.shape[0]
+    g_code = torch.empty(G_local, dtype=torch.int32, device=dev)
+    local_pid = g_pid_all[g_offset:g_offset + G_local].contiguous()
+    check(L.reid_pid_lookup(ptr(sorted_pid), G_total, ptr(local_pid), G_local, ptr(g_code), None, stream_ptr()),
+          "reid_pid_lookup")
+    pmax = int(max_run.item())          # one-time host read when a gallery is installed
+    return GalleryShard(g32, g16, g_code, sorted_pid, order, max(1, pmax), int(g_offset), int(G_total))
+
+
+def _pick_chunks(n_qblocks: int, G_local: int, sms: int) -> int:
+    """Gallery chunks per query block: the smallest split whose last wave is >= 95% full."""
+    best, best_eff = 1, 0.0
+    max_chunks = max(1, min(8, G_local // (128 * 32)))
+    for c in range(1, max_chunks + 1):
+        items = n_qblocks * c
+        waves = -(-items // sms)
+        eff = items / (waves * sms)
+        if eff > best_eff + 1e-9:
+            best, best_eff = c, eff
+        if eff >= 0.95:
+            return c
+    return best
+
+
+@dataclass
+class RetrievalResult:
+    metrics: Dict[str, float]
+    top_idx: torch.Tensor            # [Q, topk] int32 global gallery index (-1 pad)
+    top_score: torch.Tensor          # [Q, topk] fp32 exact scores
+    ap: Optional[torch.Tensor]       # [Q] float64, -1 for skipped queries
+    n_flagged: int                   # queries re-run through the exact kernel (this rank)
+    pos_above: torch.Tensor          # [Q, Pmax] int32
+    n_pos: torch.Tensor              # [Q] int32
+
+
+def retrieve(shard: GalleryShard, q_f32: torch.Tensor, q_f16: Optional[torch.Tensor], q_pid: torch.Tensor,
+             excl: Optional[torch.Tensor] = None, topk: int = 10, mode: str = "fused", eps: float = EPS_FP16,
+             cand_cap: int = 512, query_block: int = 32768, group=None, want_ap: bool = False) -> RetrievalResult:
+    """Ranking statistics of a batch of fused queries against the gallery shard(s).
+
+    mode "fused": tcgen05 GEMM with the counting / candidate epilogue, exact fp32 re-score of the
+    candidates, exact fp32 re-run of the (rare) queries whose top-k / CMC is not decidable within eps.
+    mode "exact": everything through the fp32 SIMT kernel.
+    group: a torch.distributed process group whose ranks hold disjoint contiguous gallery shards.
+    """
+    assert mode in ("fused", "exact")
+    assert 1 <= topk <= _cabi.RTOP
+    L = _cabi.lib()
+    dev = q_f32.device
+    Q, d = q_f32.shape
+    Pmax = shard.pmax
+    q_pid = q_pid.to(device=dev, dtype=torch.int64).contiguous()
+    E = 0
+    if excl is not None and excl.numel() > 0:
+        excl = excl.to(device=dev, dtype=torch.int32).contiguous()
+        E = excl.shape[1]
+    else:
+        excl = None
+    dist = None
+    world = 1
+    if group is not None:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        world = dist.get_world_size(group)
+    st = stream_ptr()
+    sms = L.reid_device_sm_count()
+
+    q_code = torch.empty(Q, dtype=torch.int32, device=dev)
+    q_count = torch.empty(Q, dtype=torch.int32, device=dev)
+    check(L.reid_pid_lookup(ptr(shard.sorted_pid), shard.G_total, ptr(q_pid), Q, ptr(q_code), ptr(q_count), st),
+          "reid_pid_lookup")
+    pos_thr = torch.empty(Q, Pmax, dtype=torch.float32, device=dev)
+    check(L.reid_pos_scores(ptr(q_f32), ptr(shard.g_f32), ptr(shard.order), ptr(q_code), ptr(q_count), ptr(excl), E,
+                            Q, shard.G_local, shard.g_offset, d, Pmax, ptr(pos_thr), st), "reid_pos_scores")
+    if world > 1:
+        sharding.exchange_pos_scores(pos_thr, group)                    # owner rank holds the score, others -inf
+    n_pos = torch.empty(Q, dtype=torch.int32, device=dev)
+    check(L.reid_pos_sort(ptr(pos_thr), ptr(n_pos), Q, Pmax, st), "reid_pos_sort")
+
+    pos_above = torch.zeros(Q, Pmax, dtype=torch.int32, device=dev)
+    top_score = torch.empty(Q, _cabi.RTOP, dtype=torch.float32, device=dev)
+    top_idx = torch.empty(Q, _cabi.RTOP, dtype=torch.int32, device=dev)
+    flag = torch.zeros(Q, dtype=torch.int32, device=dev)
+    n_flagged = 0
+
+    use_fused = mode == "fused" and Pmax <= 64 and d % 64 == 0 and d <= 512 and q_f16 is not None
+    for b0 in range(0, Q, query_block):
+        b1 = min(Q, b0 + query_block)
+        nb = b1 - b0
+        sl = slice(b0, b1)
+        ex_b = excl[sl] if excl is not None else None
+        if use_fused:
+            n_chunks = _pick_chunks(-(-nb // 128), shard.G_local, sms)
+        else:
+            n_chunks = max(1, min(16, (2 * sms) // max(1, -(-nb // 8)), shard.G_local // 1024 or 1))
+        cap = max(cand_cap, 256)
+        cand_score = torch.empty(nb, n_chunks, cap, dtype=torch.float32, device=dev)
+        cand_idx = torch.empty(nb, n_chunks, cap, dtype=torch.int32, device=dev)
+        cand_count = torch.zeros(nb, n_chunks, dtype=torch.int32, device=dev)
+        common_tail = (nb, shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap)
+        if use_fused:
+            check(L.reid_retrieve_fused(ptr(q_f16[sl]), ptr(shard.g_f16), ptr(q_code[sl]), ptr(shard.g_code), ptr(ex_b), E,
+                                        ptr(pos_thr[sl]), ptr(n_pos[sl]), *common_tail, ptr(pos_above[sl]),
+                                        ptr(cand_score), ptr(cand_idx), ptr(cand_count), None, 0, st),
+                  "reid_retrieve_fused")
+        else:
+            check(L.reid_retrieve_exact(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code), ptr(ex_b), E,
+                                        ptr(pos_thr[sl]), ptr(n_pos[sl]), None, nb, *common_tail, ptr(pos_above[sl]),
+                                        ptr(cand_score), ptr(cand_idx), ptr(cand_count), st), "reid_retrieve_exact")
+        check(L.reid_rescore_topk(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code), ptr(pos_thr[sl]),
+                                  ptr(n_pos[sl]), ptr(cand_score), ptr(cand_idx), ptr(cand_count), None, nb, nb,
+                                  shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap, topk,
+                                  float(eps if use_fused else 0.0), ptr(pos_above[sl]), ptr(top_score[sl]),
+                                  ptr(top_idx[sl]), ptr(flag[sl]), st), "reid_rescore_topk")
+        if use_fused:
+            sel = torch.nonzero(flag[sl]).flatten().to(torch.int32)      # host sync: how many to re-run
+            ns = int(sel.numel())
+            if ns:
+                n_flagged += ns
+                pa = pos_above[sl]
+                pa[sel.long()] = 0
+                cand_count[sel.long()] = 0
+                check(L.reid_retrieve_exact(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code),
+                                            ptr(ex_b), E, ptr(pos_thr[sl]), ptr(n_pos[sl]), ptr(sel), ns,
+                                            *common_tail, ptr(pa), ptr(cand_score), ptr(cand_idx), ptr(cand_count), st),
+                      "reid_retrieve_exact(fallback)")
+                check(L.reid_rescore_topk(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code),
+                                          ptr(pos_thr[sl]), ptr(n_pos[sl]), ptr(cand_score), ptr(cand_idx),
+                                          ptr(cand_count), ptr(sel), ns, nb, shard.G_local, shard.g_offset, d, Pmax,
+                                          n_chunks, cap, topk, 0.0, ptr(pa), ptr(top_score[sl]), ptr(top_idx[sl]),
+                                          ptr(flag[sl]), st), "reid_rescore_topk(fallback)")
+
+    if world > 1:
+        sharding.exchange_counts(pos_above, group)                      # counts are additive over shards
+        all_s, all_i = sharding.gather_top_lists(top_score, top_idx, group)
+        n_lists = world
+    else:
+        all_s, all_i, n_lists = top_score, top_idx, 1
+    out_s = torch.empty(Q, topk, dtype=torch.float32, device=dev)
+    out_i = torch.empty(Q, topk, dtype=torch.int32, device=dev)
+    check(L.reid_merge_topk(ptr(all_s), ptr(all_i), n_lists, Q, topk, ptr(out_s), ptr(out_i), st), "reid_merge_topk")
+
+    out = torch.empty(5, dtype=torch.float64, device=dev)
+    ap = torch.empty(Q, dtype=torch.float64, device=dev) if want_ap else None
+    check(L.reid_metrics_reduce(ptr(pos_above), ptr(n_pos), Q, Pmax, ptr(out), ptr(ap), st), "reid_metrics_reduce")
+    m = out.cpu().tolist()                                               # the step's result: D2H read
+    metrics = {"mAP": m[0], "R@1": m[1], "R@5": m[2], "R@10": m[3], "num_queries": int(round(m[4]))}
+    return RetrievalResult(metrics, out_i, out_s, ap, n_flagged, pos_above, n_pos)

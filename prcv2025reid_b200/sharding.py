@@ -1,0 +1,46 @@
+"""Gallery sharding across ranks (one process per GPU) and the exchange steps of the path.
+
+The reference has no distributed code; this is the B200 design of section 8e:
+queries replicated, gallery rows partitioned contiguously, three small collectives per batch:
+  1. all_reduce(MAX) of the positives' exact scores   (owner rank holds the score, others -inf)
+  2. all_reduce(SUM) of the per-positive "rows ranked above" counts (additive over shards)
+  3. all_gather of the per-shard exact top lists, merged per query.
+These helpers are device-agnostic (NCCL on GPUs, gloo in the CPU tests).
+"""
+from typing import Tuple
+
+import torch
+
+
+def shard_range(G: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous row range [start, end) of `rank`; the first G % world ranks get one extra row."""
+    base, rem = divmod(G, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def exchange_pos_scores(pos_score: torch.Tensor, group=None) -> torch.Tensor:
+    import torch.distributed as dist
+    if group is not None or dist.is_initialized():
+        dist.all_reduce(pos_score, op=dist.ReduceOp.MAX, group=group)
+    return pos_score
+
+
+def exchange_counts(pos_above: torch.Tensor, group=None) -> torch.Tensor:
+    import torch.distributed as dist
+    if group is not None or dist.is_initialized():
+        dist.all_reduce(pos_above, op=dist.ReduceOp.SUM, group=group)
+    return pos_above
+
+
+def gather_top_lists(top_score: torch.Tensor, top_idx: torch.Tensor, group=None):
+    """-> ([world, Q, R] scores, [world, Q, R] global indices)."""
+    import torch.distributed as dist
+    if not (group is not None or dist.is_initialized()):
+        return top_score[None], top_idx[None]
+    world = dist.get_world_size(group)
+    all_s = torch.empty((world,) + tuple(top_score.shape), dtype=top_score.dtype, device=top_score.device)
+    all_i = torch.empty((world,) + tuple(top_idx.shape), dtype=top_idx.dtype, device=top_idx.device)
+    dist.all_gather_into_tensor(all_s, top_score.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, top_idx.contiguous(), group=group)
+    return all_s, all_i

@@ -48,24 +48,52 @@ class RetrievalCase:
         return self.gallery_raw.shape[0]
 
 
-def make_retrieval_case(seed: int, n_ids: int, gal_per_id: int, k: int, queries_per_id: int,
-                        excl_frac: float = 0.01, n_excl: int = 2, device="cpu",
-                        dim: int = FEAT_DIM, chunk: int = 1 << 16) -> RetrievalCase:
-    """Generate a case.  Identity centres are regenerated per chunk from the seed so the
-    1M-gallery configuration never needs more than a chunk of scratch."""
+def _chunk_gen(dev, seed: int, stream: int, chunk_index: int) -> torch.Generator:
+    g = torch.Generator(device=dev)
+    g.manual_seed((seed * 1000003 + stream * 7919 + chunk_index) & 0x7FFFFFFFFFFF)
+    return g
+
+
+def make_centres(seed: int, n_ids: int, dim: int = FEAT_DIM, device="cpu"):
     dev = torch.device(device)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(seed)
+    gen = _chunk_gen(dev, seed, 0, 0)
     centres = torch.randn(n_ids, dim, generator=gen, device=dev)
     bias = {m: BIAS_SCALE * torch.randn(dim, generator=gen, device=dev) for m in ("rgb",) + MODALITIES}
+    return centres, bias
 
+
+GALLERY_CHUNK = 1 << 14
+
+
+def make_gallery_rows(seed: int, centres, bias, gal_per_id: int, row_start: int, row_end: int) -> torch.Tensor:
+    """Rows [row_start, row_end) of the synthetic gallery.  Every GALLERY_CHUNK-aligned block has its
+    own generator, so any rank can materialise exactly its shard (chunks are generated whole)."""
+    dev = centres.device
+    out = torch.empty(row_end - row_start, centres.shape[1], device=dev)
+    G = centres.shape[0] * gal_per_id
+    c0 = row_start // GALLERY_CHUNK
+    c1 = (row_end + GALLERY_CHUNK - 1) // GALLERY_CHUNK
+    for c in range(c0, c1):
+        s, e = c * GALLERY_CHUNK, min(G, (c + 1) * GALLERY_CHUNK)
+        noise = torch.randn(e - s, centres.shape[1], generator=_chunk_gen(dev, seed, 1, c), device=dev)
+        pid = torch.arange(s, e, device=dev) // gal_per_id
+        rows = centres[pid] + bias["rgb"] + SIGMA_RGB * noise
+        a, b = max(s, row_start), min(e, row_end)
+        out[a - row_start:b - row_start] = rows[a - s:b - s]
+    return out
+
+
+def make_retrieval_case(seed: int, n_ids: int, gal_per_id: int, k: int, queries_per_id: int,
+                        excl_frac: float = 0.01, n_excl: int = 2, device="cpu",
+                        dim: int = FEAT_DIM, gallery_rows=None) -> RetrievalCase:
+    """Generate a case.  gallery_rows=(start, end) materialises only that gallery shard (g_pid is
+    always the full list)."""
+    dev = torch.device(device)
+    centres, bias = make_centres(seed, n_ids, dim, device)
     G = n_ids * gal_per_id
     g_pid = torch.arange(G, device=dev, dtype=torch.int64) // gal_per_id
-    gallery = torch.empty(G, dim, device=dev)
-    for s in range(0, G, chunk):
-        e = min(G, s + chunk)
-        noise = torch.randn(e - s, dim, generator=gen, device=dev)
-        gallery[s:e] = centres[g_pid[s:e]] + bias["rgb"] + SIGMA_RGB * noise
+    r0, r1 = (0, G) if gallery_rows is None else gallery_rows
+    gallery = make_gallery_rows(seed, centres, bias, gal_per_id, r0, r1)
 
     combos = mm_combos(k)
     Q = n_ids * queries_per_id
@@ -77,15 +105,17 @@ def make_retrieval_case(seed: int, n_ids: int, gal_per_id: int, k: int, queries_
     sig_tab = torch.tensor([SIGMA[m] for m in MODALITIES], device=dev)
     bias_tab = torch.stack([bias[m] for m in MODALITIES])  # [4, D]
     query = torch.empty(Q, k, dim, device=dev)
-    for s in range(0, Q, chunk):
-        e = min(Q, s + chunk)
-        noise = torch.randn(e - s, k, dim, generator=gen, device=dev)
+    for ci, s in enumerate(range(0, Q, GALLERY_CHUNK)):
+        e = min(Q, s + GALLERY_CHUNK)
+        noise = torch.randn(e - s, k, dim, generator=_chunk_gen(dev, seed, 2, ci), device=dev)
         mid = mod_id[s:e].long()
         query[s:e] = centres[q_pid[s:e]][:, None, :] + bias_tab[mid] + sig_tab[mid][..., None] * noise
 
     # same-image exclusions: a seeded fraction of queries masks n_excl gallery rows of its own id
+    n_excl = min(n_excl, k)
     excl = torch.full((Q, max(1, n_excl)), -1, device=dev, dtype=torch.int32)
     if excl_frac > 0 and n_excl > 0:
+        gen = _chunk_gen(dev, seed, 3, 0)
         pick = torch.rand(Q, generator=gen, device=dev) < excl_frac
         idx = torch.nonzero(pick).flatten()
         for j in range(n_excl):

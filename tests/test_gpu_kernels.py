@@ -1,0 +1,279 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval as orc
+from oracle import sdm as osdm
+from prcv2025reid_b200 import synth
+from tests import _golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from prcv2025reid_b200 import engine
+    return engine
+
+
+def _case_to_dev(case):
+    d = "cuda"
+    return (case.gallery_raw.to(d), case.g_pid.to(d), case.query_raw.to(d), case.mod_id.to(d),
+            case.q_pid.to(d), case.excl.to(d))
+
+
+# ---------------------------------------------------------------- K1 / K2
+@pytest.mark.parametrize("rows,d", [(1, 512), (37, 512), (4096, 512), (5, 128), (9, 1024), (3, 516)])
+def test_l2norm_rows_matches_F_normalize(eng, rows, d):
+    g = torch.Generator().manual_seed(rows * 7 + d)
+    x = torch.randn(rows, d, generator=g) * 3.0
+    if rows > 2:
+        x[1] = 0.0                                    # zero row -> zero row (max(norm, eps))
+    ref = orc.l2n(x)
+    out, out16 = eng.l2norm_rows(x.cuda(), want_f16=True)
+    assert torch.allclose(out.cpu(), ref, rtol=0, atol=3e-7)     # <= 2 ulp of values <= 1
+    assert torch.equal(out16.cpu(), out.cpu().to(torch.float16))
+    if rows > 2:
+        assert torch.all(out[1] == 0)
+
+
+@pytest.mark.parametrize("name", _golden.RETRIEVAL_NAMES)
+def test_fuse_normalize_matches_reference_golden(eng, name):
+    case, z = _golden.load_retrieval(name)
+    w = synth.weights_tensor()
+    q32, q16 = eng.fuse_queries(case.query_raw.cuda(), case.mod_id.cuda(), w.cuda())
+    ref = orc.fuse_queries(case.query_raw, case.mod_id, w)
+    assert torch.allclose(q32.cpu(), ref, rtol=0, atol=4e-7)
+    if "q_fused" in z:
+        assert np.abs(q32.cpu().numpy() - z["q_fused"]).max() <= 4e-7
+    assert torch.equal(q16.cpu(), q32.cpu().to(torch.float16))
+
+
+def test_fuse_skips_empty_slots(eng):
+    case = synth.make_retrieval_case(3, 8, 2, 3, 4, excl_frac=0.0)
+    w = synth.weights_tensor()
+    mod = case.mod_id.clone(); mod[:, 2] = -1          # MM-3 rows with the third slot empty == MM-2 rows
+    a, _ = eng.fuse_queries(case.query_raw.cuda(), mod.cuda(), w.cuda())
+    b = orc.fuse_queries(case.query_raw[:, :2], case.mod_id[:, :2], w)
+    assert torch.allclose(a.cpu(), b, rtol=0, atol=4e-7)
+
+
+# ---------------------------------------------------------------- K3
+@pytest.mark.parametrize("Q,G", [(1, 5), (128, 128), (200, 300), (257, 1000), (64, 4097)])
+def test_sim_gemm_matches_fp32_matmul(eng, Q, G):
+    g = torch.Generator().manual_seed(Q + G)
+    a = orc.l2n(torch.randn(Q, 512, generator=g)); b = orc.l2n(torch.randn(G, 512, generator=g))
+    a16, b16 = a.half().cuda(), b.half().cuda()
+    S = eng.cosine_sim_f16(a16, b16).cpu()
+    ref16 = a16.float().cpu() @ b16.float().cpu().T            # same rounded operands, fp32 math
+    assert torch.allclose(S, ref16, rtol=0, atol=2e-6)
+    assert (S - a @ b.T).abs().max() <= eng.EPS_FP16           # documented bound vs the fp32 product
+
+
+# ---------------------------------------------------------------- index + positives
+def test_pid_index_and_positive_scores(eng):
+    case = synth.make_retrieval_case(21, 30, 5, 2, 3, excl_frac=0.3, n_excl=2)
+    gal, gp, qr, mid, qp, ex = _case_to_dev(case)
+    perm = torch.randperm(case.G, generator=torch.Generator().manual_seed(1)).cuda()
+    gal, gp = gal[perm], gp[perm]                               # positives no longer contiguous
+    shard = eng.prepare_gallery(gal, gp)
+    assert shard.pmax == 5
+    assert torch.equal(shard.sorted_pid.cpu(), torch.sort(gp.cpu())[0])
+    assert torch.equal(gp[shard.order.long()].cpu(), shard.sorted_pid.cpu())
+    w = synth.weights_tensor().cuda()
+    q32, q16 = eng.fuse_queries(qr, mid, w)
+    res = eng.retrieve(shard, q32, q16, qp, None, mode="exact")
+    S = (q32 @ shard.g_f32.T).cpu()
+    for qi in range(0, case.Q, 7):
+        pos = torch.nonzero(gp.cpu() == qp[qi].cpu()).flatten()
+        assert int(res.n_pos[qi]) == pos.numel()
+
+
+# ---------------------------------------------------------------- retrieval parity
+def _check_against_oracle(res, case, q32_cpu, g32_cpu, topk=10, tie=2e-6):
+    o = orc.rank_and_metrics_loop(q32_cpu, g32_cpu, case.q_pid, case.g_pid, case.excl, return_per_query=True)
+    m = res.metrics
+    assert m["num_queries"] == o["num_queries"]
+    assert abs(m["mAP"] - o["mAP"]) <= 1e-4
+    for k in ("R@1", "R@5", "R@10"):
+        assert m[k] == o[k], (k, m[k], o[k])
+    # ranking indices: identical except where the reference's own scores tie within `tie`
+    S = q32_cpu @ g32_cpu.T
+    ti = res.top_idx.cpu().numpy()
+    oi = o["_top_idx"]
+    n_diff = 0
+    for qi in range(ti.shape[0]):
+        kk = min(topk, oi.shape[1])
+        if np.array_equal(ti[qi, :kk], oi[qi, :kk]):
+            continue
+        for r in range(kk):
+            if ti[qi, r] != oi[qi, r]:
+                assert abs(float(S[qi, ti[qi, r]]) - float(S[qi, oi[qi, r]])) <= tie, (qi, r)
+                n_diff += 1
+    return o, n_diff
+
+
+@pytest.mark.parametrize("mode", ["exact", "fused"])
+@pytest.mark.parametrize("name", _golden.RETRIEVAL_NAMES)
+def test_retrieve_matches_reference_golden(eng, name, mode):
+    case, z = _golden.load_retrieval(name)
+    gal, gp, qr, mid, qp, ex = _case_to_dev(case)
+    shard = eng.prepare_gallery(gal, gp)
+    q32, q16 = eng.fuse_queries(qr, mid, synth.weights_tensor().cuda())
+    res = eng.retrieve(shard, q32, q16, qp, ex, mode=mode, want_ap=True)
+    gold = z["metrics"]
+    assert res.metrics["num_queries"] == int(gold[4])
+    assert abs(res.metrics["mAP"] - gold[0]) <= 1e-4
+    assert [res.metrics["R@1"], res.metrics["R@5"], res.metrics["R@10"]] == list(gold[1:4])
+    _check_against_oracle(res, case, q32.cpu(), shard.g_f32.cpu())
+    # no mask
+    res2 = eng.retrieve(shard, q32, q16, qp, None, mode=mode)
+    g2 = z["metrics_nomask"]
+    assert abs(res2.metrics["mAP"] - g2[0]) <= 1e-4
+    assert [res2.metrics["R@1"], res2.metrics["R@5"], res2.metrics["R@10"]] == list(g2[1:4])
+
+
+@pytest.mark.parametrize("mode", ["exact", "fused"])
+def test_dropin_rank_and_metrics_matches_reference_golden(mode):
+    from prcv2025reid_b200 import eval_mm_protocol as emp
+    for name in ("mm2_tiny", "mm4_tiny", "mm1_small"):
+        case, z = _golden.load_retrieval(name)
+        queries, gmeta, ext = synth.case_to_reference_inputs(case)
+        g = emp.l2n(case.gallery_raw)                            # CPU in, CPU out like the reference
+        assert g.device.type == "cpu"
+        m = emp.rank_and_metrics(queries, g, gmeta, ext, dict(synth.DEFAULT_WEIGHTS), ignore_same_img=True, mode=mode)
+        gold = z["metrics"]
+        assert m["num_queries"] == int(gold[4])
+        assert abs(m["mAP"] - gold[0]) <= 1e-4
+        assert [m["R@1"], m["R@5"], m["R@10"]] == list(gold[1:4])
+        f = emp.extract_query_feat(queries[0], ext, dict(synth.DEFAULT_WEIGHTS))
+        assert f.shape == (512,)
+
+
+def test_dropin_unknown_modality_raises():
+    from prcv2025reid_b200 import eval_mm_protocol as emp
+    ext = synth.TensorExtractor({"a": torch.randn(512)})
+    with pytest.raises(ValueError):
+        emp.extract_query_feat({"pid": 1, "modalities": ("rgb",), "samples": {"rgb": {"img_path": "a"}}}, ext, {})
+
+
+@pytest.mark.parametrize("mode", ["exact", "fused"])
+def test_queries_without_positive_are_skipped(eng, mode):
+    case = synth.make_retrieval_case(5, 20, 4, 2, 3, excl_frac=0.0)
+    gal, gp, qr, mid, qp, ex = _case_to_dev(case)
+    qp = qp.clone(); qp[:6] = 10_000
+    case.q_pid = qp.cpu()
+    shard = eng.prepare_gallery(gal, gp)
+    q32, q16 = eng.fuse_queries(qr, mid, synth.weights_tensor().cuda())
+    res = eng.retrieve(shard, q32, q16, qp, None, mode=mode)
+    assert res.metrics["num_queries"] == case.Q - 6
+    case.excl = None
+    _check_against_oracle(res, case, q32.cpu(), shard.g_f32.cpu())
+
+
+@pytest.mark.parametrize("mode", ["exact", "fused"])
+def test_c1_config_against_oracle(eng, mode):
+    """BASELINE config 1: MM-2, 3k queries x 10k gallery (seed 1001)."""
+    case = synth.make_retrieval_case(1001, 500, 20, 2, 6, excl_frac=0.01, n_excl=2)
+    gal, gp, qr, mid, qp, ex = _case_to_dev(case)
+    shard = eng.prepare_gallery(gal, gp)
+    q32, q16 = eng.fuse_queries(qr, mid, synth.weights_tensor().cuda())
+    res = eng.retrieve(shard, q32, q16, qp, ex, mode=mode, want_ap=True)
+    o = orc.rank_and_metrics_counting(q32.cpu(), shard.g_f32.cpu(), case.q_pid, case.g_pid, case.excl,
+                                      return_per_query=True)
+    assert res.metrics["num_queries"] == o["num_queries"] == 3000
+    assert abs(res.metrics["mAP"] - o["mAP"]) <= 1e-4
+    for k in ("R@1", "R@5", "R@10"):
+        assert abs(res.metrics[k] - o[k]) <= 1.0 / 3000 + 1e-12     # a fp32-order tie may move one query
+    ap = res.ap.cpu().numpy()
+    assert np.abs(ap - o["_ap"]).max() <= (1e-9 if mode == "exact" else 5e-3)
+    same = (res.top_idx.cpu().numpy() == o["_top_idx"]).all(axis=1).mean()
+    assert same >= 0.995
+
+
+def test_fused_equals_exact_at_scale(eng):
+    """Size-independent property at a gallery larger than L2-resident tiles: the tensor-core path and
+    the all-fp32 path agree (exact CMC / top-k, mAP within 1e-4) on 100k x 2k."""
+    case = synth.make_retrieval_case(1003, 5000, 20, 3, 1, excl_frac=0.01, n_excl=2, device="cuda")
+    q_take = 2048
+    shard = eng.prepare_gallery(case.gallery_raw, case.g_pid)
+    q32, q16 = eng.fuse_queries(case.query_raw[:q_take], case.mod_id[:q_take], synth.weights_tensor().cuda())
+    a = eng.retrieve(shard, q32, q16, case.q_pid[:q_take], case.excl[:q_take], mode="fused", want_ap=True)
+    b = eng.retrieve(shard, q32, q16, case.q_pid[:q_take], case.excl[:q_take], mode="exact", want_ap=True)
+    assert a.metrics["num_queries"] == b.metrics["num_queries"] == q_take
+    assert abs(a.metrics["mAP"] - b.metrics["mAP"]) <= 1e-4
+    for k in ("R@1", "R@5", "R@10"):
+        assert a.metrics[k] == b.metrics[k]
+    assert torch.equal(a.top_idx, b.top_idx)
+    assert torch.equal(a.top_score, b.top_score)
+    assert a.n_flagged <= q_take // 20
+
+
+# ---------------------------------------------------------------- SDM
+SDM_NAMES = ["p4k2_tau02", "p4k2_tau01", "p3k2", "ragged", "no_pos", "nan_feat", "quick_check",
+             "p64k8_fp32", "p64k8_bf16", "p4k2_bf16"]
+
+
+@pytest.mark.parametrize("name", SDM_NAMES)
+def test_sdm_matches_reference_golden(name):
+    from prcv2025reid_b200.sdm_loss import sdm_loss_stable
+    c = _golden.load_sdm()[name]
+    q, v, y = _golden.sdm_inputs(c)
+    bf16 = bool(c["is_bf16"])
+    qd = q.cuda().requires_grad_(True); vd = v.cuda().requires_grad_(True)
+    loss = sdm_loss_stable(qd, vd, y.cuda(), tau=float(c["tau"]))
+    assert loss.dtype == torch.float32 and loss.dim() == 0
+    tol = 1e-3 if bf16 else 1e-5                       # north star: 1e-3 relative (bf16), 1e-5 (fp32)
+    gold = float(c["loss"])
+    assert abs(float(loss) - gold) <= tol * max(1.0, abs(gold))
+    loss.backward()
+    dq, dv = qd.grad.float().cpu().numpy(), vd.grad.float().cpu().numpy()
+    if not bool(c["differentiable"]):
+        assert float(loss) == 0.0 and not dq.any() and not dv.any()
+        return
+    gq = c["dq"] if "dq" in c else c["dq_s"]; gv = c["dv"] if "dv" in c else c["dv_s"]
+    if "dq" not in c:
+        dq, dv = dq[::16], dv[::16]
+    if bf16:
+        # gradients are returned in bf16 (half-ulp 2^-9 relative per element on both sides):
+        # compare in relative Frobenius norm
+        assert np.linalg.norm(dq - gq) <= 1e-2 * np.linalg.norm(gq)
+        assert np.linalg.norm(dv - gv) <= 1e-2 * np.linalg.norm(gv)
+    else:
+        assert np.abs(dq - gq).max() <= 1e-5 * np.abs(gq).max()
+        assert np.abs(dv - gv).max() <= 1e-5 * np.abs(gv).max()
+
+
+def test_sdm_pairs_single_launch_matches_per_pair():
+    from prcv2025reid_b200.sdm_loss import sdm_loss_pairs, sdm_loss_stable
+    feats, labels = synth.make_sdm_batch(2001, 4, 2, device="cuda")
+    y = (labels[:, None] == labels[None, :]).float()
+    vis = feats[0]
+    qs = [f.clone().requires_grad_(True) for f in feats[1:]]
+    vs = [vis.clone().requires_grad_(True) for _ in feats[1:]]
+    losses = sdm_loss_pairs(qs, vs, [y] * 4, tau=0.2)
+    losses.mean().backward()
+    for i in range(4):
+        q1 = feats[i + 1].clone().requires_grad_(True); v1 = vis.clone().requires_grad_(True)
+        l1 = sdm_loss_stable(q1, v1, y, tau=0.2)
+        (l1 / 4).backward()
+        assert float(l1) == float(losses[i])
+        assert torch.equal(q1.grad, qs[i].grad) and torch.equal(v1.grad, vs[i].grad)
+        ref = osdm.sdm_loss_oracle(feats[i + 1].cpu(), vis.cpu(), y.cpu(), tau=0.2)
+        assert abs(float(ref) - float(l1)) <= 1e-5 * float(ref)
+
+
+def test_sdm_large_bf16_grads_against_f64_closed_form():
+    """C5 shape: the kernel's math (fp32) against the float64 closed form on the bf16-rounded inputs."""
+    from prcv2025reid_b200.sdm_loss import sdm_loss_stable
+    feats, labels = synth.make_sdm_batch(2002, 64, 8, n_modalities=2, dtype=torch.bfloat16, device="cuda")
+    y = (labels[:, None] == labels[None, :]).float()
+    q = feats[1].clone().requires_grad_(True); v = feats[0].clone().requires_grad_(True)
+    loss = sdm_loss_stable(q, v, y, tau=0.2)
+    loss.backward()
+    l64, dq64, dv64 = osdm.sdm_fwd_bwd_f64(feats[1].cpu(), feats[0].cpu(), y.cpu(), tau=0.2)
+    assert abs(float(loss) - l64) <= 1e-3 * l64
+    dq = q.grad.float().cpu().numpy(); dv = v.grad.float().cpu().numpy()
+    assert np.linalg.norm(dq - dq64) <= 1e-2 * np.linalg.norm(dq64)
+    assert np.linalg.norm(dv - dv64) <= 1e-2 * np.linalg.norm(dv64)
