@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (see BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3b|c1]
+
+Metric: queries/sec for MM-4 retrieval + evaluation, 512-d features, 100k queries x 1M gallery
+(BASELINE config C4).  One "step" = one pass of the hot path over the whole
+query batch: MM-4 fusion + normalisation (K2), exact positive scores, the fused tcgen05 similarity /
+ranking kernel (K3+K4), candidate re-scoring, shard merge and the metric reduction.  The gallery is
+installed once (normalise + identity index; reported as gallery_prepare_ms, like the reference's
+cached rgb_feats.npy) and, at N > 1, sharded contiguously over the ranks (strong scaling: the job is
+fixed, the per-GPU gallery shrinks).  `value` times the step with inputs resident in HBM; `e2e`
+times the same step through the public tensor API with the query-side inputs in pinned HOST memory
+(H2D inside the timed region) and the metric dict read back (D2H).
+
+--impl reference times the reference algorithm's CPU path (the oracle port of
+tools/eval_mm_protocol.py:369-469, torch CPU, all host threads) on a bounded query sample of the
+same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (seed, n_ids, gal_per_id, k, queries_per_id)   SURVEY.md section 8d
+    "c4": (1005, 25000, 40, 4, 4),      # MM-4, Q=100k, G=1M
+    "c3b": (1004, 5000, 20, 4, 4),      # MM-4, Q=20k,  G=100k
+    "c1": (1001, 500, 20, 2, 6),        # MM-2, Q=3k,   G=10k
+}
+FEAT_DIM = 512
+
+
+def workload_name(w):
+    seed, n_ids, gpi, k, qpi = WORKLOADS[w]
+    return "MM-%d retrieval+eval, %d queries x %d gallery, 512-d synthetic CLIP-shaped features (seed %d)" % (
+        k, n_ids * qpi, n_ids * gpi, seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the reference algorithm (oracle port) on the host cores, bounded query sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import retrieval as orc
+    from prcv2025reid_b200 import synth
+    seed, n_ids, gpi, k, qpi = WORKLOADS[args.workload]
+    cores = torch.get_num_threads()
+    centres, bias = synth.make_centres(seed, n_ids)
+    G = n_ids * gpi
+    gallery = synth.make_gallery_rows(seed, centres, bias, gpi, 0, G)
+    g_pid = torch.arange(G, dtype=torch.int64) // gpi
+    g = orc.l2n(gallery)                                         # eval_mm_protocol.py:546
+    del gallery
+    sample = args.ref_queries
+    n_need = sample * (args.steps + args.warmup)
+    # the first queries of the workload, generated with the full workload's identity centres
+    small = synth.make_retrieval_case(seed, n_ids, gpi, k, qpi, excl_frac=0.0, gallery_rows=(0, 0),
+                                      max_queries=n_need)
+    w = synth.weights_tensor()
+    times = []
+    for it in range(args.steps + args.warmup):
+        sl = slice(it * sample, (it + 1) * sample)
+        t0 = time.perf_counter()
+        q = orc.fuse_queries(small.query_raw[sl], small.mod_id[sl], w)
+        orc.rank_and_metrics_loop(q, g, small.q_pid[sl], g_pid, None)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    qps = sample / t
+    line = {
+        "impl": "reference", "metric": "queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "k": k, "topk": 10},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": "%d queries per step against the full %d-row gallery, per-query loop of "
+                                   "eval_mm_protocol.py:396-455 (torch CPU GEMV + argsort + AP walk)" % (sample, G)},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def time_sdm(torch, synth, sdm_loss_pairs, P, K, n_pairs, dtype, iters=50):
+    feats, labels = synth.make_sdm_batch(2001 if P == 4 else 2002, P, K, n_modalities=5, dtype=dtype, device="cuda")
+    y = (labels[:, None] == labels[None, :]).float()
+    pairs = [(a, b) for a in range(5) for b in range(a)][:n_pairs] if n_pairs > 4 else [(m, 0) for m in range(1, 5)]
+    qs = [feats[a].clone().requires_grad_(True) for a, b in pairs]
+    vs = [feats[b].clone().requires_grad_(True) for a, b in pairs]
+    ys = [y] * len(pairs)
+
+    def step():
+        losses = sdm_loss_pairs(qs, vs, ys, tau=0.2)
+        losses.sum().backward()
+        for t in qs + vs:
+            t.grad = None
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    us = s.elapsed_time(e) * 1e3 / iters
+    N = P * K
+    esz = 2 if dtype == torch.bfloat16 else 4
+    alg_bytes = len(pairs) * (3 * (2 * N) * FEAT_DIM * esz + 2 * N * N * 4)
+    return us, alg_bytes, len(pairs)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-queries", type=int, default=8, help="queries per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-queries", type=int, default=24)
+    ap.add_argument("--no-sdm", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="fused", choices=["fused", "exact"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from prcv2025reid_b200 import _cabi, engine, synth
+    from prcv2025reid_b200 import sharding
+    from prcv2025reid_b200.sdm_loss import sdm_loss_pairs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    seed, n_ids, gpi, k, qpi = WORKLOADS[args.workload]
+    G, Q = n_ids * gpi, n_ids * qpi
+    r0, r1 = sharding.shard_range(G, rank, world)
+    case = synth.make_retrieval_case(seed, n_ids, gpi, k, qpi, excl_frac=0.01, n_excl=2, device=dev,
+                                     gallery_rows=(r0, r1))
+    weights = synth.weights_tensor(device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    shard = engine.prepare_gallery(case.gallery_raw, case.g_pid, g_offset=r0)
+    torch.cuda.synchronize()
+    gallery_prepare_ms = (time.perf_counter() - t0) * 1e3
+    case.gallery_raw = None
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(group)
+        torch.cuda.synchronize()
+
+    def step_resident():
+        q32, q16 = engine.fuse_queries(case.query_raw, case.mod_id, weights)
+        return engine.retrieve(shard, q32, q16, case.q_pid, case.excl, topk=10, mode=args.mode, group=group)
+
+    # host-side (pinned) copies of the query-side inputs for the end-to-end number
+    h_query = case.query_raw.cpu().pin_memory()
+    h_mod = case.mod_id.cpu().pin_memory()
+    h_pid = case.q_pid.cpu().pin_memory()
+    h_excl = case.excl.cpu().pin_memory()
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (h_query, h_mod, h_pid, h_excl))
+
+    def step_e2e():
+        qr = h_query.to(dev, non_blocking=True); mi = h_mod.to(dev, non_blocking=True)
+        qp = h_pid.to(dev, non_blocking=True); ex = h_excl.to(dev, non_blocking=True)
+        q32, q16 = engine.fuse_queries(qr, mi, weights)
+        return engine.retrieve(shard, q32, q16, qp, ex, topk=10, mode=args.mode, group=group)   # metrics: D2H
+
+    def timed(fn, steps, profile=False):
+        for _ in range(args.warmup):
+            res = fn()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        _cabi.LAUNCH_COUNT["n"] = 0
+        if profile:
+            _cabi.PROFILE = []
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            res = fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        prof = _cabi.PROFILE
+        _cabi.PROFILE = None
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return float(t.item()) / steps, res, _cabi.LAUNCH_COUNT["n"] // steps, prof, clocks
+
+    ms_step, res, launches, prof, clocks = timed(step_resident, args.steps, profile=True)
+    ms_e2e, res2, _, _, _ = timed(step_e2e, max(2, args.steps // 2))
+
+    # per-kernel device time over the timed region (CUDA events on the launching stream)
+    per_kernel = {}
+    for name, s, e in prof:
+        d = per_kernel.setdefault(name, [0.0, 0])
+        d[0] += s.elapsed_time(e); d[1] += 1
+    dom = "reid_retrieve_fused" if args.mode == "fused" else "reid_retrieve_exact"
+    roofline = None
+    if dom in per_kernel:
+        tot_ms, n_calls = per_kernel[dom]
+        flops_total = 2.0 * Q * (r1 - r0) * FEAT_DIM * args.steps     # this rank's shard
+        achieved = flops_total / (tot_ms * 1e-3) / 1e12
+        peak, which = 1380.3, "measured (MEASURED_PEAKS.json bf16_tflops_sustained; kernel timed inside a long step)"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak = float(mp.get("bf16_tflops_sustained", peak))
+        except Exception:
+            peak, which = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": which,
+                    "algorithmic_flop_per_launch": flops_total / max(1, n_calls),
+                    "avg_launch_ms": tot_ms / max(1, n_calls), "launches": n_calls,
+                    "share_of_step": tot_ms / (ms_step * args.steps)}
+    kernel_ms = {n: round(v[0] / args.steps, 4) for n, v in sorted(per_kernel.items())}
+
+    line = {
+        "metric": "queries_per_sec", "value": Q / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate / f32 re-score",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "k": k, "topk": 10, "mode": args.mode,
+                   "gallery_rows_per_gpu": r1 - r0, "l2": "inputs larger than L2 (query batch %d MB, gallery shard %d MB fp16)"
+                   % (h2d_bytes >> 20, ((r1 - r0) * FEAT_DIM * 2) >> 20),
+                   "gallery_prepare_ms": round(gallery_prepare_ms, 2), "flagged_queries": res.n_flagged},
+        "metrics": res.metrics,
+        "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 40, "ms_per_step": ms_e2e},
+        "gpu_launches": launches, "kernel_ms_per_step": kernel_ms, "roofline": roofline, "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1:
+        if not args.no_sdm:
+            sdm = {}
+            us, ab, npairs = time_sdm(torch, synth, sdm_loss_pairs, 4, 2, 4, torch.float32)
+            sdm["c2_p4k2_fp32_4pairs"] = {"us_per_step_fwd_bwd": us, "algorithmic_bytes": ab,
+                                          "hbm_gbs": ab / (us * 1e-6) / 1e9}
+            us, ab, npairs = time_sdm(torch, synth, sdm_loss_pairs, 64, 8, 10, torch.bfloat16)
+            sdm["c5_p64k8_bf16_10pairs"] = {"us_per_step_fwd_bwd": us, "algorithmic_bytes": ab,
+                                            "hbm_gbs": ab / (us * 1e-6) / 1e9}
+            line["sdm"] = sdm
+        if not args.no_cpu_baseline:
+            from oracle import retrieval as orc
+            nq = args.cpu_baseline_queries
+            g_cpu = shard.g_f32.cpu()
+            q32, _ = engine.fuse_queries(case.query_raw[:nq], case.mod_id[:nq], weights)
+            qraw, qmod = case.query_raw[:nq].cpu(), case.mod_id[:nq].cpu()
+            t0 = time.perf_counter()
+            qc = orc.fuse_queries(qraw, qmod, weights.cpu())
+            o = orc.rank_and_metrics_loop(qc, g_cpu, case.q_pid[:nq].cpu(), case.g_pid.cpu(), case.excl[:nq].cpu())
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": nq / dt, "unit": "queries/s", "cores": torch.get_num_threads(),
+                                    "kind": "port",
+                                    "sample": "first %d queries of the workload against the full gallery, per-query "
+                                              "loop of eval_mm_protocol.py:396-455 (oracle port, torch CPU)" % nq}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,41 @@ _SIGS = {
 EXPORTED_SYMBOLS = sorted(_SIGS)
 _lib = None
 
+# kernels of THIS library launched per C call (library plumbing such as the CUB sort is not counted)
+_LAUNCHES_PER_CALL = {
+    "reid_l2norm_rows": 1, "reid_mm_fuse_normalize": 1, "reid_sim_gemm": 1, "reid_pid_index_build": 2,
+    "reid_pid_lookup": 1, "reid_pos_scores": 1, "reid_pos_sort": 1, "reid_retrieve_fused": 1,
+    "reid_retrieve_exact": 1, "reid_rescore_topk": 1, "reid_merge_topk": 1, "reid_metrics_reduce": 2,
+    "reid_sdm_fwd": 1, "reid_sdm_bwd": 1,
+}
+LAUNCH_COUNT = {"n": 0}
+# optional per-kernel device timing: set PROFILE = [] and every kernel call appends (name, start, end) events
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, name, fn):
+        self.name, self.fn, self.n = name, fn, _LAUNCHES_PER_CALL[name]
+
+    def __call__(self, *a):
+        LAUNCH_COUNT["n"] += self.n
+        if PROFILE is None:
+            return self.fn(*a)
+        import torch
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = self.fn(*a)
+        e.record()
+        PROFILE.append((self.name, s, e))
+        return rc
+
+
+class _Lib:
+    def __init__(self, cdll):
+        for name in _SIGS:
+            fn = getattr(cdll, name)
+            setattr(self, name, _Timed(name, fn) if name in _LAUNCHES_PER_CALL else fn)
+
 
 def lib():
     """The loaded library; raises ReidError when it has not been built (no fallback path exists)."""
@@ -68,7 +103,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = L
+        _lib = _Lib(L)
     return _lib
 
 

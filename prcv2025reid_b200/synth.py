@@ -85,9 +85,9 @@ def make_gallery_rows(seed: int, centres, bias, gal_per_id: int, row_start: int,
 
 def make_retrieval_case(seed: int, n_ids: int, gal_per_id: int, k: int, queries_per_id: int,
                         excl_frac: float = 0.01, n_excl: int = 2, device="cpu",
-                        dim: int = FEAT_DIM, gallery_rows=None) -> RetrievalCase:
+                        dim: int = FEAT_DIM, gallery_rows=None, max_queries=None) -> RetrievalCase:
     """Generate a case.  gallery_rows=(start, end) materialises only that gallery shard (g_pid is
-    always the full list)."""
+    always the full list); max_queries keeps only the first queries of the workload."""
     dev = torch.device(device)
     centres, bias = make_centres(seed, n_ids, dim, device)
     G = n_ids * gal_per_id
@@ -97,6 +97,8 @@ def make_retrieval_case(seed: int, n_ids: int, gal_per_id: int, k: int, queries_
 
     combos = mm_combos(k)
     Q = n_ids * queries_per_id
+    if max_queries is not None:
+        Q = min(Q, int(max_queries))
     q_pid = torch.arange(Q, device=dev, dtype=torch.int64) // queries_per_id
     # query j of an identity uses combination j % len(combos) (mirrors the C(4,k) combos per id)
     combo_of_q = (torch.arange(Q, device=dev) % queries_per_id) % len(combos)
@@ -107,7 +109,8 @@ def make_retrieval_case(seed: int, n_ids: int, gal_per_id: int, k: int, queries_
     query = torch.empty(Q, k, dim, device=dev)
     for ci, s in enumerate(range(0, Q, GALLERY_CHUNK)):
         e = min(Q, s + GALLERY_CHUNK)
-        noise = torch.randn(e - s, k, dim, generator=_chunk_gen(dev, seed, 2, ci), device=dev)
+        full = min(n_ids * queries_per_id, s + GALLERY_CHUNK) - s      # chunks are generated whole
+        noise = torch.randn(full, k, dim, generator=_chunk_gen(dev, seed, 2, ci), device=dev)[:e - s]
         mid = mod_id[s:e].long()
         query[s:e] = centres[q_pid[s:e]][:, None, :] + bias_tab[mid] + sig_tab[mid][..., None] * noise
 
@@ -116,11 +119,11 @@ def make_retrieval_case(seed: int, n_ids: int, gal_per_id: int, k: int, queries_
     excl = torch.full((Q, max(1, n_excl)), -1, device=dev, dtype=torch.int32)
     if excl_frac > 0 and n_excl > 0:
         gen = _chunk_gen(dev, seed, 3, 0)
-        pick = torch.rand(Q, generator=gen, device=dev) < excl_frac
-        idx = torch.nonzero(pick).flatten()
-        for j in range(n_excl):
-            off = torch.randint(0, gal_per_id, (idx.numel(),), generator=gen, device=dev)
-            excl[idx, j] = (q_pid[idx] * gal_per_id + off).to(torch.int32)
+        q_full = n_ids * queries_per_id                      # drawn for the whole workload, then cut
+        pick = (torch.rand(q_full, generator=gen, device=dev) < excl_frac)[:Q]
+        off = torch.randint(0, gal_per_id, (q_full, n_excl), generator=gen, device=dev)[:Q]
+        rows = (q_pid[:, None] * gal_per_id + off).to(torch.int32)
+        excl = torch.where(pick[:, None], rows, excl)
     return RetrievalCase(gallery, g_pid, query, mod_id, q_pid, excl, k)
 
 
