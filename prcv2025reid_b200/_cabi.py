@@ -58,7 +58,7 @@ _lib = None
 # kernels of THIS library launched per C call (library plumbing such as the CUB sort is not counted)
 _LAUNCHES_PER_CALL = {
     "reid_l2norm_rows": 1, "reid_mm_fuse_normalize": 1, "reid_sim_gemm": 1, "reid_pid_index_build": 2,
-    "reid_pid_lookup": 1, "reid_pos_scores": 1, "reid_pos_sort": 1, "reid_retrieve_fused": 1,
+    "reid_pid_lookup": 1, "reid_pos_scores": 1, "reid_pos_sort": 1, "reid_retrieve_fused": 2,
     "reid_retrieve_exact": 1, "reid_rescore_topk": 1, "reid_merge_topk": 1, "reid_metrics_reduce": 2,
     "reid_sdm_fwd": 1, "reid_sdm_bwd": 1,
 }

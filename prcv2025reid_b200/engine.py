@@ -197,9 +197,11 @@ def retrieve(shard: GalleryShard, q_f32: torch.Tensor, q_f16: Optional[torch.Ten
         cand_count = torch.zeros(nb, n_chunks, dtype=torch.int32, device=dev)
         common_tail = (nb, shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap)
         if use_fused:
+            ws_bytes = L.reid_workspace_bytes(1, nb, shard.G_local, d)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             check(L.reid_retrieve_fused(ptr(q_f16[sl]), ptr(shard.g_f16), ptr(q_code[sl]), ptr(shard.g_code), ptr(ex_b), E,
                                         ptr(pos_thr[sl]), ptr(n_pos[sl]), *common_tail, ptr(pos_above[sl]),
-                                        ptr(cand_score), ptr(cand_idx), ptr(cand_count), None, 0, st),
+                                        ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(ws), ws_bytes, st),
                   "reid_retrieve_fused")
         else:
             check(L.reid_retrieve_exact(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code), ptr(ex_b), E,

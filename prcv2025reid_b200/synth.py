@@ -17,8 +17,9 @@ MOD_ID = {m: i for i, m in enumerate(MODALITIES)}
 # default weight_cfg of run_eval (eval_mm_protocol.py:504)
 DEFAULT_WEIGHTS = {"ir": 1.0, "cpencil": 1.0, "sketch": 1.0, "text": 1.2}
 
-SIGMA_RGB = 4.0
-SIGMA = {"ir": 5.0, "cpencil": 5.0, "sketch": 6.0, "text": 7.0}
+# tuned once at C1 scale (500 ids x 20): MM-1 mAP 0.14, MM-2 0.36, MM-3 0.57, MM-4 0.73; frozen
+SIGMA_RGB = 2.5
+SIGMA = {"ir": 3.5, "cpencil": 3.5, "sketch": 4.5, "text": 5.5}
 BIAS_SCALE = 0.3
 
 # MM-k modality combinations in the order build_queries emits them (sorted tuples of
