@@ -80,12 +80,14 @@ int reid_pos_sort(float* pos_score, int32_t* n_pos, int64_t Q, int Pmax, void* s
  *   (b) appends every row that beats the running REID_KLIST-th best of its (query, chunk) to
  *       cand_score/cand_idx[q, chunk, :cand_cap] (local row index), count in cand_count[q,chunk].
  * g_code / q_code: pid codes from reid_pid_lookup.  n_chunks = gallery chunks per query block
- * (work decomposition; buffers are sized with it).  pos_above and cand_count must be zeroed. */
+ * (work decomposition; buffers are sized with it).  pos_above and cand_count must be zeroed.
+ * cand_thr [Q] (optional): per-query score with >= REID_KLIST candidates at or above it (-inf if fewer);
+ * every candidate the re-scorer can need lies at or above it. */
 int reid_retrieve_fused(const void* q_f16, const void* g_f16, const int32_t* q_code,
                         const int32_t* g_code, const int32_t* excl, int E, const float* pos_thr,
                         const int32_t* n_pos, int64_t Q, int64_t G_local, int64_t g_offset, int d,
                         int Pmax, int n_chunks, int cand_cap, int32_t* pos_above,
-                        float* cand_score, int32_t* cand_idx, int32_t* cand_count,
+                        float* cand_score, int32_t* cand_idx, int32_t* cand_count, float* cand_thr,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- exact fp32 SIMT form of the same step (all scores in fp32, CUDA cores).  Used for the
@@ -108,6 +110,7 @@ int reid_retrieve_exact(const float* q_f32, const float* g_f32, const int32_t* q
 int reid_rescore_topk(const float* q_f32, const float* g_f32, const int32_t* q_code,
                       const int32_t* g_code, const float* pos_thr, const int32_t* n_pos,
                       const float* cand_score, const int32_t* cand_idx, const int32_t* cand_count,
+                      const float* cand_thr /* optional, from reid_retrieve_fused */,
                       const int32_t* q_sel, int64_t n_sel, int64_t Q, int64_t G_local,
                       int64_t g_offset, int d, int Pmax, int n_chunks, int cand_cap, int topk,
                       float eps, int32_t* pos_above, float* top_score, int32_t* top_idx,

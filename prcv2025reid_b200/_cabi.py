@@ -5,7 +5,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p, POINTER, Structure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libreid_b200.so")
+LIB_PATH = os.environ.get("REID_LIB") or os.path.join(HERE, "libreid_b200.so")
 
 KLIST = 32
 RTOP = 32
@@ -38,12 +38,12 @@ _SIGS = {
     "reid_pos_sort": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "reid_retrieve_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "reid_retrieve_exact": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "reid_rescore_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
                                   c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "reid_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "reid_metrics_reduce": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
@@ -58,7 +58,7 @@ _lib = None
 # kernels of THIS library launched per C call (library plumbing such as the CUB sort is not counted)
 _LAUNCHES_PER_CALL = {
     "reid_l2norm_rows": 1, "reid_mm_fuse_normalize": 1, "reid_sim_gemm": 1, "reid_pid_index_build": 2,
-    "reid_pid_lookup": 1, "reid_pos_scores": 1, "reid_pos_sort": 1, "reid_retrieve_fused": 2,
+    "reid_pid_lookup": 1, "reid_pos_scores": 1, "reid_pos_sort": 1, "reid_retrieve_fused": 4,
     "reid_retrieve_exact": 1, "reid_rescore_topk": 1, "reid_merge_topk": 1, "reid_metrics_reduce": 2,
     "reid_sdm_fwd": 1, "reid_sdm_bwd": 1,
 }

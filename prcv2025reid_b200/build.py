@@ -33,12 +33,13 @@ def build_library(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
+    extra = os.environ.get("REID_NVCC_EXTRA", "").split()
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o])
+            jobs.append([nvcc] + NVCC_FLAGS + extra + ["-c", s, "-o", o])
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

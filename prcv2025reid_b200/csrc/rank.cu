@@ -30,6 +30,8 @@ retrieve_exact_kernel(const float* __restrict__ q_f32, const float* __restrict__
   float* sthr = sq + XQT * d;                                      // [XQT][Pmax]
   int32_t* scnt = reinterpret_cast<int32_t*>(sthr + XQT * Pmax);   // [XQT][Pmax]
   int32_t* sexcl = scnt + XQT * Pmax;                              // [XQT][max(E,1)]
+  float* ms = reinterpret_cast<float*>(sexcl + XQT * (E > 0 ? E : 1));   // [XQT][XWARPS*32] merge staging: scores
+  int* mi = reinterpret_cast<int*>(ms + XQT * XWARPS * 32);              // [XQT][XWARPS*32] merge staging: rows
   __shared__ int s_qidx[XQT], s_code[XQT], s_npos[XQT];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -65,8 +67,12 @@ retrieve_exact_kernel(const float* __restrict__ q_f32, const float* __restrict__
   for (int t = 0; t < XQT; ++t) { lv[t] = REID_NEG_INF; li[t] = -1; lmin[t] = REID_NEG_INF; nfill[t] = 0; }
 
   const int64_t rows_per_chunk = (G_local + n_chunks - 1) / n_chunks;
-  const int64_t r0 = chunk * rows_per_chunk;
-  const int64_t r1 = reid_min64(G_local, r0 + rows_per_chunk);
+  const int64_t c0 = chunk * rows_per_chunk;
+  const int64_t c1 = reid_min64(G_local, c0 + rows_per_chunk);
+  // gridDim.z CTAs share one (query tile, chunk): each takes a contiguous slice of the chunk
+  const int64_t rows_per_split = (c1 - c0 + gridDim.z - 1) / gridDim.z;
+  const int64_t r0 = c0 + blockIdx.z * rows_per_split;
+  const int64_t r1 = reid_min64(c1, r0 + rows_per_split);
   for (int64_t r = r0 + warp; r < r1; r += XWARPS) {
     const float* grow = g_f32 + r * (int64_t)d;
     const int gcode = g_code[r];
@@ -102,16 +108,51 @@ retrieve_exact_kernel(const float* __restrict__ q_f32, const float* __restrict__
       const int c = scnt[t * Pmax + p];
       if (c) atomicAdd(&pos_above[(int64_t)qi * Pmax + p], c);
     }
-    const unsigned have = __ballot_sync(0xffffffffu, li[t] >= 0);
+  }
+  // merge the XWARPS per-warp lists of every query into the CTA's best 32 (staged in shared memory)
+  // so that a (query, chunk) buffer receives at most 32 entries per CTA
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < XQT; ++t) {
+    ms[t * XWARPS * 32 + warp * 32 + lane] = (li[t] >= 0) ? lv[t] : REID_NEG_INF;
+    mi[t * XWARPS * 32 + warp * 32 + lane] = li[t];
+  }
+  __syncthreads();
+  if (warp < XQT && s_qidx[warp] >= 0) {
+    const int t = warp, qi = s_qidx[t];
+    float v[XWARPS]; int ix[XWARPS];
+#pragma unroll
+    for (int k = 0; k < XWARPS; ++k) { v[k] = ms[t * XWARPS * 32 + k * 32 + lane]; ix[k] = mi[t * XWARPS * 32 + k * 32 + lane]; }
+    float outv = REID_NEG_INF; int outi = -1;
+    for (int round = 0; round < 32; ++round) {      // 32 rounds of warp-wide arg-max (score desc, row asc)
+      float bv = REID_NEG_INF; int bi = 0x7fffffff; int bk = -1;
+#pragma unroll
+      for (int k = 0; k < XWARPS; ++k)
+        if (ix[k] >= 0 && ranks_before(v[k], ix[k], bv, bi)) { bv = v[k]; bi = ix[k]; bk = k; }
+      float wv = bv; int wi = bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+        if (ranks_before(ov, oi, wv, wi)) { wv = ov; wi = oi; }
+      }
+      if (wi == 0x7fffffff) break;                   // fewer than 32 rows in this slice
+      if (bk >= 0 && bi == wi) {                     // the owning lane retires its entry
+#pragma unroll
+        for (int k = 0; k < XWARPS; ++k) if (k == bk) ix[k] = -1;
+      }
+      if (lane == round) { outv = wv; outi = wi; }
+    }
+    const unsigned have = __ballot_sync(0xffffffffu, outi >= 0);
     if (have) {
       int base = 0;
       if (lane == 0) base = atomicAdd(&cand_count[(int64_t)qi * n_chunks + chunk], __popc(have));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (li[t] >= 0) {
+      if (outi >= 0) {
         const int slot = base + __popc(have & ((1u << lane) - 1));
         if (slot < cand_cap) {
           const int64_t o = ((int64_t)qi * n_chunks + chunk) * cand_cap + slot;
-          cand_score[o] = lv[t]; cand_idx[o] = li[t];
+          cand_score[o] = outv; cand_idx[o] = outi;
         }
       }
     }
@@ -147,7 +188,8 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
                     const int32_t* __restrict__ q_code, const int32_t* __restrict__ g_code,
                     const float* __restrict__ pos_thr, const int32_t* __restrict__ n_pos,
                     const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
-                    const int32_t* __restrict__ cand_count, const int32_t* __restrict__ q_sel,
+                    const int32_t* __restrict__ cand_count, const float* __restrict__ cand_thr,
+                    const int32_t* __restrict__ q_sel,
                     int64_t G_local, int64_t g_offset, int d, int Pmax, int n_chunks, int cand_cap, int topk,
                     float eps, int n2, int32_t* __restrict__ pos_above, float* __restrict__ top_score,
                     int32_t* __restrict__ top_idx, int32_t* __restrict__ flag) {
@@ -163,16 +205,20 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
   if (threadIdx.x == 0) { s_total = 0; s_overflow = 0; s_flag = 0; }
   for (int i = threadIdx.x; i < n2; i += blockDim.x) { key[i] = REID_NEG_INF; val[i] = 0x7fffffff; }
   __syncthreads();
-  // gather the chunk buffers (compact, order irrelevant: sorted next)
+  // gather the chunk buffers (compact, order irrelevant: sorted next).  When the producer supplied a
+  // per-query threshold with >= KLIST candidates at or above it, only those can reach the top list.
+  const float keep = cand_thr ? cand_thr[qi] : REID_NEG_INF;
   for (int c = 0; c < n_chunks; ++c) {
     int cnt = cand_count[(int64_t)qi * n_chunks + c];
     if (cnt > cand_cap) { cnt = cand_cap; if (threadIdx.x == 0) s_overflow = 1; }
-    __syncthreads();
-    const int base = s_total;
     const int64_t o = ((int64_t)qi * n_chunks + c) * cand_cap;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) { key[base + i] = cand_score[o + i]; val[base + i] = cand_idx[o + i]; }
-    __syncthreads();
-    if (threadIdx.x == 0) s_total = base + cnt;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const float v = cand_score[o + i];
+      if (v >= keep) {
+        const int slot = atomicAdd(&s_total, 1);
+        key[slot] = v; val[slot] = cand_idx[o + i];
+      }
+    }
   }
   __syncthreads();
   const int total = s_total;
@@ -226,14 +272,14 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
     if (t > bound || cut == REID_NEG_INF) *dst = lb;       // exact local count
     else {
       if (*dst < lb) *dst = lb;                            // lb is a rigorous lower bound
-      if (j == 0 && lb < 10) s_flag = 1;                   // CMC@10 undecidable within eps
+      if (j == 0 && lb < 10) atomicOr(&s_flag, 4);          // CMC@10 undecidable within eps
     }
   }
   if (threadIdx.x == 0) {
-    if (cut > REID_NEG_INF && R >= topk && ex_s[topk - 1] < bound) s_flag = 1;        // top-k undecidable
+    if (cut > REID_NEG_INF && R >= topk && ex_s[topk - 1] < bound) atomicOr(&s_flag, 2);   // top-k undecidable
   }
   __syncthreads();
-  if (threadIdx.x == 0) flag[qi] = (s_flag || s_overflow) ? 1 : 0;
+  if (threadIdx.x == 0) flag[qi] = s_flag | (s_overflow ? 1 : 0);   // bit0 overflow, bit1 top-k, bit2 CMC
 }
 
 // merge per-shard top lists: one warp-multiple CTA per query, bitonic over n_lists*RTOP entries
@@ -317,15 +363,24 @@ extern "C" int reid_retrieve_exact(const float* q_f32, const float* g_f32, const
   if (!q_f32 || !g_f32 || !q_code || !g_code || !pos_thr || !n_pos || !pos_above || !cand_score || !cand_idx ||
       !cand_count || d <= 0 || d % 4 != 0 || Pmax <= 0 || n_chunks <= 0 || (E > 0 && !excl))
     return REID_E_INVALID;
-  if (cand_cap < XWARPS * 32) return REID_E_INVALID;   // every warp flushes up to 32 entries
+  if (cand_cap < 32) return REID_E_INVALID;
   if (!q_sel) n_sel = Q;
   if (n_sel <= 0 || G_local <= 0) return REID_OK;
-  const size_t smem = (size_t)XQT * d * 4 + (size_t)XQT * Pmax * 8 + (size_t)XQT * (E > 0 ? E : 1) * 4;
+  const size_t smem = (size_t)XQT * d * 4 + (size_t)XQT * Pmax * 8 + (size_t)XQT * (E > 0 ? E : 1) * 4 +
+                      (size_t)XQT * XWARPS * 32 * 8;
   if (smem > 200 * 1024) return REID_E_UNSUPPORTED;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(retrieve_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return REID_E_CUDA;
-  dim3 grid((unsigned)((n_sel + XQT - 1) / XQT), (unsigned)n_chunks);
+  // enough CTAs to fill the GPU even for a handful of flagged queries: split every chunk further;
+  // each CTA appends at most 32 candidates per (query, chunk)
+  const int64_t qtiles = (n_sel + XQT - 1) / XQT;
+  int64_t splits = (148 * 4 + qtiles * n_chunks - 1) / (qtiles * n_chunks);
+  const int64_t rows_chunk = (G_local + n_chunks - 1) / n_chunks;
+  if (splits > rows_chunk / 512) splits = rows_chunk / 512;
+  if (splits > cand_cap / 32) splits = cand_cap / 32;
+  if (splits < 1) splits = 1;
+  dim3 grid((unsigned)qtiles, (unsigned)n_chunks, (unsigned)splits);
   retrieve_exact_kernel<<<grid, XWARPS * 32, smem, (cudaStream_t)stream>>>(
       q_f32, g_f32, q_code, g_code, excl, E, pos_thr, n_pos, q_sel, n_sel, G_local, g_offset, d, Pmax, n_chunks,
       cand_cap, pos_above, cand_score, cand_idx, cand_count);
@@ -336,7 +391,8 @@ extern "C" int reid_retrieve_exact(const float* q_f32, const float* g_f32, const
 extern "C" int reid_rescore_topk(const float* q_f32, const float* g_f32, const int32_t* q_code,
                                  const int32_t* g_code, const float* pos_thr, const int32_t* n_pos,
                                  const float* cand_score, const int32_t* cand_idx, const int32_t* cand_count,
-                                 const int32_t* q_sel, int64_t n_sel, int64_t Q, int64_t G_local, int64_t g_offset,
+                                 const float* cand_thr, const int32_t* q_sel, int64_t n_sel, int64_t Q, int64_t G_local,
+                                 int64_t g_offset,
                                  int d, int Pmax, int n_chunks, int cand_cap, int topk, float eps,
                                  int32_t* pos_above, float* top_score, int32_t* top_idx, int32_t* flag,
                                  void* stream) {
@@ -353,7 +409,7 @@ extern "C" int reid_rescore_topk(const float* q_f32, const float* g_f32, const i
       cudaFuncSetAttribute(rescore_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return REID_E_CUDA;
   rescore_topk_kernel<<<(unsigned)n_sel, RS_THREADS, smem, (cudaStream_t)stream>>>(
-      q_f32, g_f32, q_code, g_code, pos_thr, n_pos, cand_score, cand_idx, cand_count, q_sel, G_local, g_offset, d,
+      q_f32, g_f32, q_code, g_code, pos_thr, n_pos, cand_score, cand_idx, cand_count, cand_thr, q_sel, G_local, g_offset, d,
       Pmax, n_chunks, cand_cap, topk, eps, n2, pos_above, top_score, top_idx, flag);
   REID_CHECK_LAUNCH();
   return REID_OK;

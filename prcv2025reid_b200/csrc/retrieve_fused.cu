@@ -8,7 +8,7 @@
 //     resident in shared memory; gallery tiles (A operand, 128 rows) stream through a TMA ring;
 //   * one thread issues tcgen05.mma (M=128 gallery rows -> TMEM lanes, N=128 queries -> TMEM columns,
 //     fp16 x fp16 -> fp32) into one of two 128-column TMEM accumulators;
-//   * four epilogue warps read the accumulator with tcgen05.ld: lane l of warp w owns gallery row
+//   * eight epilogue warps (two per TMEM lane quadrant) read the accumulator with tcgen05.ld: lane l owns gallery row
 //     32w+l, a column is a query, so every per-query quantity is WARP-UNIFORM and a whole column
 //     of 32 scores is tested with one compare + ballot against min(top-list threshold, lowest
 //     positive threshold).  Hits are compacted into a per-warp queue in shared memory and drained
@@ -17,144 +17,203 @@
 //           shared memory) gives the bucket b = #thresholds >= score; hist[q][b]++ (packed 16-bit
 //           counters in shared memory, spilled to a global histogram every 256 tiles); the count of
 //           rows ranked above positive j is the prefix sum over buckets <= j;
-//       (b) top list: a 32-entry running list per query (one entry per lane, bf16 rounded down so
-//           its minimum is a valid lower bound) gives the threshold above which rows are appended
-//           to the query's candidate buffer in global memory.
-//     The four warps walk the four 32-column groups of a tile in rotated order with a named barrier
-//     between phases, so a query's shared state is owned by exactly one warp at a time.
+//           Thresholds whose rank inside the chunk is estimated (calibration pre-pass over a strided
+//           2048-row sample) to exceed max(rows/128, 2048) are "deep": they are counted on a fixed
+//           1/16 stratified row sample with weight 16 (a few-% error on a rank > 2000 moves AP by
+//           < 1e-6); all shallower thresholds are counted exactly on every row;
+//       (b) candidates: rows above the query's running threshold are appended (lane-parallel) to its
+//           candidate buffer in global memory; every 64 appends the threshold is raised to the 32nd
+//           largest of the last 64 appended scores, so >= 32 appended rows always lie above it.
+//     The warp pairs walk the four 32-column groups of a tile in rotated order (each warp of a pair
+//     takes 16 columns) with a named barrier between phases, so a query's shared state is owned by
+//     exactly one warp at a time.  The top-list threshold reached by one gallery chunk is published
+//     (atomicMax) and warm-starts the later chunks of the same query.
 // Roofline: tensor cores, 2*Q*G*d flop; algorithmic HBM bytes are only operands + outputs.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
+#include <stddef.h>
 
 namespace {
 
 constexpr int NQ = 128;        // queries per block  (MMA N, TMEM columns)
 constexpr int TMG = 128;       // gallery rows per tile (MMA M, TMEM lanes)
 constexpr int BK = 64;         // K chunk: one 128-byte swizzle atom of fp16
-constexpr int KL = REID_KLIST; // running top-list length (== warp size)
+constexpr int KL = REID_KLIST; // candidates are complete down to the KL-th best score of a chunk
 constexpr int A_STAGE = TMG * BK * 2;   // 16 KB
 constexpr int B_CHUNK = NQ * BK * 2;    // 16 KB
 constexpr int MAX_STAGES = 4;
-constexpr int THREADS = 256;
-constexpr int EPI_WARP0 = 4;   // warps 4..7 are the epilogue
+constexpr int EPI_WARP0 = 4;   // warps 4.. are the epilogue: EPI_WARPS/4 warps per TMEM lane quadrant
+#ifndef REID_EPI_WARPS
+#define REID_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = REID_EPI_WARPS;
+constexpr int COLS_PER_WARP = NQ * 4 / EPI_WARPS;      // query columns each epilogue warp scans per tile
+constexpr int UPD_PER_WARP = NQ / EPI_WARPS;           // queries whose candidate threshold a warp owns
+static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps");
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;
 constexpr uint32_t TMEM_COLS = 256;      // two 128-column fp32 accumulators
-constexpr int QCAP = 128;                // per-warp hit queue entries
-constexpr int FLUSH_TILES = 256;         // 16-bit counters: <= 128 increments per tile
-constexpr uint32_t M_NOTPOS = 1u << 16;
-static_assert(KL == 32, "one list entry per lane");
+constexpr int QCAP = 64;                 // per-warp hit queue entries
+constexpr int FLUSH_TILES = 128;         // 16-bit counters: <= 240 weighted increments per tile
+#ifndef REID_SAMPLE_W
+#define REID_SAMPLE_W 16
+#endif
+constexpr int SAMPLE_W = REID_SAMPLE_W;  // deep thresholds: rows with (row % SAMPLE_W) == 5, weight SAMPLE_W
+constexpr int CALIB_ROWS = 2048;         // strided gallery sample of the calibration pre-pass
+constexpr uint32_t M_SAMPLED = 1u << 17;
+static_assert(KL == 32, "threshold update takes the 32nd largest of a 64-entry window");
 
 struct Params {
   const int32_t* q_code; const int32_t* g_code; const int32_t* excl; int E;
   const float* pos_thr; const int32_t* n_pos;
   int64_t Q, G_local, g_offset;
   int Pmax, pcap, kchunks, stages, n_chunks, n_qblocks, cand_cap;
+  int debug;       // REID_FUSED_DEBUG env: bit0 = no counting, bit1 = no hits at all (GEMM + scan only),
+                   // bit2 = epilogue only hands the accumulator back (mainloop only),
+                   // bit6 (64) = count every threshold exactly (no deep sampling)
   int64_t rows_per_chunk;
   int32_t* hist;   // [Q, Pmax] global bucket histogram (workspace)
+  uint32_t* thr_share;   // [Q] best known candidate threshold per query (ordered key), shared by all chunks
+  int32_t* n_exact;      // [Q] number of positive thresholds counted exactly (the rest on the row sample)
+  int calib;             // 1 = calibration pre-pass: all thresholds exact, no candidates
+  int64_t row_stride;    // gallery row stride of this pass (1, or the sample stride of the pre-pass)
   float* cand_score; int32_t* cand_idx; int32_t* cand_count;
 };
 
 // per-CTA shared state of the epilogue (one query block)
 struct EpiState {
-  float s_min[NQ];      // min(top-list threshold, lowest positive threshold): the fast-path test
-  float s_thrtop[NQ];   // current top-list threshold (min of the list), -inf until the list is full
+  float s_min[NQ];      // fast-path test of ordinary rows: min(candidate threshold, lowest EXACT positive threshold)
+  float s_minS[NQ];     // fast-path test of sampled rows: also covers the deep thresholds
+  float s_thrtop[NQ];   // candidate threshold: >= 32 appended rows lie above it (or -inf)
+  float s_threx[NQ];    // lowest exactly-counted positive threshold (+inf when none)
   float s_thrlow[NQ];   // lowest positive threshold (+inf when the query has no positive)
   int s_qcode[NQ];
   int s_npos[NQ];
-  int s_candcnt[NQ];
+  int s_nexact[NQ];
+  int s_candcnt[NQ];    // candidate slots allocated so far (may exceed cand_cap: overflow is flagged by the re-scorer)
+  int s_canddone[NQ];   // candidate slots whose stores are complete (== s_candcnt when no append is in flight)
+  int s_nextupd[NQ];    // append count at which the candidate threshold is next refreshed
   int s_hasexcl[NQ];
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
-// views of the per-CTA epilogue state in dynamic shared memory
-struct EpiShared {
-  EpiState* es;
-  const float* thr;        // [NQ][pcap] positive thresholds, sorted descending
-  uint32_t* hist32;        // [NQ][pcap/2] packed 16-bit bucket counters
-  uint16_t* list16;        // [NQ][KL] running top list, bf16 bit patterns (rounded down)
-  float* q_s;              // [4][QCAP] hit queue: score
-  uint32_t* q_m;           // [4][QCAP] hit queue: ql | row_in_tile << 8 | NOTPOS
-};
-
-__device__ __forceinline__ uint16_t bf16_round_down(float x) {
-  uint32_t b = __float_as_uint(x);
-  uint32_t t = b >> 16;
-  if ((b & 0x80000000u) && (b & 0xFFFFu)) t += 1;    // negative: truncation rounds up, step one down
-  return (uint16_t)t;
+// order-preserving integer key of a float (a single redux.sync.min replaces a shuffle reduction)
+__device__ __forceinline__ uint32_t key32(float x) { const uint32_t b = __float_as_uint(x); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float unkey32(uint32_t k) {
+  if (k <= 0x007FFFFFu) return -INFINITY;              // includes zero-initialised memory
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
-__device__ __forceinline__ float bf16_bits_to_float(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
 
-// Drain `n` queued hits of this warp (all from the tile starting at local gallery row tile_row0).
-__device__ __noinline__ void epi_drain(const EpiShared* shp, const Params* pp, int ew, int n, int lane, int tile_row0,
-                                       int64_t q0, int chunk) {
-  const EpiShared& sh = *shp;
+// 32-bit shared-window addresses of the per-CTA epilogue state.  The out-of-line drain / refresh
+// routines access shared memory through explicit ld/st/atom.shared PTX: one copy of the code (the
+// kernel must stay inside the 32 KB instruction cache) without degrading to generic loads.
+struct EpiAddr {
+  uint32_t es;     // EpiState
+  uint32_t thr;    // float [NQ][pcap] positive thresholds, sorted descending
+  uint32_t hist;   // u32   [NQ][pcap/2] packed 16-bit bucket counters
+  uint32_t qs;     // float [EPI_WARPS][QCAP] hit queue: score
+  uint32_t qm;     // u32   [EPI_WARPS][QCAP] hit queue: query column | SAMPLED
+  uint32_t qr;     // s32   [EPI_WARPS][QCAP] hit queue: local gallery row
+};
+#define ES_OFF(field) ((uint32_t)offsetof(EpiState, field))
+
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int atoms_add(uint32_t a, int v) { int o; asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_exch(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
+
+// Drain the first `n` (<= 32) queue entries of epilogue warp `ew`, one entry per lane.
+__device__ __noinline__ void epi_drain32(EpiAddr A, const Params* pp, int ew, int n, int lane, int64_t q0, int chunk) {
   const Params& p = *pp;
-  EpiState* es = sh.es;
   __syncwarp();
-  for (int base = 0; base < n; base += 32) {
-    const int e = base + lane;
-    const bool have = e < n;
-    const float s = have ? sh.q_s[ew * QCAP + e] : 0.f;
-    const uint32_t meta = have ? sh.q_m[ew * QCAP + e] : 0u;
-    const int ql = meta & 127;
-    const int row = (meta >> 8) & 127;
-    bool ok = have;
-    if (have && es->s_hasexcl[ql]) {                 // same-image mask (eval_mm_protocol.py:408-418)
-      const int32_t gidx = (int32_t)(p.g_offset + tile_row0 + row);
-      for (int x = 0; x < p.E; ++x) ok = ok && (p.excl[(q0 + ql) * p.E + x] != gidx);
-    }
-    // (a) bucket among the query's positive thresholds: b = #{j : t_j >= s}; rows that are positives of
-    //     the query are skipped (positives are ordered exactly among themselves: rank_j = 1 + above_j + j)
-    if (ok && (meta & M_NOTPOS) && s > es->s_thrlow[ql]) {
-      const float* t = sh.thr + ql * p.pcap;
-      int lo = 0, hi = es->s_npos[ql] - 1;           // invariant: t[hi] < s
+  const bool have = lane < n;
+  const uint32_t qoff = (uint32_t)(ew * QCAP + lane) * 4u;
+  const float s = have ? lds_f32(A.qs + qoff) : 0.f;
+  const uint32_t meta = have ? lds_u32(A.qm + qoff) : 0u;
+  const int row = have ? lds_s32(A.qr + qoff) : 0;
+  const uint32_t ql4 = (meta & 127u) * 4u;
+  const int ql = meta & 127;
+  bool ok = have;
+  if (have && lds_s32(A.es + ES_OFF(s_hasexcl) + ql4)) {      // same-image mask (eval_mm_protocol.py:408-418)
+    const int32_t gidx = (int32_t)(p.g_offset + (int64_t)row * p.row_stride);
+#pragma unroll 1
+    for (int x = 0; x < p.E; ++x) ok = ok && (p.excl[(q0 + ql) * p.E + x] != gidx);
+  }
+  // (a) bucket among the query's positive thresholds: b = #{j : t_j >= s}.  Rows that are positives of
+  //     the query are skipped (positives are ordered exactly among themselves: rank_j = 1 + above_j + j).
+  //     Ordinary rows only see the exactly-counted thresholds [0, n_exact); sampled rows see all of them
+  //     and stand for SAMPLE_W rows in the deep buckets.
+  if (ok) {
+    const int ne = lds_s32(A.es + ES_OFF(s_nexact) + ql4);
+    int hi = ((meta & M_SAMPLED) ? lds_s32(A.es + ES_OFF(s_npos) + ql4) : ne) - 1;
+    const uint32_t t = A.thr + (uint32_t)(ql * p.pcap) * 4u;
+    if (hi >= 0 && s > lds_f32(t + hi * 4) &&                 // invariant: t[hi] < s
+        p.g_code[(int64_t)row * p.row_stride] != lds_s32(A.es + ES_OFF(s_qcode) + ql4)) {
+      int lo = 0;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (t[mid] < s) hi = mid; else lo = mid + 1;
+        if (lds_f32(t + mid * 4) < s) hi = mid; else lo = mid + 1;
       }
-      atomicAdd(&sh.hist32[(ql * p.pcap + lo) >> 1], (lo & 1) ? 0x10000u : 1u);    // pcap is even
+      const uint32_t w = (lo < ne) ? 1u : (uint32_t)SAMPLE_W;
+      reds_add(A.hist + (uint32_t)((ql * p.pcap + lo) >> 1) * 4u, w << ((lo & 1) * 16));   // pcap is even
     }
-    // (b) running top list -> candidate buffer (serial per accepted row; rare after warm-up)
-    unsigned tm = __ballot_sync(0xffffffffu, ok && s > es->s_thrtop[ql]);
-    while (tm) {
-      const int src = __ffs(tm) - 1;
-      tm &= tm - 1;
-      const float v = __shfl_sync(0xffffffffu, s, src);
-      const uint32_t m2 = __shfl_sync(0xffffffffu, meta, src);
-      const int qq = m2 & 127;
-      const float thr = es->s_thrtop[qq];             // may have moved within this batch
-      if (v > thr) {
-        const float lv = bf16_bits_to_float(sh.list16[qq * KL + lane]);
-        const float lmin = warp_min(lv);                // == thr once the list is full, -inf before
-        const unsigned holders = __ballot_sync(0xffffffffu, lv == lmin);
-        const int victim = __ffs(holders) - 1;
-        const uint16_t nv16 = bf16_round_down(v);
-        const float nlv = (lane == victim) ? bf16_bits_to_float(nv16) : lv;
-        const float nthr = warp_min(nlv);
-        if (lane == victim) sh.list16[qq * KL + lane] = nv16;
-        if (lane == 0) {
-          const int cc = es->s_candcnt[qq];
-          if (cc < p.cand_cap) {
-            const int64_t o = ((q0 + qq) * p.n_chunks + chunk) * (int64_t)p.cand_cap + cc;
-            p.cand_score[o] = v;
-            p.cand_idx[o] = tile_row0 + (int)((m2 >> 8) & 127);
-          }
-          es->s_candcnt[qq] = cc + 1;
-          es->s_thrtop[qq] = nthr;
-          es->s_min[qq] = fminf(nthr, es->s_thrlow[qq]);
-        }
-        __syncwarp();
-      }
+  }
+  // (b) candidates: lane-parallel append; the threshold is refreshed at tile boundaries
+  if (ok && s > lds_f32(A.es + ES_OFF(s_thrtop) + ql4)) {
+    const int slot = atoms_add(A.es + ES_OFF(s_candcnt) + ql4, 1);
+    if (slot < p.cand_cap) {
+      const int64_t o = ((q0 + ql) * p.n_chunks + chunk) * (int64_t)p.cand_cap + slot;
+      p.cand_score[o] = s;
+      p.cand_idx[o] = row;
+    }
+    __threadfence_block();                                     // the stores above precede the "done" count
+    atoms_add(A.es + ES_OFF(s_canddone) + ql4, 1);
+  }
+  __syncwarp();
+}
+
+// Candidate-threshold refresh for query qq (whole warp): 32nd largest of the last 64 appended scores.
+__device__ __noinline__ void epi_refresh_thr(EpiAddr A, const Params* pp, int qq, int cnt, int lane, int64_t q0, int chunk) {
+  const Params& p = *pp;
+  const float* win = p.cand_score + ((q0 + qq) * p.n_chunks + chunk) * (int64_t)p.cand_cap + (cnt - 64);
+  const float a0 = __ldcg(win + lane), a1 = __ldcg(win + 32 + lane);
+  int r0 = 0, r1 = 0;                                          // number of window values greater than a0 / a1
+#pragma unroll 4
+  for (int k = 0; k < 32; ++k) {
+    const float b0 = __shfl_sync(0xffffffffu, a0, k), b1 = __shfl_sync(0xffffffffu, a1, k);
+    r0 += (b0 > a0) + (b1 > a0);
+    r1 += (b0 > a1) + (b1 > a1);
+  }
+  // the values with fewer than 32 greater ones are >= 32 scores; their minimum bounds the 32nd largest
+  const float cand = fminf(r0 < 32 ? a0 : INFINITY, r1 < 32 ? a1 : INFINITY);
+  const float nthr = unkey32(__reduce_min_sync(0xffffffffu, key32(cand)));
+  if (lane == 0) {
+    const uint32_t q4 = (uint32_t)qq * 4u;
+    sts_s32(A.es + ES_OFF(s_nextupd) + q4, cnt + 16);
+    if (nthr > lds_f32(A.es + ES_OFF(s_thrtop) + q4)) {
+      sts_f32(A.es + ES_OFF(s_thrtop) + q4, nthr);
+      const float ma = fminf(nthr, lds_f32(A.es + ES_OFF(s_threx) + q4));
+      sts_f32(A.es + ES_OFF(s_min) + q4, ma);
+      sts_f32(A.es + ES_OFF(s_minS) + q4, fminf(ma, lds_f32(A.es + ES_OFF(s_thrlow) + q4)));
     }
   }
   __syncwarp();
 }
 
 // spill the packed 16-bit counters of this CTA into the global histogram
-__device__ __forceinline__ void epi_flush_hist(const EpiShared& sh, const Params& p, int et, int64_t q0) {
+__device__ __noinline__ void epi_flush_hist(EpiAddr A, const Params* pp, int et, int64_t q0) {
+  const Params& p = *pp;
   const int words = NQ * p.pcap / 2;
-  for (int i = et; i < words; i += 128) {
-    const uint32_t w = sh.hist32[i];
+#pragma unroll 1
+  for (int i = et; i < words; i += EPI_THREADS) {
+    if (lds_u32(A.hist + i * 4) == 0) continue;
+    const uint32_t w = atoms_exch(A.hist + i * 4, 0u);         // other warps keep adding concurrently
     if (w) {
       const int ql = (2 * i) / p.pcap, b = (2 * i) % p.pcap;
       const int64_t q = q0 + ql;
@@ -162,15 +221,40 @@ __device__ __forceinline__ void epi_flush_hist(const EpiShared& sh, const Params
         if ((w & 0xFFFFu) && b < p.Pmax) atomicAdd(&p.hist[q * p.Pmax + b], (int)(w & 0xFFFFu));
         if ((w >> 16) && b + 1 < p.Pmax) atomicAdd(&p.hist[q * p.Pmax + b + 1], (int)(w >> 16));
       }
-      sh.hist32[i] = 0;
     }
   }
 }
 
+// calibration: thresholds whose estimated rank inside a chunk exceeds `limit` rows are counted on the
+// row sample only.  hist holds bucket counts over the n_sample calibration rows; it is zeroed for the
+// main pass.
+__global__ void calib_split_kernel(int32_t* __restrict__ hist, const int32_t* __restrict__ n_pos, int64_t Q, int Pmax,
+                                   float scale, float limit, int32_t* __restrict__ n_exact) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
+    const int np = min(n_pos[q], Pmax);
+    int acc = 0, ne = 0;
+    bool open = true;
+    for (int j = 0; j < Pmax; ++j) {
+      acc += hist[q * Pmax + j];
+      hist[q * Pmax + j] = 0;
+      if (j < np && open) {
+        if ((float)acc * scale <= limit) ne = j + 1; else open = false;
+      }
+    }
+    n_exact[q] = ne;
+  }
+}
+__global__ void fill_n_exact_kernel(const int32_t* __restrict__ n_pos, int64_t Q, int Pmax, int32_t* __restrict__ n_exact) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x)
+    n_exact[q] = min(n_pos[q], Pmax);
+}
+
 // pos_above[q, j] += sum_{b <= j} hist[q, b]
 __global__ void hist_to_above_kernel(const int32_t* __restrict__ hist, const int32_t* __restrict__ n_pos, int64_t Q,
-                                     int Pmax, int32_t* __restrict__ pos_above) {
+                                     int Pmax, int32_t* __restrict__ pos_above, const uint32_t* __restrict__ thr_share,
+                                     float* __restrict__ cand_thr) {
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
+    if (cand_thr) cand_thr[q] = unkey32(thr_share[q]);
     const int np = min(n_pos[q], Pmax);
     int acc = 0;
     for (int j = 0; j < np; ++j) {
@@ -190,11 +274,10 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
   uint8_t* sA = sB + p.kchunks * B_CHUNK;                      // [stages][A_STAGE]  gallery ring
   float* s_thr = reinterpret_cast<float*>(sA + p.stages * A_STAGE);              // [NQ][pcap]
   uint32_t* s_hist32 = reinterpret_cast<uint32_t*>(s_thr + NQ * p.pcap);         // [NQ][pcap/2]
-  uint16_t* s_list16 = reinterpret_cast<uint16_t*>(s_hist32 + NQ * p.pcap / 2);  // [NQ][KL]
-  float* s_qs = reinterpret_cast<float*>(s_list16 + NQ * KL);                    // [4][QCAP]
-  uint32_t* s_qm = reinterpret_cast<uint32_t*>(s_qs + 4 * QCAP);                 // [4][QCAP]
-  EpiState* es = reinterpret_cast<EpiState*>(s_qm + 4 * QCAP);
-  __shared__ EpiShared sh_views;
+  float* s_qs = reinterpret_cast<float*>(s_hist32 + NQ * p.pcap / 2);            // [EPI_WARPS][QCAP]
+  uint32_t* s_qm = reinterpret_cast<uint32_t*>(s_qs + EPI_WARPS * QCAP);         // [EPI_WARPS][QCAP]
+  int32_t* s_qr = reinterpret_cast<int32_t*>(s_qm + EPI_WARPS * QCAP);           // [EPI_WARPS][QCAP]
+  EpiState* es = reinterpret_cast<EpiState*>(s_qr + EPI_WARPS * QCAP);
   __shared__ __align__(8) uint64_t full[MAX_STAGES], empty[MAX_STAGES], bfull, bempty, tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -202,7 +285,7 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(&bfull, 1); tc::mbar_init(&bempty, 1);
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], 4); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], EPI_WARPS); }
     tc::fence_barrier_init();
     tc::prefetch_tensormap(&tmG); tc::prefetch_tensormap(&tmQ);
   }
@@ -215,7 +298,8 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
-    uint32_t it = 0, ring = 0;
+    uint32_t it = 0, ph = 0;
+    int st = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int chunk = item / p.n_qblocks, qb = item % p.n_qblocks;
       const int64_t row0 = chunk * p.rows_per_chunk;
@@ -223,20 +307,24 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
       const int ntiles = (int)((row1 - row0 + TMG - 1) / TMG);
       tc::mbar_wait(&bempty, (it & 1) ^ 1);            // previous item's MMAs have finished with B
       tc::mbar_arrive_expect_tx(&bfull, (uint32_t)(p.kchunks * B_CHUNK));
+#pragma unroll 1
       for (int kc = 0; kc < p.kchunks; ++kc) tc::tma_load_2d(sB + kc * B_CHUNK, &tmQ, &bfull, kc * BK, qb * NQ);
+#pragma unroll 1
       for (int t = 0; t < ntiles; ++t) {
-        for (int kc = 0; kc < p.kchunks; ++kc, ++ring) {
-          const int st = ring % p.stages; const uint32_t ph = (ring / p.stages) & 1;
+#pragma unroll 1
+        for (int kc = 0; kc < p.kchunks; ++kc) {
           tc::mbar_wait(&empty[st], ph ^ 1);
           tc::mbar_arrive_expect_tx(&full[st], A_STAGE);
           tc::tma_load_2d(sA + st * A_STAGE, &tmG, &full[st], kc * BK, (int)(row0 + (int64_t)t * TMG));
+          if (++st == p.stages) { st = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = tc::make_idesc_f16(TMG, NQ, 0);
-    uint32_t it = 0, ring = 0, tilecount = 0;
+    uint32_t it = 0, ph = 0, tilecount = 0;
+    int st = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int chunk = item / p.n_qblocks;
       const int64_t row0 = chunk * p.rows_per_chunk;
@@ -244,12 +332,13 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
       const int ntiles = (int)((row1 - row0 + TMG - 1) / TMG);
       tc::mbar_wait(&bfull, it & 1);
       tc::fence_after_sync();
+#pragma unroll 1
       for (int t = 0; t < ntiles; ++t, ++tilecount) {
         const uint32_t buf = tilecount & 1, bph = (tilecount >> 1) & 1;
         tc::mbar_wait(&tempty[buf], bph ^ 1);          // epilogue has drained this accumulator
         tc::fence_after_sync();
-        for (int kc = 0; kc < p.kchunks; ++kc, ++ring) {
-          const int st = ring % p.stages; const uint32_t ph = (ring / p.stages) & 1;
+#pragma unroll 1
+        for (int kc = 0; kc < p.kchunks; ++kc) {
           tc::mbar_wait(&full[st], ph);
           tc::fence_after_sync();
           const uint64_t ad = tc::make_smem_desc_sw128(tc::smem_u32(sA + st * A_STAGE));
@@ -259,27 +348,32 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
             tc::mma_f16_ss(tmem_base + buf * NQ, tc::advance_desc_k(ad, k), tc::advance_desc_k(bd, k), idesc,
                            (kc | k) != 0);
           tc::mma_commit(&empty[st]);                   // frees the gallery stage when the MMAs retire
+          if (++st == p.stages) { st = 0; ph ^= 1; }
         }
         tc::mma_commit(&tfull[buf]);                    // accumulator complete -> epilogue
       }
       tc::mma_commit(&bempty);                          // query block no longer read
     }
   } else if (warp >= EPI_WARP0) {
-    // ------------------------------------------------------------------ epilogue (128 threads)
+    // ------------------------------------------------------------------ epilogue (256 threads)
     const int quad = warp & 3;                          // TMEM lane quadrant of this warp
-    const int et = threadIdx.x - EPI_WARP0 * 32;        // 0..127
+    const int ew = warp - EPI_WARP0;                    // 0..EPI_WARPS-1
+    const int part = ew >> 2;                           // which COLS_PER_WARP query columns of the tile
+    const int et = threadIdx.x - EPI_WARP0 * 32;        // 0..EPI_THREADS-1
     const uint32_t tmem_q = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t row_bits = (uint32_t)(quad * 32 + lane) << 8;
-    float* my_qs = s_qs + quad * QCAP;
-    uint32_t* my_qm = s_qm + quad * QCAP;
-    if (et == 0) {
-      sh_views.es = es; sh_views.thr = s_thr; sh_views.hist32 = s_hist32; sh_views.list16 = s_list16;
-      sh_views.q_s = s_qs; sh_views.q_m = s_qm;
-    }
-    for (int i = et; i < NQ * p.pcap / 2; i += 128) s_hist32[i] = 0;
+    // this lane's rows belong to the 1/SAMPLE_W stratified sample (SAMPLE_W > 32: only some quadrants sample)
+    const bool smp = ((quad * 32 + lane) & (SAMPLE_W - 1)) == 5;
+    const uint32_t lane_bits = smp ? M_SAMPLED : 0u;
+    float* my_qs = s_qs + ew * QCAP;
+    uint32_t* my_qm = s_qm + ew * QCAP;
+    int32_t* my_qr = s_qr + ew * QCAP;
+    EpiAddr A;
+    A.es = tc::smem_u32(es); A.thr = tc::smem_u32(s_thr); A.hist = tc::smem_u32(s_hist32);
+    A.qs = tc::smem_u32(s_qs); A.qm = tc::smem_u32(s_qm); A.qr = tc::smem_u32(s_qr);
+#pragma unroll 1
+    for (int i = et; i < NQ * p.pcap / 2; i += EPI_THREADS) s_hist32[i] = 0;
     epi_bar();
-    const EpiShared& sh = sh_views;
     uint32_t tilecount = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int chunk = item / p.n_qblocks, qb = item % p.n_qblocks;
@@ -288,74 +382,125 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
       const int ntiles = (int)((row1 - row0 + TMG - 1) / TMG);
       const int64_t q0 = (int64_t)qb * NQ;
       // ---- item setup: per-query state
-      {
+      if (et < NQ) {
         const int64_t q = q0 + et;
         const bool live = q < p.Q;
-        const int np = live ? min(p.n_pos[q], p.Pmax) : 0;
+        const int np = (live && !(p.debug & 1)) ? min(p.n_pos[q], p.Pmax) : 0;
+        const int ne = p.calib ? np : (live ? min(p.n_exact[q], np) : 0);
         es->s_qcode[et] = live ? p.q_code[q] : -2;
         es->s_npos[et] = np;
-        es->s_thrlow[et] = np > 0 ? p.pos_thr[q * p.Pmax + np - 1] : INFINITY;
-        es->s_thrtop[et] = live ? -INFINITY : INFINITY;      // padded queries never hit
-        es->s_min[et] = live ? -INFINITY : INFINITY;
+        es->s_nexact[et] = ne;
+        const float tex = ne > 0 ? p.pos_thr[q * p.Pmax + ne - 1] : INFINITY;
+        const float tl = np > 0 ? p.pos_thr[q * p.Pmax + np - 1] : INFINITY;
+        es->s_threx[et] = tex;
+        es->s_thrlow[et] = tl;
+        // candidates: warm start from the best threshold any earlier chunk of this query has published;
+        // padded queries and the calibration pre-pass never append
+        const float tt = (live && !p.calib && !(p.debug & 2)) ? unkey32(__ldcg(&p.thr_share[q])) : INFINITY;
+        es->s_thrtop[et] = tt;
+        es->s_min[et] = fminf(tt, tex);
+        es->s_minS[et] = fminf(fminf(tt, tex), tl);
         es->s_candcnt[et] = 0;
+        es->s_canddone[et] = 0;
+        es->s_nextupd[et] = 64;
         int he = 0;
-        if (live) for (int e = 0; e < p.E; ++e) he |= (p.excl[q * p.E + e] >= 0);
-        es->s_hasexcl[et] = he;
-        for (int i = et; i < NQ * KL; i += 128) s_list16[i] = 0xFF80;   // bf16 -inf
-        for (int i = et; i < NQ * p.pcap; i += 128) {
-          const int ql = i / p.pcap, j = i % p.pcap;
-          const int64_t qq = q0 + ql;
-          s_thr[i] = (qq < p.Q && j < p.Pmax) ? p.pos_thr[qq * p.Pmax + j] : -INFINITY;
+        if (live) {
+#pragma unroll 1
+          for (int e = 0; e < p.E; ++e) he |= (p.excl[q * p.E + e] >= 0);
         }
+        es->s_hasexcl[et] = he;
+      }
+#pragma unroll 1
+      for (int ql = ew; ql < NQ; ql += EPI_WARPS) {          // one warp per query row of the threshold table
+        const int64_t qq = q0 + ql;
+#pragma unroll 1
+        for (int j = lane; j < p.pcap; j += 32)
+          s_thr[ql * p.pcap + j] = (qq < p.Q && j < p.Pmax) ? p.pos_thr[qq * p.Pmax + j] : -INFINITY;
       }
       epi_bar();
+      int qn = 0;                                          // queued hits of this warp (persist across tiles)
       // ---- tiles
       for (int t = 0; t < ntiles; ++t, ++tilecount) {
         const uint32_t buf = tilecount & 1, bph = (tilecount >> 1) & 1;
-        const int tile_row0 = (int)(row0 + (int64_t)t * TMG);
-        const int grow_local = tile_row0 + quad * 32 + lane;
+        const int grow_local = (int)(row0 + (int64_t)t * TMG) + quad * 32 + lane;
         const bool valid = grow_local < row1;
-        const int gcode = valid ? p.g_code[grow_local] : -3;
         tc::mbar_wait(&tfull[buf], bph);
         tc::fence_after_sync();
 #pragma unroll 1
-        for (int ph = 0; ph < 4; ++ph) {
-          const int cg = (quad + ph) & 3;                 // rotated column group: exclusive per warp
-          uint32_t r[32];
-          tc::tmem_ld_x32(tmem_q + buf * NQ + cg * 32, r);
+        for (int step = 0; step < ((p.debug & 4) ? 0 : COLS_PER_WARP / 16); ++step) {
+          const int c0 = part * COLS_PER_WARP + step * 16;
+          uint32_t r[16];
+          tc::tmem_ld_x16(tmem_q + buf * NQ + c0, r);
+          float mm[16];
+          {
+            const float* msrc = smp ? es->s_minS : es->s_min;      // lane-constant choice of threshold set
+#pragma unroll
+            for (int i4 = 0; i4 < 16; i4 += 4) {
+              const float4 m4 = *reinterpret_cast<const float4*>(&msrc[c0 + i4]);
+              mm[i4] = m4.x; mm[i4 + 1] = m4.y; mm[i4 + 2] = m4.z; mm[i4 + 3] = m4.w;
+            }
+          }
           tc::tmem_wait_ld();
-          int qn = 0;                                      // queued hits of this warp
+          unsigned cb[16];
+          unsigned any = 0;
 #pragma unroll
-          for (int i4 = 0; i4 < 32; i4 += 4) {
-            const float4 m4 = *reinterpret_cast<const float4*>(&es->s_min[cg * 32 + i4]);
-            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+          for (int i = 0; i < 16; ++i) {                   // branch-free: all ballots first (ILP)
+            cb[i] = __ballot_sync(0xffffffffu, valid && __uint_as_float(r[i]) > mm[i]);
+            any |= cb[i];
+          }
+          if (any) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float s = __uint_as_float(r[i4 + u]);
-              const bool hit = valid && s > mm[u];
-              const unsigned c = __ballot_sync(0xffffffffu, hit);
+            for (int i = 0; i < 16; ++i) {
+              const unsigned c = cb[i];
               if (c) {                                     // warp-uniform
-                const int ql = cg * 32 + i4 + u;
-                if (hit) {
+                const int ql = c0 + i;
+                if ((c >> lane) & 1u) {
                   const int pos = qn + __popc(c & lt_mask);
-                  my_qs[pos] = s;
-                  my_qm[pos] = (uint32_t)ql | row_bits | ((gcode != es->s_qcode[ql]) ? M_NOTPOS : 0u);
+                  my_qs[pos] = __uint_as_float(r[i]);
+                  my_qr[pos] = grow_local;
+                  my_qm[pos] = (uint32_t)ql | lane_bits;
                 }
                 qn += __popc(c);
-                if (qn > QCAP - 32) { epi_drain(&sh, &p, quad, qn, lane, tile_row0, q0, chunk); qn = 0; }
+                if (qn >= 32) {                            // drain one full batch, keep the tail
+                  epi_drain32(A, &p, ew, 32, lane, q0, chunk);
+                  const int rest = qn - 32;              // <= 31 entries move to the front
+                  const float ts = my_qs[32 + (lane & 31)]; const uint32_t tm2 = my_qm[32 + (lane & 31)];
+                  const int tr = my_qr[32 + (lane & 31)];
+                  __syncwarp();
+                  if (lane < rest) { my_qs[lane] = ts; my_qm[lane] = tm2; my_qr[lane] = tr; }
+                  qn = rest;
+                }
               }
             }
           }
-          if (qn) epi_drain(&sh, &p, quad, qn, lane, tile_row0, q0, chunk);
-          epi_bar();
         }
         tc::fence_before_sync();
         if (lane == 0) tc::mbar_arrive(&tempty[buf]);
-        if (((t + 1) % FLUSH_TILES) == 0) { epi_flush_hist(sh, p, et, q0); epi_bar(); }
+        // ---- tile boundary: this warp owns the candidate thresholds of a fixed group of queries
+        //      (UPD_PER_WARP each).  A threshold is refreshed only when no append of that query is in flight (done == allocated;
+        //      `done` is read first), so every slot of the window has been stored.  No CTA barrier needed.
+        if (!p.calib) {
+          const int uq = ew * UPD_PER_WARP + (lane & (UPD_PER_WARP - 1));
+          const int done = *(volatile int*)&es->s_canddone[uq];
+          const int alloc = *(volatile int*)&es->s_candcnt[uq];
+          const int cnt = min(alloc, p.cand_cap);
+          unsigned um = __ballot_sync(0xffffffffu, lane < UPD_PER_WARP && done == alloc && cnt >= 64 && cnt >= es->s_nextupd[uq]);
+          while (um) {
+            const int src = __ffs(um) - 1;
+            um &= um - 1;
+            epi_refresh_thr(A, &p, ew * UPD_PER_WARP + src, __shfl_sync(0xffffffffu, cnt, src), lane, q0, chunk);
+          }
+        }
+        if (((t + 1) % FLUSH_TILES) == 0) epi_flush_hist(A, &p, et, q0);
       }
-      // ---- item flush
-      epi_flush_hist(sh, p, et, q0);
-      if (q0 + et < p.Q) p.cand_count[(q0 + et) * p.n_chunks + chunk] = es->s_candcnt[et];
+      // ---- item end: drain the queue tail, spill the histogram, publish candidate state
+      if (qn) epi_drain32(A, &p, ew, qn, lane, q0, chunk);
+      epi_bar();
+      epi_flush_hist(A, &p, et, q0);
+      if (et < NQ && q0 + et < p.Q && !p.calib) {
+        p.cand_count[(q0 + et) * p.n_chunks + chunk] = es->s_candcnt[et];
+        atomicMax(&p.thr_share[q0 + et], key32(es->s_thrtop[et]));
+      }
       epi_bar();
     }
   }
@@ -366,20 +511,21 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
 
 size_t fused_smem_bytes(int kchunks, int stages, int pcap) {
   return (size_t)kchunks * B_CHUNK + (size_t)stages * A_STAGE + (size_t)NQ * pcap * 4 /*thr*/ +
-         (size_t)NQ * pcap * 2 /*hist*/ + (size_t)NQ * KL * 2 /*list*/ + (size_t)4 * QCAP * 8 /*queues*/ +
+         (size_t)NQ * pcap * 2 /*hist*/ + (size_t)EPI_WARPS * QCAP * 12 /*queues*/ +
          sizeof(EpiState) + 1024;
 }
 
 }  // namespace
 
 // workspace = the global bucket histogram [Q, 64] int32 (Pmax <= 64)
-extern "C" size_t reid_retrieve_fused_workspace_bytes(int64_t Q, int64_t, int) { return (size_t)Q * 64 * sizeof(int32_t); }
+// workspace = histogram [Q, Pmax<=64] + candidate threshold [Q] + exact-threshold count [Q]
+extern "C" size_t reid_retrieve_fused_workspace_bytes(int64_t Q, int64_t, int) { return (size_t)Q * 66 * sizeof(int32_t); }
 
 extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const int32_t* q_code, const int32_t* g_code,
                                    const int32_t* excl, int E, const float* pos_thr, const int32_t* n_pos, int64_t Q,
                                    int64_t G_local, int64_t g_offset, int d, int Pmax, int n_chunks, int cand_cap,
                                    int32_t* pos_above, float* cand_score, int32_t* cand_idx, int32_t* cand_count,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+                                   float* cand_thr, void* workspace, size_t workspace_bytes, void* stream) {
   if (!q_f16 || !g_f16 || !q_code || !g_code || !pos_thr || !n_pos || !pos_above || !cand_score || !cand_idx ||
       !cand_count || Q <= 0 || G_local <= 0 || n_chunks <= 0 || cand_cap <= 0 || (E > 0 && !excl) || E < 0)
     return REID_E_INVALID;
@@ -387,12 +533,14 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
   Params p;
   p.q_code = q_code; p.g_code = g_code; p.excl = excl; p.E = E; p.pos_thr = pos_thr; p.n_pos = n_pos;
   p.Q = Q; p.G_local = G_local; p.g_offset = g_offset;
-  if (!workspace || workspace_bytes < (size_t)Q * Pmax * sizeof(int32_t)) return REID_E_WORKSPACE;
+  if (!workspace || workspace_bytes < (size_t)Q * (Pmax + 2) * sizeof(int32_t)) return REID_E_WORKSPACE;
   p.Pmax = Pmax; p.pcap = (Pmax + 3) / 4 * 4; p.kchunks = d / BK;
   p.n_chunks = n_chunks; p.n_qblocks = (int)((Q + NQ - 1) / NQ); p.cand_cap = cand_cap;
   const int64_t rpc = (G_local + n_chunks - 1) / n_chunks;
   p.rows_per_chunk = (rpc + TMG - 1) / TMG * TMG;
-  p.hist = (int32_t*)workspace; p.cand_score = cand_score; p.cand_idx = cand_idx; p.cand_count = cand_count;
+  p.hist = (int32_t*)workspace; p.thr_share = (uint32_t*)workspace + (size_t)Q * Pmax;
+  p.n_exact = (int32_t*)workspace + (size_t)Q * (Pmax + 1); p.calib = 0; p.row_stride = 1; p.cand_score = cand_score;
+  { const char* dbg = getenv("REID_FUSED_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; } p.cand_idx = cand_idx; p.cand_count = cand_count;
   int stages = MAX_STAGES;
   const size_t smem_max = 227 * 1024;
   while (stages > 2 && fused_smem_bytes(p.kchunks, stages, p.pcap) > smem_max) --stages;
@@ -410,10 +558,44 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
   const int n_items = p.n_qblocks * n_chunks;
   const int grid = n_items < sms ? n_items : sms;
   cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(workspace, 0, (size_t)Q * Pmax * sizeof(int32_t), st) != cudaSuccess) return REID_E_CUDA;
+  if (cudaMemsetAsync(workspace, 0, (size_t)Q * (Pmax + 2) * sizeof(int32_t), st) != cudaSuccess) return REID_E_CUDA;
+  const int aux_grid = (int)reid_min64((Q + 255) / 256, 148 * 8);
+  const bool sample_deep = (G_local >= 16 * CALIB_ROWS) && !(p.debug & 64);
+  if (sample_deep) {
+    // calibration pre-pass: the same kernel over a strided sample of CALIB_ROWS gallery rows, every
+    // threshold counted exactly, no candidates -> per-query bucket histogram of the sample
+    Params c = p;
+    c.calib = 1;
+    c.row_stride = G_local / CALIB_ROWS;
+    c.G_local = CALIB_ROWS;
+    c.n_chunks = 1;
+    c.rows_per_chunk = CALIB_ROWS;
+    CUtensorMap tmS;
+    {
+      tc_host::EncodeTiledFn enc = tc_host::get_encode();
+      if (!enc) return REID_E_CUDA;
+      cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)CALIB_ROWS};
+      cuuint64_t strides[1] = {(cuuint64_t)d * 2 * (cuuint64_t)c.row_stride};
+      cuuint32_t box[2] = {64, (cuuint32_t)TMG};
+      cuuint32_t estr[2] = {1, 1};
+      if (enc(&tmS, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(g_f16), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return REID_E_CUDA;
+    }
+    const int cgrid = c.n_qblocks < sms ? c.n_qblocks : sms;
+    retrieve_fused_kernel<<<cgrid, THREADS, smem, st>>>(tmS, tmQ, c);
+    REID_CHECK_LAUNCH();
+    const float limit = fmaxf((float)p.rows_per_chunk / 128.f, 2048.f);
+    const float scale = (float)p.rows_per_chunk / (float)CALIB_ROWS;
+    calib_split_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, scale, limit, p.n_exact);
+  } else {
+    fill_n_exact_kernel<<<aux_grid, 256, 0, st>>>(n_pos, Q, Pmax, p.n_exact);
+  }
+  REID_CHECK_LAUNCH();
   retrieve_fused_kernel<<<grid, THREADS, smem, st>>>(tmG, tmQ, p);
   REID_CHECK_LAUNCH();
-  hist_to_above_kernel<<<(int)reid_min64((Q + 255) / 256, 148 * 8), 256, 0, st>>>(p.hist, n_pos, Q, Pmax, pos_above);
+  hist_to_above_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, pos_above, p.thr_share, cand_thr);
   REID_CHECK_LAUNCH();
   return REID_OK;
 }

@@ -20,6 +20,7 @@ from ._cabi import check, ptr, stream_ptr
 # plus fp32 accumulation slack.  Queries whose top-k / CMC cannot be decided within this bound are
 # re-run through the all-fp32 kernel, so the bound only affects speed, never results.
 EPS_FP16 = 2.0 ** -10 + 2.0 ** -13
+_DEBUG_KEEP = None   # set to a dict to keep the flags / candidate counts of the last block (debug scripts)
 
 
 def _f32c(t):
@@ -133,7 +134,7 @@ class RetrievalResult:
 
 def retrieve(shard: GalleryShard, q_f32: torch.Tensor, q_f16: Optional[torch.Tensor], q_pid: torch.Tensor,
              excl: Optional[torch.Tensor] = None, topk: int = 10, mode: str = "fused", eps: float = EPS_FP16,
-             cand_cap: int = 512, query_block: int = 32768, group=None, want_ap: bool = False) -> RetrievalResult:
+             cand_cap: int = 2048, query_block: int = 32768, group=None, want_ap: bool = False) -> RetrievalResult:
     """Ranking statistics of a batch of fused queries against the gallery shard(s).
 
     mode "fused": tcgen05 GEMM with the counting / candidate epilogue, exact fp32 re-score of the
@@ -191,27 +192,30 @@ def retrieve(shard: GalleryShard, q_f32: torch.Tensor, q_f16: Optional[torch.Ten
             n_chunks = _pick_chunks(-(-nb // 128), shard.G_local, sms)
         else:
             n_chunks = max(1, min(16, (2 * sms) // max(1, -(-nb // 8)), shard.G_local // 1024 or 1))
-        cap = max(cand_cap, 256)
+        cap = max(cand_cap, 64)
         cand_score = torch.empty(nb, n_chunks, cap, dtype=torch.float32, device=dev)
         cand_idx = torch.empty(nb, n_chunks, cap, dtype=torch.int32, device=dev)
         cand_count = torch.zeros(nb, n_chunks, dtype=torch.int32, device=dev)
         common_tail = (nb, shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap)
+        cand_thr = torch.empty(nb, dtype=torch.float32, device=dev) if use_fused else None
         if use_fused:
             ws_bytes = L.reid_workspace_bytes(1, nb, shard.G_local, d)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             check(L.reid_retrieve_fused(ptr(q_f16[sl]), ptr(shard.g_f16), ptr(q_code[sl]), ptr(shard.g_code), ptr(ex_b), E,
                                         ptr(pos_thr[sl]), ptr(n_pos[sl]), *common_tail, ptr(pos_above[sl]),
-                                        ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(ws), ws_bytes, st),
+                                        ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), ptr(ws), ws_bytes, st),
                   "reid_retrieve_fused")
         else:
             check(L.reid_retrieve_exact(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code), ptr(ex_b), E,
                                         ptr(pos_thr[sl]), ptr(n_pos[sl]), None, nb, *common_tail, ptr(pos_above[sl]),
                                         ptr(cand_score), ptr(cand_idx), ptr(cand_count), st), "reid_retrieve_exact")
         check(L.reid_rescore_topk(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code), ptr(pos_thr[sl]),
-                                  ptr(n_pos[sl]), ptr(cand_score), ptr(cand_idx), ptr(cand_count), None, nb, nb,
+                                  ptr(n_pos[sl]), ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), None, nb, nb,
                                   shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap, topk,
                                   float(eps if use_fused else 0.0), ptr(pos_above[sl]), ptr(top_score[sl]),
                                   ptr(top_idx[sl]), ptr(flag[sl]), st), "reid_rescore_topk")
+        if _DEBUG_KEEP is not None:
+            _DEBUG_KEEP.update(flag=flag[sl].clone(), cand_count=cand_count.clone())
         if use_fused:
             sel = torch.nonzero(flag[sl]).flatten().to(torch.int32)      # host sync: how many to re-run
             ns = int(sel.numel())
@@ -226,7 +230,7 @@ def retrieve(shard: GalleryShard, q_f32: torch.Tensor, q_f16: Optional[torch.Ten
                       "reid_retrieve_exact(fallback)")
                 check(L.reid_rescore_topk(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code),
                                           ptr(pos_thr[sl]), ptr(n_pos[sl]), ptr(cand_score), ptr(cand_idx),
-                                          ptr(cand_count), ptr(sel), ns, nb, shard.G_local, shard.g_offset, d, Pmax,
+                                          ptr(cand_count), None, ptr(sel), ns, nb, shard.G_local, shard.g_offset, d, Pmax,
                                           n_chunks, cap, topk, 0.0, ptr(pa), ptr(top_score[sl]), ptr(top_idx[sl]),
                                           ptr(flag[sl]), st), "reid_rescore_topk(fallback)")
 
