@@ -203,7 +203,6 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
   const int qi = q_sel ? q_sel[blockIdx.x] : (int)blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { s_total = 0; s_overflow = 0; s_flag = 0; }
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) { key[i] = REID_NEG_INF; val[i] = 0x7fffffff; }
   __syncthreads();
   // gather the chunk buffers (compact, order irrelevant: sorted next).  When the producer supplied a
   // per-query threshold with >= KLIST candidates at or above it, only those can reach the top list.
@@ -216,14 +215,17 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
       const float v = cand_score[o + i];
       if (v >= keep) {
         const int slot = atomicAdd(&s_total, 1);
-        key[slot] = v; val[slot] = cand_idx[o + i];
+        if (slot < n2) { key[slot] = v; val[slot] = cand_idx[o + i]; }
       }
     }
   }
   __syncthreads();
-  const int total = s_total;
+  int total = s_total;
+  if (total > n2) { total = n2; if (threadIdx.x == 0) s_overflow = 1; }   // staging full: re-run exactly
   int ns = 32;                       // sort only the occupied power-of-two prefix
   while (ns < total) ns <<= 1;
+  for (int i = total + threadIdx.x; i < ns; i += blockDim.x) { key[i] = REID_NEG_INF; val[i] = 0x7fffffff; }
+  __syncthreads();
   block_bitonic_desc(key, val, ns);
   const int R = min(total, REID_RTOP);
   // completeness cut-off: every local row whose approximate score exceeds `cut` is a candidate
@@ -401,10 +403,9 @@ extern "C" int reid_rescore_topk(const float* q_f32, const float* g_f32, const i
     return REID_E_INVALID;
   if (!q_sel) n_sel = Q;
   if (n_sel <= 0) return REID_OK;
-  int n2 = 32;
-  while (n2 < n_chunks * cand_cap) n2 <<= 1;
+  int n2 = 32;                                   // staging entries: enough for every candidate, at most 4096
+  while (n2 < n_chunks * cand_cap && n2 < 4096) n2 <<= 1;
   const size_t smem = (size_t)n2 * 8;
-  if (smem > 200 * 1024) return REID_E_UNSUPPORTED;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(rescore_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return REID_E_CUDA;

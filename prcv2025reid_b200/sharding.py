@@ -39,8 +39,11 @@ def gather_top_lists(top_score: torch.Tensor, top_idx: torch.Tensor, group=None)
     if not (group is not None or dist.is_initialized()):
         return top_score[None], top_idx[None]
     world = dist.get_world_size(group)
-    all_s = torch.empty((world,) + tuple(top_score.shape), dtype=top_score.dtype, device=top_score.device)
-    all_i = torch.empty((world,) + tuple(top_idx.shape), dtype=top_idx.dtype, device=top_idx.device)
+    Q = top_score.shape[0]
+    rest = tuple(top_score.shape[1:])
+    # concatenated along dim 0 (the layout both NCCL and gloo accept), viewed as [world, Q, R]
+    all_s = torch.empty((world * Q,) + rest, dtype=top_score.dtype, device=top_score.device)
+    all_i = torch.empty((world * Q,) + rest, dtype=top_idx.dtype, device=top_idx.device)
     dist.all_gather_into_tensor(all_s, top_score.contiguous(), group=group)
     dist.all_gather_into_tensor(all_i, top_idx.contiguous(), group=group)
-    return all_s, all_i
+    return all_s.view((world, Q) + rest), all_i.view((world, Q) + rest)
