@@ -232,10 +232,9 @@ def main():
     h2d_bytes = sum(t.numel() * t.element_size() for t in (h_query, h_mod, h_pid, h_excl))
 
     def step_e2e():
-        qr = h_query.to(dev, non_blocking=True); mi = h_mod.to(dev, non_blocking=True)
-        qp = h_pid.to(dev, non_blocking=True); ex = h_excl.to(dev, non_blocking=True)
-        q32, q16 = engine.fuse_queries(qr, mi, weights)
-        return engine.retrieve(shard, q32, q16, qp, ex, topk=10, mode=args.mode, group=group)   # metrics: D2H
+        # public tensor API with HOST inputs: block-wise H2D on a side stream, metrics read back (D2H)
+        return engine.retrieve(shard, None, None, h_pid, h_excl, topk=10, mode=args.mode, group=group,
+                               host_queries=(h_query, h_mod, weights))
 
     def timed(fn, steps, profile=False):
         for _ in range(args.warmup):

@@ -132,63 +132,99 @@ class RetrievalResult:
     n_pos: torch.Tensor              # [Q] int32
 
 
-def retrieve(shard: GalleryShard, q_f32: torch.Tensor, q_f16: Optional[torch.Tensor], q_pid: torch.Tensor,
+def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional[torch.Tensor], q_pid: torch.Tensor,
              excl: Optional[torch.Tensor] = None, topk: int = 10, mode: str = "fused", eps: float = EPS_FP16,
-             cand_cap: int = 2048, query_block: int = 32768, group=None, want_ap: bool = False) -> RetrievalResult:
-    """Ranking statistics of a batch of fused queries against the gallery shard(s).
+             cand_cap: int = 2048, query_block: int = 32768, group=None, want_ap: bool = False,
+             host_queries=None) -> RetrievalResult:
+    """Ranking statistics of a batch of queries against the gallery shard(s).
 
     mode "fused": tcgen05 GEMM with the counting / candidate epilogue, exact fp32 re-score of the
     candidates, exact fp32 re-run of the (rare) queries whose top-k / CMC is not decidable within eps.
     mode "exact": everything through the fp32 SIMT kernel.
     group: a torch.distributed process group whose ranks hold disjoint contiguous gallery shards.
+    host_queries: (query_raw [Q,k,D], mod_id [Q,k], weights) in pinned HOST memory instead of q_f32/q_f16;
+    q_pid / excl may then be host tensors too.  Query blocks are copied on a side stream while the previous
+    block computes (H2D overlapped with the kernels).
     """
     assert mode in ("fused", "exact")
     assert 1 <= topk <= _cabi.RTOP
     L = _cabi.lib()
-    dev = q_f32.device
-    Q, d = q_f32.shape
+    dev = shard.g_f32.device
+    d = shard.d
     Pmax = shard.pmax
-    q_pid = q_pid.to(device=dev, dtype=torch.int64).contiguous()
-    E = 0
-    if excl is not None and excl.numel() > 0:
-        excl = excl.to(device=dev, dtype=torch.int32).contiguous()
-        E = excl.shape[1]
-    else:
-        excl = None
-    dist = None
+    Q = q_pid.shape[0]
     world = 1
     if group is not None:
         import torch.distributed as dist_mod
-        dist = dist_mod
-        world = dist.get_world_size(group)
+        world = dist_mod.get_world_size(group)
     st = stream_ptr()
     sms = L.reid_device_sm_count()
-
-    q_code = torch.empty(Q, dtype=torch.int32, device=dev)
-    q_count = torch.empty(Q, dtype=torch.int32, device=dev)
-    check(L.reid_pid_lookup(ptr(shard.sorted_pid), shard.G_total, ptr(q_pid), Q, ptr(q_code), ptr(q_count), st),
-          "reid_pid_lookup")
-    pos_thr = torch.empty(Q, Pmax, dtype=torch.float32, device=dev)
-    check(L.reid_pos_scores(ptr(q_f32), ptr(shard.g_f32), ptr(shard.order), ptr(q_code), ptr(q_count), ptr(excl), E,
-                            Q, shard.G_local, shard.g_offset, d, Pmax, ptr(pos_thr), st), "reid_pos_scores")
-    if world > 1:
-        sharding.exchange_pos_scores(pos_thr, group)                    # owner rank holds the score, others -inf
-    n_pos = torch.empty(Q, dtype=torch.int32, device=dev)
-    check(L.reid_pos_sort(ptr(pos_thr), ptr(n_pos), Q, Pmax, st), "reid_pos_sort")
+    E = 0 if excl is None or excl.numel() == 0 else excl.shape[1]
+    if E == 0:
+        excl = None
 
     pos_above = torch.zeros(Q, Pmax, dtype=torch.int32, device=dev)
+    n_pos = torch.empty(Q, dtype=torch.int32, device=dev)
     top_score = torch.empty(Q, _cabi.RTOP, dtype=torch.float32, device=dev)
     top_idx = torch.empty(Q, _cabi.RTOP, dtype=torch.int32, device=dev)
     flag = torch.zeros(Q, dtype=torch.int32, device=dev)
     n_flagged = 0
+    use_fused = mode == "fused" and Pmax <= 64 and d % 64 == 0 and d <= 512
 
-    use_fused = mode == "fused" and Pmax <= 64 and d % 64 == 0 and d <= 512 and q_f16 is not None
-    for b0 in range(0, Q, query_block):
-        b1 = min(Q, b0 + query_block)
+    blocks = [(b0, min(Q, b0 + query_block)) for b0 in range(0, Q, query_block)]
+    staged = {}
+    copy_stream = None
+    if host_queries is not None:
+        h_raw, h_mod, weights = host_queries
+        weights = weights.to(dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def stage(bi):
+            b0, b1 = blocks[bi]
+            with torch.cuda.stream(copy_stream):
+                t = [h_raw[b0:b1].to(dev, non_blocking=True), h_mod[b0:b1].to(dev, non_blocking=True),
+                     q_pid[b0:b1].to(dev, non_blocking=True),
+                     excl[b0:b1].to(dev, non_blocking=True) if excl is not None else None]
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            staged[bi] = (t, ev)
+        stage(0)
+    else:
+        q_pid = q_pid.to(device=dev, dtype=torch.int64).contiguous()
+        if excl is not None:
+            excl = excl.to(device=dev, dtype=torch.int32).contiguous()
+
+    for bi, (b0, b1) in enumerate(blocks):
         nb = b1 - b0
         sl = slice(b0, b1)
-        ex_b = excl[sl] if excl is not None else None
-        if use_fused:
+        if host_queries is not None:
+            if bi + 1 < len(blocks):
+                stage(bi + 1)                                    # next block's H2D overlaps this block's kernels
+            (raw_b, mod_b, pid_b, ex_b), ev = staged.pop(bi)
+            torch.cuda.current_stream().wait_event(ev)
+            for t in (raw_b, mod_b, pid_b, ex_b):
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream())
+            q32_b, q16_b = fuse_queries(raw_b, mod_b, weights)
+            pid_b = pid_b.to(torch.int64)
+            ex_b = ex_b.to(torch.int32) if ex_b is not None else None
+        else:
+            q32_b, q16_b = q_f32[sl], (q_f16[sl] if q_f16 is not None else None)
+            pid_b, ex_b = q_pid[sl], (excl[sl] if excl is not None else None)
+        fused_b = use_fused and q16_b is not None
+
+        q_code = torch.empty(nb, dtype=torch.int32, device=dev)
+        q_count = torch.empty(nb, dtype=torch.int32, device=dev)
+        check(L.reid_pid_lookup(ptr(shard.sorted_pid), shard.G_total, ptr(pid_b), nb, ptr(q_code), ptr(q_count), st),
+              "reid_pid_lookup")
+        pos_thr = torch.empty(nb, Pmax, dtype=torch.float32, device=dev)
+        check(L.reid_pos_scores(ptr(q32_b), ptr(shard.g_f32), ptr(shard.order), ptr(q_code), ptr(q_count), ptr(ex_b), E,
+                                nb, shard.G_local, shard.g_offset, d, Pmax, ptr(pos_thr), st), "reid_pos_scores")
+        if world > 1:
+            sharding.exchange_pos_scores(pos_thr, group)                # owner rank holds the score, others -inf
+        check(L.reid_pos_sort(ptr(pos_thr), ptr(n_pos[sl]), nb, Pmax, st), "reid_pos_sort")
+
+        if fused_b:
             n_chunks = _pick_chunks(-(-nb // 128), shard.G_local, sms)
         else:
             n_chunks = max(1, min(16, (2 * sms) // max(1, -(-nb // 8)), shard.G_local // 1024 or 1))
@@ -197,26 +233,26 @@ def retrieve(shard: GalleryShard, q_f32: torch.Tensor, q_f16: Optional[torch.Ten
         cand_idx = torch.empty(nb, n_chunks, cap, dtype=torch.int32, device=dev)
         cand_count = torch.zeros(nb, n_chunks, dtype=torch.int32, device=dev)
         common_tail = (nb, shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap)
-        cand_thr = torch.empty(nb, dtype=torch.float32, device=dev) if use_fused else None
-        if use_fused:
+        cand_thr = torch.empty(nb, dtype=torch.float32, device=dev) if fused_b else None
+        if fused_b:
             ws_bytes = L.reid_workspace_bytes(1, nb, shard.G_local, d)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            check(L.reid_retrieve_fused(ptr(q_f16[sl]), ptr(shard.g_f16), ptr(q_code[sl]), ptr(shard.g_code), ptr(ex_b), E,
-                                        ptr(pos_thr[sl]), ptr(n_pos[sl]), *common_tail, ptr(pos_above[sl]),
+            check(L.reid_retrieve_fused(ptr(q16_b), ptr(shard.g_f16), ptr(q_code), ptr(shard.g_code), ptr(ex_b), E,
+                                        ptr(pos_thr), ptr(n_pos[sl]), *common_tail, ptr(pos_above[sl]),
                                         ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), ptr(ws), ws_bytes, st),
                   "reid_retrieve_fused")
         else:
-            check(L.reid_retrieve_exact(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code), ptr(ex_b), E,
-                                        ptr(pos_thr[sl]), ptr(n_pos[sl]), None, nb, *common_tail, ptr(pos_above[sl]),
+            check(L.reid_retrieve_exact(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code), ptr(ex_b), E,
+                                        ptr(pos_thr), ptr(n_pos[sl]), None, nb, *common_tail, ptr(pos_above[sl]),
                                         ptr(cand_score), ptr(cand_idx), ptr(cand_count), st), "reid_retrieve_exact")
-        check(L.reid_rescore_topk(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code), ptr(pos_thr[sl]),
+        check(L.reid_rescore_topk(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code), ptr(pos_thr),
                                   ptr(n_pos[sl]), ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), None, nb, nb,
                                   shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap, topk,
-                                  float(eps if use_fused else 0.0), ptr(pos_above[sl]), ptr(top_score[sl]),
+                                  float(eps if fused_b else 0.0), ptr(pos_above[sl]), ptr(top_score[sl]),
                                   ptr(top_idx[sl]), ptr(flag[sl]), st), "reid_rescore_topk")
         if _DEBUG_KEEP is not None:
             _DEBUG_KEEP.update(flag=flag[sl].clone(), cand_count=cand_count.clone())
-        if use_fused:
+        if fused_b:
             sel = torch.nonzero(flag[sl]).flatten().to(torch.int32)      # host sync: how many to re-run
             ns = int(sel.numel())
             if ns:
@@ -224,12 +260,12 @@ def retrieve(shard: GalleryShard, q_f32: torch.Tensor, q_f16: Optional[torch.Ten
                 pa = pos_above[sl]
                 pa[sel.long()] = 0
                 cand_count[sel.long()] = 0
-                check(L.reid_retrieve_exact(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code),
-                                            ptr(ex_b), E, ptr(pos_thr[sl]), ptr(n_pos[sl]), ptr(sel), ns,
+                check(L.reid_retrieve_exact(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code),
+                                            ptr(ex_b), E, ptr(pos_thr), ptr(n_pos[sl]), ptr(sel), ns,
                                             *common_tail, ptr(pa), ptr(cand_score), ptr(cand_idx), ptr(cand_count), st),
                       "reid_retrieve_exact(fallback)")
-                check(L.reid_rescore_topk(ptr(q_f32[sl]), ptr(shard.g_f32), ptr(q_code[sl]), ptr(shard.g_code),
-                                          ptr(pos_thr[sl]), ptr(n_pos[sl]), ptr(cand_score), ptr(cand_idx),
+                check(L.reid_rescore_topk(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code),
+                                          ptr(pos_thr), ptr(n_pos[sl]), ptr(cand_score), ptr(cand_idx),
                                           ptr(cand_count), None, ptr(sel), ns, nb, shard.G_local, shard.g_offset, d, Pmax,
                                           n_chunks, cap, topk, 0.0, ptr(pa), ptr(top_score[sl]), ptr(top_idx[sl]),
                                           ptr(flag[sl]), st), "reid_rescore_topk(fallback)")
