@@ -228,6 +228,41 @@ def test_fused_equals_exact_at_scale(eng):
     assert a.n_flagged <= q_take // 20
 
 
+def test_export_submission_matches_reference_golden(tmp_path):
+    """export_submission_csv (:595-649): ranking WITHOUT mask, top-20 of the golden; CSV format."""
+    import csv
+    from prcv2025reid_b200 import eval_mm_protocol as emp
+    for name in ("mm2_tiny", "mm4_small"):
+        case, z = _golden.load_retrieval(name)
+        queries, gmeta, ext = synth.case_to_reference_inputs(case)
+        g = emp.l2n(case.gallery_raw)
+        path = str(tmp_path / ("sub_%s.csv" % name))
+        emp.export_submission_csv(queries, g, gmeta, ext, dict(synth.DEFAULT_WEIGHTS), path, top_k=20)
+        rows = list(csv.DictReader(open(path, newline="")))
+        assert len(rows) == case.Q and set(rows[0]) == {"query_key", "ranked_gallery_ids"}
+        got = np.array([[int(t[1:]) for t in r["ranked_gallery_ids"].split()] for r in rows])
+        gold = z["submission"]
+        S = orc.fuse_queries(case.query_raw, case.mod_id, synth.weights_tensor()) @ orc.l2n(case.gallery_raw).T
+        for qi in range(case.Q):
+            for r in range(20):
+                if got[qi, r] != gold[qi, r]:       # only where the reference's own scores tie
+                    assert abs(float(S[qi, got[qi, r]]) - float(S[qi, gold[qi, r]])) <= 2e-6
+
+
+def test_topk_ranking_top100_matches_argsort(eng):
+    from prcv2025reid_b200 import topk
+    g = torch.Generator().manual_seed(9)
+    q = orc.l2n(torch.randn(37, 512, generator=g)); gal = orc.l2n(torch.randn(3000, 512, generator=g))
+    idx = topk.topk_ranking(q.cuda(), gal.cuda(), 100).cpu().numpy()
+    S = q @ gal.T
+    ref = torch.argsort(S, dim=1, descending=True)[:, :100].numpy()
+    for qi in range(37):
+        for r in range(100):
+            if idx[qi, r] != ref[qi, r]:
+                assert abs(float(S[qi, idx[qi, r]]) - float(S[qi, ref[qi, r]])) <= 2e-6
+        assert len(set(idx[qi].tolist())) == 100
+
+
 # ---------------------------------------------------------------- SDM
 SDM_NAMES = ["p4k2_tau02", "p4k2_tau01", "p3k2", "ragged", "no_pos", "nan_feat", "quick_check",
              "p64k8_fp32", "p64k8_bf16", "p4k2_bf16"]
