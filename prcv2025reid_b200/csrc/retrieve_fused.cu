@@ -7,7 +7,7 @@
 //   * the query block (B operand, 128 x d fp16 = up to 128 KB) is TMA-loaded once per item and stays
 //     resident in shared memory; gallery tiles (A operand, 128 rows) stream through a TMA ring;
 //   * one thread issues tcgen05.mma (M=128 gallery rows -> TMEM lanes, N=128 queries -> TMEM columns,
-//     fp16 x fp16 -> fp32) into one of two 128-column TMEM accumulators;
+//     fp16 x fp16 -> fp32) into one of four 128-column TMEM accumulators (the epilogue may lag 3 tiles);
 //   * eight epilogue warps (two per TMEM lane quadrant) read the accumulator with tcgen05.ld: lane l owns gallery row
 //     32w+l, a column is a query, so every per-query quantity is WARP-UNIFORM and a whole column
 //     of 32 scores is tested with one compare + ballot against min(top-list threshold, lowest
@@ -53,7 +53,8 @@ constexpr int UPD_PER_WARP = NQ / EPI_WARPS;           // queries whose candidat
 static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps");
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;
-constexpr uint32_t TMEM_COLS = 256;      // two 128-column fp32 accumulators
+constexpr int NBUF = 4;                  // TMEM accumulators: the epilogue may lag the MMA by up to 3 tiles
+constexpr uint32_t TMEM_COLS = NBUF * NQ; // 4 x 128 fp32 columns = all of TMEM
 constexpr int QCAP = 64;                 // per-warp hit queue entries
 constexpr int FLUSH_TILES = 128;         // 16-bit counters: <= 240 weighted increments per tile
 #ifndef REID_SAMPLE_W
@@ -278,14 +279,14 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
   uint32_t* s_qm = reinterpret_cast<uint32_t*>(s_qs + EPI_WARPS * QCAP);         // [EPI_WARPS][QCAP]
   int32_t* s_qr = reinterpret_cast<int32_t*>(s_qm + EPI_WARPS * QCAP);           // [EPI_WARPS][QCAP]
   EpiState* es = reinterpret_cast<EpiState*>(s_qr + EPI_WARPS * QCAP);
-  __shared__ __align__(8) uint64_t full[MAX_STAGES], empty[MAX_STAGES], bfull, bempty, tfull[2], tempty[2];
+  __shared__ __align__(8) uint64_t full[MAX_STAGES], empty[MAX_STAGES], bfull, bempty, tfull[NBUF], tempty[NBUF];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(&bfull, 1); tc::mbar_init(&bempty, 1);
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], EPI_WARPS); }
+    for (int b = 0; b < NBUF; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], EPI_WARPS); }
     tc::fence_barrier_init();
     tc::prefetch_tensormap(&tmG); tc::prefetch_tensormap(&tmQ);
   }
@@ -334,7 +335,7 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
       tc::fence_after_sync();
 #pragma unroll 1
       for (int t = 0; t < ntiles; ++t, ++tilecount) {
-        const uint32_t buf = tilecount & 1, bph = (tilecount >> 1) & 1;
+        const uint32_t buf = tilecount % NBUF, bph = (tilecount / NBUF) & 1;
         tc::mbar_wait(&tempty[buf], bph ^ 1);          // epilogue has drained this accumulator
         tc::fence_after_sync();
 #pragma unroll 1
@@ -421,7 +422,7 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
       int qn = 0;                                          // queued hits of this warp (persist across tiles)
       // ---- tiles
       for (int t = 0; t < ntiles; ++t, ++tilecount) {
-        const uint32_t buf = tilecount & 1, bph = (tilecount >> 1) & 1;
+        const uint32_t buf = tilecount % NBUF, bph = (tilecount / NBUF) & 1;
         const int grow_local = (int)(row0 + (int64_t)t * TMG) + quad * 32 + lane;
         const bool valid = grow_local < row1;
         tc::mbar_wait(&tfull[buf], bph);
