@@ -42,13 +42,12 @@ constexpr int BK = 64;         // K chunk: one 128-byte swizzle atom of fp16
 constexpr int KL = REID_KLIST; // candidates are complete down to the KL-th best score of a chunk
 constexpr int A_STAGE = TMG * BK * 2;   // 16 KB
 constexpr int B_CHUNK = NQ * BK * 2;    // 16 KB
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int EPI_WARP0 = 4;   // warps 4.. are the epilogue: EPI_WARPS/4 warps per TMEM lane quadrant
 #ifndef REID_EPI_WARPS
 #define REID_EPI_WARPS 16
 #endif
 constexpr int EPI_WARPS = REID_EPI_WARPS;
-constexpr int COLS_PER_WARP = NQ * 4 / EPI_WARPS;      // query columns each epilogue warp scans per tile
 constexpr int UPD_PER_WARP = NQ / EPI_WARPS;           // queries whose candidate threshold a warp owns
 static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps");
 constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -58,7 +57,7 @@ constexpr uint32_t TMEM_COLS = NBUF * NQ; // 4 x 128 fp32 columns = all of TMEM
 constexpr int QCAP = 64;                 // per-warp hit queue entries
 constexpr int FLUSH_TILES = 128;         // 16-bit counters: <= 240 weighted increments per tile
 #ifndef REID_SAMPLE_W
-#define REID_SAMPLE_W 16
+#define REID_SAMPLE_W 64
 #endif
 constexpr int SAMPLE_W = REID_SAMPLE_W;  // deep thresholds: rows with (row % SAMPLE_W) == 5, weight SAMPLE_W
 constexpr int CALIB_ROWS = 2048;         // strided gallery sample of the calibration pre-pass
@@ -93,7 +92,6 @@ struct EpiState {
   int s_npos[NQ];
   int s_nexact[NQ];
   int s_candcnt[NQ];    // candidate slots allocated so far (may exceed cand_cap: overflow is flagged by the re-scorer)
-  int s_canddone[NQ];   // candidate slots whose stores are complete (== s_candcnt when no append is in flight)
   int s_nextupd[NQ];    // append count at which the candidate threshold is next refreshed
   int s_hasexcl[NQ];
 };
@@ -173,8 +171,6 @@ __device__ __noinline__ void epi_drain32(EpiAddr A, const Params* pp, int ew, in
       p.cand_score[o] = s;
       p.cand_idx[o] = row;
     }
-    __threadfence_block();                                     // the stores above precede the "done" count
-    atoms_add(A.es + ES_OFF(s_canddone) + ql4, 1);
   }
   __syncwarp();
 }
@@ -265,9 +261,26 @@ __global__ void hist_to_above_kernel(const int32_t* __restrict__ hist, const int
   }
 }
 
+// PAIR = false ("T" layout, one CTA): A = gallery tile (M = 128 rows -> TMEM lanes, streamed), B = 128 resident
+//   queries (N = 128 -> TMEM columns).  An M128 x N128 SS-mode MMA is bound by the A-operand shared-memory
+//   read (~146 cycles per instruction, 43% of the tensor peak: measured with gallery loads disabled).
+// PAIR = true ("R" layout, cta_group::2 pair of a 2-CTA cluster): A = 256 resident queries (128 per CTA -> the
+//   128 TMEM lanes of that CTA), B = 256 streamed gallery rows (each CTA loads half of every tile), one
+//   M256 x N256 MMA issued by the leader: ~175 cycles for 4x the math (73% of the tensor peak = the cuBLAS burst
+//   rate), half the L2->SM operand traffic per flop.  Lane = query, column = gallery row: the per-query
+//   thresholds sit in registers, the sampled rows are compile-time columns.  Hit queue / drain are shared.
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmQ,
                       const __grid_constant__ Params prm) {
+  constexpr int TROWS = PAIR ? 256 : TMG;              // gallery rows per tile step
+  constexpr int DCOLS = PAIR ? 256 : NQ;               // accumulator columns per TMEM buffer
+  constexpr int NB = PAIR ? 2 : NBUF;                  // TMEM accumulators
+  constexpr int QSTEP = PAIR ? 2 * NQ : NQ;            // queries per work item
+  const uint32_t crank = PAIR ? tc::cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // scheduling unit: CTA or CTA pair
+  const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const Params& p = prm;
@@ -279,91 +292,110 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
   uint32_t* s_qm = reinterpret_cast<uint32_t*>(s_qs + EPI_WARPS * QCAP);         // [EPI_WARPS][QCAP]
   int32_t* s_qr = reinterpret_cast<int32_t*>(s_qm + EPI_WARPS * QCAP);           // [EPI_WARPS][QCAP]
   EpiState* es = reinterpret_cast<EpiState*>(s_qr + EPI_WARPS * QCAP);
-  __shared__ __align__(8) uint64_t full[MAX_STAGES], empty[MAX_STAGES], bfull, bempty, tfull[NBUF], tempty[NBUF];
+  __shared__ __align__(8) uint64_t full[MAX_STAGES], empty[MAX_STAGES], bfull, bempty, tfull[NBUF], tempty[NBUF];   // (pair mode uses 2 of the NBUF)
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(&bfull, 1); tc::mbar_init(&bempty, 1);
-    for (int b = 0; b < NBUF; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], EPI_WARPS); }
+    // in a pair the leader's tempty collects the epilogue warps of BOTH CTAs
+    for (int b = 0; b < NBUF; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
     tc::fence_barrier_init();
     tc::prefetch_tensormap(&tmG); tc::prefetch_tensormap(&tmQ);
   }
-  if (warp == 2) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (warp == 2) { if (PAIR) tc::tmem_alloc_pair(&tmem_base_s, TMEM_COLS); else tc::tmem_alloc(&tmem_base_s, TMEM_COLS); }
   tc::fence_before_sync();
-  __syncthreads();
+  if (PAIR) tc::cluster_sync_all(); else __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
-  const int n_items = p.n_qblocks * p.n_chunks;
+  const int n_items = p.n_qblocks * p.n_chunks;     // n_qblocks counts blocks of QSTEP queries
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
+    // sB holds the RESIDENT query block of this CTA (128 queries; the MMA's B operand in T layout, A in R);
+    // sA is the gallery ring (128 rows per stage per CTA; in pair mode the two CTAs load the two halves of a tile)
     uint32_t it = 0, ph = 0;
     int st = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    const uint32_t bfull_l = tc::leader_addr(&bfull);
+    for (int item = unit; item < n_items; item += n_units, ++it) {
       const int chunk = item / p.n_qblocks, qb = item % p.n_qblocks;
       const int64_t row0 = chunk * p.rows_per_chunk;
       const int64_t row1 = reid_min64(p.G_local, row0 + p.rows_per_chunk);
-      const int ntiles = (int)((row1 - row0 + TMG - 1) / TMG);
-      tc::mbar_wait(&bempty, (it & 1) ^ 1);            // previous item's MMAs have finished with B
-      tc::mbar_arrive_expect_tx(&bfull, (uint32_t)(p.kchunks * B_CHUNK));
+      const int ntiles = (int)((row1 - row0 + TROWS - 1) / TROWS);
+      const int qrow = qb * QSTEP + (int)crank * NQ;
+      tc::mbar_wait(&bempty, (it & 1) ^ 1);            // previous item's MMAs have finished with the queries
+      if (leader) tc::mbar_arrive_expect_tx(&bfull, (uint32_t)(p.kchunks * B_CHUNK) * (PAIR ? 2u : 1u));
 #pragma unroll 1
-      for (int kc = 0; kc < p.kchunks; ++kc) tc::tma_load_2d(sB + kc * B_CHUNK, &tmQ, &bfull, kc * BK, qb * NQ);
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        if (PAIR) tc::tma_load_2d_pair(sB + kc * B_CHUNK, &tmQ, bfull_l, kc * BK, qrow);
+        else tc::tma_load_2d(sB + kc * B_CHUNK, &tmQ, &bfull, kc * BK, qrow);
+      }
 #pragma unroll 1
       for (int t = 0; t < ntiles; ++t) {
+        const int grow = (int)(row0 + (int64_t)t * TROWS) + (int)crank * TMG;
 #pragma unroll 1
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int kc = 0; kc < p.kchunks && !(p.debug & 128); ++kc) {     // debug 128: no gallery loads at all
           tc::mbar_wait(&empty[st], ph ^ 1);
-          tc::mbar_arrive_expect_tx(&full[st], A_STAGE);
-          tc::tma_load_2d(sA + st * A_STAGE, &tmG, &full[st], kc * BK, (int)(row0 + (int64_t)t * TMG));
+          if (leader) tc::mbar_arrive_expect_tx(&full[st], A_STAGE * (PAIR ? 2u : 1u));
+          if (PAIR) tc::tma_load_2d_pair(sA + st * A_STAGE, &tmG, tc::leader_addr(&full[st]), kc * BK, grow);
+          else tc::tma_load_2d(sA + st * A_STAGE, &tmG, &full[st], kc * BK, grow);
           if (++st == p.stages) { st = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = tc::make_idesc_f16(TMG, NQ, 0);
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
+    // T: D[gallery 128 x queries 128] = A(gallery stage) . B(queries)^T ;  R: D[queries 256 x gallery 256] = A(queries) . B(gallery)^T
+    constexpr uint32_t idesc_n = PAIR ? tc::make_idesc_f16(256, 256, 0) : tc::make_idesc_f16(TMG, NQ, 0);
+    // debug 512 / 1024 (timing experiments in T layout, results invalid): issue N=256 / N=192 instructions
+    const uint32_t idesc = (!PAIR && (p.debug & 512)) ? tc::make_idesc_f16(TMG, 256, 0)
+                         : (!PAIR && (p.debug & 1024)) ? tc::make_idesc_f16(TMG, 192, 0) : idesc_n;
     uint32_t it = 0, ph = 0, tilecount = 0;
     int st = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int item = unit; item < n_items; item += n_units, ++it) {
       const int chunk = item / p.n_qblocks;
       const int64_t row0 = chunk * p.rows_per_chunk;
       const int64_t row1 = reid_min64(p.G_local, row0 + p.rows_per_chunk);
-      const int ntiles = (int)((row1 - row0 + TMG - 1) / TMG);
+      const int ntiles = (int)((row1 - row0 + TROWS - 1) / TROWS);
       tc::mbar_wait(&bfull, it & 1);
       tc::fence_after_sync();
 #pragma unroll 1
       for (int t = 0; t < ntiles; ++t, ++tilecount) {
-        const uint32_t buf = tilecount % NBUF, bph = (tilecount / NBUF) & 1;
+        const uint32_t buf = tilecount % NB, bph = (tilecount / NB) & 1;
         tc::mbar_wait(&tempty[buf], bph ^ 1);          // epilogue has drained this accumulator
         tc::fence_after_sync();
 #pragma unroll 1
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          tc::mbar_wait(&full[st], ph);
+          if (!(p.debug & 128)) tc::mbar_wait(&full[st], ph);
           tc::fence_after_sync();
-          const uint64_t ad = tc::make_smem_desc_sw128(tc::smem_u32(sA + st * A_STAGE));
-          const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(sB + kc * B_CHUNK));
+          const uint64_t gd = tc::make_smem_desc_sw128(tc::smem_u32(sA + st * A_STAGE));    // gallery stage
+          const uint64_t qd = tc::make_smem_desc_sw128(tc::smem_u32(sB + kc * B_CHUNK));    // resident queries
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc::mma_f16_ss(tmem_base + buf * NQ, tc::advance_desc_k(ad, k), tc::advance_desc_k(bd, k), idesc,
-                           (kc | k) != 0);
-          tc::mma_commit(&empty[st]);                   // frees the gallery stage when the MMAs retire
+          for (int k = 0; k < ((p.debug & 256) ? 0 : BK / 16); ++k) {   // debug 256: loads only, no MMA
+            if (PAIR) {
+              tc::mma_f16_ss_pair(tmem_base + buf * DCOLS, tc::advance_desc_k(qd, k), tc::advance_desc_k(gd, k), idesc, (kc | k) != 0);
+            } else {
+              const uint32_t dcol = (p.debug & (512 | 1024)) ? (buf & 1) * 256 : buf * DCOLS;   // wide-N experiment stays inside TMEM
+              tc::mma_f16_ss(tmem_base + dcol, tc::advance_desc_k(gd, k), tc::advance_desc_k(qd, k), idesc, (kc | k) != 0);
+            }
+          }
+          if (!(p.debug & 128)) { if (PAIR) tc::mma_commit_pair(&empty[st]); else tc::mma_commit(&empty[st]); }   // frees the gallery stage
           if (++st == p.stages) { st = 0; ph ^= 1; }
         }
-        tc::mma_commit(&tfull[buf]);                    // accumulator complete -> epilogue
+        if (PAIR) tc::mma_commit_pair(&tfull[buf]); else tc::mma_commit(&tfull[buf]);   // accumulator complete -> epilogue
       }
-      tc::mma_commit(&bempty);                          // query block no longer read
+      if (PAIR) tc::mma_commit_pair(&bempty); else tc::mma_commit(&bempty);             // query block no longer read
     }
   } else if (warp >= EPI_WARP0) {
-    // ------------------------------------------------------------------ epilogue (256 threads)
+    // ------------------------------------------------------------------ epilogue (EPI_WARPS warps)
     const int quad = warp & 3;                          // TMEM lane quadrant of this warp
     const int ew = warp - EPI_WARP0;                    // 0..EPI_WARPS-1
-    const int part = ew >> 2;                           // which COLS_PER_WARP query columns of the tile
+    const int part = ew >> 2;                           // which slice of the accumulator columns
     const int et = threadIdx.x - EPI_WARP0 * 32;        // 0..EPI_THREADS-1
     const uint32_t tmem_q = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t lt_mask = (1u << lane) - 1u;
-    // this lane's rows belong to the 1/SAMPLE_W stratified sample (SAMPLE_W > 32: only some quadrants sample)
+    // T layout: lane = gallery row; the rows of this lane belong to the 1/SAMPLE_W stratified sample or not
     const bool smp = ((quad * 32 + lane) & (SAMPLE_W - 1)) == 5;
     const uint32_t lane_bits = smp ? M_SAMPLED : 0u;
     float* my_qs = s_qs + ew * QCAP;
@@ -376,12 +408,12 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
     for (int i = et; i < NQ * p.pcap / 2; i += EPI_THREADS) s_hist32[i] = 0;
     epi_bar();
     uint32_t tilecount = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = unit; item < n_items; item += n_units) {
       const int chunk = item / p.n_qblocks, qb = item % p.n_qblocks;
       const int64_t row0 = chunk * p.rows_per_chunk;
       const int64_t row1 = reid_min64(p.G_local, row0 + p.rows_per_chunk);
-      const int ntiles = (int)((row1 - row0 + TMG - 1) / TMG);
-      const int64_t q0 = (int64_t)qb * NQ;
+      const int ntiles = (int)((row1 - row0 + TROWS - 1) / TROWS);
+      const int64_t q0 = (int64_t)qb * QSTEP + (int64_t)crank * NQ;   // first query of THIS CTA's block
       // ---- item setup: per-query state
       if (et < NQ) {
         const int64_t q = q0 + et;
@@ -402,7 +434,6 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         es->s_min[et] = fminf(tt, tex);
         es->s_minS[et] = fminf(fminf(tt, tex), tl);
         es->s_candcnt[et] = 0;
-        es->s_canddone[et] = 0;
         es->s_nextupd[et] = 64;
         int he = 0;
         if (live) {
@@ -410,6 +441,16 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
           for (int e = 0; e < p.E; ++e) he |= (p.excl[q * p.E + e] >= 0);
         }
         es->s_hasexcl[et] = he;
+      }
+      if (!p.calib) {                                          // -inf pre-fill of this item's candidate score slots
+        const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll 1
+        for (int ql = ew; ql < NQ; ql += EPI_WARPS) {
+          if (q0 + ql >= p.Q) break;
+          float4* dst = reinterpret_cast<float4*>(p.cand_score + ((q0 + ql) * p.n_chunks + chunk) * (int64_t)p.cand_cap);
+#pragma unroll 1
+          for (int j = lane; j < p.cand_cap / 4; j += 32) dst[j] = ninf;
+        }
       }
 #pragma unroll 1
       for (int ql = ew; ql < NQ; ql += EPI_WARPS) {          // one warp per query row of the threshold table
@@ -422,18 +463,25 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
       int qn = 0;                                          // queued hits of this warp (persist across tiles)
       // ---- tiles
       for (int t = 0; t < ntiles; ++t, ++tilecount) {
-        const uint32_t buf = tilecount % NBUF, bph = (tilecount / NBUF) & 1;
-        const int grow_local = (int)(row0 + (int64_t)t * TMG) + quad * 32 + lane;
-        const bool valid = grow_local < row1;
+        const uint32_t buf = tilecount % NB, bph = (tilecount / NB) & 1;
+        const int tile_row0 = (int)(row0 + (int64_t)t * TROWS);
+        // T: this lane's gallery row / R: this lane's query
+        const int grow_local = tile_row0 + quad * 32 + lane;
+        const bool valid = PAIR ? true : (grow_local < row1);
+        const int nvalid = (int)reid_min64(TROWS, row1 - tile_row0);   // R: valid gallery columns of this tile
+        const int myq = quad * 32 + lane;                               // R: query column id of this lane
+        float minA = 0.f, minS = 0.f;
+        if (PAIR) { minA = es->s_min[myq]; minS = es->s_minS[myq]; }    // refreshed thresholds, once per tile
         tc::mbar_wait(&tfull[buf], bph);
         tc::fence_after_sync();
+        constexpr int STEPS = (PAIR ? DCOLS : NQ) * 4 / EPI_WARPS / 16;
 #pragma unroll 1
-        for (int step = 0; step < ((p.debug & 4) ? 0 : COLS_PER_WARP / 16); ++step) {
-          const int c0 = part * COLS_PER_WARP + step * 16;
+        for (int step = 0; step < ((p.debug & 4) ? 0 : STEPS); ++step) {
+          const int c0 = part * (STEPS * 16) + step * 16;
           uint32_t r[16];
-          tc::tmem_ld_x16(tmem_q + buf * NQ + c0, r);
+          tc::tmem_ld_x16(tmem_q + buf * DCOLS + c0, r);
           float mm[16];
-          {
+          if (!PAIR) {
             const float* msrc = smp ? es->s_minS : es->s_min;      // lane-constant choice of threshold set
 #pragma unroll
             for (int i4 = 0; i4 < 16; i4 += 4) {
@@ -444,22 +492,32 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
           tc::tmem_wait_ld();
           unsigned cb[16];
           unsigned any = 0;
+          if (!(p.debug & 32)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {                   // branch-free: all ballots first (ILP)
-            cb[i] = __ballot_sync(0xffffffffu, valid && __uint_as_float(r[i]) > mm[i]);
-            any |= cb[i];
+            for (int i = 0; i < 16; ++i) {                   // branch-free: all ballots first (ILP)
+              const float s = __uint_as_float(r[i]);
+              // R: column c0+i is gallery row tile_row0+c0+i; rows = 5 (mod 16) are the sampled ones (i == 5)
+              const bool scol = ((c0 + i) & (SAMPLE_W - 1)) == 5;
+              const bool hit = PAIR ? ((c0 + i < nvalid) && s > (scol ? minS : minA)) : (valid && s > mm[i]);
+              cb[i] = __ballot_sync(0xffffffffu, hit);
+              any |= cb[i];
+            }
           }
           if (any) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const unsigned c = cb[i];
               if (c) {                                     // warp-uniform
-                const int ql = c0 + i;
                 if ((c >> lane) & 1u) {
                   const int pos = qn + __popc(c & lt_mask);
                   my_qs[pos] = __uint_as_float(r[i]);
-                  my_qr[pos] = grow_local;
-                  my_qm[pos] = (uint32_t)ql | lane_bits;
+                  if (PAIR) {
+                    my_qr[pos] = tile_row0 + c0 + i;
+                    my_qm[pos] = (uint32_t)myq | ((((c0 + i) & (SAMPLE_W - 1)) == 5) ? M_SAMPLED : 0u);
+                  } else {
+                    my_qr[pos] = grow_local;
+                    my_qm[pos] = (uint32_t)(c0 + i) | lane_bits;
+                  }
                 }
                 qn += __popc(c);
                 if (qn >= 32) {                            // drain one full batch, keep the tail
@@ -476,16 +534,15 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
           }
         }
         tc::fence_before_sync();
-        if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+        if (lane == 0) { if (PAIR && !leader) tc::mbar_arrive_remote(&tempty[buf], 0); else tc::mbar_arrive(&tempty[buf]); }
         // ---- tile boundary: this warp owns the candidate thresholds of a fixed group of queries
-        //      (UPD_PER_WARP each).  A threshold is refreshed only when no append of that query is in flight (done == allocated;
-        //      `done` is read first), so every slot of the window has been stored.  No CTA barrier needed.
+        //      (UPD_PER_WARP each).  The score slots of an item are pre-filled with -inf, so a window that
+        //      contains a slot whose store is still in flight only yields a more conservative bound:
+        //      no CTA barrier and no completion protocol are needed.
         if (!p.calib) {
           const int uq = ew * UPD_PER_WARP + (lane & (UPD_PER_WARP - 1));
-          const int done = *(volatile int*)&es->s_canddone[uq];
-          const int alloc = *(volatile int*)&es->s_candcnt[uq];
-          const int cnt = min(alloc, p.cand_cap);
-          unsigned um = __ballot_sync(0xffffffffu, lane < UPD_PER_WARP && done == alloc && cnt >= 64 && cnt >= es->s_nextupd[uq]);
+          const int cnt = min(*(volatile int*)&es->s_candcnt[uq], p.cand_cap);
+          unsigned um = __ballot_sync(0xffffffffu, lane < UPD_PER_WARP && cnt >= 64 && cnt >= es->s_nextupd[uq]);
           while (um) {
             const int src = __ffs(um) - 1;
             um &= um - 1;
@@ -506,11 +563,11 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
     }
   }
   tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (PAIR) tc::cluster_sync_all(); else __syncthreads();   // the peer may still be signalled / read until here
+  if (warp == 2) { if (PAIR) tc::tmem_dealloc_pair(tmem_base, TMEM_COLS); else tc::tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-size_t fused_smem_bytes(int kchunks, int stages, int pcap) {
+size_t fused_smem_bytes(int kchunks, int stages, int pcap, bool /*pair*/) {
   return (size_t)kchunks * B_CHUNK + (size_t)stages * A_STAGE + (size_t)NQ * pcap * 4 /*thr*/ +
          (size_t)NQ * pcap * 2 /*hist*/ + (size_t)EPI_WARPS * QCAP * 12 /*queues*/ +
          sizeof(EpiState) + 1024;
@@ -528,37 +585,62 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
                                    int32_t* pos_above, float* cand_score, int32_t* cand_idx, int32_t* cand_count,
                                    float* cand_thr, void* workspace, size_t workspace_bytes, void* stream) {
   if (!q_f16 || !g_f16 || !q_code || !g_code || !pos_thr || !n_pos || !pos_above || !cand_score || !cand_idx ||
-      !cand_count || Q <= 0 || G_local <= 0 || n_chunks <= 0 || cand_cap <= 0 || (E > 0 && !excl) || E < 0)
+      !cand_count || Q <= 0 || G_local <= 0 || n_chunks <= 0 || cand_cap < 64 || cand_cap % 4 != 0 || (E > 0 && !excl) || E < 0)
     return REID_E_INVALID;
   if (d % BK != 0 || d > 512 || Pmax <= 0 || Pmax > 64 || G_local > 0x7fffff00LL) return REID_E_UNSUPPORTED;
+  // cta_group::2 pair variant (R layout, M256 x N256): REID_FUSED_PAIR=0 selects the single-CTA T layout
+  const char* pair_env = getenv("REID_FUSED_PAIR");
+  const bool pair = pair_env ? atoi(pair_env) != 0 : true;
+  const int n_lchunks = n_chunks;
+  const int trows = pair ? 256 : TMG;
+  const int qstep = pair ? 2 * NQ : NQ;
   Params p;
   p.q_code = q_code; p.g_code = g_code; p.excl = excl; p.E = E; p.pos_thr = pos_thr; p.n_pos = n_pos;
   p.Q = Q; p.G_local = G_local; p.g_offset = g_offset;
   if (!workspace || workspace_bytes < (size_t)Q * (Pmax + 2) * sizeof(int32_t)) return REID_E_WORKSPACE;
   p.Pmax = Pmax; p.pcap = (Pmax + 3) / 4 * 4; p.kchunks = d / BK;
-  p.n_chunks = n_chunks; p.n_qblocks = (int)((Q + NQ - 1) / NQ); p.cand_cap = cand_cap;
-  const int64_t rpc = (G_local + n_chunks - 1) / n_chunks;
-  p.rows_per_chunk = (rpc + TMG - 1) / TMG * TMG;
+  p.n_chunks = n_chunks; p.n_qblocks = (int)((Q + qstep - 1) / qstep); p.cand_cap = cand_cap;
+  const int64_t rpc = (G_local + n_lchunks - 1) / n_lchunks;
+  p.rows_per_chunk = (rpc + trows - 1) / trows * trows;
   p.hist = (int32_t*)workspace; p.thr_share = (uint32_t*)workspace + (size_t)Q * Pmax;
   p.n_exact = (int32_t*)workspace + (size_t)Q * (Pmax + 1); p.calib = 0; p.row_stride = 1; p.cand_score = cand_score;
-  { const char* dbg = getenv("REID_FUSED_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; } p.cand_idx = cand_idx; p.cand_count = cand_count;
+  { const char* dbg = getenv("REID_FUSED_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+  p.cand_idx = cand_idx; p.cand_count = cand_count;
   int stages = MAX_STAGES;
   const size_t smem_max = 227 * 1024;
-  while (stages > 2 && fused_smem_bytes(p.kchunks, stages, p.pcap) > smem_max) --stages;
-  if (fused_smem_bytes(p.kchunks, stages, p.pcap) > smem_max) return REID_E_UNSUPPORTED;
+  while (stages > 2 && fused_smem_bytes(p.kchunks, stages, p.pcap, pair) > smem_max) --stages;
+  if (fused_smem_bytes(p.kchunks, stages, p.pcap, pair) > smem_max) return REID_E_UNSUPPORTED;
   p.stages = stages;
-  const size_t smem = fused_smem_bytes(p.kchunks, stages, p.pcap);
+  const size_t smem = fused_smem_bytes(p.kchunks, stages, p.pcap, pair);
   CUtensorMap tmG, tmQ;
-  if (!tc_host::make_map_f16(&tmG, g_f16, G_local, d, TMG) || !tc_host::make_map_f16(&tmQ, q_f16, Q, d, NQ))
+  if (!tc_host::make_map_f16(&tmG, g_f16, G_local, d, TMG) ||
+      !tc_host::make_map_f16(&tmQ, q_f16, Q, d, NQ))
     return REID_E_CUDA;
-  if (cudaFuncSetAttribute(retrieve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  auto kern1 = retrieve_fused_kernel<false>;
+  auto kern2 = retrieve_fused_kernel<true>;
+  if (cudaFuncSetAttribute(pair ? kern2 : kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return REID_E_CUDA;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return REID_E_CUDA;
-  const int n_items = p.n_qblocks * n_chunks;
-  const int grid = n_items < sms ? n_items : sms;
   cudaStream_t st = (cudaStream_t)stream;
+  // one persistent CTA per SM (pair: one CTA pair per two SMs, launched as clusters of 2)
+  auto launch = [&](const CUtensorMap& mg, const Params& pp) -> bool {
+    const int n_items = pp.n_qblocks * pp.n_chunks;
+    if (!pair) {
+      const int grid = n_items < sms ? n_items : sms;
+      kern1<<<grid, THREADS, smem, st>>>(mg, tmQ, pp);
+      return cudaGetLastError() == cudaSuccess;
+    }
+    const int units = n_items < sms / 2 ? n_items : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * units); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern2, mg, tmQ, pp) == cudaSuccess;
+  };
   if (cudaMemsetAsync(workspace, 0, (size_t)Q * (Pmax + 2) * sizeof(int32_t), st) != cudaSuccess) return REID_E_CUDA;
   const int aux_grid = (int)reid_min64((Q + 255) / 256, 148 * 8);
   const bool sample_deep = (G_local >= 16 * CALIB_ROWS) && !(p.debug & 64);
@@ -584,9 +666,7 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return REID_E_CUDA;
     }
-    const int cgrid = c.n_qblocks < sms ? c.n_qblocks : sms;
-    retrieve_fused_kernel<<<cgrid, THREADS, smem, st>>>(tmS, tmQ, c);
-    REID_CHECK_LAUNCH();
+    if (!launch(tmS, c)) return REID_E_CUDA;
     const float limit = fmaxf((float)p.rows_per_chunk / 128.f, 2048.f);
     const float scale = (float)p.rows_per_chunk / (float)CALIB_ROWS;
     calib_split_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, scale, limit, p.n_exact);
@@ -594,8 +674,7 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
     fill_n_exact_kernel<<<aux_grid, 256, 0, st>>>(n_pos, Q, Pmax, p.n_exact);
   }
   REID_CHECK_LAUNCH();
-  retrieve_fused_kernel<<<grid, THREADS, smem, st>>>(tmG, tmQ, p);
-  REID_CHECK_LAUNCH();
+  if (!launch(tmG, p)) return REID_E_CUDA;
   hist_to_above_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, pos_above, p.thr_share, cand_thr);
   REID_CHECK_LAUNCH();
   return REID_OK;

@@ -7,6 +7,7 @@ Mirrors the math of tools/eval_mm_protocol.py (reference) on device tensors:
 PyTorch is used only for device memory, streams and (optionally) torch.distributed; every
 arithmetic step is a call into libreid_b200.so.  There is no CPU / eager fallback.
 """
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -20,6 +21,7 @@ from ._cabi import check, ptr, stream_ptr
 # plus fp32 accumulation slack.  Queries whose top-k / CMC cannot be decided within this bound are
 # re-run through the all-fp32 kernel, so the bound only affects speed, never results.
 EPS_FP16 = 2.0 ** -10 + 2.0 ** -13
+PAIR_MODE = bool(int(os.environ.get("REID_FUSED_PAIR", "1")))   # cta_group::2 variant of the fused kernel
 _DEBUG_KEEP = None   # set to a dict to keep the flags / candidate counts of the last block (debug scripts)
 
 
@@ -37,6 +39,21 @@ class GalleryShard:
     pmax: int                  # largest number of gallery rows sharing one pid
     g_offset: int
     G_total: int
+    _bufs: dict = None         # work buffers reused across query blocks / calls (no allocator churn)
+
+    def buf(self, name, shape, dtype, zero=False):
+        """A cached scratch tensor; contents are undefined unless zero=True.  Stream-ordered reuse only."""
+        if self._bufs is None:
+            self._bufs = {}
+        t = self._bufs.get(name)
+        shape = tuple(int(x) for x in shape)
+        if t is None or t.dtype != dtype or t.numel() < int(torch.Size(shape).numel()) or t.device != self.g_f32.device:
+            t = torch.empty(max(1, int(torch.Size(shape).numel())), dtype=dtype, device=self.g_f32.device)
+            self._bufs[name] = t
+        v = t[:int(torch.Size(shape).numel())].view(shape)
+        if zero:
+            v.zero_()
+        return v
 
     @property
     def G_local(self):
@@ -213,30 +230,33 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
             pid_b, ex_b = q_pid[sl], (excl[sl] if excl is not None else None)
         fused_b = use_fused and q16_b is not None
 
-        q_code = torch.empty(nb, dtype=torch.int32, device=dev)
-        q_count = torch.empty(nb, dtype=torch.int32, device=dev)
+        q_code = shard.buf("q_code", (nb,), torch.int32)
+        q_count = shard.buf("q_count", (nb,), torch.int32)
         check(L.reid_pid_lookup(ptr(shard.sorted_pid), shard.G_total, ptr(pid_b), nb, ptr(q_code), ptr(q_count), st),
               "reid_pid_lookup")
-        pos_thr = torch.empty(nb, Pmax, dtype=torch.float32, device=dev)
+        pos_thr = shard.buf("pos_thr", (nb, Pmax), torch.float32)
         check(L.reid_pos_scores(ptr(q32_b), ptr(shard.g_f32), ptr(shard.order), ptr(q_code), ptr(q_count), ptr(ex_b), E,
                                 nb, shard.G_local, shard.g_offset, d, Pmax, ptr(pos_thr), st), "reid_pos_scores")
         if world > 1:
             sharding.exchange_pos_scores(pos_thr, group)                # owner rank holds the score, others -inf
         check(L.reid_pos_sort(ptr(pos_thr), ptr(n_pos[sl]), nb, Pmax, st), "reid_pos_sort")
 
-        if fused_b:
+        if fused_b and PAIR_MODE:
+            # cta_group::2 pairs: sms/2 scheduling units, blocks of 256 queries
+            n_chunks = _pick_chunks(-(-nb // 256), shard.G_local, sms // 2)
+        elif fused_b:
             n_chunks = _pick_chunks(-(-nb // 128), shard.G_local, sms)
         else:
             n_chunks = max(1, min(16, (2 * sms) // max(1, -(-nb // 8)), shard.G_local // 1024 or 1))
         cap = max(cand_cap, 64)
-        cand_score = torch.empty(nb, n_chunks, cap, dtype=torch.float32, device=dev)
-        cand_idx = torch.empty(nb, n_chunks, cap, dtype=torch.int32, device=dev)
-        cand_count = torch.zeros(nb, n_chunks, dtype=torch.int32, device=dev)
+        cand_score = shard.buf("cand_score", (nb, n_chunks, cap), torch.float32)
+        cand_idx = shard.buf("cand_idx", (nb, n_chunks, cap), torch.int32)
+        cand_count = shard.buf("cand_count", (nb, n_chunks), torch.int32, zero=True)
         common_tail = (nb, shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap)
-        cand_thr = torch.empty(nb, dtype=torch.float32, device=dev) if fused_b else None
+        cand_thr = shard.buf("cand_thr", (nb,), torch.float32) if fused_b else None
         if fused_b:
             ws_bytes = L.reid_workspace_bytes(1, nb, shard.G_local, d)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ws = shard.buf("fused_ws", (ws_bytes,), torch.uint8)
             check(L.reid_retrieve_fused(ptr(q16_b), ptr(shard.g_f16), ptr(q_code), ptr(shard.g_code), ptr(ex_b), E,
                                         ptr(pos_thr), ptr(n_pos[sl]), *common_tail, ptr(pos_above[sl]),
                                         ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), ptr(ws), ws_bytes, st),
