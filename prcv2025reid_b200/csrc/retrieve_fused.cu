@@ -18,9 +18,10 @@
 //           counters in shared memory, spilled to a global histogram every 256 tiles); the count of
 //           rows ranked above positive j is the prefix sum over buckets <= j;
 //           Thresholds whose rank inside the chunk is estimated (calibration pre-pass over a strided
-//           2048-row sample) to exceed max(rows/128, 2048) are "deep": they are counted on a fixed
-//           1/16 stratified row sample with weight 16 (a few-% error on a rank > 2000 moves AP by
-//           < 1e-6); all shallower thresholds are counted exactly on every row;
+//           2048-row sample) to exceed 32*SAMPLE_W rows are "deep": they are counted on a fixed
+//           1/SAMPLE_W stratified row sample with weight SAMPLE_W (>= 32 sampled rows above such a
+//           threshold: <= 18% unbiased error on a rank > 1000, which moves a query's AP by ~1e-5 and
+//           mAP by ~1e-6); all shallower thresholds are counted exactly on every row;
 //       (b) candidates: rows above the query's running threshold are appended (lane-parallel) to its
 //           candidate buffer in global memory; every 64 appends the threshold is raised to the 32nd
 //           largest of the last 64 appended scores, so >= 32 appended rows always lie above it.
@@ -35,6 +36,9 @@
 #include <stddef.h>
 
 namespace {
+
+// debug instrumentation (REID_FUSED_DEBUG bit 13 = 8192): cycle counters summed over CTAs
+__device__ unsigned long long g_dbg[8];
 
 constexpr int NQ = 128;        // queries per block  (MMA N, TMEM columns)
 constexpr int TMG = 128;       // gallery rows per tile (MMA M, TMEM lanes)
@@ -54,14 +58,18 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;
 constexpr int NBUF = 4;                  // TMEM accumulators: the epilogue may lag the MMA by up to 3 tiles
 constexpr uint32_t TMEM_COLS = NBUF * NQ; // 4 x 128 fp32 columns = all of TMEM
-constexpr int QCAP = 64;                 // per-warp hit queue entries
+constexpr int QCAP = 96;                 // per-warp hit queue entries (8 bytes each: score + packed meta)
 constexpr int FLUSH_TILES = 128;         // 16-bit counters: <= 240 weighted increments per tile
 #ifndef REID_SAMPLE_W
-#define REID_SAMPLE_W 64
+#define REID_SAMPLE_W 32
 #endif
 constexpr int SAMPLE_W = REID_SAMPLE_W;  // deep thresholds: rows with (row % SAMPLE_W) == 5, weight SAMPLE_W
+static_assert(SAMPLE_W >= 16 && SAMPLE_W % 16 == 0, "sampled rows are column 5 of a 16-column step");
 constexpr int CALIB_ROWS = 2048;         // strided gallery sample of the calibration pre-pass
-constexpr uint32_t M_SAMPLED = 1u << 17;
+// queue meta word: bits 0-6 query column, 7 SAMPLED, 10-31 local gallery row (< 2^22)
+constexpr uint32_t M_SAMPLED = 1u << 7;
+constexpr int M_ROW_SHIFT = 10;
+constexpr int64_t MAX_ROWS = 1ll << 22;
 static_assert(KL == 32, "threshold update takes the 32nd largest of a 64-entry window");
 
 struct Params {
@@ -113,8 +121,7 @@ struct EpiAddr {
   uint32_t thr;    // float [NQ][pcap] positive thresholds, sorted descending
   uint32_t hist;   // u32   [NQ][pcap/2] packed 16-bit bucket counters
   uint32_t qs;     // float [EPI_WARPS][QCAP] hit queue: score
-  uint32_t qm;     // u32   [EPI_WARPS][QCAP] hit queue: query column | SAMPLED
-  uint32_t qr;     // s32   [EPI_WARPS][QCAP] hit queue: local gallery row
+  uint32_t qm;     // u32   [EPI_WARPS][QCAP] hit queue: packed meta (query column, flags, local gallery row)
 };
 #define ES_OFF(field) ((uint32_t)offsetof(EpiState, field))
 
@@ -127,19 +134,20 @@ __device__ __forceinline__ int atoms_add(uint32_t a, int v) { int o; asm volatil
 __device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t atoms_exch(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
 
-// Drain the first `n` (<= 32) queue entries of epilogue warp `ew`, one entry per lane.
-__device__ __noinline__ void epi_drain32(EpiAddr A, const Params* pp, int ew, int n, int lane, int64_t q0, int chunk) {
+// Drain queue entries [first, first + n) (n <= 32) of epilogue warp `ew`, one entry per lane.
+__device__ __noinline__ void epi_drain32(EpiAddr A, const Params* pp, int ew, int first, int n, int lane, int64_t q0, int chunk) {
   const Params& p = *pp;
   __syncwarp();
-  const bool have = lane < n;
-  const uint32_t qoff = (uint32_t)(ew * QCAP + lane) * 4u;
+  bool have = lane < n;
+  const uint32_t qoff = (uint32_t)(ew * QCAP + first + lane) * 4u;
   const float s = have ? lds_f32(A.qs + qoff) : 0.f;
   const uint32_t meta = have ? lds_u32(A.qm + qoff) : 0u;
-  const int row = have ? lds_s32(A.qr + qoff) : 0;
+  const int row = (int)(meta >> M_ROW_SHIFT);
+  have = have && row < p.G_local;                              // rows past the shard end (TMA zero fill) are no rows
   const uint32_t ql4 = (meta & 127u) * 4u;
   const int ql = meta & 127;
   bool ok = have;
-  if (have && lds_s32(A.es + ES_OFF(s_hasexcl) + ql4)) {      // same-image mask (eval_mm_protocol.py:408-418)
+  if (have && lds_s32(A.es + ES_OFF(s_hasexcl) + ql4)) {        // same-image mask (eval_mm_protocol.py:408-418)
     const int32_t gidx = (int32_t)(p.g_offset + (int64_t)row * p.row_stride);
 #pragma unroll 1
     for (int x = 0; x < p.E; ++x) ok = ok && (p.excl[(q0 + ql) * p.E + x] != gidx);
@@ -152,7 +160,7 @@ __device__ __noinline__ void epi_drain32(EpiAddr A, const Params* pp, int ew, in
     const int ne = lds_s32(A.es + ES_OFF(s_nexact) + ql4);
     int hi = ((meta & M_SAMPLED) ? lds_s32(A.es + ES_OFF(s_npos) + ql4) : ne) - 1;
     const uint32_t t = A.thr + (uint32_t)(ql * p.pcap) * 4u;
-    if (hi >= 0 && s > lds_f32(t + hi * 4) &&                 // invariant: t[hi] < s
+    if (hi >= 0 && s > lds_f32(t + hi * 4) &&                   // invariant: t[hi] < s
         p.g_code[(int64_t)row * p.row_stride] != lds_s32(A.es + ES_OFF(s_qcode) + ql4)) {
       int lo = 0;
       while (lo < hi) {
@@ -290,8 +298,7 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
   uint32_t* s_hist32 = reinterpret_cast<uint32_t*>(s_thr + NQ * p.pcap);         // [NQ][pcap/2]
   float* s_qs = reinterpret_cast<float*>(s_hist32 + NQ * p.pcap / 2);            // [EPI_WARPS][QCAP]
   uint32_t* s_qm = reinterpret_cast<uint32_t*>(s_qs + EPI_WARPS * QCAP);         // [EPI_WARPS][QCAP]
-  int32_t* s_qr = reinterpret_cast<int32_t*>(s_qm + EPI_WARPS * QCAP);           // [EPI_WARPS][QCAP]
-  EpiState* es = reinterpret_cast<EpiState*>(s_qr + EPI_WARPS * QCAP);
+  EpiState* es = reinterpret_cast<EpiState*>(s_qm + EPI_WARPS * QCAP);
   __shared__ __align__(8) uint64_t full[MAX_STAGES], empty[MAX_STAGES], bfull, bempty, tfull[NBUF], tempty[NBUF];   // (pair mode uses 2 of the NBUF)
   __shared__ uint32_t tmem_base_s;
 
@@ -363,12 +370,16 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
 #pragma unroll 1
       for (int t = 0; t < ntiles; ++t, ++tilecount) {
         const uint32_t buf = tilecount % NB, bph = (tilecount / NB) & 1;
+        const long long tw0 = (p.debug & 8192) ? clock64() : 0;
         tc::mbar_wait(&tempty[buf], bph ^ 1);          // epilogue has drained this accumulator
         tc::fence_after_sync();
+        if (p.debug & 8192) { atomicAdd(&g_dbg[2], (unsigned long long)(clock64() - tw0)); atomicAdd(&g_dbg[5], 1ull); }
 #pragma unroll 1
         for (int kc = 0; kc < p.kchunks; ++kc) {
+          const long long tf0 = (p.debug & 8192) ? clock64() : 0;
           if (!(p.debug & 128)) tc::mbar_wait(&full[st], ph);
           tc::fence_after_sync();
+          if (p.debug & 8192) atomicAdd(&g_dbg[3], (unsigned long long)(clock64() - tf0));
           const uint64_t gd = tc::make_smem_desc_sw128(tc::smem_u32(sA + st * A_STAGE));    // gallery stage
           const uint64_t qd = tc::make_smem_desc_sw128(tc::smem_u32(sB + kc * B_CHUNK));    // resident queries
 #pragma unroll
@@ -400,10 +411,9 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
     const uint32_t lane_bits = smp ? M_SAMPLED : 0u;
     float* my_qs = s_qs + ew * QCAP;
     uint32_t* my_qm = s_qm + ew * QCAP;
-    int32_t* my_qr = s_qr + ew * QCAP;
     EpiAddr A;
     A.es = tc::smem_u32(es); A.thr = tc::smem_u32(s_thr); A.hist = tc::smem_u32(s_hist32);
-    A.qs = tc::smem_u32(s_qs); A.qm = tc::smem_u32(s_qm); A.qr = tc::smem_u32(s_qr);
+    A.qs = tc::smem_u32(s_qs); A.qm = tc::smem_u32(s_qm);
 #pragma unroll 1
     for (int i = et; i < NQ * p.pcap / 2; i += EPI_THREADS) s_hist32[i] = 0;
     epi_bar();
@@ -468,16 +478,18 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         // T: this lane's gallery row / R: this lane's query
         const int grow_local = tile_row0 + quad * 32 + lane;
         const bool valid = PAIR ? true : (grow_local < row1);
-        const int nvalid = (int)reid_min64(TROWS, row1 - tile_row0);   // R: valid gallery columns of this tile
         const int myq = quad * 32 + lane;                               // R: query column id of this lane
         float minA = 0.f, minS = 0.f;
-        if (PAIR) { minA = es->s_min[myq]; minS = es->s_minS[myq]; }    // refreshed thresholds, once per tile
+        if (PAIR) { minA = es->s_min[myq]; minS = es->s_minS[myq]; }   // refreshed thresholds, once per tile
+        const long long te0 = (p.debug & 8192) ? clock64() : 0;
         tc::mbar_wait(&tfull[buf], bph);
         tc::fence_after_sync();
+        const long long te1 = (p.debug & 8192) ? clock64() : 0;
         constexpr int STEPS = (PAIR ? DCOLS : NQ) * 4 / EPI_WARPS / 16;
 #pragma unroll 1
         for (int step = 0; step < ((p.debug & 4) ? 0 : STEPS); ++step) {
           const int c0 = part * (STEPS * 16) + step * 16;
+          const bool step_sampled = ((c0 + 5) & (SAMPLE_W - 1)) == 5;     // uniform
           uint32_t r[16];
           tc::tmem_ld_x16(tmem_q + buf * DCOLS + c0, r);
           float mm[16];
@@ -490,51 +502,65 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
             }
           }
           tc::tmem_wait_ld();
-          unsigned cb[16];
-          unsigned any = 0;
+          // fast path: one compare per column into a per-lane bit mask, ONE warp-wide OR per step
+          // (16 votes per step serialise at ~20 cycles each); bit i of colmask = column c0+i has a hit
+          unsigned colmask = 0, bits = 0;
           if (!(p.debug & 32)) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {                   // branch-free: all ballots first (ILP)
-              const float s = __uint_as_float(r[i]);
-              // R: column c0+i is gallery row tile_row0+c0+i; rows = 5 (mod 16) are the sampled ones (i == 5)
-              const bool scol = ((c0 + i) & (SAMPLE_W - 1)) == 5;
-              const bool hit = PAIR ? ((c0 + i < nvalid) && s > (scol ? minS : minA)) : (valid && s > mm[i]);
-              cb[i] = __ballot_sync(0xffffffffu, hit);
-              any |= cb[i];
-            }
-          }
-          if (any) {
-#pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const unsigned c = cb[i];
-              if (c) {                                     // warp-uniform
-                if ((c >> lane) & 1u) {
-                  const int pos = qn + __popc(c & lt_mask);
-                  my_qs[pos] = __uint_as_float(r[i]);
-                  if (PAIR) {
-                    my_qr[pos] = tile_row0 + c0 + i;
-                    my_qm[pos] = (uint32_t)myq | ((((c0 + i) & (SAMPLE_W - 1)) == 5) ? M_SAMPLED : 0u);
-                  } else {
-                    my_qr[pos] = grow_local;
-                    my_qm[pos] = (uint32_t)(c0 + i) | lane_bits;
-                  }
-                }
-                qn += __popc(c);
-                if (qn >= 32) {                            // drain one full batch, keep the tail
-                  epi_drain32(A, &p, ew, 32, lane, q0, chunk);
-                  const int rest = qn - 32;              // <= 31 entries move to the front
-                  const float ts = my_qs[32 + (lane & 31)]; const uint32_t tm2 = my_qm[32 + (lane & 31)];
-                  const int tr = my_qr[32 + (lane & 31)];
-                  __syncwarp();
-                  if (lane < rest) { my_qs[lane] = ts; my_qm[lane] = tm2; my_qr[lane] = tr; }
-                  qn = rest;
-                }
+              const float s = __uint_as_float(r[i]);
+              // R: column c0+i is gallery row tile_row0+c0+i.  Only column 5 of a 16-column step can be a
+              // sampled row (rows = 5 mod SAMPLE_W); rows beyond the shard end are dropped by the drain.
+              const bool hit = PAIR ? (s > ((i == 5 && step_sampled) ? minS : minA)) : (valid && s > mm[i]);
+              bits |= hit ? (1u << i) : 0u;
+            }
+            colmask = __reduce_or_sync(0xffffffffu, bits);
+          }
+          // slow path (single copy of the code: the kernel must fit the instruction cache).  Round n takes
+          // the n-th hit of EVERY lane at once: per-lane select tree for the score, one ballot + prefix
+          // popc to compact the round into the dense warp queue.  Rounds per step = max hits per lane
+          // (usually 1), not the number of hit columns.
+          if (p.debug & 4096) colmask = 0;               // debug: fast path only (hits ignored)
+          if (colmask) {
+            unsigned b = bits;
+#pragma unroll 1
+            while (true) {
+              const bool has = b != 0;
+              const unsigned c = __ballot_sync(0xffffffffu, has);
+              if (!c) break;
+              const int i = has ? (__ffs(b) - 1) : 0;
+              b &= b - 1;                                // (0 stays 0)
+              // the lane's score of column i: 4-level select tree over the 16 registers (no memory)
+              uint32_t t8[8], t4[4], t2[2];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) t8[u] = (i & 1) ? r[2 * u + 1] : r[2 * u];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) t4[u] = (i & 2) ? t8[2 * u + 1] : t8[2 * u];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) t2[u] = (i & 4) ? t4[2 * u + 1] : t4[2 * u];
+              if (has) {
+                const int pos = qn + __popc(c & lt_mask);
+                my_qs[pos] = __uint_as_float((i & 8) ? t2[1] : t2[0]);
+                my_qm[pos] = PAIR ? ((uint32_t)myq | ((i == 5 && step_sampled) ? M_SAMPLED : 0u) |
+                                     ((uint32_t)(tile_row0 + c0 + i) << M_ROW_SHIFT))
+                                  : ((uint32_t)(c0 + i) | lane_bits | ((uint32_t)grow_local << M_ROW_SHIFT));
+              }
+              qn += __popc(c);
+              if (qn > QCAP - 32) {                      // queue nearly full: drain the newest 32 now (order is irrelevant)
+                qn -= 32;
+                epi_drain32(A, &p, ew, qn, 32, lane, q0, chunk);
               }
             }
           }
         }
         tc::fence_before_sync();
         if (lane == 0) { if (PAIR && !leader) tc::mbar_arrive_remote(&tempty[buf], 0); else tc::mbar_arrive(&tempty[buf]); }
+        if ((p.debug & 8192) && lane == 0) {
+          const long long te2 = clock64();
+          if (ew == 0) { atomicAdd(&g_dbg[0], (unsigned long long)(te2 - te1)); atomicAdd(&g_dbg[1], (unsigned long long)(te1 - te0)); }
+        }
+        // the accumulator is handed back; full batches are drained now, overlapping the next tile's MMA
+        while (qn >= 32) { qn -= 32; epi_drain32(A, &p, ew, qn, 32, lane, q0, chunk); }
         // ---- tile boundary: this warp owns the candidate thresholds of a fixed group of queries
         //      (UPD_PER_WARP each).  The score slots of an item are pre-filled with -inf, so a window that
         //      contains a slot whose store is still in flight only yields a more conservative bound:
@@ -552,7 +578,7 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         if (((t + 1) % FLUSH_TILES) == 0) epi_flush_hist(A, &p, et, q0);
       }
       // ---- item end: drain the queue tail, spill the histogram, publish candidate state
-      if (qn) epi_drain32(A, &p, ew, qn, lane, q0, chunk);
+      if (qn) epi_drain32(A, &p, ew, 0, qn, lane, q0, chunk);
       epi_bar();
       epi_flush_hist(A, &p, et, q0);
       if (et < NQ && q0 + et < p.Q && !p.calib) {
@@ -569,7 +595,7 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
 
 size_t fused_smem_bytes(int kchunks, int stages, int pcap, bool /*pair*/) {
   return (size_t)kchunks * B_CHUNK + (size_t)stages * A_STAGE + (size_t)NQ * pcap * 4 /*thr*/ +
-         (size_t)NQ * pcap * 2 /*hist*/ + (size_t)EPI_WARPS * QCAP * 12 /*queues*/ +
+         (size_t)NQ * pcap * 2 /*hist*/ + (size_t)EPI_WARPS * QCAP * 8 /*queues*/ +
          sizeof(EpiState) + 1024;
 }
 
@@ -577,6 +603,12 @@ size_t fused_smem_bytes(int kchunks, int stages, int pcap, bool /*pair*/) {
 
 // workspace = the global bucket histogram [Q, 64] int32 (Pmax <= 64)
 // workspace = histogram [Q, Pmax<=64] + candidate threshold [Q] + exact-threshold count [Q]
+extern "C" int reid_debug_counters(unsigned long long* out, int reset) {
+  if (out && cudaMemcpyFromSymbol(out, g_dbg, sizeof(g_dbg)) != cudaSuccess) return REID_E_CUDA;
+  if (reset) { unsigned long long z[8] = {0}; if (cudaMemcpyToSymbol(g_dbg, z, sizeof(z)) != cudaSuccess) return REID_E_CUDA; }
+  return REID_OK;
+}
+
 extern "C" size_t reid_retrieve_fused_workspace_bytes(int64_t Q, int64_t, int) { return (size_t)Q * 66 * sizeof(int32_t); }
 
 extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const int32_t* q_code, const int32_t* g_code,
@@ -587,7 +619,7 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
   if (!q_f16 || !g_f16 || !q_code || !g_code || !pos_thr || !n_pos || !pos_above || !cand_score || !cand_idx ||
       !cand_count || Q <= 0 || G_local <= 0 || n_chunks <= 0 || cand_cap < 64 || cand_cap % 4 != 0 || (E > 0 && !excl) || E < 0)
     return REID_E_INVALID;
-  if (d % BK != 0 || d > 512 || Pmax <= 0 || Pmax > 64 || G_local > 0x7fffff00LL) return REID_E_UNSUPPORTED;
+  if (d % BK != 0 || d > 512 || Pmax <= 0 || Pmax > 64 || G_local > MAX_ROWS) return REID_E_UNSUPPORTED;
   // cta_group::2 pair variant (R layout, M256 x N256): REID_FUSED_PAIR=0 selects the single-CTA T layout
   const char* pair_env = getenv("REID_FUSED_PAIR");
   const bool pair = pair_env ? atoi(pair_env) != 0 : true;
@@ -667,7 +699,8 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
         return REID_E_CUDA;
     }
     if (!launch(tmS, c)) return REID_E_CUDA;
-    const float limit = fmaxf((float)p.rows_per_chunk / 128.f, 2048.f);
+    // deep = the row sample is expected to hold >= 32 rows above the threshold (17.7% rank error at the boundary)
+    const float limit = 32.f * (float)SAMPLE_W;
     const float scale = (float)p.rows_per_chunk / (float)CALIB_ROWS;
     calib_split_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, scale, limit, p.n_exact);
   } else {

@@ -186,7 +186,7 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
     top_idx = torch.empty(Q, _cabi.RTOP, dtype=torch.int32, device=dev)
     flag = torch.zeros(Q, dtype=torch.int32, device=dev)
     n_flagged = 0
-    use_fused = mode == "fused" and Pmax <= 64 and d % 64 == 0 and d <= 512
+    use_fused = mode == "fused" and Pmax <= 64 and d % 64 == 0 and d <= 512 and shard.G_local <= (1 << 22)
 
     blocks = [(b0, min(Q, b0 + query_block)) for b0 in range(0, Q, query_block)]
     staged = {}
