@@ -196,15 +196,27 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
         weights = weights.to(dev)
         copy_stream = torch.cuda.Stream(device=dev)
 
+        done_ev = {}                                          # compute-stream event after block bi has consumed its staging set
+
         def stage(bi):
             b0, b1 = blocks[bi]
+            n = b1 - b0
+            tag = "stage%d_" % (bi & 1)                        # two alternating staging sets (cached, no allocator churn)
             with torch.cuda.stream(copy_stream):
-                t = [h_raw[b0:b1].to(dev, non_blocking=True), h_mod[b0:b1].to(dev, non_blocking=True),
-                     q_pid[b0:b1].to(dev, non_blocking=True),
-                     excl[b0:b1].to(dev, non_blocking=True) if excl is not None else None]
+                if bi - 2 in done_ev:
+                    copy_stream.wait_event(done_ev.pop(bi - 2))   # the set is free once block bi-2 has finished
+                raw = shard.buf(tag + "raw", (n,) + tuple(h_raw.shape[1:]), h_raw.dtype)
+                mod = shard.buf(tag + "mod", (n,) + tuple(h_mod.shape[1:]), h_mod.dtype)
+                pid = shard.buf(tag + "pid", (n,), q_pid.dtype)
+                raw.copy_(h_raw[b0:b1], non_blocking=True); mod.copy_(h_mod[b0:b1], non_blocking=True)
+                pid.copy_(q_pid[b0:b1], non_blocking=True)
+                ex = None
+                if excl is not None:
+                    ex = shard.buf(tag + "excl", (n,) + tuple(excl.shape[1:]), excl.dtype)
+                    ex.copy_(excl[b0:b1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            staged[bi] = (t, ev)
+            staged[bi] = ([raw, mod, pid, ex], ev)
         stage(0)
     else:
         q_pid = q_pid.to(device=dev, dtype=torch.int64).contiguous()
@@ -219,9 +231,6 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
                 stage(bi + 1)                                    # next block's H2D overlaps this block's kernels
             (raw_b, mod_b, pid_b, ex_b), ev = staged.pop(bi)
             torch.cuda.current_stream().wait_event(ev)
-            for t in (raw_b, mod_b, pid_b, ex_b):
-                if t is not None:
-                    t.record_stream(torch.cuda.current_stream())
             q32_b, q16_b = fuse_queries(raw_b, mod_b, weights)
             pid_b = pid_b.to(torch.int64)
             ex_b = ex_b.to(torch.int32) if ex_b is not None else None
@@ -272,6 +281,8 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
                                   ptr(top_idx[sl]), ptr(flag[sl]), st), "reid_rescore_topk")
         if _DEBUG_KEEP is not None:
             _DEBUG_KEEP.update(flag=flag[sl].clone(), cand_count=cand_count.clone())
+        if host_queries is not None and not fused_b:
+            done_ev[bi] = torch.cuda.Event(); done_ev[bi].record()
         if fused_b:
             sel = torch.nonzero(flag[sl]).flatten().to(torch.int32)      # host sync: how many to re-run
             ns = int(sel.numel())
@@ -289,6 +300,8 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
                                           ptr(cand_count), None, ptr(sel), ns, nb, shard.G_local, shard.g_offset, d, Pmax,
                                           n_chunks, cap, topk, 0.0, ptr(pa), ptr(top_score[sl]), ptr(top_idx[sl]),
                                           ptr(flag[sl]), st), "reid_rescore_topk(fallback)")
+            if host_queries is not None:
+                done_ev[bi] = torch.cuda.Event(); done_ev[bi].record()
 
     if world > 1:
         sharding.exchange_counts(pos_above, group)                      # counts are additive over shards
