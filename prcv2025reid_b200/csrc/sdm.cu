@@ -32,10 +32,10 @@ struct SdmBatch {
 };
 
 struct Saved {
-  float *den_q, *den_g, *lse_r, *lse_c, *cnt_r, *cnt_c, *ce_r, *ce_c, *hdr, *S, *dqn, *dgn;
+  float *den_q, *den_g, *lse_r, *lse_c, *cnt_r, *cnt_c, *ce_r, *ce_c, *hdr, *S, *dqn, *dgn, *qn, *gn;
 };
 __host__ __device__ inline size_t saved_floats(int N, int M, int d) {
-  return (size_t)4 * N + (size_t)4 * M + 8 + (size_t)N * M + (size_t)(N + M) * d;
+  return (size_t)4 * N + (size_t)4 * M + 8 + (size_t)N * M + (size_t)2 * (N + M) * d;
 }
 __device__ inline Saved carve(float* base, int N, int M, int d) {
   Saved s;
@@ -47,6 +47,8 @@ __device__ inline Saved carve(float* base, int N, int M, int d) {
   s.S = s.hdr + 8;
   s.dqn = s.S + (size_t)N * M;
   s.dgn = s.dqn + (size_t)N * d;
+  s.qn = s.dgn + (size_t)M * d;          // normalised features exactly as the reference forms them (fp32 copy)
+  s.gn = s.qn + (size_t)N * d;
   return s;
 }
 
@@ -108,7 +110,7 @@ __device__ __forceinline__ void tile_gemm(int K, LA la, LB lb, float (&acc)[4][4
 
 // row denominators max(||x||, eps) in the reference's dtype path + non-finite detection
 template <bool BF16>
-__device__ void phase_norms(const void* x, int rows, int d, float eps, float* den, int* flags, int cta, int nctas) {
+__device__ void phase_norms(const void* x, int rows, int d, float eps, float* den, float* xn, int* flags, int cta, int nctas) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = cta * (TB / 32) + warp; r < rows; r += nctas * (TB / 32)) {
     float ss = 0.f;
@@ -118,7 +120,11 @@ __device__ void phase_norms(const void* x, int rows, int d, float eps, float* de
     if (BF16) { nrm = __bfloat162float(__float2bfloat16_rn(nrm)); e = __bfloat162float(__float2bfloat16_rn(eps)); }
     const float dn = fmaxf(nrm, e);
     bool bad = false;
-    for (int c = lane; c < d; c += 32) bad |= !isfinite(norm_elem<BF16>(x, (size_t)r * d + c, dn));
+    for (int c = lane; c < d; c += 32) {
+      const float v = norm_elem<BF16>(x, (size_t)r * d + c, dn);
+      xn[(size_t)r * d + c] = v;
+      bad |= !isfinite(v);
+    }
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 2);     // sdm_loss.py:79-81
     if (lane == 0) den[r] = dn;
   }
@@ -138,16 +144,16 @@ sdm_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   if (cta == 0 && threadIdx.x == 0) *flags = 0;
   sync_all(multi);
   // ---- phase 0: denominators (:31-32) ----
-  phase_norms<BF16>(P.qry, N, d, eps, sv.den_q, flags, cta, nctas);
-  phase_norms<BF16>(P.gal, M, d, eps, sv.den_g, flags, cta, nctas);
+  phase_norms<BF16>(P.qry, N, d, eps, sv.den_q, sv.qn, flags, cta, nctas);
+  phase_norms<BF16>(P.gal, M, d, eps, sv.den_g, sv.gn, flags, cta, nctas);
   sync_all(multi);
   // ---- phase 1: S = q^ g^T / tau, clamp (:86, :94) ----
   const int tiles_m = (N + TM - 1) / TM, tiles_n = (M + TN - 1) / TN;
   for (int tile = cta; tile < tiles_m * tiles_n; tile += nctas) {
     const int i0 = (tile / tiles_n) * TM, j0 = (tile % tiles_n) * TN;
     float acc[4][4];
-    auto la = [&](int r, int k) { const int i = i0 + r; return i < N ? norm_elem<BF16>(P.qry, (size_t)i * d + k, sv.den_q[i]) : 0.f; };
-    auto lb = [&](int k, int c) { const int j = j0 + c; return j < M ? norm_elem<BF16>(P.gal, (size_t)j * d + k, sv.den_g[j]) : 0.f; };
+    auto la = [&](int r, int k) { const int i = i0 + r; return i < N ? sv.qn[(size_t)i * d + k] : 0.f; };
+    auto lb = [&](int k, int c) { const int j = j0 + c; return j < M ? sv.gn[(size_t)j * d + k] : 0.f; };
     tile_gemm<true, true>(d, la, lb, acc, As, Bs);
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     bool bad = false;
@@ -282,7 +288,7 @@ sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
     if (tile < tq) {        // dq^[i][c] = sum_j dS[i][j] g^[j][c]
       const int i0 = (tile / tiles_d) * TM, c0 = (tile % tiles_d) * TN;
       auto la = [&](int r, int k) { return dS(i0 + r, k); };
-      auto lb = [&](int k, int c) { return (c0 + c < d) ? norm_elem<BF16>(P.gal, (size_t)k * d + c0 + c, sv.den_g[k]) : 0.f; };
+      auto lb = [&](int k, int c) { return (c0 + c < d) ? sv.gn[(size_t)k * d + c0 + c] : 0.f; };
       tile_gemm<true, false>(M, la, lb, acc, As, Bs);
 #pragma unroll
       for (int a = 0; a < 4; ++a)
@@ -295,7 +301,7 @@ sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
       const int t2 = tile - tq;
       const int j0 = (t2 / tiles_d) * TM, c0 = (t2 % tiles_d) * TN;
       auto la = [&](int r, int k) { return dS(k, j0 + r); };
-      auto lb = [&](int k, int c) { return (c0 + c < d) ? norm_elem<BF16>(P.qry, (size_t)k * d + c0 + c, sv.den_q[k]) : 0.f; };
+      auto lb = [&](int k, int c) { return (c0 + c < d) ? sv.qn[(size_t)k * d + c0 + c] : 0.f; };
       tile_gemm<false, false>(N, la, lb, acc, As, Bs);
 #pragma unroll
       for (int a = 0; a < 4; ++a)
@@ -312,7 +318,6 @@ sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   for (int r = cta * (TB / 32) + warp; r < N + M; r += nctas * (TB / 32)) {
     const bool isq = r < N;
     const int row = isq ? r : r - N;
-    const void* x = isq ? P.qry : P.gal;
     void* out = isq ? P.dqry : P.dgal;
     const float den = isq ? sv.den_q[row] : sv.den_g[row];
     const float* dxn = (isq ? sv.dqn : sv.dgn) + (size_t)row * d;
@@ -324,12 +329,12 @@ sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
       continue;
     }
     float dot = 0.f;
-    for (int c = lane; c < d; c += 32) dot = fmaf(dxn[c], norm_elem<BF16>(x, (size_t)row * d + c, den), dot);
+    const float* xnr = (isq ? sv.qn : sv.gn) + (size_t)row * d;
+    for (int c = lane; c < d; c += 32) dot = fmaf(dxn[c], xnr[c], dot);
     dot = warp_sum(dot);
     if (clamped) dot = 0.f;
     for (int c = lane; c < d; c += 32) {
-      const float xn = norm_elem<BF16>(x, (size_t)row * d + c, den);
-      st_out<BF16>(out, (size_t)row * d + c, (dxn[c] - xn * dot) / den);
+      st_out<BF16>(out, (size_t)row * d + c, (dxn[c] - xnr[c] * dot) / den);
     }
   }
 }
