@@ -130,7 +130,8 @@ int reid_metrics_reduce(const int32_t* pos_above, const int32_t* n_pos, int64_t 
  * One launch computes every pair; pair p uses qry[p] [N_p, d], gal[p] [M_p, d] (dtype F32 or
  * BF16), y[p] [N_p, M_p] float {0,1}.  loss[p] (fp32), status[p] (bit0: returned the reference's
  * non-differentiable zero; bit1: non-finite feature; bit2: non-finite S; bit3: no positives).
- * saved[p]: fp32 scratch of reid_sdm_saved_floats(N,M) floats kept for the backward. */
+ * saved[p]: scratch of reid_sdm_saved_floats(N,M,d) floats kept for the backward (S, row / column
+ * statistics and the normalised operands). */
 typedef struct {
   const void* qry; const void* gal; const float* y;
   int32_t N; int32_t M;
@@ -140,6 +141,9 @@ typedef struct {
 } reid_sdm_pair;
 #define REID_SDM_MAX_PAIRS 16
 size_t reid_sdm_saved_floats(int N, int M, int d);
+/* 1 when this batch runs on the tcgen05 path (csrc/sdm_tc.cu: bf16, 64 <= N,M <= 512 multiples of 8,
+ * d % 64 == 0, d <= 512, 16-byte aligned tensors), 0 when it runs on the fp32 CUDA-core path (csrc/sdm.cu). */
+int reid_sdm_uses_tensor_cores(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d);
 int reid_sdm_fwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps,
                  void* stream);
 int reid_sdm_bwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps,

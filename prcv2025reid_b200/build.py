@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libreid_b200.so")
-SOURCES = ["normalize.cu", "pos_index.cu", "rank.cu", "sdm.cu", "sim_gemm.cu", "retrieve_fused.cu", "api.cu"]
+SOURCES = ["normalize.cu", "pos_index.cu", "rank.cu", "sdm.cu", "sdm_tc.cu", "sim_gemm.cu", "retrieve_fused.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

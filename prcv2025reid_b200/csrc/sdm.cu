@@ -15,7 +15,7 @@
 // bf16 F.normalize rounds them); a grid of CTAs per pair cooperates through grid-wide barriers
 // (cooperative launch), a single CTA per pair is used when the pair is one tile (C2: N=M=8).
 // HBM roofline per pair, fwd+bwd: 3*(N+M)*d*s + 2*N*M*4 bytes.
-#include "common.cuh"
+#include "sdm_common.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -26,10 +26,10 @@ constexpr int TM = 64;       // tile rows
 constexpr int TN = 64;       // tile cols
 constexpr int KC = 16;       // k chunk
 
-struct SdmBatch {
-  reid_sdm_pair p[REID_SDM_MAX_PAIRS];
-  int n_pairs;
-};
+using SdmBatch = sdm::Batch;
+using sdm::ld_elem;
+using sdm::norm_elem;
+using sdm::st_out;
 
 struct Saved {
   float *den_q, *den_g, *lse_r, *lse_c, *cnt_r, *cnt_c, *ce_r, *ce_c, *hdr, *S, *dqn, *dgn, *qn, *gn;
@@ -50,19 +50,6 @@ __device__ inline Saved carve(float* base, int N, int M, int d) {
   s.qn = s.dgn + (size_t)M * d;          // normalised features exactly as the reference forms them (fp32 copy)
   s.gn = s.qn + (size_t)N * d;
   return s;
-}
-
-template <bool BF16>
-__device__ __forceinline__ float ld_elem(const void* base, size_t i) {
-  if (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
-  return reinterpret_cast<const float*>(base)[i];
-}
-// normalised element exactly as the reference forms it: fp32: x / den ; bf16: round_bf16(x / den)
-template <bool BF16>
-__device__ __forceinline__ float norm_elem(const void* base, size_t i, float den) {
-  const float v = __fdiv_rn(ld_elem<BF16>(base, i), den);
-  if (BF16) return __bfloat162float(__float2bfloat16_rn(v));
-  return v;
 }
 
 __device__ __forceinline__ void sync_all(bool multi) {
@@ -249,12 +236,6 @@ sdm_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
 }
 
 template <bool BF16>
-__device__ __forceinline__ void st_out(void* base, size_t i, float v) {
-  if (BF16) reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
-  else reinterpret_cast<float*>(base)[i] = v;
-}
-
-template <bool BF16>
 __global__ void __launch_bounds__(TB)
 sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   __shared__ __align__(16) float As[KC][TM + 4];
@@ -339,6 +320,222 @@ sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small-batch path (BASELINE C2: P x K = 4 x 2 -> N = M = 8; any N, M <= 32, d % 128 == 0, d <= 512): one CTA per
+// pair, everything in shared memory, no grid barrier.  The step is pure latency at this size (a few KB).
+// Uses the same `saved` layout as the general path (den, lse, cnt, ce, hdr, S).
+// ------------------------------------------------------------------------------------------------
+constexpr int SMALL_MAX = 32;
+
+template <bool BF16>
+__global__ void __launch_bounds__(TB)
+sdm_small_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
+  extern __shared__ __align__(16) float small_smem[];
+  const reid_sdm_pair& P = batch.p[blockIdx.x];
+  const int N = P.N, M = P.M;
+  Saved sv = carve(P.saved, N, M, d);
+  float* xs = small_smem;                              // [N + M][d] normalised rows
+  float* Ss = xs + (size_t)(N + M) * d;                // [N][M + 1]
+  float* st_r = Ss + N * (M + 1);                      // cnt / ce per row, then per column
+  __shared__ int s_flags;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_flags = 0;
+  __syncthreads();
+  // ---- rows: denominators in the reference's dtype path (:31-32), normalised copies, non-finite check (:79-81)
+  for (int r = warp; r < N + M; r += TB / 32) {
+    const bool isq = r < N;
+    const int row = isq ? r : r - N;
+    const void* x = isq ? P.qry : P.gal;
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) { const float v = ld_elem<BF16>(x, (size_t)row * d + c); ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    float nrm = sqrtf(ss), e = eps;
+    if (BF16) { nrm = __bfloat162float(__float2bfloat16_rn(nrm)); e = __bfloat162float(__float2bfloat16_rn(eps)); }
+    const float dn = fmaxf(nrm, e);
+    bool bad = false;
+    for (int c = lane; c < d; c += 32) {
+      const float v = norm_elem<BF16>(x, (size_t)row * d + c, dn);
+      xs[(size_t)r * d + c] = v;
+      bad |= !isfinite(v);
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_flags, 2);
+    if (lane == 0) (isq ? sv.den_q : sv.den_g)[row] = dn;
+  }
+  __syncthreads();
+  // ---- S = q^ g^T / tau, clamp (:86, :94): one warp per element
+  for (int idx = warp; idx < N * M; idx += TB / 32) {
+    const int i = idx / M, j = idx % M;
+    const float dot = warp_dot(xs + (size_t)i * d, xs + (size_t)(N + j) * d, d, lane);
+    if (lane == 0) {
+      const float s = __fdiv_rn(dot, tau_eff);
+      if (!isfinite(s)) atomicOr(&s_flags, 4);                               // :89-91
+      const float sc = fminf(fmaxf(s, -20.f), 20.f);
+      Ss[i * (M + 1) + j] = sc;
+      sv.S[(size_t)i * M + j] = sc;
+    }
+  }
+  __syncthreads();
+  // ---- per-row / per-column log-sum-exp and cross-entropy (:34-57): one warp per row or column, one lane per element
+  for (int r = warp; r < N + M; r += TB / 32) {
+    const bool isrow = r < N;
+    const int a = isrow ? r : r - N, len = isrow ? M : N;
+    const bool in = lane < len;
+    const float s = in ? (isrow ? Ss[a * (M + 1) + lane] : Ss[lane * (M + 1) + a]) : -INFINITY;
+    const float yv = in ? (isrow ? P.y[(size_t)a * M + lane] : P.y[(size_t)lane * M + a]) : 0.f;
+    const float mx = warp_max(s);
+    const float se = warp_sum(in ? expf(s - mx) : 0.f);
+    const float ps = warp_sum(yv > 0.f ? s : 0.f), pc = warp_sum(yv > 0.f ? 1.f : 0.f);
+    if (lane == 0) {
+      const float lse = mx + logf(se);
+      const float ce = pc > 0.f ? (lse - ps / pc) : 0.f;
+      (isrow ? sv.lse_r : sv.lse_c)[a] = lse;
+      (isrow ? sv.cnt_r : sv.cnt_c)[a] = pc;
+      (isrow ? sv.ce_r : sv.ce_c)[a] = ce;
+      st_r[2 * r] = pc; st_r[2 * r + 1] = ce;
+    }
+  }
+  __syncthreads();
+  // ---- means over valid rows / columns and the guards (:60-68, :101-106, :121-123, :142-147)
+  if (threadIdx.x == 0) {
+    double t[4] = {0, 0, 0, 0};
+    int anypos = 0;
+    for (int r = 0; r < N; ++r) {
+      const float pc = st_r[2 * r], ce = st_r[2 * r + 1];
+      if (pc > 0.f) { anypos = 1; if (isfinite(ce)) { t[0] += ce; t[1] += 1.0; } }
+    }
+    for (int r = N; r < N + M; ++r) {
+      const float pc = st_r[2 * r], ce = st_r[2 * r + 1];
+      if (pc > 0.f && isfinite(ce)) { t[2] += ce; t[3] += 1.0; }
+    }
+    int st = s_flags;
+    if (!anypos) st |= 8;
+    const float lr = t[1] > 0 ? (float)(t[0] / t[1]) : 0.f;
+    const float lc = t[3] > 0 ? (float)(t[2] / t[3]) : 0.f;
+    float loss = 0.5f * (lr + lc);
+    if (!(st & (2 | 4 | 8)) && (isnan(loss) || isinf(loss) || loss < 0.f)) st |= 16;
+    if (st & (2 | 4 | 8 | 16)) { st |= 1; loss = 0.f; }
+    sv.hdr[0] = (float)t[1]; sv.hdr[1] = (float)t[3]; sv.hdr[3] = loss;
+    *reinterpret_cast<int*>(sv.hdr + 2) = st;
+    *P.loss = loss;
+    *P.status = st;
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(TB)
+sdm_small_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
+  extern __shared__ __align__(16) float small_smem[];
+  const reid_sdm_pair& P = batch.p[blockIdx.x];
+  const int N = P.N, M = P.M;
+  Saved sv = carve(P.saved, N, M, d);
+  float* xs = small_smem;                              // [N + M][d] normalised rows
+  float* dSs = xs + (size_t)(N + M) * d;               // [N][M + 1]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int st = *reinterpret_cast<const int*>(sv.hdr + 2);
+  if (st & 1) {                                        // the reference returned its non-differentiable zero
+    for (int idx = threadIdx.x; idx < (N + M) * d; idx += TB) {
+      const bool isq = idx < N * d;
+      st_out<BF16>(isq ? P.dqry : P.dgal, isq ? idx : idx - N * d, 0.f);
+    }
+    return;
+  }
+  const float nR = sv.hdr[0], nC = sv.hdr[1];
+  const float gscale = (*P.grad_out) * 0.5f / tau_eff;
+  const float wr = nR > 0.f ? gscale / nR : 0.f, wc = nC > 0.f ? gscale / nC : 0.f;
+  for (int idx = threadIdx.x; idx < N * M; idx += TB) {
+    const int i = idx / M, j = idx % M;
+    const float s = sv.S[idx];
+    float g = 0.f;
+    if (s < 20.f && s > -20.f) {
+      const float pos = P.y[idx] > 0.f ? 1.f : 0.f;
+      const float cr = sv.cnt_r[i], cc = sv.cnt_c[j];
+      if (cr > 0.f && isfinite(sv.ce_r[i])) g += wr * (expf(s - sv.lse_r[i]) - pos / cr);
+      if (cc > 0.f && isfinite(sv.ce_c[j])) g += wc * (expf(s - sv.lse_c[j]) - pos / cc);
+    }
+    dSs[i * (M + 1) + j] = g;
+  }
+  for (int r = warp; r < N + M; r += TB / 32) {
+    const bool isq = r < N;
+    const int row = isq ? r : r - N;
+    const void* x = isq ? P.qry : P.gal;
+    const float dn = (isq ? sv.den_q : sv.den_g)[row];
+    for (int c = lane; c < d; c += 32) xs[(size_t)r * d + c] = norm_elem<BF16>(x, (size_t)row * d + c, dn);
+  }
+  __syncthreads();
+  // one warp per output row: dx^ = sum_k dS * (other side's x^), then the normalisation Jacobian
+  const int nchunk = d >> 7;                           // 128 columns per chunk, 4 per lane (d <= 512)
+  float e = eps;
+  if (BF16) e = __bfloat162float(__float2bfloat16_rn(eps));
+  for (int r = warp; r < N + M; r += TB / 32) {
+    const bool isq = r < N;
+    const int row = isq ? r : r - N, len = isq ? M : N;
+    const float* other = xs + (size_t)(isq ? N : 0) * d;
+    float4 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k2 = 0; k2 < len; ++k2) {
+      const float w = isq ? dSs[row * (M + 1) + k2] : dSs[k2 * (M + 1) + row];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < nchunk) {
+          const float4 v = *reinterpret_cast<const float4*>(other + (size_t)k2 * d + k * 128 + lane * 4);
+          acc[k].x = fmaf(w, v.x, acc[k].x); acc[k].y = fmaf(w, v.y, acc[k].y);
+          acc[k].z = fmaf(w, v.z, acc[k].z); acc[k].w = fmaf(w, v.w, acc[k].w);
+        }
+    }
+    const float den = (isq ? sv.den_q : sv.den_g)[row];
+    float dot = 0.f;
+    float4 xh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < nchunk) {
+        xh[k] = *reinterpret_cast<const float4*>(xs + (size_t)r * d + k * 128 + lane * 4);
+        dot = fmaf(acc[k].x, xh[k].x, dot); dot = fmaf(acc[k].y, xh[k].y, dot);
+        dot = fmaf(acc[k].z, xh[k].z, dot); dot = fmaf(acc[k].w, xh[k].w, dot);
+      }
+    dot = warp_sum(dot);
+    if (!(den > e)) dot = 0.f;                         // norm <= eps: the denominator is the constant eps
+    void* out = isq ? P.dqry : P.dgal;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < nchunk) {
+        const size_t o = (size_t)row * d + k * 128 + lane * 4;
+        st_out<BF16>(out, o, (acc[k].x - xh[k].x * dot) / den);
+        st_out<BF16>(out, o + 1, (acc[k].y - xh[k].y * dot) / den);
+        st_out<BF16>(out, o + 2, (acc[k].z - xh[k].z * dot) / den);
+        st_out<BF16>(out, o + 3, (acc[k].w - xh[k].w * dot) / den);
+      }
+  }
+}
+
+bool small_eligible(const reid_sdm_pair* pairs, int n_pairs, int d) {
+  if (!pairs || n_pairs <= 0 || n_pairs > REID_SDM_MAX_PAIRS || d % 128 != 0 || d > 512) return false;
+  for (int i = 0; i < n_pairs; ++i)
+    if (pairs[i].N <= 0 || pairs[i].M <= 0 || pairs[i].N > SMALL_MAX || pairs[i].M > SMALL_MAX) return false;
+  return true;
+}
+
+template <class K>
+int launch_small(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float eps, bool bwd, cudaStream_t st) {
+  SdmBatch b;
+  b.n_pairs = n_pairs;
+  size_t smem = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    const reid_sdm_pair& p = pairs[i];
+    if (!p.qry || !p.gal || !p.y || !p.loss || !p.status || !p.saved) return REID_E_INVALID;
+    if (bwd && (!p.grad_out || !p.dqry || !p.dgal)) return REID_E_INVALID;
+    b.p[i] = p;
+    const size_t need = ((size_t)(p.N + p.M) * d + (size_t)p.N * (p.M + 1) + 2 * (size_t)(p.N + p.M)) * sizeof(float);
+    if (need > smem) smem = need;
+  }
+  const float tau_eff = fmaxf(0.15f, fminf(0.5f, tau));                    // sdm_loss.py:28
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return REID_E_CUDA;
+  kernel<<<n_pairs, TB, smem, st>>>(b, d, tau_eff, eps);
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}
+
 template <class K>
 int launch_sdm(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float eps, bool bwd, cudaStream_t st) {
   if (!pairs || n_pairs <= 0 || n_pairs > REID_SDM_MAX_PAIRS || d <= 0) return REID_E_INVALID;
@@ -378,16 +575,35 @@ int launch_sdm(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float t
 
 }  // namespace
 
-extern "C" size_t reid_sdm_saved_floats(int N, int M, int d) { return saved_floats(N, M, d); }
+// large enough for either code path (the tcgen05 path keeps bf16 operand images instead of fp32 copies)
+extern "C" size_t reid_sdm_saved_floats(int N, int M, int d) {
+  const size_t a = saved_floats(N, M, d);
+  const size_t b = (sdm::tc_layout(N, M, d).total_bytes + 3) / 4;
+  return a > b ? a : b;
+}
+
+extern "C" int reid_sdm_uses_tensor_cores(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d) {
+  return sdm::tc_eligible(pairs, n_pairs, dtype, d) ? 1 : 0;
+}
 
 extern "C" int reid_sdm_fwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps, void* stream) {
+  if (small_eligible(pairs, n_pairs, d)) {
+    if (dtype == REID_DTYPE_F32) return launch_small(sdm_small_fwd_kernel<false>, pairs, n_pairs, d, tau, eps, false, (cudaStream_t)stream);
+    if (dtype == REID_DTYPE_BF16) return launch_small(sdm_small_fwd_kernel<true>, pairs, n_pairs, d, tau, eps, false, (cudaStream_t)stream);
+  }
   if (dtype == REID_DTYPE_F32) return launch_sdm(sdm_fwd_kernel<false>, pairs, n_pairs, d, tau, eps, false, (cudaStream_t)stream);
+  if (sdm::tc_eligible(pairs, n_pairs, dtype, d)) return sdm::tc_forward(pairs, n_pairs, d, tau, eps, (cudaStream_t)stream);
   if (dtype == REID_DTYPE_BF16) return launch_sdm(sdm_fwd_kernel<true>, pairs, n_pairs, d, tau, eps, false, (cudaStream_t)stream);
   return REID_E_UNSUPPORTED;
 }
 
 extern "C" int reid_sdm_bwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps, void* stream) {
+  if (small_eligible(pairs, n_pairs, d)) {
+    if (dtype == REID_DTYPE_F32) return launch_small(sdm_small_bwd_kernel<false>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
+    if (dtype == REID_DTYPE_BF16) return launch_small(sdm_small_bwd_kernel<true>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
+  }
   if (dtype == REID_DTYPE_F32) return launch_sdm(sdm_bwd_kernel<false>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
+  if (sdm::tc_eligible(pairs, n_pairs, dtype, d)) return sdm::tc_backward(pairs, n_pairs, d, tau, eps, (cudaStream_t)stream);
   if (dtype == REID_DTYPE_BF16) return launch_sdm(sdm_bwd_kernel<true>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
   return REID_E_UNSUPPORTED;
 }

@@ -1,0 +1,700 @@
+// sdm_tc.cu -- SDM loss forward / backward on the 5th-generation tensor cores (bf16 inputs, large batch).
+//
+// Replaces models/sdm_loss.py:13-149 (`sdm_loss_stable`) and its autograd backward for the large-batch
+// configuration (BASELINE C5: P x K = 64 x 8 -> N = M = 512, d = 512, bf16, up to 16 modality pairs per
+// launch).  With bf16 inputs the reference normalises in bf16 (sdm_loss.py:31-32) and only then converts
+// to fp32 (:75), so the operands of S = q^ g^T (:86) are exactly representable in bf16: a kind::f16
+// tcgen05.mma with bf16 operands and fp32 accumulation computes the reference's S up to summation order.
+//
+// Three launches per step, no host synchronisation, no cooperative grid barrier:
+//   tc_prep_kernel  normalise rows (reference bf16 rounding), write each operand twice -- row-major-K image
+//                   and transposed image -- directly in the UMMA K-major 128B-swizzle layout, so that every
+//                   operand tile is ONE contiguous cp.async.bulk (no tensor maps, any number of pairs).
+//   tc_fwd_kernel   CTA = (pair, side, 128-row block).  side 0: rows = qry, columns = gal; side 1 = the transposed
+//                   problem.  The whole row block x all columns (<= 512) accumulates in TMEM (128 lanes x 512
+//                   fp32 columns = all of it), so the epilogue thread that owns a TMEM lane owns a full row of S:
+//                   S/tau, clamp (:94), log-sum-exp and the positive statistics of _one_side_ce (:34-57) need no
+//                   cross-thread reduction.  The last CTA of a pair (completion counter) reduces the per-row
+//                   cross-entropies to the loss and evaluates the guards (:60-68, :79-81, :89-91, :105-106, :142-147).
+//   tc_bwd_kernel   CTA = (pair, side, 128-row block).  side 0: dq^ = dS g^ (K = gal rows), side 1: dg^ = dS^T q^.
+//                   Eight producer warps form dL/dS tiles from S, the row / column LSE and y, split them into
+//                   bf16 hi + lo (16 mantissa bits) and store them in the swizzled operand layout; the MMA warp
+//                   multiplies them with the transposed operand image streamed by bulk copies; the accumulator
+//                   (128 rows x d columns) again gives every epilogue thread a full output row, so the
+//                   normalisation Jacobian (I - x^ x^T)/den is applied in registers and the gradient is written
+//                   once, in bf16.
+// Rooflines: algorithmic HBM bytes per pair fwd+bwd = 3*(N+M)*d*2 + 2*N*M*4; tensor work 3 * 2*N*M*d flop
+// (+ the lo pass of the backward).  See DESIGN.md section 6.
+#include "sdm_common.cuh"
+#include "tc_common.cuh"
+
+namespace sdm {
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+// exp(x) for |x| <= ~40 (the clamp :94 bounds every argument): one FMUL + MUFU.EX2, relative error ~2^-22
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// =============================================================================================== prep
+constexpr int PREP_ROWS = 32;
+constexpr int PREP_THREADS = 256;
+
+__global__ void __launch_bounds__(PREP_THREADS)
+tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
+  const reid_sdm_pair& P = batch.p[blockIdx.z];
+  const int which = blockIdx.y;                      // 0 = qry, 1 = gal, 2 = positive masks of y
+  if (which == 2) {
+    // one 32 x 32 tile of y per warp: row words by ballot, transposed words accumulated per lane
+    const TcLayout L = tc_layout(P.N, P.M, d);
+    uint8_t* bytes = reinterpret_cast<uint8_t*>(tc_base(P.saved));
+    uint32_t* ybits = reinterpret_cast<uint32_t*>(bytes + L.ybits);
+    uint32_t* ybitsT = reinterpret_cast<uint32_t*>(bytes + L.ybitsT);
+    const int lane = threadIdx.x & 31;
+    const int tiles_m = (P.M + 31) >> 5, tiles_n = (P.N + 31) >> 5;
+    const int tix = blockIdx.x * (PREP_THREADS / 32) + (threadIdx.x >> 5);
+    if (tix >= tiles_m * tiles_n) return;
+    const int ti = tix / tiles_m, tj = tix % tiles_m;
+    const int j = tj * 32 + lane;
+    uint32_t mine = 0, wordT = 0;
+    float yv[32];
+#pragma unroll
+    for (int ii = 0; ii < 32; ++ii) {                          // all 32 row loads in flight before the first vote
+      const int i = ti * 32 + ii;
+      yv[ii] = (i < P.N && j < P.M) ? __ldg(P.y + (size_t)i * P.M + j) : 0.f;
+    }
+#pragma unroll
+    for (int ii = 0; ii < 32; ++ii) {
+      const bool v = yv[ii] > 0.f;
+      const uint32_t b = __ballot_sync(0xffffffffu, v);
+      if (lane == ii) mine = b;
+      wordT |= (v ? 1u : 0u) << ii;
+    }
+    if (ti * 32 + lane < P.N) ybits[(size_t)(ti * 32 + lane) * 16 + tj] = mine;
+    if (j < P.M) ybitsT[(size_t)j * 16 + ti] = wordT;
+    return;
+  }
+  const int R = which ? P.M : P.N;
+  const int Rp = round_up(R, 128);
+  const int r0 = blockIdx.x * PREP_ROWS;
+  if (r0 >= Rp) return;
+  const TcLayout L = tc_layout(P.N, P.M, d);
+  float* base = tc_base(P.saved);
+  uint8_t* bytes = reinterpret_cast<uint8_t*>(base);
+  const bf16* x = reinterpret_cast<const bf16*>(which ? P.gal : P.qry);
+  float* den = base + (which ? L.den_g : L.den_q);
+  uint8_t* img = bytes + (which ? L.gn : L.qn);
+  uint8_t* imgT = bytes + (which ? L.gnt : L.qnt);
+  int* hdr_i = reinterpret_cast<int*>(base + L.hdr);
+  extern __shared__ __align__(16) uint8_t prep_smem[];
+  bf16* tile = reinterpret_cast<bf16*>(prep_smem);   // [PREP_ROWS][d + 8]
+  __shared__ int s_bad;
+  const int ld = d + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_bad = 0;
+  if (blockIdx.x == 0 && which == 0 && threadIdx.x == 0) hdr_i[4] = 0;     // forward completion counter
+  __syncthreads();
+  const float e_b = bf16r(eps);
+  const int nchunk = d >> 3;                         // 16-byte chunks per row (<= 64)
+  bool bad = false;
+  for (int rr = warp; rr < PREP_ROWS; rr += PREP_THREADS / 32) {
+    const int r = r0 + rr;
+    const bool live = r < R;
+    uint4 raw[2];
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = lane + 32 * u;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (live && c < nchunk) raw[u] = *reinterpret_cast<const uint4*>(x + (size_t)r * d + c * 8);
+      float f[8];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+    }
+    ss = warp_sum(ss);
+    const float dn = fmaxf(bf16r(sqrtf(ss)), e_b);   // F.normalize in bf16: max(||x||, eps), :31-32
+    if (lane == 0 && live) den[r] = dn;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = lane + 32 * u;
+      if (c >= nchunk) continue;
+      float f[8];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        f[e] = live ? bf16r(__fdiv_rn(f[e], dn)) : 0.f;
+        bad |= !isfinite(f[e]);
+      }
+      const uint4 o = pack8(f);
+      const int kb = c >> 3, ch = c & 7;
+      *reinterpret_cast<uint4*>(img + (size_t)kb * ((size_t)Rp * 128) + (size_t)(r >> 3) * 1024 + (r & 7) * 128 +
+                                ((ch ^ (r & 7)) << 4)) = o;
+      *reinterpret_cast<uint4*>(tile + rr * ld + c * 8) = o;
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_bad, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) hdr_i[8 + which * 16 + blockIdx.x] = s_bad;          // sdm_loss.py:79-81
+  // transposed image: rows = feature index c, K = row index r (this CTA: 4 chunks of 8 rows)
+  for (int c = threadIdx.x; c < d; c += PREP_THREADS) {
+#pragma unroll
+    for (int q = 0; q < PREP_ROWS / 8; ++q) {
+      uint4 o;
+      bf16* ob = reinterpret_cast<bf16*>(&o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ob[e] = tile[(q * 8 + e) * ld + c];
+      const int k0 = r0 + q * 8;
+      const int kb = k0 >> 6, ch = (k0 & 63) >> 3;
+      *reinterpret_cast<uint4*>(imgT + (size_t)kb * ((size_t)d * 128) + (size_t)(c >> 3) * 1024 + (c & 7) * 128 +
+                                ((ch ^ (c & 7)) << 4)) = o;
+    }
+  }
+}
+
+// =============================================================================================== forward
+constexpr int FWD_EPI_WARPS = 16;     // four warps per TMEM lane quadrant, a quarter of the columns each
+constexpr int FWD_EPI_THREADS = FWD_EPI_WARPS * 32;
+constexpr int FWD_THREADS = 64 + FWD_EPI_THREADS;   // warp 0: bulk-copy producer, warp 1: MMA + TMEM, warps 2-17: epilogue
+constexpr int A_TILE = 128 * 128;        // 128 rows x 64 bf16 = 16 KB
+constexpr int B_TILE_MAX = 512 * 128;    // up to 512 rows x 64 bf16 = 64 KB
+constexpr int FWD_STAGE = A_TILE + B_TILE_MAX;
+constexpr int FWD_STAGES = 2;
+constexpr size_t FWD_SMEM = (size_t)FWD_STAGES * FWD_STAGE + 1024;
+
+__device__ __forceinline__ uint32_t tmem_cols_for(int c) { return c <= 32 ? 32u : c <= 64 ? 64u : c <= 128 ? 128u : c <= 256 ? 256u : 512u; }
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
+  const reid_sdm_pair& P = batch.p[blockIdx.z];
+  const int side = blockIdx.y;
+  const int N = P.N, M = P.M;
+  const int R = side ? M : N, C = side ? N : M;              // rows / columns of this side's view of S
+  const int Rp = round_up(R, 128), Cp = round_up(C, 128);
+  const int rb = blockIdx.x;
+  if (rb * 128 >= R) return;
+  const TcLayout L = tc_layout(N, M, d);
+  float* base = tc_base(P.saved);
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(base);
+  const uint8_t* imgA = bytes + (side ? L.gn : L.qn);
+  const uint8_t* imgB = bytes + (side ? L.qn : L.gn);
+  int* hdr_i = reinterpret_cast<int*>(base + L.hdr);
+  extern __shared__ uint8_t fwd_smem_raw[];
+  uint8_t* smem = fwd_smem_raw + ((1024u - (tc::smem_u32(fwd_smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full[FWD_STAGES], empty[FWD_STAGES], accfull;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_bad, s_last;
+  __shared__ float s_part[FWD_EPI_WARPS / 4 - 1][3][128];
+  __shared__ double s_red[FWD_EPI_WARPS][5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = d >> 6;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < FWD_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    tc::mbar_init(&accfull, 1);
+    tc::fence_barrier_init();
+    s_bad = 0; s_last = 0;
+  }
+  const uint32_t ncols = tmem_cols_for(Cp);
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, ncols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % FWD_STAGES;
+      tc::mbar_wait(&empty[s], ((kb / FWD_STAGES) & 1) ^ 1);
+      tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(A_TILE + Cp * 128));
+      tc::bulk_load(smem + s * FWD_STAGE, imgA + (size_t)kb * ((size_t)Rp * 128) + (size_t)rb * A_TILE, A_TILE, &full[s]);
+      tc::bulk_load(smem + s * FWD_STAGE + A_TILE, imgB + (size_t)kb * ((size_t)Cp * 128), (uint32_t)(Cp * 128), &full[s]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % FWD_STAGES;
+      tc::mbar_wait(&full[s], (kb / FWD_STAGES) & 1);
+      tc::fence_after_sync();
+      const uint64_t ad = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * FWD_STAGE));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        for (int n0 = 0; n0 < Cp; n0 += 256) {
+          const int n = Cp - n0 < 256 ? Cp - n0 : 256;
+          const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * FWD_STAGE + A_TILE + n0 * 128));
+          tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(ad, k), tc::advance_desc_k(bd, k),
+                         tc::make_idesc_f16(128, n, 1), (kb | k) != 0);
+        }
+      }
+      tc::mma_commit(&empty[s]);
+    }
+    tc::mma_commit(&accfull);
+  } else if (warp >= 2) {
+    // ---------------------------------------------------------------- epilogue: four threads per row of S (a quarter of the columns each)
+    const int quad = warp & 3;
+    constexpr int PARTS = FWD_EPI_WARPS / 4;
+    const int part = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;                       // 0..FWD_EPI_THREADS-1
+    const int row = quad * 32 + lane;
+    const int i = rb * 128 + row;
+    const bool live = i < R;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float* Sout = base + (side ? L.St : L.S) + (size_t)(live ? i : 0) * C;     // side 0: S[i][:]  side 1: St[j][:]
+    // positive mask of this row: 512 bits = 16 words (L1-resident after the first touch)
+    const uint32_t* bitrow = reinterpret_cast<const uint32_t*>(bytes + (side ? L.ybitsT : L.ybits) + (size_t)(live ? i : 0) * 64);
+    const int cstep = round_up((C + PARTS - 1) / PARTS, 16);
+    const int c_begin = part * cstep < C ? part * cstep : C, c_end = (part + 1) * cstep < C ? (part + 1) * cstep : C;
+    const float inv_tau = 1.f / tau_eff;
+    float se = 0.f, ps = 0.f, pc = 0.f;
+    bool bad = false;
+    tc::mbar_wait(&accfull, 0);
+    tc::fence_after_sync();
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+      uint32_t r[16];
+      __syncwarp();                                          // tcgen05.ld is .sync.aligned: reconverge first
+      const uint32_t bw = __ldg(bitrow + (c0 >> 5)) >> (c0 & 31);
+      tc::tmem_ld_x16(taddr + c0, r);
+      tc::tmem_wait_ld();
+      if (!live) continue;
+      float sv[16];
+      if (c_end - c0 >= 16) {
+        float se2 = 0.f;                                          // two accumulation chains
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float s = __uint_as_float(r[e]) * inv_tau;              // :86 (x 1/tau: <= 1 ulp from the reference's division)
+          bad |= !(fabsf(s) <= 3.0e38f);                          // :89-91 (NaN or Inf)
+          s = fminf(fmaxf(s, -20.f), 20.f);                       // :94 (and :46)
+          sv[e] = s;
+          if (e & 1) se2 += fast_exp(s); else se += fast_exp(s);  // |s| <= 20: no overflow without max subtraction
+          if ((bw >> e) & 1u) { ps += s; pc += 1.f; }
+        }
+        se += se2;
+        float* sp = Sout + c0;
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4)
+          *reinterpret_cast<float4*>(sp + 4 * e4) = make_float4(sv[4 * e4], sv[4 * e4 + 1], sv[4 * e4 + 2], sv[4 * e4 + 3]);
+      } else {
+        const int nv = c_end - c0;                                // ragged tail (C is a multiple of 8)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          if (e < nv) {
+            float s = __uint_as_float(r[e]) * inv_tau;
+            bad |= !(fabsf(s) <= 3.0e38f);
+            s = fminf(fmaxf(s, -20.f), 20.f);
+            se += fast_exp(s);
+            if ((bw >> e) & 1u) { ps += s; pc += 1.f; }
+            Sout[c0 + e] = s;
+          }
+        }
+      }
+    }
+    if (part > 0) { s_part[part - 1][0][row] = se; s_part[part - 1][1][row] = ps; s_part[part - 1][2][row] = pc; }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_bad, 1);
+    named_bar(1, FWD_EPI_THREADS);
+    if (part == 0 && live) {
+#pragma unroll
+      for (int q = 0; q < PARTS - 1; ++q) { se += s_part[q][0][row]; ps += s_part[q][1][row]; pc += s_part[q][2][row]; }
+      const float lse = logf(se);
+      float* lse_a = base + (side ? L.lse_c : L.lse_r);
+      float* cnt_a = base + (side ? L.cnt_c : L.cnt_r);
+      float* ce_a = base + (side ? L.ce_c : L.ce_r);
+      lse_a[i] = lse; cnt_a[i] = pc;
+      ce_a[i] = pc > 0.f ? (lse - ps / pc) : 0.f;               // -(q * log_p).sum, q uniform over positives (:49-57)
+    }
+    named_bar(1, FWD_EPI_THREADS);
+    if (et == 0) {
+      hdr_i[40 + side * 4 + rb] = s_bad;
+      __threadfence();
+      const int total = (N + 127) / 128 + (M + 127) / 128;
+      s_last = (atomicAdd(&hdr_i[4], 1) == total - 1);
+    }
+    named_bar(1, FWD_EPI_THREADS);
+    if (s_last) {
+      // ---- the last CTA of the pair: means over valid rows / columns and the guards
+      __threadfence();
+      double v[5] = {0, 0, 0, 0, 0};                              // sum ce_r, #valid rows, sum ce_c, #valid cols, #rows with a positive
+      for (int a = et; a < N; a += FWD_EPI_THREADS) {
+        const float c = __ldcg(base + L.cnt_r + a), ce = __ldcg(base + L.ce_r + a);
+        if (c > 0.f) { v[4] += 1.0; if (isfinite(ce)) { v[0] += ce; v[1] += 1.0; } }
+      }
+      for (int a = et; a < M; a += FWD_EPI_THREADS) {
+        const float c = __ldcg(base + L.cnt_c + a), ce = __ldcg(base + L.ce_c + a);
+        if (c > 0.f && isfinite(ce)) { v[2] += ce; v[3] += 1.0; }
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if (lane == 0) s_red[warp - 2][k] = v[k];
+      }
+      named_bar(1, FWD_EPI_THREADS);
+      if (et == 0) {
+        double t[5] = {0, 0, 0, 0, 0};
+        for (int w = 0; w < FWD_EPI_WARPS; ++w)
+          for (int k = 0; k < 5; ++k) t[k] += s_red[w][k];
+        int st = 0;
+        for (int s = 0; s < (L.Np >> 5); ++s) if (__ldcg(&hdr_i[8 + s])) st |= 2;
+        for (int s = 0; s < (L.Mp >> 5); ++s) if (__ldcg(&hdr_i[8 + 16 + s])) st |= 2;
+        for (int s = 0; s < (N + 127) / 128; ++s) if (__ldcg(&hdr_i[40 + s])) st |= 4;
+        for (int s = 0; s < (M + 127) / 128; ++s) if (__ldcg(&hdr_i[40 + 4 + s])) st |= 4;
+        if (t[4] == 0.0) st |= 8;                                                  // :105-106
+        const float lr = t[1] > 0 ? (float)(t[0] / t[1]) : 0.f;
+        const float lc = t[3] > 0 ? (float)(t[2] / t[3]) : 0.f;
+        float loss = 0.5f * (lr + lc);                                             // :123
+        if (!(st & (2 | 4 | 8)) && (isnan(loss) || isinf(loss) || loss < 0.f)) st |= 16;   // :145-147
+        if (st & (2 | 4 | 8 | 16)) { st |= 1; loss = 0.f; }
+        float* hdr = base + L.hdr;
+        hdr[0] = (float)t[1]; hdr[1] = (float)t[3]; hdr[3] = loss;
+        hdr_i[2] = st;
+        *P.loss = loss;
+        *P.status = st;
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, ncols);
+}
+
+// =============================================================================================== backward
+constexpr int BWD_PROD_WARPS = 8;
+constexpr int BWD_PROD_THREADS = BWD_PROD_WARPS * 32;
+constexpr int BWD_THREADS = 64 + BWD_PROD_THREADS;   // warp 0: bulk-copy producer, warp 1: MMA + TMEM, warps 2-9: dS producers, then epilogue
+constexpr int BWD_STAGE = 2 * A_TILE + B_TILE_MAX;   // dS hi, dS lo, transposed operand chunk (d rows x 64)
+constexpr int BWD_STAGES = 2;
+constexpr int BWD_KMAX = 512;
+constexpr size_t BWD_SMEM = (size_t)BWD_STAGES * BWD_STAGE + (3 * BWD_KMAX + 3 * 128) * sizeof(float) + 1024;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+tc_bwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff, float eps) {
+  const reid_sdm_pair& P = batch.p[blockIdx.z];
+  const int side = blockIdx.y;                               // 0: dqry rows, K = gal rows; 1: dgal rows, K = qry rows
+  const int N = P.N, M = P.M;
+  const int R = side ? M : N, K = side ? N : M;
+  const int rb = blockIdx.x;
+  if (rb * 128 >= R) return;
+  const int row0 = rb * 128;
+  const TcLayout L = tc_layout(N, M, d);
+  float* base = tc_base(P.saved);
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(base);
+  const uint8_t* imgB = bytes + (side ? L.qnt : L.gnt);      // [d rows][K] transposed operand image
+  const int* hdr_i = reinterpret_cast<const int*>(base + L.hdr);
+  const float* hdr = base + L.hdr;
+  const int st = hdr_i[2];
+  bf16* out = reinterpret_cast<bf16*>(side ? P.dgal : P.dqry);
+  const int rows_here = R - row0 < 128 ? R - row0 : 128;
+  if (st & 1) {      // the reference returned its non-differentiable zero: gradients are exact zeros
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)row0 * d);
+    for (int a = threadIdx.x; a < rows_here * d / 8; a += BWD_THREADS) o[a] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  extern __shared__ uint8_t bwd_smem_raw[];
+  uint8_t* smem = bwd_smem_raw + ((1024u - (tc::smem_u32(bwd_smem_raw) & 1023u)) & 1023u);
+  float* KL = reinterpret_cast<float*>(smem + BWD_STAGES * BWD_STAGE);   // per K index: lse, weight, 1/count
+  float* KW = KL + BWD_KMAX;
+  float* KIC = KW + BWD_KMAX;
+  float* RL = KIC + BWD_KMAX;                                            // per tile row
+  float* RW = RL + 128;
+  float* RIC = RW + 128;
+  __shared__ __align__(8) uint64_t bfull[BWD_STAGES], afull[BWD_STAGES], empty[BWD_STAGES], accfull, xfull;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = (K + 63) >> 6;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < BWD_STAGES; ++s) { tc::mbar_init(&bfull[s], 1); tc::mbar_init(&afull[s], BWD_PROD_WARPS); tc::mbar_init(&empty[s], 1); }
+    tc::mbar_init(&accfull, 1); tc::mbar_init(&xfull, 1);
+    tc::fence_barrier_init();
+  }
+  const uint32_t ncols = tmem_cols_for(d);
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, ncols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % BWD_STAGES;
+      tc::mbar_wait(&empty[s], ((kb / BWD_STAGES) & 1) ^ 1);
+      tc::mbar_arrive_expect_tx(&bfull[s], (uint32_t)(d * 128));
+      tc::bulk_load(smem + s * BWD_STAGE + 2 * A_TILE, imgB + (size_t)kb * ((size_t)d * 128), (uint32_t)(d * 128), &bfull[s]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % BWD_STAGES;
+      const uint32_t ph = (kb / BWD_STAGES) & 1;
+      tc::mbar_wait(&bfull[s], ph);
+      tc::mbar_wait(&afull[s], ph);
+      tc::fence_after_sync();
+      const uint64_t ah = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * BWD_STAGE));
+      const uint64_t al = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * BWD_STAGE + A_TILE));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        for (int n0 = 0; n0 < d; n0 += 256) {
+          const int n = d - n0 < 256 ? d - n0 : 256;
+          const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * BWD_STAGE + 2 * A_TILE + n0 * 128));
+          const uint32_t idesc = tc::make_idesc_f16(128, n, 1);
+          tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(ah, k), tc::advance_desc_k(bd, k), idesc, (kb | k) != 0);
+          tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(al, k), tc::advance_desc_k(bd, k), idesc, 1);
+        }
+      }
+      tc::mma_commit(&empty[s]);
+    }
+    tc::mma_commit(&accfull);
+  } else if (warp >= 2) {
+    // ---------------------------------------------------------------- dS producers
+    const int t = threadIdx.x - 64;                          // 0..255
+    const float nR = hdr[0], nC = hdr[1];
+    const float gscale = (*P.grad_out) * 0.5f / tau_eff;
+    const float wr = nR > 0.f ? gscale / nR : 0.f, wc = nC > 0.f ? gscale / nC : 0.f;
+    {
+      const float* lse_k = base + (side ? L.lse_r : L.lse_c);
+      const float* cnt_k = base + (side ? L.cnt_r : L.cnt_c);
+      const float* ce_k = base + (side ? L.ce_r : L.ce_c);
+      const float wk = side ? wr : wc;
+      for (int k = t; k < KB * 64; k += BWD_PROD_THREADS) {
+        const bool in = k < K;
+        const float c = in ? cnt_k[k] : 0.f;
+        const bool valid = in && c > 0.f && isfinite(ce_k[k]);
+        KL[k] = in ? lse_k[k] : 0.f;
+        KW[k] = valid ? wk : 0.f;
+        KIC[k] = c > 0.f ? 1.f / c : 0.f;
+      }
+      const float* lse_r = base + (side ? L.lse_c : L.lse_r);
+      const float* cnt_r = base + (side ? L.cnt_c : L.cnt_r);
+      const float* ce_r = base + (side ? L.ce_c : L.ce_r);
+      const float wrow = side ? wc : wr;
+      if (t < 128) {
+        const int gi = row0 + t;
+        const bool in = gi < R;
+        const float c = in ? cnt_r[gi] : 0.f;
+        const bool valid = in && c > 0.f && isfinite(ce_r[gi]);
+        RL[t] = in ? lse_r[gi] : 0.f;
+        RW[t] = valid ? wrow : 0.f;
+        RIC[t] = c > 0.f ? 1.f / c : 0.f;
+      }
+    }
+    named_bar(1, BWD_PROD_THREADS);
+    // this side's view of S (side 0: S [N][M], side 1: St [M][N]) and of the positive mask: rows = tile rows, K contiguous
+    const float* Sv = base + (side ? L.St : L.S);
+    const uint32_t* bitsv = reinterpret_cast<const uint32_t*>(bytes + (side ? L.ybitsT : L.ybits));
+    const int ch = t & 7;                                    // 8 lanes cover 64 consecutive K indices of one row
+    // global loads of one K block: 4 rows x 32 bytes of S + 4 mask words per thread
+    auto load_block = [&](int kb, float4 (&sa)[4], float4 (&sb)[4], uint32_t (&bw)[4]) {
+      const int k0 = kb * 64 + ch * 8;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int gr = row0 + (t >> 3) + 32 * u;
+        sa[u] = sb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bw[u] = 0;
+        if (gr < R && k0 < K) {
+          sa[u] = *reinterpret_cast<const float4*>(Sv + (size_t)gr * K + k0);
+          sb[u] = *reinterpret_cast<const float4*>(Sv + (size_t)gr * K + k0 + 4);
+          bw[u] = bitsv[(size_t)gr * 16 + (k0 >> 5)] >> (k0 & 31);
+        }
+      }
+    };
+    float4 sa[4], sb[4];
+    uint32_t bw[4];
+    load_block(0, sa, sb, bw);
+#pragma unroll 1
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % BWD_STAGES;
+      const int k0 = kb * 64 + ch * 8;
+      float4 na[4], nb[4];
+      uint32_t nw[4];
+      if (kb + 1 < KB) load_block(kb + 1, na, nb, nw);       // next block's loads fly while this one is formed
+      float kl[8], kw[8], kic[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { kl[e] = KL[k0 + e]; kw[e] = KW[k0 + e]; kic[e] = KIC[k0 + e]; }
+      tc::mbar_wait(&empty[s], ((kb / BWD_STAGES) & 1) ^ 1);
+      uint8_t* Ahi = smem + s * BWD_STAGE;
+      uint8_t* Alo = Ahi + A_TILE;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int row = (t >> 3) + 32 * u;
+        const bool in = row0 + row < R && k0 < K;
+        const float rl = RL[row], rw = RW[row], ric = RIC[row];
+        const float sv[8] = {sa[u].x, sa[u].y, sa[u].z, sa[u].w, sb[u].x, sb[u].y, sb[u].z, sb[u].w};
+        float hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          // dL/dS (chain through the clamp: zero where saturated); row statistics r*, K-index statistics k*
+          const float pos = ((bw[u] >> e) & 1u) ? 1.f : 0.f;
+          float g = rw * (fast_exp(sv[e] - rl) - pos * ric) + kw[e] * (fast_exp(sv[e] - kl[e]) - pos * kic[e]);
+          if (!in || sv[e] >= 20.f || sv[e] <= -20.f) g = 0.f;
+          hi[e] = bf16r(g);
+          lo[e] = g - hi[e];
+        }
+        const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(Ahi + off) = pack8(hi);
+        *reinterpret_cast<uint4*>(Alo + off) = pack8(lo);
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&afull[s]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { sa[u] = na[u]; sb[u] = nb[u]; bw[u] = nw[u]; }
+    }
+    // ---------------------------------------------------------------- epilogue: two threads per output row (half the columns each)
+    {
+      const int quad = warp & 3, half = (warp - 2) >> 2;
+      const int row = quad * 32 + lane, gi = row0 + row;
+      const bool live = gi < R;
+      const int gl = live ? gi : row0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+      const float den = (base + (side ? L.den_g : L.den_q))[gl];
+      const float rden = 1.f / den;
+      const bool clamped = !(den > bf16r(eps));          // norm <= eps: the denominator is the constant eps
+      bf16* orow = out + (size_t)gl * d;
+      const int dh = d >> 1;
+      const int c_begin = half * dh, c_end = c_begin + dh;
+      float* pdot = RL;                                  // the row statistics are dead now: reuse as [2][128] partial dots
+      tc::mbar_wait(&accfull, 0);                        // every MMA has retired: the stage buffers are free
+      tc::fence_after_sync();
+      // x^ of this row block (the values the forward multiplied): 128 rows x d of the K-major operand image,
+      // one contiguous 16 KB bulk copy per 64-feature block, into the (now idle) stage buffers
+      if (t == 0) {
+        const uint8_t* ximg = bytes + (side ? L.gn : L.qn);
+        const size_t kstride = (size_t)(side ? L.Mp : L.Np) * 128;
+        tc::mbar_arrive_expect_tx(&xfull, (uint32_t)((d >> 6) * A_TILE));
+        for (int kb = 0; kb < (d >> 6); ++kb)
+          tc::bulk_load(smem + kb * A_TILE, ximg + (size_t)kb * kstride + (size_t)rb * A_TILE, A_TILE, &xfull);
+      }
+      named_bar(1, BWD_PROD_THREADS);                    // every producer is past its last read of RL / RW
+      tc::mbar_wait(&xfull, 0);
+      const uint8_t* xrow = smem + (row >> 3) * 1024 + (row & 7) * 128;
+      auto xchunk = [&](int c) -> uint4 {                // 8 consecutive features starting at c (multiple of 8)
+        return *reinterpret_cast<const uint4*>(xrow + (c >> 6) * A_TILE + ((((c & 63) >> 3) ^ (row & 7)) << 4));
+      };
+      float dot = 0.f, dot2 = 0.f;
+#pragma unroll 1
+      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+        uint32_t r[16];
+        __syncwarp();
+        tc::tmem_ld_x16(taddr + c0, r);
+        float fa[8], fb[8];
+        unpack8(xchunk(c0), fa); unpack8(xchunk(c0 + 8), fb);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          dot = fmaf(__uint_as_float(r[e]), fa[e], dot);
+          dot2 = fmaf(__uint_as_float(r[8 + e]), fb[e], dot2);
+        }
+      }
+      pdot[half * 128 + row] = dot + dot2;
+      named_bar(1, BWD_PROD_THREADS);
+      dot = clamped ? 0.f : (pdot[row] + pdot[128 + row]);
+#pragma unroll 1
+      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+        uint32_t r[16];
+        __syncwarp();
+        tc::tmem_ld_x16(taddr + c0, r);
+        float fa[8], fb[8], oa[8], ob[8];
+        unpack8(xchunk(c0), fa); unpack8(xchunk(c0 + 8), fb);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          oa[e] = (__uint_as_float(r[e]) - fa[e] * dot) * rden;
+          ob[e] = (__uint_as_float(r[8 + e]) - fb[e] * dot) * rden;
+        }
+        if (live) {
+          *reinterpret_cast<uint4*>(orow + c0) = pack8(oa);
+          *reinterpret_cast<uint4*>(orow + c0 + 8) = pack8(ob);
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, ncols);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int fill_batch(Batch& b, const reid_sdm_pair* pairs, int n_pairs, bool bwd, int* max_blocks) {
+  if (!pairs || n_pairs <= 0 || n_pairs > REID_SDM_MAX_PAIRS) return REID_E_INVALID;
+  b.n_pairs = n_pairs;
+  int mb = 1;
+  for (int i = 0; i < n_pairs; ++i) {
+    const reid_sdm_pair& p = pairs[i];
+    if (!p.qry || !p.gal || !p.y || !p.loss || !p.status || !p.saved) return REID_E_INVALID;
+    if (bwd && (!p.grad_out || !p.dqry || !p.dgal || !aligned16(p.dqry) || !aligned16(p.dgal))) return REID_E_INVALID;
+    b.p[i] = p;
+    const int blocks = ((p.N > p.M ? p.N : p.M) + 127) / 128;
+    if (blocks > mb) mb = blocks;
+  }
+  *max_blocks = mb;
+  return REID_OK;
+}
+
+}  // namespace
+
+// the tcgen05 path serves bf16 batches whose every pair is one TMEM-resident problem
+bool tc_eligible(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d) {
+  if (dtype != REID_DTYPE_BF16 || !pairs || n_pairs <= 0 || n_pairs > REID_SDM_MAX_PAIRS) return false;
+  if (d % 64 != 0 || d < 64 || d > 512) return false;
+  for (int i = 0; i < n_pairs; ++i) {
+    const reid_sdm_pair& p = pairs[i];
+    if (p.N < 64 || p.M < 64 || p.N > 512 || p.M > 512 || (p.N & 7) || (p.M & 7)) return false;
+    if (!aligned16(p.qry) || !aligned16(p.gal) || !aligned16(p.y)) return false;
+  }
+  return true;
+}
+
+int tc_forward(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float eps, cudaStream_t st) {
+  Batch b;
+  int mb = 1;
+  const int rc = fill_batch(b, pairs, n_pairs, false, &mb);
+  if (rc != REID_OK) return rc;
+  const float tau_eff = fmaxf(0.15f, fminf(0.5f, tau));                    // sdm_loss.py:28
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess) return REID_E_CUDA;
+    if (cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess) return REID_E_CUDA;
+    attr_done = true;
+  }
+  const size_t prep_smem = (size_t)PREP_ROWS * (d + 8) * 2;
+  int gx = mb * 128 / PREP_ROWS;                          // y = 0, 1: 32-row slabs of qry / gal; y = 2: 32 x 32 tiles of y, 8 per CTA
+  for (int i = 0; i < n_pairs; ++i) {
+    const int tiles = ((pairs[i].N + 31) / 32) * ((pairs[i].M + 31) / 32);
+    const int need = (tiles + PREP_THREADS / 32 - 1) / (PREP_THREADS / 32);
+    if (need > gx) gx = need;
+  }
+  tc_prep_kernel<<<dim3(gx, 3, n_pairs), PREP_THREADS, prep_smem, st>>>(b, d, eps);
+  REID_CHECK_LAUNCH();
+  tc_fwd_kernel<<<dim3(mb, 2, n_pairs), FWD_THREADS, FWD_SMEM, st>>>(b, d, tau_eff);
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}
+
+int tc_backward(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float eps, cudaStream_t st) {
+  Batch b;
+  int mb = 1;
+  const int rc = fill_batch(b, pairs, n_pairs, true, &mb);
+  if (rc != REID_OK) return rc;
+  const float tau_eff = fmaxf(0.15f, fminf(0.5f, tau));
+  if (cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess) return REID_E_CUDA;
+  tc_bwd_kernel<<<dim3(mb, 2, n_pairs), BWD_THREADS, BWD_SMEM, st>>>(b, d, tau_eff, eps);
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}
+
+}  // namespace sdm

@@ -1,9 +1,10 @@
 """Drop-in for the reference's models/sdm_loss.py.
 
 `sdm_loss_stable(qry, gal, y, tau=0.2, eps=1e-8)` keeps the reference signature (sdm_loss.py:13).
-Forward and backward are one CUDA launch each (csrc/sdm.cu); `sdm_loss_pairs` runs all modality
-pairs of a training step (the four `sdm_loss_stable` calls of models/model.py:586-622) in ONE
-forward launch and ONE backward launch.  No host synchronisation happens on the numeric path: the
+`sdm_loss_pairs` runs all modality pairs of a training step (the four `sdm_loss_stable` calls of
+models/model.py:586-622) together: one forward and one backward launch on the fp32 CUDA-core path
+(csrc/sdm.cu: fp32 inputs, small or odd shapes), normalise + forward and one backward launch on the
+bf16 tcgen05 path (csrc/sdm_tc.cu: 64 <= N, M <= 512).  No host synchronisation happens on the numeric path: the
 reference's guards (sdm_loss.py:79-81, 89-91, 105-106, 145-147) are evaluated on the device.
 
 Documented differences from the reference (non-numeric):
@@ -12,12 +13,13 @@ Documented differences from the reference (non-numeric):
     returns a zero WITHOUT grad_fn (so inputs get no gradient), here the value is the same zero and
     the gradients are exact zeros.
 """
+import ctypes
 from typing import List, Sequence
 
 import torch
 
 from . import _cabi
-from ._cabi import SdmPair, check, stream_ptr
+from ._cabi import check
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -28,18 +30,41 @@ def _dtype_code(t: torch.Tensor) -> int:
     raise TypeError("sdm_loss: features must be float32 or bfloat16 (got %s)" % t.dtype)
 
 
-def _make_pairs(qrys, gals, ys, losses, status, saved, grad=None, dq=None, dg=None):
-    n = len(qrys)
-    arr = (SdmPair * n)()
-    for i in range(n):
-        arr[i].qry = qrys[i].data_ptr(); arr[i].gal = gals[i].data_ptr(); arr[i].y = ys[i].data_ptr()
-        arr[i].N = qrys[i].shape[0]; arr[i].M = gals[i].shape[0]
-        arr[i].loss = losses[i:i + 1].data_ptr(); arr[i].status = status[i:i + 1].data_ptr()
-        arr[i].saved = saved[i].data_ptr()
-        if grad is not None:
-            arr[i].grad_out = grad[i:i + 1].data_ptr()
-            arr[i].dqry = dq[i].data_ptr(); arr[i].dgal = dg[i].data_ptr()
-    return arr
+_SAVED_FLOATS = {}
+
+
+def _saved_floats(L, N, M, d):
+    key = (N, M, d)
+    v = _SAVED_FLOATS.get(key)
+    if v is None:
+        v = _SAVED_FLOATS[key] = (L.reid_sdm_saved_floats(N, M, d) + 63) // 64 * 64
+    return v
+
+
+def _raw_stream(dev):
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device()))
+
+
+def _pair_words(qs, gs, ys, losses, status, saved):
+    """The `reid_sdm_pair` array (include/reid_b200.h) as 10 64-bit words per pair (N and M share one);
+    the three backward-only slots stay zero."""
+    words = []
+    lp, sp = losses.data_ptr(), status.data_ptr()
+    for i, (q, g, y) in enumerate(zip(qs, gs, ys)):
+        words += [q.data_ptr(), g.data_ptr(), y.data_ptr(), q.shape[0] | (g.shape[0] << 32), lp + 4 * i, sp + 4 * i,
+                  saved[i].data_ptr(), 0, 0, 0]
+    return words
+
+
+def _pair_table(qs, gs, ys, losses, status, saved, grad=None, dq=None, dg=None):
+    words = _pair_words(qs, gs, ys, losses, status, saved)
+    if grad is not None:
+        gp = grad.data_ptr()
+        for i in range(len(qs)):
+            words[10 * i + 7] = gp + 4 * i
+            words[10 * i + 8] = dq[i].data_ptr()
+            words[10 * i + 9] = dg[i].data_ptr()
+    return (ctypes.c_uint64 * len(words))(*words)
 
 
 class _SdmPairsFn(torch.autograd.Function):
@@ -49,36 +74,101 @@ class _SdmPairsFn(torch.autograd.Function):
         L = _cabi.lib()
         dev = qrys[0].device
         d = qrys[0].shape[1]
+        dt = qrys[0].dtype
         code = _dtype_code(qrys[0])
-        qs = [q.detach().contiguous() for q in qrys]
-        gs = [g.detach().contiguous() for g in gals]
-        yy = [y.detach().to(torch.float32).contiguous() for y in ys]
+        qs = [q if q.is_contiguous() else q.contiguous() for q in qrys]
+        gs = [g if g.is_contiguous() else g.contiguous() for g in gals]
+        yy = [y if (y.dtype == torch.float32 and y.is_contiguous()) else y.to(torch.float32).contiguous() for y in ys]
         for q, g, y in zip(qs, gs, yy):
-            if q.dtype != qs[0].dtype or g.dtype != qs[0].dtype or q.shape[1] != d or g.shape[1] != d:
+            if q.dtype != dt or g.dtype != dt or q.shape[1] != d or g.shape[1] != d:
                 raise TypeError("sdm_loss: all features of a batch must share dtype and width")
-            if tuple(y.shape) != (q.shape[0], g.shape[0]):
+            if y.shape[0] != q.shape[0] or y.shape[1] != g.shape[0]:
                 raise ValueError("sdm_loss: y must be [N, M]")
         losses = torch.empty(n, dtype=torch.float32, device=dev)
         status = torch.empty(n, dtype=torch.int32, device=dev)
-        saved = [torch.empty(L.reid_sdm_saved_floats(q.shape[0], g.shape[0], d), dtype=torch.float32, device=dev)
-                 for q, g in zip(qs, gs)]
-        arr = _make_pairs(qs, gs, yy, losses, status, saved)
-        check(L.reid_sdm_fwd(arr, n, code, d, float(tau), float(eps), stream_ptr()), "reid_sdm_fwd")
+        sizes = [_saved_floats(L, q.shape[0], g.shape[0], d) for q, g in zip(qs, gs)]
+        saved = torch.empty(sum(sizes), dtype=torch.float32, device=dev).split(sizes)
+        words = _pair_words(qs, gs, yy, losses, status, saved)
+        arr = (ctypes.c_uint64 * len(words))(*words)
+        if L.reid_sdm_uses_tensor_cores(arr, n, code, d):
+            _cabi.LAUNCH_COUNT["n"] += 1                              # normalise/pack + forward = 2 launches
+        check(L.reid_sdm_fwd(arr, n, code, d, float(tau), float(eps), _raw_stream(dev)), "reid_sdm_fwd")
         ctx.n, ctx.tau, ctx.eps, ctx.code, ctx.d = n, float(tau), float(eps), code, d
-        ctx.keep = (qs, gs, yy, losses, status, saved)
-        ctx.status = status
+        # NOTE: the output must not be reachable from ctx (output -> grad_fn -> ctx -> output would keep every
+        # step's buffers alive until the cyclic GC runs); the backward only needs the device-side status bits
+        for i in range(n):
+            words[10 * i + 4] = words[10 * i + 5]                     # (the loss slot is not written again)
+        ctx.keep = (qs, gs, yy, status, saved, words)
         return losses
 
     @staticmethod
     def backward(ctx, grad_losses):
-        qs, gs, yy, losses, status, saved = ctx.keep
+        qs, gs, yy, status, saved, words = ctx.keep
         L = _cabi.lib()
-        grad = grad_losses.detach().to(torch.float32).contiguous()
-        dq = [torch.empty_like(q) for q in qs]
-        dg = [torch.empty_like(g) for g in gs]
-        arr = _make_pairs(qs, gs, yy, losses, status, saved, grad, dq, dg)
-        check(L.reid_sdm_bwd(arr, ctx.n, ctx.code, ctx.d, ctx.tau, ctx.eps, stream_ptr()), "reid_sdm_bwd")
-        return (None, None, None) + tuple(dq) + tuple(dg) + (None,) * ctx.n
+        n = ctx.n
+        grad = grad_losses
+        if grad.dtype != torch.float32 or not grad.is_contiguous():
+            grad = grad.to(torch.float32).contiguous()
+        q0, g0 = qs[0], gs[0]
+        if all(q.shape == q0.shape for q in qs) and all(g.shape == g0.shape for g in gs):
+            dq = torch.empty((n,) + tuple(q0.shape), dtype=q0.dtype, device=q0.device).unbind(0)
+            dg = torch.empty((n,) + tuple(g0.shape), dtype=g0.dtype, device=g0.device).unbind(0)
+        else:
+            nq = [q.numel() for q in qs]
+            ng = [g.numel() for g in gs]
+            parts = torch.empty(sum(nq) + sum(ng), dtype=q0.dtype, device=q0.device).split(nq + ng)
+            dq = [p.view(q.shape) for p, q in zip(parts[:n], qs)]
+            dg = [p.view(g.shape) for p, g in zip(parts[n:], gs)]
+        gp = grad.data_ptr()
+        w = list(words)
+        for i in range(n):
+            w[10 * i + 7] = gp + 4 * i
+            w[10 * i + 8] = dq[i].data_ptr()
+            w[10 * i + 9] = dg[i].data_ptr()
+        arr = (ctypes.c_uint64 * len(w))(*w)
+        check(L.reid_sdm_bwd(arr, n, ctx.code, ctx.d, ctx.tau, ctx.eps, _raw_stream(q0.device)), "reid_sdm_bwd")
+        return (None, None, None) + tuple(dq) + tuple(dg) + (None,) * n
+
+
+class SdmGraphStep:
+    """One SDM training step (all pairs: forward, loss sum, backward) captured in a CUDA graph.
+
+    The step is launch-bound at the reference's batch sizes (P x K = 4 x 2: a few KB of data), so the
+    whole forward + backward is recorded once and replayed with a single graph launch.  Inputs are
+    copied into the graph's static buffers (`load`), gradients are read from `dq` / `dg`.
+    """
+
+    def __init__(self, qrys, gals, ys, tau=0.2, eps=1e-8, warmup=3):
+        self.q = [q.detach().clone().requires_grad_(True) for q in qrys]
+        self.g = [g.detach().clone().requires_grad_(True) for g in gals]
+        self.y = [y.detach().clone() for y in ys]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager(tau, eps)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses, grads = self._eager(tau, eps)
+        self.dq, self.dg = grads[:len(self.q)], grads[len(self.q):]
+
+    def _eager(self, tau, eps):
+        losses = sdm_loss_pairs(self.q, self.g, self.y, tau, eps)
+        grads = torch.autograd.grad(losses.sum(), self.q + self.g)
+        return losses, grads
+
+    def load(self, qrys, gals, ys=None):
+        with torch.no_grad():
+            for dst, src in zip(self.q + self.g, list(qrys) + list(gals)):
+                dst.copy_(src)
+            if ys is not None:
+                for dst, src in zip(self.y, ys):
+                    dst.copy_(src)
+
+    def replay(self):
+        self.graph.replay()
+        return self.losses
 
 
 def sdm_loss_pairs(qrys: Sequence[torch.Tensor], gals: Sequence[torch.Tensor], ys: Sequence[torch.Tensor],

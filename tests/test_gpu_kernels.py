@@ -330,3 +330,127 @@ def test_sdm_large_bf16_grads_against_f64_closed_form():
     dq = q.grad.float().cpu().numpy(); dv = v.grad.float().cpu().numpy()
     assert np.linalg.norm(dq - dq64) <= 1e-2 * np.linalg.norm(dq64)
     assert np.linalg.norm(dv - dv64) <= 1e-2 * np.linalg.norm(dv64)
+
+
+# ---------------------------------------------------------------- SDM, tcgen05 path (csrc/sdm_tc.cu)
+def _sdm_uses_tc(q, v, y):
+    import ctypes
+    from prcv2025reid_b200 import _cabi
+    from prcv2025reid_b200.sdm_loss import _pair_table
+    z = torch.zeros(2, device=q.device)
+    arr = _pair_table([q], [v], [y], z[:1], z[1:].view(torch.int32), [z])
+    return bool(_cabi.lib().reid_sdm_uses_tensor_cores(arr, 1, _cabi.DTYPE_BF16 if q.dtype == torch.bfloat16 else _cabi.DTYPE_F32, q.shape[1]))
+
+
+def _tc_case(seed, N, M, d=512, n_ids=24, orphan=0.15):
+    """bf16 features clustered by identity; a fraction of the rows / columns carries an identity nobody shares."""
+    gen = torch.Generator().manual_seed(seed)
+    centres = torch.randn(n_ids, d, generator=gen)
+    lq = torch.randint(0, n_ids, (N,), generator=gen)
+    lv = torch.randint(0, n_ids, (M,), generator=gen)
+    lq[torch.rand(N, generator=gen) < orphan] = 1000            # qry rows without a positive
+    lv[torch.rand(M, generator=gen) < orphan] = 2000            # gal rows without a positive
+    q = (centres[lq.clamp(max=n_ids - 1)] + 1.5 * torch.randn(N, d, generator=gen)).to(torch.bfloat16)
+    v = (centres[lv.clamp(max=n_ids - 1)] + 1.5 * torch.randn(M, d, generator=gen)).to(torch.bfloat16)
+    y = (lq[:, None] == lv[None, :]).float()
+    return q, v, y
+
+
+def _check_against_oracle(q, v, y, loss, dq, dv, tau):
+    qc = q.clone().requires_grad_(True); vc = v.clone().requires_grad_(True)
+    ref = osdm.sdm_loss_oracle(qc, vc, y, tau=tau)              # the reference's bf16 dtype path, torch CPU autograd
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-3 * max(1.0, abs(float(ref)))       # north star: 1e-3 relative (bf16)
+    l64, dq64, dv64 = osdm.sdm_fwd_bwd_f64(q, v, y, tau=tau)
+    assert abs(float(loss) - l64) <= 2e-4 * max(1.0, abs(l64))
+    for got, gref, g64 in ((dq, qc.grad, dq64), (dv, vc.grad, dv64)):
+        got = got.float().cpu().numpy(); gref = gref.float().numpy()
+        # both sides end in a bf16 rounding (2^-9 relative per element): relative Frobenius norm
+        assert np.linalg.norm(got - gref) <= 1e-2 * np.linalg.norm(gref)
+        assert np.linalg.norm(got - g64) <= 6e-3 * np.linalg.norm(g64)
+
+
+@pytest.mark.parametrize("N,M,d", [(512, 512, 512), (72, 200, 512), (512, 64, 512), (128, 384, 256), (320, 136, 64)])
+def test_sdm_tensor_core_path_matches_oracle(N, M, d):
+    from prcv2025reid_b200.sdm_loss import sdm_loss_stable
+    q, v, y = _tc_case(100 + N + M, N, M, d)
+    qd = q.cuda().requires_grad_(True); vd = v.cuda().requires_grad_(True); yd = y.cuda()
+    assert _sdm_uses_tc(qd.detach(), vd.detach(), yd)
+    loss = sdm_loss_stable(qd, vd, yd, tau=0.2)
+    (3.0 * loss).backward()
+    _check_against_oracle(q, v, y, loss.detach().cpu(), qd.grad / 3.0, vd.grad / 3.0, 0.2)
+
+
+def test_sdm_tensor_core_pairs_of_different_shapes_in_one_launch():
+    from prcv2025reid_b200.sdm_loss import sdm_loss_pairs
+    shapes = [(512, 512), (64, 512), (200, 72), (384, 128), (256, 256)]
+    cases = [_tc_case(7 + i, n, m) for i, (n, m) in enumerate(shapes)]
+    qs = [c[0].cuda().requires_grad_(True) for c in cases]
+    vs = [c[1].cuda().requires_grad_(True) for c in cases]
+    losses = sdm_loss_pairs(qs, vs, [c[2].cuda() for c in cases], tau=0.3)
+    losses.sum().backward()
+    for i, (q, v, y) in enumerate(cases):
+        _check_against_oracle(q, v, y, losses[i].detach().cpu(), qs[i].grad, vs[i].grad, 0.3)
+
+
+def test_sdm_tensor_core_guards():
+    """sdm_loss.py:79-81 / :105-106 on the tcgen05 path: zero loss, exact-zero gradients, other pairs untouched."""
+    from prcv2025reid_b200.sdm_loss import sdm_loss_pairs
+    q0, v0, y0 = _tc_case(31, 128, 128)
+    q1, v1, y1 = _tc_case(32, 128, 192)
+    q2, v2, y2 = _tc_case(33, 256, 64)
+    y1 = torch.zeros_like(y1)                                     # no positives at all
+    q2 = q2.clone(); q2[5, 17] = float("nan")                     # non-finite feature
+    qs = [t.cuda().requires_grad_(True) for t in (q0, q1, q2)]
+    vs = [t.cuda().requires_grad_(True) for t in (v0, v1, v2)]
+    losses = sdm_loss_pairs(qs, vs, [y0.cuda(), y1.cuda(), y2.cuda()], tau=0.2)
+    losses.sum().backward()
+    assert float(losses[1]) == 0.0 and float(losses[2]) == 0.0
+    for i in (1, 2):
+        assert not qs[i].grad.float().abs().sum().item() and not vs[i].grad.float().abs().sum().item()
+    _check_against_oracle(q0, v0, y0, losses[0].detach().cpu(), qs[0].grad, vs[0].grad, 0.2)
+
+
+def test_sdm_graph_step_matches_eager():
+    """The CUDA-graph replay of a whole step (both code paths) reproduces the eager losses and gradients bit for bit."""
+    from prcv2025reid_b200.sdm_loss import SdmGraphStep, sdm_loss_pairs
+    for P, K, dtype in ((4, 2, torch.float32), (16, 8, torch.bfloat16)):
+        feats, labels = synth.make_sdm_batch(2003, P, K, dtype=dtype, device="cuda")
+        y = (labels[:, None] == labels[None, :]).float()
+        qs = [f.clone().requires_grad_(True) for f in feats[1:]]
+        vs = [feats[0].clone().requires_grad_(True) for _ in feats[1:]]
+        losses = sdm_loss_pairs(qs, vs, [y] * 4, tau=0.2)
+        grads = torch.autograd.grad(losses.sum(), qs + vs)
+        step = SdmGraphStep([torch.zeros_like(q) for q in qs], [torch.zeros_like(v) for v in vs], [y] * 4, tau=0.2)
+        step.load(qs, vs)
+        got = step.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(got, losses)
+        for a, b in zip(list(step.dq) + list(step.dg), grads):
+            assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("N,M,d,dtype", [(32, 20, 512, torch.float32), (5, 32, 256, torch.float32), (1, 1, 128, torch.float32),
+                                          (33, 8, 512, torch.float32), (24, 24, 512, torch.bfloat16)])
+def test_sdm_small_and_general_paths_match_oracle(N, M, d, dtype):
+    """fp32 CUDA-core paths (csrc/sdm.cu): the one-CTA small-batch kernels (N, M <= 32) and the general kernels."""
+    from prcv2025reid_b200.sdm_loss import sdm_loss_stable
+    gen = torch.Generator().manual_seed(N * 100 + M)
+    lq = torch.randint(0, 6, (N,), generator=gen); lv = torch.randint(0, 6, (M,), generator=gen)
+    lv[0] = lq[0]
+    q = torch.randn(N, d, generator=gen).to(dtype); v = torch.randn(M, d, generator=gen).to(dtype)
+    y = (lq[:, None] == lv[None, :]).float()
+    qd = q.cuda().requires_grad_(True); vd = v.cuda().requires_grad_(True)
+    loss = sdm_loss_stable(qd, vd, y.cuda(), tau=0.2)
+    loss.backward()
+    qc = q.clone().requires_grad_(True); vc = v.clone().requires_grad_(True)
+    ref = osdm.sdm_loss_oracle(qc, vc, y, tau=0.2)
+    ref.backward()
+    if dtype == torch.float32:
+        assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+        for got, want in ((qd.grad, qc.grad), (vd.grad, vc.grad)):
+            assert (got.cpu() - want).abs().max() <= 1e-5 * max(float(want.abs().max()), 1e-12)
+    else:
+        assert abs(float(loss) - float(ref)) <= 1e-3 * max(1.0, abs(float(ref)))
+        for got, want in ((qd.grad, qc.grad), (vd.grad, vc.grad)):
+            assert (got.float().cpu() - want.float()).norm() <= 1e-2 * want.float().norm()
