@@ -139,6 +139,9 @@ def run_reference(args):
 
 
 def time_sdm(torch, synth, sdm_loss_pairs, P, K, n_pairs, dtype, iters=50):
+    """SDM forward + backward of one training step (all pairs).  Returns
+    (eager us/step through autograd, algorithmic bytes, pairs, device us/step of the same step replayed as a CUDA graph)."""
+    from prcv2025reid_b200.sdm_loss import SdmGraphStep
     feats, labels = synth.make_sdm_batch(2001 if P == 4 else 2002, P, K, n_modalities=5, dtype=dtype, device="cuda")
     y = (labels[:, None] == labels[None, :]).float()
     pairs = [(a, b) for a in range(5) for b in range(a)][:n_pairs] if n_pairs > 4 else [(m, 0) for m in range(1, 5)]
@@ -161,18 +164,21 @@ def time_sdm(torch, synth, sdm_loss_pairs, P, K, n_pairs, dtype, iters=50):
     e.record()
     torch.cuda.synchronize()
     us = s.elapsed_time(e) * 1e3 / iters
-    # device time of the two kernels alone (CUDA events around each launch)
-    from prcv2025reid_b200 import _cabi
-    _cabi.PROFILE = []
-    for _ in range(10):
-        step()
+    # the same step as one CUDA-graph launch: device time of the kernels without the host-side launch gaps
+    g = SdmGraphStep(qs, vs, ys, tau=0.2)
+    for _ in range(5):
+        g.replay()
     torch.cuda.synchronize()
-    kern_us = sum(a.elapsed_time(b) for _, a, b in _cabi.PROFILE) * 1e3 / 10
-    _cabi.PROFILE = None
+    s.record()
+    for _ in range(iters):
+        g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    graph_us = s.elapsed_time(e) * 1e3 / iters
     N = P * K
     esz = 2 if dtype == torch.bfloat16 else 4
     alg_bytes = len(pairs) * (3 * (2 * N) * FEAT_DIM * esz + 2 * N * N * 4)
-    return us, alg_bytes, len(pairs), kern_us
+    return us, alg_bytes, len(pairs), graph_us
 
 
 def main():
@@ -315,13 +321,17 @@ def main():
     if rank == 0 and world == 1:
         if not args.no_sdm:
             sdm = {}
-            us, ab, npairs, ku = time_sdm(torch, synth, sdm_loss_pairs, 4, 2, 4, torch.float32)
-            sdm["c2_p4k2_fp32_4pairs"] = {"us_per_step_fwd_bwd": us, "kernels_us": ku, "algorithmic_bytes": ab,
-                                          "hbm_gbs_kernels": ab / (ku * 1e-6) / 1e9,
-                                          "note": "us_per_step = autograd step on the stream (2 launches + torch glue); kernels_us = device time of the 2 launches"}
-            us, ab, npairs, ku = time_sdm(torch, synth, sdm_loss_pairs, 64, 8, 10, torch.bfloat16)
-            sdm["c5_p64k8_bf16_10pairs"] = {"us_per_step_fwd_bwd": us, "kernels_us": ku, "algorithmic_bytes": ab,
-                                            "hbm_gbs_kernels": ab / (ku * 1e-6) / 1e9}
+            note = ("us_per_step_eager = autograd step on the stream (host-bound: Python + launches); "
+                    "us_per_step_graph = the same forward+backward replayed as one CUDA graph (device time)")
+            us, ab, npairs, gu = time_sdm(torch, synth, sdm_loss_pairs, 4, 2, 4, torch.float32)
+            sdm["c2_p4k2_fp32_4pairs"] = {"us_per_step_eager": us, "us_per_step_graph": gu, "algorithmic_bytes": ab,
+                                          "hbm_gbs_graph": ab / (gu * 1e-6) / 1e9, "kernels": "sdm_small_fwd/bwd (fp32 SIMT, 1 CTA per pair)",
+                                          "note": note}
+            us, ab, npairs, gu = time_sdm(torch, synth, sdm_loss_pairs, 64, 8, 10, torch.bfloat16)
+            sdm["c5_p64k8_bf16_10pairs"] = {"us_per_step_eager": us, "us_per_step_graph": gu, "algorithmic_bytes": ab,
+                                            "hbm_gbs_graph": ab / (gu * 1e-6) / 1e9,
+                                            "tensor_tflops_graph": 10 * 3 * 2.0 * 512 * 512 * 512 / (gu * 1e-6) / 1e12,
+                                            "kernels": "tc_prep + tc_fwd + tc_bwd (tcgen05, bf16)"}
             line["sdm"] = sdm
         if not args.no_cpu_baseline:
             from oracle import retrieval as orc

@@ -356,7 +356,7 @@ def _tc_case(seed, N, M, d=512, n_ids=24, orphan=0.15):
     return q, v, y
 
 
-def _check_against_oracle(q, v, y, loss, dq, dv, tau):
+def _check_sdm_against_oracle(q, v, y, loss, dq, dv, tau):
     qc = q.clone().requires_grad_(True); vc = v.clone().requires_grad_(True)
     ref = osdm.sdm_loss_oracle(qc, vc, y, tau=tau)              # the reference's bf16 dtype path, torch CPU autograd
     ref.backward()
@@ -378,7 +378,7 @@ def test_sdm_tensor_core_path_matches_oracle(N, M, d):
     assert _sdm_uses_tc(qd.detach(), vd.detach(), yd)
     loss = sdm_loss_stable(qd, vd, yd, tau=0.2)
     (3.0 * loss).backward()
-    _check_against_oracle(q, v, y, loss.detach().cpu(), qd.grad / 3.0, vd.grad / 3.0, 0.2)
+    _check_sdm_against_oracle(q, v, y, loss.detach().cpu(), qd.grad / 3.0, vd.grad / 3.0, 0.2)
 
 
 def test_sdm_tensor_core_pairs_of_different_shapes_in_one_launch():
@@ -390,7 +390,7 @@ def test_sdm_tensor_core_pairs_of_different_shapes_in_one_launch():
     losses = sdm_loss_pairs(qs, vs, [c[2].cuda() for c in cases], tau=0.3)
     losses.sum().backward()
     for i, (q, v, y) in enumerate(cases):
-        _check_against_oracle(q, v, y, losses[i].detach().cpu(), qs[i].grad, vs[i].grad, 0.3)
+        _check_sdm_against_oracle(q, v, y, losses[i].detach().cpu(), qs[i].grad, vs[i].grad, 0.3)
 
 
 def test_sdm_tensor_core_guards():
@@ -408,7 +408,7 @@ def test_sdm_tensor_core_guards():
     assert float(losses[1]) == 0.0 and float(losses[2]) == 0.0
     for i in (1, 2):
         assert not qs[i].grad.float().abs().sum().item() and not vs[i].grad.float().abs().sum().item()
-    _check_against_oracle(q0, v0, y0, losses[0].detach().cpu(), qs[0].grad, vs[0].grad, 0.2)
+    _check_sdm_against_oracle(q0, v0, y0, losses[0].detach().cpu(), qs[0].grad, vs[0].grad, 0.2)
 
 
 def test_sdm_graph_step_matches_eager():
