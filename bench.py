@@ -243,7 +243,10 @@ def main():
     h_mod = case.mod_id.cpu().pin_memory()
     h_pid = case.q_pid.cpu().pin_memory()
     h_excl = case.excl.cpu().pin_memory()
-    h2d_bytes = sum(t.numel() * t.element_size() for t in (h_query, h_mod, h_pid, h_excl))
+    # whole-job bytes: every query's features are uploaded by exactly one rank (engine.retrieve shards the upload
+    # and all-gathers the fused block over NVLink); the small id / exclusion arrays go to every rank
+    nbytes = lambda t: t.numel() * t.element_size()
+    h2d_bytes = nbytes(h_query) + nbytes(h_mod) + world * (nbytes(h_pid) + nbytes(h_excl))
 
     def step_e2e():
         # public tensor API with HOST inputs: block-wise H2D on a side stream, metrics read back (D2H)
@@ -251,12 +254,12 @@ def main():
                                host_queries=(h_query, h_mod, weights))
 
     def timed(fn, steps, profile=False):
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()                      # nvidia-smi needs ~0.3 s to start: the warm-up steps run the same load
         for _ in range(args.warmup):
             res = fn()
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         _cabi.LAUNCH_COUNT["n"] = 0
         if profile:
             _cabi.PROFILE = []

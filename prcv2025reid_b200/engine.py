@@ -161,7 +161,8 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
     group: a torch.distributed process group whose ranks hold disjoint contiguous gallery shards.
     host_queries: (query_raw [Q,k,D], mod_id [Q,k], weights) in pinned HOST memory instead of q_f32/q_f16;
     q_pid / excl may then be host tensors too.  Query blocks are copied on a side stream while the previous
-    block computes (H2D overlapped with the kernels).
+    block computes (H2D overlapped with the kernels); with a process group every rank uploads and fuses only its
+    1/world slice of a block and the fused block is all-gathered over NVLink (sharding.gather_query_block).
     """
     assert mode in ("fused", "exact")
     assert 1 <= topk <= _cabi.RTOP
@@ -198,17 +199,27 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
 
         done_ev = {}                                          # compute-stream event after block bi has consumed its staging set
 
+        rank = 0
+        if world > 1:
+            rank = dist_mod.get_rank(group)
+
         def stage(bi):
+            # upload this rank's slice of block bi (the features: 8 KB per query at k = 4) and the whole block's ids
             b0, b1 = blocks[bi]
             n = b1 - b0
+            s0, s1, m = sharding.block_slice(n, rank, world)
             tag = "stage%d_" % (bi & 1)                        # two alternating staging sets (cached, no allocator churn)
             with torch.cuda.stream(copy_stream):
                 if bi - 2 in done_ev:
                     copy_stream.wait_event(done_ev.pop(bi - 2))   # the set is free once block bi-2 has finished
-                raw = shard.buf(tag + "raw", (n,) + tuple(h_raw.shape[1:]), h_raw.dtype)
-                mod = shard.buf(tag + "mod", (n,) + tuple(h_mod.shape[1:]), h_mod.dtype)
+                raw = shard.buf(tag + "raw", (m,) + tuple(h_raw.shape[1:]), h_raw.dtype)
+                mod = shard.buf(tag + "mod", (m,) + tuple(h_mod.shape[1:]), h_mod.dtype)
                 pid = shard.buf(tag + "pid", (n,), q_pid.dtype)
-                raw.copy_(h_raw[b0:b1], non_blocking=True); mod.copy_(h_mod[b0:b1], non_blocking=True)
+                if s1 > s0:
+                    raw[:s1 - s0].copy_(h_raw[b0 + s0:b0 + s1], non_blocking=True)
+                    mod[:s1 - s0].copy_(h_mod[b0 + s0:b0 + s1], non_blocking=True)
+                if s1 - s0 < m:
+                    mod[s1 - s0:].fill_(-1)                      # unused slot rows: empty queries (dropped after the gather)
                 pid.copy_(q_pid[b0:b1], non_blocking=True)
                 ex = None
                 if excl is not None:
@@ -232,6 +243,9 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
             (raw_b, mod_b, pid_b, ex_b), ev = staged.pop(bi)
             torch.cuda.current_stream().wait_event(ev)
             q32_b, q16_b = fuse_queries(raw_b, mod_b, weights)
+            if world > 1:                                        # every rank fused 1/world of the block: exchange over NVLink
+                q32_b = sharding.gather_query_block(q32_b, nb, group)
+                q16_b = sharding.gather_query_block(q16_b, nb, group)
             pid_b = pid_b.to(torch.int64)
             ex_b = ex_b.to(torch.int32) if ex_b is not None else None
         else:

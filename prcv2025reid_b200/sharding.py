@@ -5,6 +5,9 @@ queries replicated, gallery rows partitioned contiguously, three small collectiv
   1. all_reduce(MAX) of the positives' exact scores   (owner rank holds the score, others -inf)
   2. all_reduce(SUM) of the per-positive "rows ranked above" counts (additive over shards)
   3. all_gather of the per-shard exact top lists, merged per query.
+With HOST-resident query features a fourth step precedes them: every rank uploads and fuses only its
+1/world slice of a query block and `gather_query_block` assembles the fused block on every rank over
+NVLink (all_gather), so the PCIe upload of a block is paid once per box instead of once per GPU.
 These helpers are device-agnostic (NCCL on GPUs, gloo in the CPU tests).
 """
 from typing import Tuple
@@ -47,3 +50,20 @@ def gather_top_lists(top_score: torch.Tensor, top_idx: torch.Tensor, group=None)
     dist.all_gather_into_tensor(all_s, top_score.contiguous(), group=group)
     dist.all_gather_into_tensor(all_i, top_idx.contiguous(), group=group)
     return all_s.view((world, Q) + rest), all_i.view((world, Q) + rest)
+
+
+def block_slice(n: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """Rows [start, end) of an n-row query block that `rank` uploads and fuses, and the common slot size m =
+    ceil(n / world) of the all-gather (the last ranks may hold fewer than m, possibly zero, rows)."""
+    m = -(-n // world)
+    start = min(n, rank * m)
+    return start, min(n, start + m), m
+
+
+def gather_query_block(part: torch.Tensor, n: int, group=None) -> torch.Tensor:
+    """part: [m, ...] this rank's slot (rows beyond its slice are don't-care) -> [n, ...] the whole block."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world * part.shape[0],) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
+    dist.all_gather_into_tensor(out, part.contiguous(), group=group)
+    return out[:n]

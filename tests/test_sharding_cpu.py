@@ -97,3 +97,34 @@ def test_two_rank_exchange_matches_unsharded_oracle(tmp_path):
     assert abs(res["mAP"] - ref["mAP"]) < 1e-9
     assert res["R1"] == ref["R@1"] and res["R10"] == ref["R@10"]
     assert np.array_equal(res["top10"].numpy(), ref["_top_idx"])
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for n in (1, 5, 6, 17):
+        full = torch.arange(n * 3, dtype=torch.float32).view(n, 3)
+        s0, s1, m = sharding.block_slice(n, rank, world)
+        part = torch.full((m, 3), -7.0)
+        part[:s1 - s0] = full[s0:s1]
+        got = sharding.gather_query_block(part, n)
+        ok = ok and torch.equal(got, full)
+    if rank == 0:
+        torch.save({"ok": ok}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_query_block_upload_is_sharded_and_gathered(tmp_path, world):
+    """Every rank contributes its block_slice; the gathered block equals the original for ragged sizes."""
+    for n in (1, 5, 6, 17, 32768):
+        edges = [sharding.block_slice(n, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and max(e[1] for e in edges) == n
+        assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+        assert all(e[1] - e[0] <= e[2] for e in edges) and len({e[2] for e in edges}) == 1
+    out = str(tmp_path / "g.pt")
+    port = 31500 + (os.getpid() % 2000) + world
+    mp.spawn(_gather_worker, args=(world, port, out), nprocs=world, join=True)
+    assert torch.load(out)["ok"]
