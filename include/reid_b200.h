@@ -82,11 +82,15 @@ int reid_pos_sort(float* pos_score, int32_t* n_pos, int64_t Q, int Pmax, void* s
  * g_code / q_code: pid codes from reid_pid_lookup.  n_chunks = gallery chunks per query block
  * (work decomposition; buffers are sized with it).  pos_above and cand_count must be zeroed.
  * cand_thr [Q] (optional): per-query score with >= REID_KLIST candidates at or above it (-inf if fewer);
- * every candidate the re-scorer can need lies at or above it. */
+ * every candidate the re-scorer can need lies at or above it.
+ * total_chunks = chunks the WHOLE gallery of a query is cut into over all ranks (n_chunks x world size;
+ * 0 = n_chunks): thresholds deeper than max(1024 * n_chunks / total_chunks, 8 calibration hits) rows of a
+ * chunk are counted on the 1/32 row sample; a deep rank still rests on >= 32 sampled rows per chunk position
+ * gallery-wide (single-rank behaviour is unchanged). */
 int reid_retrieve_fused(const void* q_f16, const void* g_f16, const int32_t* q_code,
                         const int32_t* g_code, const int32_t* excl, int E, const float* pos_thr,
                         const int32_t* n_pos, int64_t Q, int64_t G_local, int64_t g_offset, int d,
-                        int Pmax, int n_chunks, int cand_cap, int32_t* pos_above,
+                        int Pmax, int n_chunks, int total_chunks, int cand_cap, int32_t* pos_above,
                         float* cand_score, int32_t* cand_idx, int32_t* cand_count, float* cand_thr,
                         void* workspace, size_t workspace_bytes, void* stream);
 

@@ -37,7 +37,7 @@ _SIGS = {
                                 c_int64, c_int, c_int, c_void_p, c_void_p]),
     "reid_pos_sort": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "reid_retrieve_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                    c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "reid_retrieve_exact": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,

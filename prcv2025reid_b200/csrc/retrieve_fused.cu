@@ -613,7 +613,7 @@ extern "C" size_t reid_retrieve_fused_workspace_bytes(int64_t Q, int64_t, int) {
 
 extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const int32_t* q_code, const int32_t* g_code,
                                    const int32_t* excl, int E, const float* pos_thr, const int32_t* n_pos, int64_t Q,
-                                   int64_t G_local, int64_t g_offset, int d, int Pmax, int n_chunks, int cand_cap,
+                                   int64_t G_local, int64_t g_offset, int d, int Pmax, int n_chunks, int total_chunks, int cand_cap,
                                    int32_t* pos_above, float* cand_score, int32_t* cand_idx, int32_t* cand_count,
                                    float* cand_thr, void* workspace, size_t workspace_bytes, void* stream) {
   if (!q_f16 || !g_f16 || !q_code || !g_code || !pos_thr || !n_pos || !pos_above || !cand_score || !cand_idx ||
@@ -699,9 +699,11 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
         return REID_E_CUDA;
     }
     if (!launch(tmS, c)) return REID_E_CUDA;
-    // deep = the row sample is expected to hold >= 32 rows above the threshold (17.7% rank error at the boundary)
-    const float limit = 32.f * (float)SAMPLE_W;
+    // deep = the row sample is expected to hold >= 32 rows above the threshold OVER ALL CHUNKS OF ALL RANKS
+    // (17.7% rank error at the boundary); never classify on fewer than 8 calibration hits
     const float scale = (float)p.rows_per_chunk / (float)CALIB_ROWS;
+    const int tc_all = total_chunks > n_chunks ? total_chunks : n_chunks;
+    const float limit = fmaxf(32.f * (float)SAMPLE_W * (float)n_chunks / (float)tc_all, 8.f * scale);
     calib_split_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, scale, limit, p.n_exact);
   } else {
     fill_n_exact_kernel<<<aux_grid, 256, 0, st>>>(n_pos, Q, Pmax, p.n_exact);

@@ -281,7 +281,8 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
             ws_bytes = L.reid_workspace_bytes(1, nb, shard.G_local, d)
             ws = shard.buf("fused_ws", (ws_bytes,), torch.uint8)
             check(L.reid_retrieve_fused(ptr(q16_b), ptr(shard.g_f16), ptr(q_code), ptr(shard.g_code), ptr(ex_b), E,
-                                        ptr(pos_thr), ptr(n_pos[sl]), *common_tail, ptr(pos_above[sl]),
+                                        ptr(pos_thr), ptr(n_pos[sl]), nb, shard.G_local, shard.g_offset, d, Pmax, n_chunks,
+                                        n_chunks * world, cap, ptr(pos_above[sl]),
                                         ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), ptr(ws), ws_bytes, st),
                   "reid_retrieve_fused")
         else:
