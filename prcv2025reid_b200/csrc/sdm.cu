@@ -327,6 +327,48 @@ sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
 // ------------------------------------------------------------------------------------------------
 constexpr int SMALL_MAX = 32;
 
+// one row (d <= 512, d % 128 == 0) into registers: lane owns elements k*128 + lane*4 .. +3; all loads issued up front
+template <bool BF16>
+__device__ __forceinline__ void small_load_row(const void* x, size_t row, int d, int lane, float (&v)[16]) {
+  const int nchunk = d >> 7;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < nchunk) {
+      const size_t o = row * d + k * 128 + lane * 4;
+      if (BF16) {
+        const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + o);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+        v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = b.x; v[4 * k + 3] = b.y;
+      } else {
+        const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + o);
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+      }
+    } else {
+      v[4 * k] = v[4 * k + 1] = v[4 * k + 2] = v[4 * k + 3] = 0.f;
+    }
+  }
+}
+// normalised row into shared memory (reference dtype path); returns whether every element is finite
+template <bool BF16>
+__device__ __forceinline__ bool small_store_norm(const float (&v)[16], float dn, float* dst, int d, int lane) {
+  const int nchunk = d >> 7;
+  bool fin = true;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < nchunk) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[e] = __fdiv_rn(v[4 * k + e], dn);
+        if (BF16) o[e] = __bfloat162float(__float2bfloat16_rn(o[e]));
+        fin = fin && isfinite(o[e]);
+      }
+      *reinterpret_cast<float4*>(dst + k * 128 + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  return fin;
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(TB)
 sdm_small_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
@@ -346,18 +388,16 @@ sdm_small_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
     const bool isq = r < N;
     const int row = isq ? r : r - N;
     const void* x = isq ? P.qry : P.gal;
+    float v[16];
+    small_load_row<BF16>(x, (size_t)row, d, lane, v);
     float ss = 0.f;
-    for (int c = lane; c < d; c += 32) { const float v = ld_elem<BF16>(x, (size_t)row * d + c); ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) ss = fmaf(v[c], v[c], ss);
     ss = warp_sum(ss);
     float nrm = sqrtf(ss), e = eps;
     if (BF16) { nrm = __bfloat162float(__float2bfloat16_rn(nrm)); e = __bfloat162float(__float2bfloat16_rn(eps)); }
     const float dn = fmaxf(nrm, e);
-    bool bad = false;
-    for (int c = lane; c < d; c += 32) {
-      const float v = norm_elem<BF16>(x, (size_t)row * d + c, dn);
-      xs[(size_t)r * d + c] = v;
-      bad |= !isfinite(v);
-    }
+    const bool bad = !small_store_norm<BF16>(v, dn, xs + (size_t)r * d, d, lane);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_flags, 2);
     if (lane == 0) (isq ? sv.den_q : sv.den_g)[row] = dn;
   }
@@ -459,7 +499,9 @@ sdm_small_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
     const int row = isq ? r : r - N;
     const void* x = isq ? P.qry : P.gal;
     const float dn = (isq ? sv.den_q : sv.den_g)[row];
-    for (int c = lane; c < d; c += 32) xs[(size_t)r * d + c] = norm_elem<BF16>(x, (size_t)row * d + c, dn);
+    float v[16];
+    small_load_row<BF16>(x, (size_t)row, d, lane, v);
+    small_store_norm<BF16>(v, dn, xs + (size_t)r * d, d, lane);
   }
   __syncthreads();
   // one warp per output row: dx^ = sum_k dS * (other side's x^), then the normalisation Jacobian
@@ -510,8 +552,10 @@ sdm_small_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
 
 bool small_eligible(const reid_sdm_pair* pairs, int n_pairs, int d) {
   if (!pairs || n_pairs <= 0 || n_pairs > REID_SDM_MAX_PAIRS || d % 128 != 0 || d > 512) return false;
-  for (int i = 0; i < n_pairs; ++i)
+  for (int i = 0; i < n_pairs; ++i) {
     if (pairs[i].N <= 0 || pairs[i].M <= 0 || pairs[i].N > SMALL_MAX || pairs[i].M > SMALL_MAX) return false;
+    if ((reinterpret_cast<uintptr_t>(pairs[i].qry) | reinterpret_cast<uintptr_t>(pairs[i].gal)) & 15u) return false;   // vector row loads
+  }
   return true;
 }
 

@@ -36,13 +36,13 @@ __device__ __forceinline__ void st_out(void* base, size_t i, float v) {
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---- tcgen05 path: layout of the per-pair `saved` buffer (offsets in floats unless noted) ----
-// [den_q N][den_g M][lse_r N][lse_c M][cnt_r N][cnt_c M][ce_r N][ce_c M][hdr 64][S N*M][St M*N] then, 128-byte
+// [den_q N][den_g M][lse_r N][lse_c M][cnt_r N][cnt_c M][ce_r N][ce_c M][hdr 96][S N*M][St M*N] then, 128-byte
 // aligned, the positive masks of y as bit rows (ybits [N][16] / ybitsT [M][16] 32-bit words) and four bf16 operand images in the UMMA K-major 128B-swizzle layout (8-row x 64-element atoms of 1024 bytes,
 // [k block][row group]) so that an operand tile is ONE contiguous cp.async.bulk:
 //   Qn  [Np rows][d]   Gn  [Mp rows][d]   QnT [d rows][Np]   GnT [d rows][Mp]      (Np, Mp = N, M rounded up to 128)
 // hdr: [0] nR  [1] nC  [2] status bits (int)  [3] loss  [4] CTA completion counter (int)
-//      [8 .. 8+32)  non-finite-feature flag per 32-row slab of qry / gal (int, 16 each)
-//      [40 .. 48)   non-finite-S flag per forward CTA (int)
+//      [8 .. 8+64)  non-finite-feature flag per 16-row slab of qry / gal (int, 32 each)
+//      [72 .. 80)   non-finite-S flag per forward CTA (int)
 struct TcLayout {
   int N, M, d, Np, Mp;
   size_t den_q, den_g, lse_r, lse_c, cnt_r, cnt_c, ce_r, ce_c, hdr, S, St;
@@ -50,7 +50,7 @@ struct TcLayout {
   size_t qn, gn, qnt, gnt;         // byte offsets of the images
   size_t total_bytes;
 };
-constexpr int TC_HDR_FLOATS = 64;
+constexpr int TC_HDR_FLOATS = 96;
 __host__ __device__ inline TcLayout tc_layout(int N, int M, int d) {
   TcLayout L;
   L.N = N; L.M = M; L.d = d; L.Np = round_up(N, 128); L.Mp = round_up(M, 128);

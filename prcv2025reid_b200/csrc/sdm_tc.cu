@@ -27,6 +27,7 @@
 // (+ the lo pass of the backward).  See DESIGN.md section 6.
 #include "sdm_common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace sdm {
 namespace {
@@ -55,43 +56,17 @@ __device__ __forceinline__ float fast_exp(float x) {
 __device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // =============================================================================================== prep
-constexpr int PREP_ROWS = 32;
+#ifndef REID_PREP_ROWS
+#define REID_PREP_ROWS 16
+#endif
+constexpr int PREP_ROWS = REID_PREP_ROWS;   // rows per CTA (8-row K chunks of the transposed image)
+
 constexpr int PREP_THREADS = 256;
 
-__global__ void __launch_bounds__(PREP_THREADS)
+__global__ void __launch_bounds__(PREP_THREADS, 5)
 tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
   const reid_sdm_pair& P = batch.p[blockIdx.z];
-  const int which = blockIdx.y;                      // 0 = qry, 1 = gal, 2 = positive masks of y
-  if (which == 2) {
-    // one 32 x 32 tile of y per warp: row words by ballot, transposed words accumulated per lane
-    const TcLayout L = tc_layout(P.N, P.M, d);
-    uint8_t* bytes = reinterpret_cast<uint8_t*>(tc_base(P.saved));
-    uint32_t* ybits = reinterpret_cast<uint32_t*>(bytes + L.ybits);
-    uint32_t* ybitsT = reinterpret_cast<uint32_t*>(bytes + L.ybitsT);
-    const int lane = threadIdx.x & 31;
-    const int tiles_m = (P.M + 31) >> 5, tiles_n = (P.N + 31) >> 5;
-    const int tix = blockIdx.x * (PREP_THREADS / 32) + (threadIdx.x >> 5);
-    if (tix >= tiles_m * tiles_n) return;
-    const int ti = tix / tiles_m, tj = tix % tiles_m;
-    const int j = tj * 32 + lane;
-    uint32_t mine = 0, wordT = 0;
-    float yv[32];
-#pragma unroll
-    for (int ii = 0; ii < 32; ++ii) {                          // all 32 row loads in flight before the first vote
-      const int i = ti * 32 + ii;
-      yv[ii] = (i < P.N && j < P.M) ? __ldg(P.y + (size_t)i * P.M + j) : 0.f;
-    }
-#pragma unroll
-    for (int ii = 0; ii < 32; ++ii) {
-      const bool v = yv[ii] > 0.f;
-      const uint32_t b = __ballot_sync(0xffffffffu, v);
-      if (lane == ii) mine = b;
-      wordT |= (v ? 1u : 0u) << ii;
-    }
-    if (ti * 32 + lane < P.N) ybits[(size_t)(ti * 32 + lane) * 16 + tj] = mine;
-    if (j < P.M) ybitsT[(size_t)j * 16 + ti] = wordT;
-    return;
-  }
+  const int which = blockIdx.y;                      // 0 = qry, 1 = gal
   const int R = which ? P.M : P.N;
   const int Rp = round_up(R, 128);
   const int r0 = blockIdx.x * PREP_ROWS;
@@ -115,18 +90,28 @@ tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
   const float e_b = bf16r(eps);
   const int nchunk = d >> 3;                         // 16-byte chunks per row (<= 64)
   bool bad = false;
-  for (int rr = warp; rr < PREP_ROWS; rr += PREP_THREADS / 32) {
-    const int r = r0 + rr;
-    const bool live = r < R;
-    uint4 raw[2];
-    float ss = 0.f;
+  constexpr int RPW = PREP_ROWS / (PREP_THREADS / 32);   // rows per warp: all their loads are issued before the first use
+  uint4 raw[RPW][2];
+#pragma unroll
+  for (int a = 0; a < RPW; ++a) {
+    const int r = r0 + warp + a * (PREP_THREADS / 32);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int c = lane + 32 * u;
-      raw[u] = make_uint4(0, 0, 0, 0);
-      if (live && c < nchunk) raw[u] = *reinterpret_cast<const uint4*>(x + (size_t)r * d + c * 8);
+      raw[a][u] = make_uint4(0, 0, 0, 0);
+      if (r < R && c < nchunk) raw[a][u] = *reinterpret_cast<const uint4*>(x + (size_t)r * d + c * 8);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < RPW; ++a) {
+    const int rr = warp + a * (PREP_THREADS / 32);
+    const int r = r0 + rr;
+    const bool live = r < R;
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
       float f[8];
-      unpack8(raw[u], f);
+      unpack8(raw[a][u], f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
     }
@@ -138,7 +123,7 @@ tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
       const int c = lane + 32 * u;
       if (c >= nchunk) continue;
       float f[8];
-      unpack8(raw[u], f);
+      unpack8(raw[a][u], f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         f[e] = live ? bf16r(__fdiv_rn(f[e], dn)) : 0.f;
@@ -153,7 +138,7 @@ tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_bad, 1);
   __syncthreads();
-  if (threadIdx.x == 0) hdr_i[8 + which * 16 + blockIdx.x] = s_bad;          // sdm_loss.py:79-81
+  if (threadIdx.x == 0) hdr_i[8 + which * 32 + blockIdx.x] = s_bad;          // sdm_loss.py:79-81
   // transposed image: rows = feature index c, K = row index r (this CTA: 4 chunks of 8 rows)
   for (int c = threadIdx.x; c < d; c += PREP_THREADS) {
 #pragma unroll
@@ -201,7 +186,7 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
   uint8_t* smem = fwd_smem_raw + ((1024u - (tc::smem_u32(fwd_smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full[FWD_STAGES], empty[FWD_STAGES], accfull;
   __shared__ uint32_t tmem_base_s;
-  __shared__ int s_bad, s_last;
+  __shared__ int s_bad, s_last, s_st;
   __shared__ float s_part[FWD_EPI_WARPS / 4 - 1][3][128];
   __shared__ double s_red[FWD_EPI_WARPS][5];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,7 +195,7 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
     for (int s = 0; s < FWD_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(&accfull, 1);
     tc::fence_barrier_init();
-    s_bad = 0; s_last = 0;
+    s_bad = 0; s_last = 0; s_st = 0;
   }
   const uint32_t ncols = tmem_cols_for(Cp);
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, ncols);
@@ -256,10 +241,35 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
     const bool live = i < R;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     float* Sout = base + (side ? L.St : L.S) + (size_t)(live ? i : 0) * C;     // side 0: S[i][:]  side 1: St[j][:]
-    // positive mask of this row: 512 bits = 16 words (L1-resident after the first touch)
-    const uint32_t* bitrow = reinterpret_cast<const uint32_t*>(bytes + (side ? L.ybitsT : L.ybits) + (size_t)(live ? i : 0) * 64);
-    const int cstep = round_up((C + PARTS - 1) / PARTS, 16);
+    const int cstep = round_up((C + PARTS - 1) / PARTS, 32);
     const int c_begin = part * cstep < C ? part * cstep : C, c_end = (part + 1) * cstep < C ? (part + 1) * cstep : C;
+    // positive mask of this thread's columns (<= 128 = 4 words), formed from y WHILE the MMAs run and kept in
+    // registers; also stored as bit rows (ybits [N][16] / ybitsT [M][16]) for the backward
+    uint32_t mb[4] = {0u, 0u, 0u, 0u};
+    if (live) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int cw = c_begin + 32 * w;
+        if (cw < c_end) {
+          if (side == 0) {
+            const float* yp = P.y + (size_t)i * M + cw;
+            float4 t[8];
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) t[e4] = (cw + 4 * e4 < c_end) ? *reinterpret_cast<const float4*>(yp + 4 * e4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4)
+              mb[w] |= ((t[e4].x > 0.f ? 1u : 0u) | (t[e4].y > 0.f ? 2u : 0u) | (t[e4].z > 0.f ? 4u : 0u) | (t[e4].w > 0.f ? 8u : 0u)) << (4 * e4);
+          } else {
+            float t[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) t[e] = (cw + e < c_end) ? P.y[(size_t)(cw + e) * M + i] : 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mb[w] |= (t[e] > 0.f ? 1u : 0u) << e;
+          }
+          reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(bytes) + (side ? L.ybitsT : L.ybits))[(size_t)i * 16 + (cw >> 5)] = mb[w];
+        }
+      }
+    }
     const float inv_tau = 1.f / tau_eff;
     float se = 0.f, ps = 0.f, pc = 0.f;
     bool bad = false;
@@ -269,7 +279,8 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
       uint32_t r[16];
       __syncwarp();                                          // tcgen05.ld is .sync.aligned: reconverge first
-      const uint32_t bw = __ldg(bitrow + (c0 >> 5)) >> (c0 & 31);
+      const int wsel = (c0 - c_begin) >> 5;
+      const uint32_t bw = (wsel == 0 ? mb[0] : wsel == 1 ? mb[1] : wsel == 2 ? mb[2] : mb[3]) >> ((c0 - c_begin) & 31);
       tc::tmem_ld_x16(taddr + c0, r);
       tc::tmem_wait_ld();
       if (!live) continue;
@@ -320,7 +331,7 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
     }
     named_bar(1, FWD_EPI_THREADS);
     if (et == 0) {
-      hdr_i[40 + side * 4 + rb] = s_bad;
+      hdr_i[72 + side * 4 + rb] = s_bad;
       __threadfence();
       const int total = (N + 127) / 128 + (M + 127) / 128;
       s_last = (atomicAdd(&hdr_i[4], 1) == total - 1);
@@ -329,6 +340,13 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
     if (s_last) {
       // ---- the last CTA of the pair: means over valid rows / columns and the guards
       __threadfence();
+      if (et < 64) {                                              // non-finite feature flags of the 16-row slabs (:79-81)
+        const int lim = ((et >> 5) ? L.Mp : L.Np) / PREP_ROWS;
+        if ((et & 31) < lim && __ldcg(&hdr_i[8 + et])) atomicOr(&s_st, 2);
+      } else if (et < 72) {                                       // non-finite S flags of the forward CTAs (:89-91)
+        const int lim = ((((et - 64) >> 2) ? M : N) + 127) / 128;
+        if (((et - 64) & 3) < lim && __ldcg(&hdr_i[72 + et - 64])) atomicOr(&s_st, 4);
+      }
       double v[5] = {0, 0, 0, 0, 0};                              // sum ce_r, #valid rows, sum ce_c, #valid cols, #rows with a positive
       for (int a = et; a < N; a += FWD_EPI_THREADS) {
         const float c = __ldcg(base + L.cnt_r + a), ce = __ldcg(base + L.ce_r + a);
@@ -349,11 +367,7 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
         double t[5] = {0, 0, 0, 0, 0};
         for (int w = 0; w < FWD_EPI_WARPS; ++w)
           for (int k = 0; k < 5; ++k) t[k] += s_red[w][k];
-        int st = 0;
-        for (int s = 0; s < (L.Np >> 5); ++s) if (__ldcg(&hdr_i[8 + s])) st |= 2;
-        for (int s = 0; s < (L.Mp >> 5); ++s) if (__ldcg(&hdr_i[8 + 16 + s])) st |= 2;
-        for (int s = 0; s < (N + 127) / 128; ++s) if (__ldcg(&hdr_i[40 + s])) st |= 4;
-        for (int s = 0; s < (M + 127) / 128; ++s) if (__ldcg(&hdr_i[40 + 4 + s])) st |= 4;
+        int st = s_st;
         if (t[4] == 0.0) st |= 8;                                                  // :105-106
         const float lr = t[1] > 0 ? (float)(t[0] / t[1]) : 0.f;
         const float lc = t[3] > 0 ? (float)(t[2] / t[3]) : 0.f;
@@ -672,13 +686,7 @@ int tc_forward(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float 
     attr_done = true;
   }
   const size_t prep_smem = (size_t)PREP_ROWS * (d + 8) * 2;
-  int gx = mb * 128 / PREP_ROWS;                          // y = 0, 1: 32-row slabs of qry / gal; y = 2: 32 x 32 tiles of y, 8 per CTA
-  for (int i = 0; i < n_pairs; ++i) {
-    const int tiles = ((pairs[i].N + 31) / 32) * ((pairs[i].M + 31) / 32);
-    const int need = (tiles + PREP_THREADS / 32 - 1) / (PREP_THREADS / 32);
-    if (need > gx) gx = need;
-  }
-  tc_prep_kernel<<<dim3(gx, 3, n_pairs), PREP_THREADS, prep_smem, st>>>(b, d, eps);
+  tc_prep_kernel<<<dim3(mb * 128 / PREP_ROWS, 2, n_pairs), PREP_THREADS, prep_smem, st>>>(b, d, eps);
   REID_CHECK_LAUNCH();
   tc_fwd_kernel<<<dim3(mb, 2, n_pairs), FWD_THREADS, FWD_SMEM, st>>>(b, d, tau_eff);
   REID_CHECK_LAUNCH();

@@ -7,7 +7,17 @@ rows = list(csv.reader(raw.splitlines()))
 hdr = rows[1]
 ia, isrc, isamp = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-body = [r for r in rows[2:] if len(r) == len(hdr)]
+body = []
+for r in rows[2:]:                      # several captured launches of the kernel: keep the first one
+    if len(r) != len(hdr):
+        if body:
+            break
+        continue
+    if r[isamp] == "# Samples":
+        if body:
+            break
+        continue
+    body.append(r)
 tot = sum(int(r[isamp]) for r in body)
 print("total samples", tot)
 order = sorted(range(len(body)), key=lambda k: -int(body[k][isamp]))[:n]
