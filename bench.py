@@ -299,8 +299,16 @@ def main():
             peak = float(mp.get("bf16_tflops_sustained", peak))
         except Exception:
             peak, which = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+        traffic, traffic_src = None, None
+        try:      # DRAM bytes per launch from the committed ncu --set full capture of this exact configuration
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01c_traffic.json")))[dom]
+            if tr["workload"] == args.workload and tr["n_gpus"] == world:
+                traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+        except Exception:
+            pass
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": which,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes (dram read+write per launch)",
+                    "traffic_source": traffic_src, "peak_source": which,
                     "algorithmic_flop_per_launch": flops_total / max(1, n_calls),
                     "avg_launch_ms": tot_ms / max(1, n_calls), "launches": n_calls,
                     "share_of_step": tot_ms / (ms_step * args.steps)}
