@@ -130,6 +130,12 @@ int reid_merge_topk(const float* scores, const int32_t* idx, int n_lists, int64_
 int reid_metrics_reduce(const int32_t* pos_above, const int32_t* n_pos, int64_t Q, int Pmax,
                         double* out, double* ap_per_query, void* stream);
 
+/* ---- train-time evaluator reductions, train.py:101-138 (`compute_map` AP@k :116-124, `compute_cmc` :133-136):
+ * top_idx [Q, list_len] exact ranking (global gallery indices, -1 pad), labels int64.  ap[q] = AP over the
+ * matches inside the first k positions (fp32 like the reference), -1 when there is none; hit[q] = any match. */
+int reid_topk_label_metrics(const int32_t* top_idx, const int64_t* q_label, const int64_t* g_label,
+                            int64_t Q, int list_len, int k, float* ap, int32_t* hit, void* stream);
+
 /* ---- SDM loss: models/sdm_loss.py:13-149 `sdm_loss_stable`, batched over modality pairs.
  * One launch computes every pair; pair p uses qry[p] [N_p, d], gal[p] [M_p, d] (dtype F32 or
  * BF16), y[p] [N_p, M_p] float {0,1}.  loss[p] (fp32), status[p] (bit0: returned the reference's

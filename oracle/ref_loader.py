@@ -74,3 +74,26 @@ def quiet(fn, *a, **kw):
     """Call fn with stdout swallowed (the reference prints warnings / debug lines)."""
     with contextlib.redirect_stdout(io.StringIO()):
         return fn(*a, **kw)
+
+
+def load_reference_train_eval():
+    """The UNMODIFIED `compute_map`, `compute_cmc` and `_reid_map` of train.py (:101-138, :451-479).  train.py cannot
+    be imported (dataset / model / CLIP imports at module level), so the three function definitions are cut out of
+    its source with `ast` and executed as they stand in a namespace that holds what they use (torch, F, np)."""
+    if "train_eval" in _cache:
+        return _cache["train_eval"]
+    import ast
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    path = os.path.join(REFERENCE_ROOT, "train.py")
+    if not os.path.isfile(path):
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    src = open(path, encoding="utf-8").read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "F": F, "np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("compute_map", "compute_cmc", "_reid_map"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    _cache["train_eval"] = ns
+    return ns

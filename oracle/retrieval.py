@@ -173,3 +173,52 @@ def submission_ranking(q_feat: torch.Tensor, g_feat: torch.Tensor, top_k: int = 
         sims = cosine_sim(q_feat[qi:qi + 1], g_feat).squeeze(0)
         out[qi] = torch.argsort(sims, descending=True)[:top_k].numpy()
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Train-time evaluator: restatement of /root/reference/train.py:101-138 and
+# :451-479.  Pinned against the UNMODIFIED reference functions, whose source is extracted from
+# train.py with `ast` and executed as-is (oracle.ref_loader.load_reference_train_eval), in
+# tests/test_oracle_cpu.py.
+# ---------------------------------------------------------------------------------------------
+def compute_map_oracle(qf, gf, ql, gl, k=100):
+    qf = torch.nn.functional.normalize(qf.float(), p=2, dim=1)          # train.py:105-109
+    gf = torch.nn.functional.normalize(gf.float(), p=2, dim=1)
+    sim = qf @ gf.t()
+    aps = []
+    for i in range(sim.shape[0]):                                        # :113-124
+        idx = torch.sort(sim[i], descending=True)[1]
+        matches = (gl[idx[:k]] == ql[i]).float()
+        if matches.sum() > 0:
+            prec = torch.cumsum(matches, 0) / torch.arange(1, matches.numel() + 1, dtype=matches.dtype)
+            aps.append(prec[matches.bool()].mean().item())
+    return float(np.mean(aps)) if aps else 0.0                           # :126
+
+
+def compute_cmc_oracle(qf, gf, ql, gl, k=10):
+    qf = torch.nn.functional.normalize(qf, p=2, dim=1)                   # train.py:130-131
+    gf = torch.nn.functional.normalize(gf, p=2, dim=1)
+    sim = qf @ gf.t()
+    correct = 0
+    for i in range(sim.shape[0]):                                        # :134-137
+        idx = torch.sort(sim[i], descending=True)[1]
+        correct += bool((gl[idx[:k]] == ql[i]).any())
+    return correct / sim.shape[0] if sim.shape[0] > 0 else 0.0
+
+
+def reid_map_oracle(sim, q_ids, g_ids):
+    """train.py:451-479 `_reid_map`."""
+    Nq = sim.shape[0]
+    mAP, top1 = 0.0, 0.0
+    ar = torch.arange(sim.shape[1], dtype=torch.float32) + 1.0
+    for i in range(Nq):
+        order = torch.argsort(sim[i], descending=True)
+        matches = (g_ids[order] == q_ids[i]).to(sim.dtype)
+        rel = matches.sum().item()
+        if rel == 0:
+            continue
+        prec = torch.cumsum(matches, 0) / ar
+        mAP += (torch.sum(prec * matches) / rel).item()
+        top1 += matches[0].item()
+    valid = max(1, (q_ids.unsqueeze(1) == g_ids.unsqueeze(0)).any(dim=1).sum().item())
+    return mAP / valid, top1 / Nq

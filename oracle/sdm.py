@@ -108,3 +108,32 @@ def sdm_fwd_bwd_f64(qry, gal, y, tau=0.2, eps=1e-8):
         xh = x / nrm
         return (dxn - xh * (dxn * xh).sum(1, keepdims=True)) / nrm
     return loss, back_norm(qry, qn, dqn), back_norm(gal, gn, dgn)
+
+
+def sdm_alignment_oracle(raw_modality_features, feature_masks, labels, tau=0.2):
+    """CPU restatement of the SDM section of compute_loss, /root/reference/models/model.py:556-625
+    (mask filtering :570-602, y :605, no-positive skip :608-613, finite check :617-618, mean :621-625)."""
+    vis = raw_modality_features.get("vis"); vmask = feature_masks.get("vis")
+    if vis is None or vmask is None:
+        return torch.tensor(0.0)
+    vidx = (vmask > 0).squeeze(-1) if vmask.dim() > 1 else (vmask > 0)
+    if vidx.sum() == 0:
+        return torch.tensor(0.0)
+    vfeat, vlab = vis[vidx], labels[vidx]
+    out = []
+    for name, feat in raw_modality_features.items():
+        if name == "vis":
+            continue
+        mask = feature_masks.get(name)
+        if feat is None or mask is None:
+            continue
+        idx = (mask > 0).squeeze(-1) if mask.dim() > 1 else (mask > 0)
+        if idx.sum() == 0:
+            continue
+        y = (labels[idx].view(-1, 1) == vlab.view(1, -1)).float()
+        if y.numel() == 0 or y.sum() == 0:
+            continue
+        L = sdm_loss_oracle(feat[idx], vfeat, y, tau=tau)
+        if torch.isfinite(L):
+            out.append(L)
+    return torch.stack(out).mean() if out else torch.tensor(0.0)

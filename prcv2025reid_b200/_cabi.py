@@ -47,6 +47,7 @@ _SIGS = {
                                   c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "reid_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "reid_metrics_reduce": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "reid_topk_label_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "reid_sdm_saved_floats": (c_size_t, [c_int, c_int, c_int]),
     "reid_sdm_uses_tensor_cores": (c_int, [c_void_p, c_int, c_int, c_int]),
     "reid_sdm_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
@@ -61,7 +62,7 @@ _LAUNCHES_PER_CALL = {
     "reid_l2norm_rows": 1, "reid_mm_fuse_normalize": 1, "reid_sim_gemm": 1, "reid_pid_index_build": 2,
     "reid_pid_lookup": 1, "reid_pos_scores": 1, "reid_pos_sort": 1, "reid_retrieve_fused": 4,
     "reid_retrieve_exact": 1, "reid_rescore_topk": 1, "reid_merge_topk": 1, "reid_metrics_reduce": 2,
-    "reid_sdm_fwd": 1, "reid_sdm_bwd": 1,   # (tcgen05 path: fwd = 2 launches, counted in sdm_loss.py)
+    "reid_topk_label_metrics": 1, "reid_sdm_fwd": 1, "reid_sdm_bwd": 1,   # (tcgen05 path: fwd = 2 launches, counted in sdm_loss.py)
 }
 LAUNCH_COUNT = {"n": 0}
 # optional per-kernel device timing: set PROFILE = [] and every kernel call appends (name, start, end) events

@@ -442,3 +442,40 @@ extern "C" int reid_metrics_reduce(const int32_t* pos_above, const int32_t* n_po
   REID_CHECK_LAUNCH();
   return REID_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Train-time evaluator reductions (train.py:101-138): given each query's exact top-k gallery list,
+//   compute_map : AP@k = mean over the matched positions r (1-based) of (#matches among the first r) / r   (:116-124)
+//   compute_cmc : hit@k = any match inside the top-k                                                          (:133-136)
+// One warp per query; ap[q] = -1 when the top-k holds no match (the reference skips such queries, :120).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+topk_label_metrics_kernel(const int32_t* __restrict__ top_idx, const int64_t* __restrict__ q_label,
+                          const int64_t* __restrict__ g_label, int64_t Q, int list_len, int k,
+                          float* __restrict__ ap, int32_t* __restrict__ hit) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const int64_t ql = q_label[q];
+  int before = 0;        // matches in earlier 32-position groups
+  float sum = 0.f;
+  for (int r0 = 0; r0 < k; r0 += 32) {
+    const int r = r0 + lane;
+    bool m = false;
+    if (r < k) { const int32_t gi = top_idx[q * list_len + r]; m = gi >= 0 && g_label[gi] == ql; }
+    const unsigned b = __ballot_sync(0xffffffffu, m);
+    if (m) sum += (float)(before + __popc(b & ((2u << lane) - 1u))) / (float)(r + 1);     // fp32 like the reference
+    before += __popc(b);
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) { ap[q] = before > 0 ? sum / (float)before : -1.f; hit[q] = before > 0 ? 1 : 0; }
+}
+
+extern "C" int reid_topk_label_metrics(const int32_t* top_idx, const int64_t* q_label, const int64_t* g_label,
+                                       int64_t Q, int list_len, int k, float* ap, int32_t* hit, void* stream) {
+  if (!top_idx || !q_label || !g_label || !ap || !hit || Q <= 0 || k <= 0 || k > list_len) return REID_E_INVALID;
+  topk_label_metrics_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, (cudaStream_t)stream>>>(top_idx, q_label, g_label, Q, list_len, k, ap, hit);
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}

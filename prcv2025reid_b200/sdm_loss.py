@@ -192,3 +192,42 @@ def sdm_loss_stable(qry, gal, y, tau=0.2, eps=1e-8):
         dev = torch.device("cuda", torch.cuda.current_device())
         return sdm_loss_stable(qry.to(dev), gal.to(dev), y.to(dev), tau, eps).to(qry.device)
     return sdm_loss_pairs([qry], [gal], [y.to(qry.device)], tau, eps)[0]
+
+
+def sdm_alignment_loss(raw_modality_features, feature_masks, labels, tau=0.2, eps=1e-8):
+    """The SDM section of `CLIPBasedMultiModalReIDModel.compute_loss` (models/model.py:556-622): every non-vis
+    modality is aligned to vis over the rows whose feature mask is set, pairs without a positive are skipped and
+    the remaining per-modality losses are averaged (zero when none remains).
+
+    The reference issues one `sdm_loss_stable` call and >= 3 host synchronisations per modality (`.sum() == 0`
+    at :572/:597/:608 plus those inside the loss); here ONE host read fetches all masks (the row filtering has
+    data-dependent shapes), all modalities go through one `sdm_loss_pairs` launch pair, and the "has a positive"
+    / finiteness selection of :608-618 is evaluated on the device."""
+    vis = raw_modality_features.get("vis")
+    vmask = feature_masks.get("vis")
+    dev = labels.device
+    zero = torch.tensor(0.0, device=dev, dtype=torch.float32)
+    if vis is None or vmask is None:
+        return zero                                                              # :566-568
+    names = [m for m, f in raw_modality_features.items()
+             if m != "vis" and f is not None and feature_masks.get(m) is not None]                # :586-592
+    flat = [(feature_masks[m] > 0).reshape(labels.shape[0], -1)[:, 0] for m in ["vis"] + names]
+    host = torch.stack(flat).cpu()                                               # the one host read
+    vis_idx = torch.nonzero(host[0]).flatten()
+    if vis_idx.numel() == 0:
+        return zero                                                              # :572-574
+    vis_idx = vis_idx.to(dev)
+    vfeat, vlab = vis.float()[vis_idx], labels[vis_idx]                            # compute_loss runs the SDM part in fp32 (:561)
+    qs, ys = [], []
+    for k, m in enumerate(names):
+        idx = torch.nonzero(host[k + 1]).flatten()
+        if idx.numel() == 0:
+            continue                                                             # :597-598
+        idx = idx.to(dev)
+        qs.append(raw_modality_features[m].float()[idx])
+        ys.append((labels[idx].view(-1, 1) == vlab.view(1, -1)).float())          # :605
+    if not qs:
+        return zero
+    losses = sdm_loss_pairs(qs, [vfeat] * len(qs), ys, tau, eps)
+    has_pos = torch.stack([y.any() for y in ys]) & torch.isfinite(losses)         # :608-618, on the device
+    return (losses * has_pos).sum() / has_pos.sum().clamp_min(1)                   # :621-625

@@ -454,3 +454,52 @@ def test_sdm_small_and_general_paths_match_oracle(N, M, d, dtype):
         assert abs(float(loss) - float(ref)) <= 1e-3 * max(1.0, abs(float(ref)))
         for got, want in ((qd.grad, qc.grad), (vd.grad, vc.grad)):
             assert (got.float().cpu() - want.float()).norm() <= 1e-2 * want.float().norm()
+
+
+def test_sdm_alignment_section_matches_compute_loss_restatement():
+    """N1: models/model.py:556-625 (mask filtering, y from labels, skip pairs without a positive, mean)."""
+    from prcv2025reid_b200.sdm_loss import sdm_alignment_loss
+    gen = torch.Generator().manual_seed(77)
+    B = 12
+    labels = torch.randint(0, 4, (B,), generator=gen)
+    feats = {m: torch.randn(B, 512, generator=gen) for m in ("vis", "nir", "sk", "cp", "text")}
+    masks = {m: (torch.rand(B, 1, generator=gen) > 0.3).float() for m in feats}
+    masks["cp"] = torch.zeros(B, 1)                              # a modality without valid rows (:597)
+    labels_sk = labels.clone()
+    masks["sk"] = torch.zeros(B, 1); masks["sk"][0] = 1.0        # one row ...
+    feats_d = {m: f.cuda().requires_grad_(True) for m, f in feats.items()}
+    loss = sdm_alignment_loss(feats_d, {m: v.cuda() for m, v in masks.items()}, labels.cuda(), tau=0.2)
+    loss.backward()
+    fc = {m: f.clone().requires_grad_(True) for m, f in feats.items()}
+    ref = osdm.sdm_alignment_oracle(fc, masks, labels, tau=0.2)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+    for m in feats:
+        g, r = feats_d[m].grad, fc[m].grad
+        if r is None:
+            assert g is None or not g.abs().sum().item()
+        else:
+            assert (g.cpu() - r).abs().max() <= 1e-5 * max(float(r.abs().max()), 1e-12)
+    # no valid vis row -> zero (:572-574)
+    z = sdm_alignment_loss({m: f.cuda() for m, f in feats.items()}, {m: torch.zeros(B, 1).cuda() for m in feats}, labels.cuda())
+    assert float(z) == 0.0
+
+
+# ---------------------------------------------------------------- train-time evaluator drop-ins (SURVEY 8f N2)
+def test_train_eval_dropins_match_reference_golden():
+    import os
+    from oracle.make_golden_train_eval import make_case
+    from prcv2025reid_b200 import train_eval
+    z = np.load(os.path.join(_golden.GOLDEN, "train_eval.npz"))
+    qf, gf, ql, gl = make_case()
+    cs = float(qf.double().abs().sum()) + float(gf.double().abs().sum())
+    if abs(cs - float(z["checksum"])) > 1e-6 * abs(cs):
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    for k in (1, 5, 100):
+        assert abs(train_eval.compute_map(qf, gf, ql, gl, k=k) - float(z["map_k%d" % k])) <= 1e-4
+    for k in (1, 10):
+        assert train_eval.compute_cmc(qf.cuda(), gf.cuda(), ql.cuda(), gl.cuda(), k=k) == float(z["cmc_k%d" % k])
+    qn = torch.nn.functional.normalize(qf, dim=1); gn = torch.nn.functional.normalize(gf, dim=1)
+    m, t1 = train_eval.reid_map(qn, gn, ql, gl)
+    assert abs(m - float(z["reid_map"][0])) <= 1e-4 and t1 == float(z["reid_map"][1])
+    assert train_eval.compute_map(qf[:0], gf, ql[:0], gl) == 0.0 and train_eval.compute_cmc(qf[:0], gf, ql[:0], gl) == 0.0

@@ -110,3 +110,39 @@ def test_sdm_oracle_matches_live_reference():
     a = ref_loader.quiet(sdm, q, v, y, tau=0.3)
     b = osdm.sdm_loss_oracle(q, v, y, tau=0.3)
     assert float(a) == float(b)
+
+
+# ---------------------------------------------------------------- train-time evaluator
+def _train_eval_case():
+    import os
+    from oracle.make_golden_train_eval import make_case
+    z = np.load(os.path.join(_golden.GOLDEN, "train_eval.npz"))
+    qf, gf, ql, gl = make_case()
+    cs = float(qf.double().abs().sum()) + float(gf.double().abs().sum())
+    if abs(cs - float(z["checksum"])) > 1e-6 * abs(cs):
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    return z, qf, gf, ql, gl
+
+
+def test_train_eval_oracle_matches_reference_golden():
+    z, qf, gf, ql, gl = _train_eval_case()
+    for k in (1, 5, 100):
+        assert orc.compute_map_oracle(qf, gf, ql, gl, k=k) == float(z["map_k%d" % k])
+    for k in (1, 10):
+        assert orc.compute_cmc_oracle(qf, gf, ql, gl, k=k) == float(z["cmc_k%d" % k])
+    qn = torch.nn.functional.normalize(qf, dim=1); gn = torch.nn.functional.normalize(gf, dim=1)
+    assert list(orc.reid_map_oracle(qn @ gn.T, ql, gl)) == list(z["reid_map"])
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_train_eval_oracle_matches_live_reference():
+    ns = ref_loader.load_reference_train_eval()
+    g = torch.Generator().manual_seed(3)
+    gl = torch.arange(120) // 4; ql = torch.randint(0, 34, (40,), generator=g)
+    c = torch.randn(34, 32, generator=g)
+    gf = c[gl] + 2.0 * torch.randn(120, 32, generator=g); qf = c[ql.clamp(max=29)] + 2.0 * torch.randn(40, 32, generator=g)
+    for k in (3, 100):
+        assert ns["compute_map"](qf, gf, ql, gl, k) == orc.compute_map_oracle(qf, gf, ql, gl, k)
+        assert ns["compute_cmc"](qf, gf, ql, gl, k) == orc.compute_cmc_oracle(qf, gf, ql, gl, k)
+    qn = torch.nn.functional.normalize(qf, dim=1); gn = torch.nn.functional.normalize(gf, dim=1)
+    assert ns["_reid_map"](qn @ gn.T, ql, gl) == orc.reid_map_oracle(qn @ gn.T, ql, gl)
