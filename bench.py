@@ -221,6 +221,15 @@ def main():
                                      gallery_rows=(r0, r1))
     weights = synth.weights_tensor(device=dev)
     torch.cuda.synchronize()
+    # K1 alone (gallery normalisation, one-time): HBM roofline of the pass
+    k1 = []
+    for _ in range(4):
+        s_ = torch.cuda.Event(enable_timing=True); e_ = torch.cuda.Event(enable_timing=True)
+        s_.record(); _n32, _n16 = engine.l2norm_rows(case.gallery_raw, want_f16=True); e_.record()
+        torch.cuda.synchronize(); k1.append(s_.elapsed_time(e_))
+    del _n32, _n16
+    k1_ms = min(k1[1:])
+    k1_bytes = (r1 - r0) * FEAT_DIM * (4 + 4 + 2)
     t0 = time.perf_counter()
     shard = engine.prepare_gallery(case.gallery_raw, case.g_pid, g_offset=r0)
     torch.cuda.synchronize()
@@ -313,6 +322,21 @@ def main():
                     "avg_launch_ms": tot_ms / max(1, n_calls), "launches": n_calls,
                     "share_of_step": tot_ms / (ms_step * args.steps)}
     kernel_ms = {n: round(v[0] / args.steps, 4) for n, v in sorted(per_kernel.items())}
+    hbm_peak = 6534.1
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", hbm_peak))
+    except Exception:
+        pass
+    hbm_kernels = {"reid_l2norm_rows": {"ms": round(k1_ms, 4), "algorithmic_bytes": k1_bytes,
+                                        "gbs": k1_bytes / (k1_ms * 1e-3) / 1e9, "frac_of_hbm_peak": k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak,
+                                        "note": "gallery shard: 4 B read + 4 B fp32 + 2 B fp16 written per element"}}
+    if "reid_mm_fuse_normalize" in per_kernel:
+        k2_ms = per_kernel["reid_mm_fuse_normalize"][0] / args.steps
+        k2_bytes = Q * (k * FEAT_DIM * 4 + FEAT_DIM * (4 + 2))
+        hbm_kernels["reid_mm_fuse_normalize"] = {"ms": round(k2_ms, 4), "algorithmic_bytes": k2_bytes,
+                                                 "gbs": k2_bytes / (k2_ms * 1e-3) / 1e9,
+                                                 "frac_of_hbm_peak": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak,
+                                                 "note": "k x 2 KB read + 3 KB (fp32 + fp16) written per query"}
 
     line = {
         "metric": "queries_per_sec", "value": Q / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
@@ -326,7 +350,8 @@ def main():
         "metrics": res.metrics,
         "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 40, "ms_per_step": ms_e2e},
-        "gpu_launches": launches, "kernel_ms_per_step": kernel_ms, "roofline": roofline, "clocks": clocks,
+        "gpu_launches": launches, "kernel_ms_per_step": kernel_ms, "roofline": roofline,
+        "hbm_kernels": hbm_kernels, "clocks": clocks,
     }
 
     if rank == 0 and world == 1:

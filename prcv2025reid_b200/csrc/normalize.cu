@@ -123,9 +123,9 @@ mm_fuse_normalize_kernel(const float* __restrict__ feats, const int32_t* __restr
   }
 }
 
-inline int grid_for_rows(int64_t rows) {
+inline int grid_for_rows(int64_t rows, int waves = 4) {
   int64_t ctas = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
-  const int64_t cap = 148LL * 8 * 4;  // 4 waves of 8 resident CTAs per SM, grid-stride beyond
+  const int64_t cap = 148LL * 8 * waves;  // `waves` waves of 8 resident CTAs per SM, grid-stride beyond
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   return (int)ctas;
@@ -158,7 +158,10 @@ extern "C" int reid_mm_fuse_normalize(const float* feats, const int32_t* mod_id,
   if (Q == 0) return REID_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int nv = (d + 127) / 128;
-  const int grid = grid_for_rows(Q);
+  // a query is 8-11 KB of traffic: one query per warp up to 300k queries (an uneven 2-vs-3 grid-stride split of
+  // the last wave costs more than the extra CTA launches; measured 62 % -> 67 % of the HBM peak at Q = 100k).
+  // Prefetching all k rows of a query, or software-pipelining them, costs occupancy and was slower (48-50 %).
+  const int grid = grid_for_rows(Q, 32);
 #define LAUNCH(NV) mm_fuse_normalize_kernel<NV><<<grid, kWarpsPerCta * 32, 0, st>>>(feats, mod_id, w, n_mod, out_f32, (__half*)out_f16, Q, k, d)
   switch (nv) {
     case 1: LAUNCH(1); break; case 2: LAUNCH(2); break; case 3: LAUNCH(3); break; case 4: LAUNCH(4); break;

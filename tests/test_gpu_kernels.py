@@ -503,3 +503,22 @@ def test_train_eval_dropins_match_reference_golden():
     m, t1 = train_eval.reid_map(qn, gn, ql, gl)
     assert abs(m - float(z["reid_map"][0])) <= 1e-4 and t1 == float(z["reid_map"][1])
     assert train_eval.compute_map(qf[:0], gf, ql[:0], gl) == 0.0 and train_eval.compute_cmc(qf[:0], gf, ql[:0], gl) == 0.0
+
+
+def test_gallery_store_shards_match_direct_install(eng, tmp_path):
+    """N3: rgb_feats.npy + rgb_meta.json -> per-rank shards through the pinned slab upload."""
+    from prcv2025reid_b200 import gallery_store
+    case = synth.make_retrieval_case(41, 50, 5, 2, 2, excl_frac=0.0)
+    meta = [{"img_id": "g%d" % i, "pid": int(p), "camid": None} for i, p in enumerate(case.g_pid.tolist())]
+    gallery_store.save_cache(str(tmp_path), case.gallery_raw, meta)
+    ref = eng.prepare_gallery(case.gallery_raw.cuda(), case.g_pid.cuda())
+    rows = []
+    for rank in range(3):
+        feats = gallery_store.open_feats(str(tmp_path))
+        shard, (r0, r1) = gallery_store.install_shard(feats, [m["pid"] for m in meta], rank, 3, slab_rows=40)
+        assert shard.g_offset == r0 and shard.G_local == r1 - r0 and shard.G_total == case.G
+        assert torch.equal(shard.g_f32, ref.g_f32[r0:r1]) and torch.equal(shard.g_code, ref.g_code[r0:r1])
+        rows.append(r1 - r0)
+    assert sum(rows) == case.G
+    shard, meta2, _ = gallery_store.load_shard(str(tmp_path))
+    assert meta2 == meta and torch.equal(shard.g_f16, ref.g_f16)

@@ -146,3 +146,25 @@ def test_train_eval_oracle_matches_live_reference():
         assert ns["compute_cmc"](qf, gf, ql, gl, k) == orc.compute_cmc_oracle(qf, gf, ql, gl, k)
     qn = torch.nn.functional.normalize(qf, dim=1); gn = torch.nn.functional.normalize(gf, dim=1)
     assert ns["_reid_map"](qn @ gn.T, ql, gl) == orc.reid_map_oracle(qn @ gn.T, ql, gl)
+
+
+# ---------------------------------------------------------------- gallery store, host logic only
+def test_gallery_store_reads_the_reference_cache_format(tmp_path):
+    import json, pickle
+    from prcv2025reid_b200 import gallery_store
+    feats = torch.randn(37, 16)
+    meta = [{"img_id": "g%d" % i, "pid": i // 3, "camid": None} for i in range(37)]
+    # written exactly as the reference writes it (eval_mm_protocol.py:320-323)
+    np.save(str(tmp_path / "rgb_feats.npy"), np.stack([f.numpy() for f in feats], 0))
+    json.dump(meta, open(str(tmp_path / "rgb_meta.json"), "w", encoding="utf-8"))
+    mm = gallery_store.open_feats(str(tmp_path))
+    assert isinstance(mm, np.memmap) and mm.shape == (37, 16) and np.array_equal(np.asarray(mm), feats.numpy())
+    assert gallery_store.load_meta(str(tmp_path)) == meta
+    # and what this module writes is what the reference reads (:296-302)
+    gallery_store.save_cache(str(tmp_path / "out"), feats, meta)
+    back = torch.from_numpy(np.load(str(tmp_path / "out" / "rgb_feats.npy"))).float()
+    assert torch.equal(back, feats) and json.load(open(str(tmp_path / "out" / "rgb_meta.json"), encoding="utf-8")) == meta
+    with open(str(tmp_path / "c.pkl"), "wb") as f:                       # train.py:626-631
+        pickle.dump({"g_feat": feats, "g_id": torch.arange(37)}, f)
+    gf, gi = gallery_store.load_pickle_cache(str(tmp_path / "c.pkl"))
+    assert gf.dtype == np.float32 and gi.dtype == np.int64 and np.array_equal(gf, feats.numpy())
