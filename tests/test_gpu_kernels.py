@@ -228,6 +228,33 @@ def test_fused_equals_exact_at_scale(eng):
     assert a.n_flagged <= q_take // 20
 
 
+def test_fused_equals_exact_c4_gallery(eng):
+    """BASELINE config C4 gallery (1M rows, 40 per identity, MM-4 queries): the fused path -- fp16 tensor-core scores,
+    deep ranks counted on the 1/32 row sample -- against the all-fp32 exact path on the first 1024 queries:
+    identical CMC and top-10, mAP within 1e-4, per-query AP within the documented sampling error."""
+    import bench
+    seed, n_ids, gpi, k, qpi = bench.WORKLOADS["c4"]
+    nq = 1024
+    case = synth.make_retrieval_case(seed, n_ids, gpi, k, qpi, excl_frac=0.01, n_excl=2, device="cuda", max_queries=nq)
+    shard = eng.prepare_gallery(case.gallery_raw, case.g_pid)
+    case.gallery_raw = None
+    q32, q16 = eng.fuse_queries(case.query_raw, case.mod_id, synth.weights_tensor().cuda())
+    a = eng.retrieve(shard, q32, q16, case.q_pid, case.excl, mode="fused", want_ap=True)
+    b = eng.retrieve(shard, q32, q16, case.q_pid, case.excl, mode="exact", want_ap=True)
+    assert a.metrics["num_queries"] == b.metrics["num_queries"] == nq
+    assert abs(a.metrics["mAP"] - b.metrics["mAP"]) <= 1e-4
+    for kk in ("R@1", "R@5", "R@10"):
+        assert a.metrics[kk] == b.metrics[kk]
+    assert torch.equal(a.top_idx, b.top_idx) and torch.equal(a.top_score, b.top_score)
+    d = (a.ap - b.ap).abs()
+    assert float(d.max()) <= 2e-3 and float(d.mean()) <= 1e-4
+    # positives that rank inside the re-scored head are exact: queries whose positives all rank in the top 32
+    head = (b.pos_above.max(dim=1)[0] < 16) & (b.n_pos > 0)
+    if bool(head.any()):
+        assert float(d[head].max()) == 0.0
+    assert a.n_flagged <= nq // 20
+
+
 def test_export_submission_matches_reference_golden(tmp_path):
     """export_submission_csv (:595-649): ranking WITHOUT mask, top-20 of the golden; CSV format."""
     import csv
