@@ -38,6 +38,20 @@ def test_l2norm_rows_matches_F_normalize(eng, rows, d):
         assert torch.all(out[1] == 0)
 
 
+def test_l2norm_division_is_correctly_rounded(eng):
+    """The kernels divide through a rounded reciprocal + two FMAs (Markstein).  On rows of small integers the sum
+    of squares is exact in fp32 in any order, so the denominator equals torch's bit for bit and every quotient must
+    equal the IEEE division `x / max(||x||, eps)` of F.normalize bit for bit."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.randint(-8, 9, (4096, 512), generator=g).float()
+    x[7] = 0.0                                                   # zero row: 0 / eps
+    scale = torch.tensor([1.0, 2.0 ** -20, 2.0 ** 20, 3.0])[torch.arange(4096) % 4].unsqueeze(1)   # exact scalings (3x: exact too)
+    x = (x * scale).cuda()
+    out, _ = eng.l2norm_rows(x)
+    ref = torch.nn.functional.normalize(x.cpu(), dim=-1)
+    assert torch.equal(out.cpu(), ref)
+
+
 @pytest.mark.parametrize("name", _golden.RETRIEVAL_NAMES)
 def test_fuse_normalize_matches_reference_golden(eng, name):
     case, z = _golden.load_retrieval(name)
