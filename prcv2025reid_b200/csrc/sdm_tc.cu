@@ -167,15 +167,36 @@ constexpr size_t FWD_SMEM = (size_t)FWD_STAGES * FWD_STAGE + 1024;
 
 __device__ __forceinline__ uint32_t tmem_cols_for(int c) { return c <= 32 ? 32u : c <= 64 ? 64u : c <= 128 ? 128u : c <= 256 ? 256u : 512u; }
 
+// PAIR = true: the two CTAs of a cluster take row blocks 2p and 2p+1 of one (pair, side) and issue ONE
+// cta_group::2 MMA per step (M = 256: 128 accumulator lanes in each CTA).  Each CTA loads its own A tile and only
+// HALF of the column operand (the leader's MMA reads both halves), so the operand stream per CTA drops from 80 KB to
+// 48 KB per K block and the ring is 4 deep instead of 2.  Tiles come through per-pair tensor maps over the operand
+// images (cp.async.bulk.tensor ... cta_group::2 signals the LEADER's barrier from both CTAs).
+struct PairMaps {
+  CUtensorMap q[REID_SDM_MAX_PAIRS];      // image Qn viewed as [Np * d/64][64] bf16 (one row = one swizzled 128-byte row)
+  CUtensorMap g[REID_SDM_MAX_PAIRS];
+  CUtensorMap qt[REID_SDM_MAX_PAIRS];     // transposed images QnT / GnT viewed as [d * Np/64][64] (backward)
+  CUtensorMap gt[REID_SDM_MAX_PAIRS];
+};
+constexpr int FWDP_STAGE = A_TILE + 2 * A_TILE;      // own A tile + this CTA's half of up to two 256-column chunks
+constexpr int FWDP_STAGES = 4;
+constexpr size_t FWDP_SMEM = (size_t)FWDP_STAGES * FWDP_STAGE + 1024;
+
+template <bool PAIR>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
+tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairMaps maps, int d, float tau_eff) {
+  constexpr int STAGES = PAIR ? FWDP_STAGES : FWD_STAGES;
+  constexpr int STAGE = PAIR ? FWDP_STAGE : FWD_STAGE;
   const reid_sdm_pair& P = batch.p[blockIdx.z];
   const int side = blockIdx.y;
   const int N = P.N, M = P.M;
   const int R = side ? M : N, C = side ? N : M;              // rows / columns of this side's view of S
   const int Rp = round_up(R, 128), Cp = round_up(C, 128);
   const int rb = blockIdx.x;
-  if (rb * 128 >= R) return;
+  const uint32_t crank = PAIR ? (uint32_t)(rb & 1) : 0u;     // cluster rank (cluster = 2 consecutive CTAs in x)
+  const bool leader = crank == 0;
+  if ((PAIR ? (rb & ~1) : rb) * 128 >= R) return;            // (uniform over the pair)
+  const bool active = rb * 128 < R;                          // pair mode: the peer of the last odd block only feeds operands
   const TcLayout L = tc_layout(N, M, d);
   float* base = tc_base(P.saved);
   const uint8_t* bytes = reinterpret_cast<const uint8_t*>(base);
@@ -184,7 +205,7 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
   int* hdr_i = reinterpret_cast<int*>(base + L.hdr);
   extern __shared__ uint8_t fwd_smem_raw[];
   uint8_t* smem = fwd_smem_raw + ((1024u - (tc::smem_u32(fwd_smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t full[FWD_STAGES], empty[FWD_STAGES], accfull;
+  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], accfull;
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_bad, s_last, s_st;
   __shared__ float s_part[FWD_EPI_WARPS / 4 - 1][3][128];
@@ -192,45 +213,78 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = d >> 6;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < FWD_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(&accfull, 1);
     tc::fence_barrier_init();
     s_bad = 0; s_last = 0; s_st = 0;
+    if (PAIR) { tc::prefetch_tensormap(&maps.q[blockIdx.z]); tc::prefetch_tensormap(&maps.g[blockIdx.z]); }
   }
   const uint32_t ncols = tmem_cols_for(Cp);
-  if (warp == 1) tc::tmem_alloc(&tmem_base_s, ncols);
+  if (warp == 1) { if (PAIR) tc::tmem_alloc_pair(&tmem_base_s, ncols); else tc::tmem_alloc(&tmem_base_s, ncols); }
   tc::fence_before_sync();
-  __syncthreads();
+  if (PAIR) tc::cluster_sync_all(); else __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0 && lane == 0) {
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % FWD_STAGES;
-      tc::mbar_wait(&empty[s], ((kb / FWD_STAGES) & 1) ^ 1);
-      tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(A_TILE + Cp * 128));
-      tc::bulk_load(smem + s * FWD_STAGE, imgA + (size_t)kb * ((size_t)Rp * 128) + (size_t)rb * A_TILE, A_TILE, &full[s]);
-      tc::bulk_load(smem + s * FWD_STAGE + A_TILE, imgB + (size_t)kb * ((size_t)Cp * 128), (uint32_t)(Cp * 128), &full[s]);
-    }
-  } else if (warp == 1 && lane == 0) {
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % FWD_STAGES;
-      tc::mbar_wait(&full[s], (kb / FWD_STAGES) & 1);
-      tc::fence_after_sync();
-      const uint64_t ad = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * FWD_STAGE));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        for (int n0 = 0; n0 < Cp; n0 += 256) {
-          const int n = Cp - n0 < 256 ? Cp - n0 : 256;
-          const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * FWD_STAGE + A_TILE + n0 * 128));
-          tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(ad, k), tc::advance_desc_k(bd, k),
-                         tc::make_idesc_f16(128, n, 1), (kb | k) != 0);
+    if (PAIR) {
+      const CUtensorMap* mapA = side ? &maps.g[blockIdx.z] : &maps.q[blockIdx.z];
+      const CUtensorMap* mapB = side ? &maps.q[blockIdx.z] : &maps.g[blockIdx.z];
+      const int rbA = active ? rb : 0;                       // an idle peer still streams (unused) rows: no special cases
+      uint32_t tx = 2u * A_TILE;                             // bytes of BOTH CTAs per stage
+      for (int n0 = 0; n0 < Cp; n0 += 256) tx += 2u * (uint32_t)(((Cp - n0 < 256 ? Cp - n0 : 256) / 2) * 128);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        tc::mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+        if (leader) tc::mbar_arrive_expect_tx(&full[s], tx);
+        const uint32_t lbar = tc::leader_addr(&full[s]);
+        uint8_t* st = smem + s * STAGE;
+        const int rowA = kb * Rp + rbA * 128;
+        tc::tma_load_2d_pair(st, mapA, lbar, 0, rowA);
+        tc::tma_load_2d_pair(st + A_TILE / 2, mapA, lbar, 0, rowA + 64);
+        int c = 0;
+        for (int n0 = 0; n0 < Cp; n0 += 256, ++c) {
+          const int hr = (Cp - n0 < 256 ? Cp - n0 : 256) / 2;     // this CTA's rows of the chunk: 64 or 128
+          const int rowB = kb * Cp + n0 + (int)crank * hr;
+          tc::tma_load_2d_pair(st + A_TILE + c * A_TILE, mapB, lbar, 0, rowB);
+          if (hr > 64) tc::tma_load_2d_pair(st + A_TILE + c * A_TILE + A_TILE / 2, mapB, lbar, 0, rowB + 64);
         }
       }
-      tc::mma_commit(&empty[s]);
+    } else {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        tc::mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(A_TILE + Cp * 128));
+        tc::bulk_load(smem + s * STAGE, imgA + (size_t)kb * ((size_t)Rp * 128) + (size_t)rb * A_TILE, A_TILE, &full[s]);
+        tc::bulk_load(smem + s * STAGE + A_TILE, imgB + (size_t)kb * ((size_t)Cp * 128), (uint32_t)(Cp * 128), &full[s]);
+      }
     }
-    tc::mma_commit(&accfull);
-  } else if (warp >= 2) {
+  } else if (warp == 1 && lane == 0 && leader) {
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      tc::mbar_wait(&full[s], (kb / STAGES) & 1);
+      tc::fence_after_sync();
+      const uint64_t ad = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * STAGE));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int c = 0;
+        for (int n0 = 0; n0 < Cp; n0 += 256, ++c) {
+          const int n = Cp - n0 < 256 ? Cp - n0 : 256;
+          if (PAIR) {
+            const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * STAGE + A_TILE + c * A_TILE));
+            tc::mma_f16_ss_pair(tmem_base + n0, tc::advance_desc_k(ad, k), tc::advance_desc_k(bd, k),
+                                tc::make_idesc_f16(256, n, 1), (kb | k) != 0);
+          } else {
+            const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * STAGE + A_TILE + n0 * 128));
+            tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(ad, k), tc::advance_desc_k(bd, k),
+                           tc::make_idesc_f16(128, n, 1), (kb | k) != 0);
+          }
+        }
+      }
+      if (PAIR) tc::mma_commit_pair(&empty[s]); else tc::mma_commit(&empty[s]);
+    }
+    if (PAIR) tc::mma_commit_pair(&accfull); else tc::mma_commit(&accfull);
+  } else if (warp >= 2 && active) {
     // ---------------------------------------------------------------- epilogue: four threads per row of S (a quarter of the columns each)
     const int quad = warp & 3;
     constexpr int PARTS = FWD_EPI_WARPS / 4;
@@ -383,8 +437,8 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff) {
     }
   }
   tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, ncols);
+  if (PAIR) tc::cluster_sync_all(); else __syncthreads();    // (pair: the peer may still be signalled / read until here)
+  if (warp == 1) { if (PAIR) tc::tmem_dealloc_pair(tmem_base, ncols); else tc::tmem_dealloc(tmem_base, ncols); }
 }
 
 // =============================================================================================== backward
@@ -393,17 +447,28 @@ constexpr int BWD_PROD_THREADS = BWD_PROD_WARPS * 32;
 constexpr int BWD_THREADS = 64 + BWD_PROD_THREADS;   // warp 0: bulk-copy producer, warp 1: MMA + TMEM, warps 2-9: dS producers, then epilogue
 constexpr int BWD_STAGE = 2 * A_TILE + B_TILE_MAX;   // dS hi, dS lo, transposed operand chunk (d rows x 64)
 constexpr int BWD_STAGES = 2;
+constexpr int BWDP_STAGE = 2 * A_TILE + 2 * A_TILE;  // pair mode: dS hi, dS lo, this CTA's half of the two 256-row chunks
+constexpr int BWDP_STAGES = 3;
 constexpr int BWD_KMAX = 512;
 constexpr size_t BWD_SMEM = (size_t)BWD_STAGES * BWD_STAGE + (3 * BWD_KMAX + 3 * 128) * sizeof(float) + 1024;
+constexpr size_t BWDP_SMEM = (size_t)BWDP_STAGES * BWDP_STAGE + (3 * BWD_KMAX + 3 * 128) * sizeof(float) + 1024;
 
+// PAIR = true: row blocks 2p / 2p+1 of one (pair, side) as a cta_group::2 pair (see tc_fwd_kernel): every CTA forms
+// its own dS tiles, loads half of the transposed operand chunk, the leader issues M = 256 MMAs; ring depth 3.
+template <bool PAIR>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-tc_bwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff, float eps) {
+tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairMaps maps, int d, float tau_eff, float eps) {
+  constexpr int STAGES = PAIR ? BWDP_STAGES : BWD_STAGES;
+  constexpr int STAGE = PAIR ? BWDP_STAGE : BWD_STAGE;
   const reid_sdm_pair& P = batch.p[blockIdx.z];
   const int side = blockIdx.y;                               // 0: dqry rows, K = gal rows; 1: dgal rows, K = qry rows
   const int N = P.N, M = P.M;
   const int R = side ? M : N, K = side ? N : M;
   const int rb = blockIdx.x;
-  if (rb * 128 >= R) return;
+  const uint32_t crank = PAIR ? (uint32_t)(rb & 1) : 0u;
+  const bool leader = crank == 0;
+  if ((PAIR ? (rb & ~1) : rb) * 128 >= R) return;            // (uniform over the pair)
+  const bool active = rb * 128 < R;                          // pair mode: the peer of the last odd block only feeds operands
   const int row0 = rb * 128;
   const TcLayout L = tc_layout(N, M, d);
   float* base = tc_base(P.saved);
@@ -413,65 +478,94 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff, float e
   const float* hdr = base + L.hdr;
   const int st = hdr_i[2];
   bf16* out = reinterpret_cast<bf16*>(side ? P.dgal : P.dqry);
-  const int rows_here = R - row0 < 128 ? R - row0 : 128;
+  const int rows_here = !active ? 0 : (R - row0 < 128 ? R - row0 : 128);
   if (st & 1) {      // the reference returned its non-differentiable zero: gradients are exact zeros
     uint4* o = reinterpret_cast<uint4*>(out + (size_t)row0 * d);
     for (int a = threadIdx.x; a < rows_here * d / 8; a += BWD_THREADS) o[a] = make_uint4(0, 0, 0, 0);
-    return;
+    return;                                                  // (uniform over the pair: same status word)
   }
   extern __shared__ uint8_t bwd_smem_raw[];
   uint8_t* smem = bwd_smem_raw + ((1024u - (tc::smem_u32(bwd_smem_raw) & 1023u)) & 1023u);
-  float* KL = reinterpret_cast<float*>(smem + BWD_STAGES * BWD_STAGE);   // per K index: lse, weight, 1/count
+  float* KL = reinterpret_cast<float*>(smem + STAGES * STAGE);           // per K index: lse, weight, 1/count
   float* KW = KL + BWD_KMAX;
   float* KIC = KW + BWD_KMAX;
   float* RL = KIC + BWD_KMAX;                                            // per tile row
   float* RW = RL + 128;
   float* RIC = RW + 128;
-  __shared__ __align__(8) uint64_t bfull[BWD_STAGES], afull[BWD_STAGES], empty[BWD_STAGES], accfull, xfull;
+  __shared__ __align__(8) uint64_t bfull[STAGES], afull[STAGES], empty[STAGES], accfull, xfull;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = (K + 63) >> 6;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < BWD_STAGES; ++s) { tc::mbar_init(&bfull[s], 1); tc::mbar_init(&afull[s], BWD_PROD_WARPS); tc::mbar_init(&empty[s], 1); }
+    // pair mode: the leader's afull collects the producer warps of BOTH CTAs
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&bfull[s], 1); tc::mbar_init(&afull[s], PAIR ? 2 * BWD_PROD_WARPS : BWD_PROD_WARPS); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(&accfull, 1); tc::mbar_init(&xfull, 1);
     tc::fence_barrier_init();
+    if (PAIR) tc::prefetch_tensormap(side ? &maps.qt[blockIdx.z] : &maps.gt[blockIdx.z]);
   }
   const uint32_t ncols = tmem_cols_for(d);
-  if (warp == 1) tc::tmem_alloc(&tmem_base_s, ncols);
+  if (warp == 1) { if (PAIR) tc::tmem_alloc_pair(&tmem_base_s, ncols); else tc::tmem_alloc(&tmem_base_s, ncols); }
   tc::fence_before_sync();
-  __syncthreads();
+  if (PAIR) tc::cluster_sync_all(); else __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0 && lane == 0) {
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % BWD_STAGES;
-      tc::mbar_wait(&empty[s], ((kb / BWD_STAGES) & 1) ^ 1);
-      tc::mbar_arrive_expect_tx(&bfull[s], (uint32_t)(d * 128));
-      tc::bulk_load(smem + s * BWD_STAGE + 2 * A_TILE, imgB + (size_t)kb * ((size_t)d * 128), (uint32_t)(d * 128), &bfull[s]);
+    if (PAIR) {
+      const CUtensorMap* mapB = side ? &maps.qt[blockIdx.z] : &maps.gt[blockIdx.z];
+      uint32_t tx = 0;                                        // bytes of BOTH CTAs per stage
+      for (int n0 = 0; n0 < d; n0 += 256) tx += 2u * (uint32_t)(((d - n0 < 256 ? d - n0 : 256) / 2) * 128);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        tc::mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+        if (leader) tc::mbar_arrive_expect_tx(&bfull[s], tx);
+        const uint32_t lbar = tc::leader_addr(&bfull[s]);
+        uint8_t* sb = smem + s * STAGE + 2 * A_TILE;
+        int c = 0;
+        for (int n0 = 0; n0 < d; n0 += 256, ++c) {
+          const int hr = (d - n0 < 256 ? d - n0 : 256) / 2;       // this CTA's rows of the chunk: 32 .. 128 (d % 64 == 0)
+          const int rowB = kb * d + n0 + (int)crank * hr;
+          for (int r = 0; r < hr; r += 32) tc::tma_load_2d_pair(sb + c * A_TILE + r * 128, mapB, lbar, 0, rowB + r);
+        }
+      }
+    } else {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        tc::mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&bfull[s], (uint32_t)(d * 128));
+        tc::bulk_load(smem + s * STAGE + 2 * A_TILE, imgB + (size_t)kb * ((size_t)d * 128), (uint32_t)(d * 128), &bfull[s]);
+      }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && lane == 0 && leader) {
     for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % BWD_STAGES;
-      const uint32_t ph = (kb / BWD_STAGES) & 1;
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
       tc::mbar_wait(&bfull[s], ph);
       tc::mbar_wait(&afull[s], ph);
       tc::fence_after_sync();
-      const uint64_t ah = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * BWD_STAGE));
-      const uint64_t al = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * BWD_STAGE + A_TILE));
+      const uint64_t ah = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * STAGE));
+      const uint64_t al = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * STAGE + A_TILE));
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        for (int n0 = 0; n0 < d; n0 += 256) {
+        int c = 0;
+        for (int n0 = 0; n0 < d; n0 += 256, ++c) {
           const int n = d - n0 < 256 ? d - n0 : 256;
-          const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * BWD_STAGE + 2 * A_TILE + n0 * 128));
-          const uint32_t idesc = tc::make_idesc_f16(128, n, 1);
-          tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(ah, k), tc::advance_desc_k(bd, k), idesc, (kb | k) != 0);
-          tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(al, k), tc::advance_desc_k(bd, k), idesc, 1);
+          if (PAIR) {
+            const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * STAGE + 2 * A_TILE + c * A_TILE));
+            const uint32_t idesc = tc::make_idesc_f16(256, n, 1);
+            tc::mma_f16_ss_pair(tmem_base + n0, tc::advance_desc_k(ah, k), tc::advance_desc_k(bd, k), idesc, (kb | k) != 0);
+            tc::mma_f16_ss_pair(tmem_base + n0, tc::advance_desc_k(al, k), tc::advance_desc_k(bd, k), idesc, 1);
+          } else {
+            const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * STAGE + 2 * A_TILE + n0 * 128));
+            const uint32_t idesc = tc::make_idesc_f16(128, n, 1);
+            tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(ah, k), tc::advance_desc_k(bd, k), idesc, (kb | k) != 0);
+            tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(al, k), tc::advance_desc_k(bd, k), idesc, 1);
+          }
         }
       }
-      tc::mma_commit(&empty[s]);
+      if (PAIR) tc::mma_commit_pair(&empty[s]); else tc::mma_commit(&empty[s]);
     }
-    tc::mma_commit(&accfull);
+    if (PAIR) tc::mma_commit_pair(&accfull); else tc::mma_commit(&accfull);
   } else if (warp >= 2) {
     // ---------------------------------------------------------------- dS producers
     const int t = threadIdx.x - 64;                          // 0..255
@@ -530,7 +624,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff, float e
     load_block(0, sa, sb, bw);
 #pragma unroll 1
     for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % BWD_STAGES;
+      const int s = kb % STAGES;
       const int k0 = kb * 64 + ch * 8;
       float4 na[4], nb[4];
       uint32_t nw[4];
@@ -538,8 +632,8 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff, float e
       float kl[8], kw[8], kic[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) { kl[e] = KL[k0 + e]; kw[e] = KW[k0 + e]; kic[e] = KIC[k0 + e]; }
-      tc::mbar_wait(&empty[s], ((kb / BWD_STAGES) & 1) ^ 1);
-      uint8_t* Ahi = smem + s * BWD_STAGE;
+      tc::mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+      uint8_t* Ahi = smem + s * STAGE;
       uint8_t* Alo = Ahi + A_TILE;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -563,12 +657,12 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff, float e
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&afull[s]);
+      if (lane == 0) { if (PAIR && !leader) tc::mbar_arrive_remote_release(&afull[s], 0); else tc::mbar_arrive(&afull[s]); }
 #pragma unroll
       for (int u = 0; u < 4; ++u) { sa[u] = na[u]; sb[u] = nb[u]; bw[u] = nw[u]; }
     }
     // ---------------------------------------------------------------- epilogue: two threads per output row (half the columns each)
-    {
+    if (active) {
       const int quad = warp & 3, half = (warp - 2) >> 2;
       const int row = quad * 32 + lane, gi = row0 + row;
       const bool live = gi < R;
@@ -637,8 +731,26 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, int d, float tau_eff, float e
     }
   }
   tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, ncols);
+  if (PAIR) tc::cluster_sync_all(); else __syncthreads();    // (pair: the peer may still be signalled / read until here)
+  if (warp == 1) { if (PAIR) tc::tmem_dealloc_pair(tmem_base, ncols); else tc::tmem_dealloc(tmem_base, ncols); }
+}
+
+// per-pair tensor maps over the operand images of the saved buffers (pair kernels)
+bool fill_maps(PairMaps& maps, const reid_sdm_pair* pairs, int n_pairs, int d, bool transposed) {
+  for (int i = 0; i < n_pairs; ++i) {
+    const TcLayout L = tc_layout(pairs[i].N, pairs[i].M, d);
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(tc_base(pairs[i].saved));
+    if (!transposed) {
+      if (!tc_host::make_map_image(&maps.q[i], bytes + L.qn, (int64_t)L.Np * (d / 64), 64) ||
+          !tc_host::make_map_image(&maps.g[i], bytes + L.gn, (int64_t)L.Mp * (d / 64), 64))
+        return false;
+    } else {
+      if (!tc_host::make_map_image(&maps.qt[i], bytes + L.qnt, (int64_t)d * (L.Np / 64), 32) ||
+          !tc_host::make_map_image(&maps.gt[i], bytes + L.gnt, (int64_t)d * (L.Mp / 64), 32))
+        return false;
+    }
+  }
+  return true;
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -681,14 +793,31 @@ int tc_forward(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float 
   const float tau_eff = fmaxf(0.15f, fminf(0.5f, tau));                    // sdm_loss.py:28
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess) return REID_E_CUDA;
-    if (cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess) return REID_E_CUDA;
+    if (cudaFuncSetAttribute(tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM) != cudaSuccess) return REID_E_CUDA;
+    if (cudaFuncSetAttribute(tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWDP_SMEM) != cudaSuccess) return REID_E_CUDA;
     attr_done = true;
   }
   const size_t prep_smem = (size_t)PREP_ROWS * (d + 8) * 2;
   tc_prep_kernel<<<dim3(mb * 128 / PREP_ROWS, 2, n_pairs), PREP_THREADS, prep_smem, st>>>(b, d, eps);
   REID_CHECK_LAUNCH();
-  tc_fwd_kernel<<<dim3(mb, 2, n_pairs), FWD_THREADS, FWD_SMEM, st>>>(b, d, tau_eff);
+  // REID_SDM_PAIR=1 selects the cta_group::2 pair kernels.  They are parity-tested but NOT the default: measured on
+  // C5 (10 pairs) the step takes 90 us against 78 us with the single-CTA kernels -- the six to eight 4-8 KB tensor-map
+  // loads per stage and the cluster launch cost more than the halved operand stream and the deeper ring save.
+  const char* pe = getenv("REID_SDM_PAIR");
+  const bool pair = pe ? atoi(pe) != 0 : false;
+  PairMaps maps;                                             // (only the entries of this launch are read by the kernel)
+  if (pair) {
+    if (!fill_maps(maps, pairs, n_pairs, d, false)) return REID_E_CUDA;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((mb + 1) / 2 * 2, 2, n_pairs); cfg.blockDim = dim3(FWD_THREADS); cfg.dynamicSmemBytes = FWDP_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc_fwd_kernel<true>, b, maps, d, tau_eff) != cudaSuccess) return REID_E_CUDA;
+  } else {
+    tc_fwd_kernel<false><<<dim3(mb, 2, n_pairs), FWD_THREADS, FWD_SMEM, st>>>(b, maps, d, tau_eff);
+  }
   REID_CHECK_LAUNCH();
   return REID_OK;
 }
@@ -699,8 +828,27 @@ int tc_backward(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float
   const int rc = fill_batch(b, pairs, n_pairs, true, &mb);
   if (rc != REID_OK) return rc;
   const float tau_eff = fmaxf(0.15f, fminf(0.5f, tau));
-  if (cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess) return REID_E_CUDA;
-  tc_bwd_kernel<<<dim3(mb, 2, n_pairs), BWD_THREADS, BWD_SMEM, st>>>(b, d, tau_eff, eps);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) != cudaSuccess) return REID_E_CUDA;
+    if (cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWDP_SMEM) != cudaSuccess) return REID_E_CUDA;
+    attr_done = true;
+  }
+  const char* pe = getenv("REID_SDM_PAIR");
+  const bool pair = pe ? atoi(pe) != 0 : false;             // (see tc_forward)
+  PairMaps maps;
+  if (pair) {
+    if (!fill_maps(maps, pairs, n_pairs, d, true)) return REID_E_CUDA;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((mb + 1) / 2 * 2, 2, n_pairs); cfg.blockDim = dim3(BWD_THREADS); cfg.dynamicSmemBytes = BWDP_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc_bwd_kernel<true>, b, maps, d, tau_eff, eps) != cudaSuccess) return REID_E_CUDA;
+  } else {
+    tc_bwd_kernel<false><<<dim3(mb, 2, n_pairs), BWD_THREADS, BWD_SMEM, st>>>(b, maps, d, tau_eff, eps);
+  }
   REID_CHECK_LAUNCH();
   return REID_OK;
 }

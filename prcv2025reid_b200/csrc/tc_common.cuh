@@ -134,6 +134,13 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   // relaxed: callers only hand back TMEM whose loads have completed (tcgen05.wait::ld + tcgen05.fence)
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
+// release-ordered remote arrive: the caller's earlier shared-memory writes (made visible to the async proxy with
+// fence.proxy.async) are ordered before the arrival observed by the waiting CTA
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -199,6 +206,19 @@ inline EncodeTiledFn get_encode() {
     fn = (EncodeTiledFn)p;
   }
   return fn;
+}
+// a pre-swizzled operand image viewed as [rows128][64] 16-bit elements (one row = one 128-byte swizzled row):
+// box = 64 x box_rows, NO swizzle (the bytes are copied verbatim), used by the cta_group::2 SDM kernels
+inline bool make_map_image(CUtensorMap* m, const void* base, int64_t rows128, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {64, (cuuint64_t)rows128};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // row-major [rows, d] fp16 matrix, box = 64 columns x box_rows rows, 128B swizzle, zero OOB fill
 inline bool make_map_f16(CUtensorMap* m, const void* base, int64_t rows, int d, int box_rows) {

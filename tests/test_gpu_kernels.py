@@ -422,8 +422,11 @@ def test_sdm_tensor_core_path_matches_oracle(N, M, d):
     _check_sdm_against_oracle(q, v, y, loss.detach().cpu(), qd.grad / 3.0, vd.grad / 3.0, 0.2)
 
 
-def test_sdm_tensor_core_pairs_of_different_shapes_in_one_launch():
+@pytest.mark.parametrize("pair_kernels", ["0", "1"])
+def test_sdm_tensor_core_pairs_of_different_shapes_in_one_launch(pair_kernels, monkeypatch):
+    """Both kernel variants of the tcgen05 path: single-CTA (default) and cta_group::2 CTA pairs (REID_SDM_PAIR=1)."""
     from prcv2025reid_b200.sdm_loss import sdm_loss_pairs
+    monkeypatch.setenv("REID_SDM_PAIR", pair_kernels)
     shapes = [(512, 512), (64, 512), (200, 72), (384, 128), (256, 256)]
     cases = [_tc_case(7 + i, n, m) for i, (n, m) in enumerate(shapes)]
     qs = [c[0].cuda().requires_grad_(True) for c in cases]
