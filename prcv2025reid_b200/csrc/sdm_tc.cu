@@ -53,6 +53,14 @@ __device__ __forceinline__ float fast_exp(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
   return y;
 }
+// REID_SDM_TIMING build only (scripts/sdm_phase_times.py): phase time stamps (ns) of the forward CTA (row block 0,
+// side 0) of every pair in hdr words 80..95
+#ifdef REID_SDM_TIMING
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define SDM_STAMP(cond, slot) do { if (cond) reinterpret_cast<unsigned long long*>(hdr_i + 80)[slot] = gtime(); } while (0)
+#else
+#define SDM_STAMP(cond, slot) do { } while (0)
+#endif
 __device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // =============================================================================================== prep
@@ -225,6 +233,9 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
   if (PAIR) tc::cluster_sync_all(); else __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
+  const bool stamp = rb == 0 && side == 0;
+  (void)stamp;
+  SDM_STAMP(stamp && threadIdx.x == 0, 0);                   // prologue done
 
   if (warp == 0 && lane == 0) {
     if (PAIR) {
@@ -327,8 +338,10 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
     const float inv_tau = 1.f / tau_eff;
     float se = 0.f, ps = 0.f, pc = 0.f;
     bool bad = false;
+    SDM_STAMP(stamp && et == 0, 1);                          // masks formed
     tc::mbar_wait(&accfull, 0);
     tc::fence_after_sync();
+    SDM_STAMP(stamp && et == 0, 2);                          // accumulator complete
 #pragma unroll 1
     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
       uint32_t r[16];
@@ -370,6 +383,7 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
         }
       }
     }
+    SDM_STAMP(stamp && et == 0, 3);                          // column loop done
     if (part > 0) { s_part[part - 1][0][row] = se; s_part[part - 1][1][row] = ps; s_part[part - 1][2][row] = pc; }
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_bad, 1);
     named_bar(1, FWD_EPI_THREADS);
@@ -384,6 +398,7 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       ce_a[i] = pc > 0.f ? (lse - ps / pc) : 0.f;               // -(q * log_p).sum, q uniform over positives (:49-57)
     }
     named_bar(1, FWD_EPI_THREADS);
+    SDM_STAMP(stamp && et == 0, 4);                          // row statistics stored
     if (et == 0) {
       hdr_i[72 + side * 4 + rb] = s_bad;
       __threadfence();
