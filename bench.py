@@ -101,6 +101,12 @@ def run_reference(args):
     from oracle import retrieval as orc
     from prcv2025reid_b200 import synth
     seed, n_ids, gpi, k, qpi = WORKLOADS[args.workload]
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(max(1, avail))
     cores = torch.get_num_threads()
     centres, bias = synth.make_centres(seed, n_ids)
     G = n_ids * gpi
