@@ -84,9 +84,8 @@ int reid_pos_sort(float* pos_score, int32_t* n_pos, int64_t Q, int Pmax, void* s
  * cand_thr [Q] (optional): per-query score with >= REID_KLIST candidates at or above it (-inf if fewer);
  * every candidate the re-scorer can need lies at or above it.
  * total_chunks = chunks the WHOLE gallery of a query is cut into over all ranks (n_chunks x world size;
- * 0 = n_chunks): thresholds deeper than max(1024 * n_chunks / total_chunks, 8 calibration hits) rows of a
- * chunk are counted on the 1/32 row sample; a deep rank still rests on >= 32 sampled rows per chunk position
- * gallery-wide (single-rank behaviour is unchanged). */
+ * 0 = n_chunks): thresholds deeper than max(1024 / total_chunks, 8 calibration hits) rows of a chunk are
+ * counted on the 1/32 row sample, so a deep rank rests on >= 32 sampled rows gallery-wide. */
 int reid_retrieve_fused(const void* q_f16, const void* g_f16, const int32_t* q_code,
                         const int32_t* g_code, const int32_t* excl, int E, const float* pos_thr,
                         const int32_t* n_pos, int64_t Q, int64_t G_local, int64_t g_offset, int d,

@@ -49,6 +49,23 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 __device__ __forceinline__ float warp_dot(const float* __restrict__ a, const float* __restrict__ b,
                                           int d, int lane) {
   float acc = 0.f;
+  if (d == 512) {
+    // the feature width of the whole reference: all eight 128-bit loads are issued before the first FMA (one
+    // memory round trip per dot instead of four); the FMA order is the one of the generic loop, so the result is
+    // bit-identical
+    float4 x[4], y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x[i] = *reinterpret_cast<const float4*>(a + lane * 4 + 128 * i);
+      y[i] = *reinterpret_cast<const float4*>(b + lane * 4 + 128 * i);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc = fmaf(x[i].x, y[i].x, acc); acc = fmaf(x[i].y, y[i].y, acc);
+      acc = fmaf(x[i].z, y[i].z, acc); acc = fmaf(x[i].w, y[i].w, acc);
+    }
+    return warp_sum(acc);
+  }
   for (int c = lane * 4; c < d; c += 128) {
     const float4 x = *reinterpret_cast<const float4*>(a + c);
     const float4 y = *reinterpret_cast<const float4*>(b + c);
@@ -56,6 +73,26 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ a, const flo
     acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
   }
   return warp_sum(acc);
+}
+
+// two dots against the same `a` with all loads of both rows in flight (d == 512); each result is bit-identical
+// to warp_dot(a, b?, 512, lane)
+__device__ __forceinline__ void warp_dot2_512(const float* __restrict__ a, const float* __restrict__ b0,
+                                              const float* __restrict__ b1, int lane, float& r0, float& r1) {
+  float4 x[4], y0[4], y1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[i] = *reinterpret_cast<const float4*>(a + lane * 4 + 128 * i);
+    y0[i] = *reinterpret_cast<const float4*>(b0 + lane * 4 + 128 * i);
+    y1[i] = *reinterpret_cast<const float4*>(b1 + lane * 4 + 128 * i);
+  }
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a0 = fmaf(x[i].x, y0[i].x, a0); a0 = fmaf(x[i].y, y0[i].y, a0); a0 = fmaf(x[i].z, y0[i].z, a0); a0 = fmaf(x[i].w, y0[i].w, a0);
+    a1 = fmaf(x[i].x, y1[i].x, a1); a1 = fmaf(x[i].y, y1[i].y, a1); a1 = fmaf(x[i].z, y1[i].z, a1); a1 = fmaf(x[i].w, y1[i].w, a1);
+  }
+  r0 = warp_sum(a0); r1 = warp_sum(a1);
 }
 
 // total order used by every top-list in the library: score descending, index ascending

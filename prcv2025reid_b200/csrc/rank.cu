@@ -206,11 +206,49 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
   __syncthreads();
   // gather the chunk buffers (compact, order irrelevant: sorted next).  When the producer supplied a
   // per-query threshold with >= KLIST candidates at or above it, only those can reach the top list.
+  // The chunk counts are fetched first and the candidates are read over the flattened index space, four
+  // independent loads per thread in flight (one memory round trip per 512 candidates, not one per chunk slice).
   const float keep = cand_thr ? cand_thr[qi] : REID_NEG_INF;
-  for (int c = 0; c < n_chunks; ++c) {
+  __shared__ int s_pre[65];                                   // prefix sums of the clamped chunk counts (n_chunks <= 64)
+  const int nck = n_chunks < 64 ? n_chunks : 64;
+  if (threadIdx.x < nck) {
+    int cnt = cand_count[(int64_t)qi * n_chunks + threadIdx.x];
+    if (cnt > cand_cap) { cnt = cand_cap; s_overflow = 1; }
+    s_pre[threadIdx.x + 1] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_pre[0] = 0;
+    for (int c = 0; c < nck; ++c) s_pre[c + 1] += s_pre[c];
+  }
+  __syncthreads();
+  const int total_in = s_pre[nck];
+  const int64_t qbase = (int64_t)qi * n_chunks * cand_cap;
+  for (int b = threadIdx.x; b < total_in; b += 4 * RS_THREADS) {
+    float v[4]; int64_t off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = b + u * RS_THREADS;
+      v[u] = REID_NEG_INF; off[u] = 0;
+      if (e < total_in) {
+        int c = 0;
+        while (c + 1 < nck && e >= s_pre[c + 1]) ++c;
+        off[u] = qbase + (int64_t)c * cand_cap + (e - s_pre[c]);
+        v[u] = cand_score[off[u]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (b + u * RS_THREADS < total_in && v[u] >= keep) {
+        const int slot = atomicAdd(&s_total, 1);
+        if (slot < n2) { key[slot] = v[u]; val[slot] = cand_idx[off[u]]; }
+      }
+    }
+  }
+  for (int c = 64; c < n_chunks; ++c) {                        // (more than 64 chunks: never produced by the host side)
     int cnt = cand_count[(int64_t)qi * n_chunks + c];
     if (cnt > cand_cap) { cnt = cand_cap; if (threadIdx.x == 0) s_overflow = 1; }
-    const int64_t o = ((int64_t)qi * n_chunks + c) * cand_cap;
+    const int64_t o = qbase + (int64_t)c * cand_cap;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
       const float v = cand_score[o + i];
       if (v >= keep) {
@@ -231,13 +269,20 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
   // completeness cut-off: every local row whose approximate score exceeds `cut` is a candidate
   const float cut = (total >= REID_KLIST) ? key[REID_KLIST - 1] : REID_NEG_INF;
   // exact fp32 re-score of the R best candidates (same dot routine as reid_pos_scores)
-  for (int r = warp; r < REID_RTOP; r += RS_THREADS / 32) {
-    float s = REID_NEG_INF; int gi = 0x7fffffff;
-    if (r < R) {
-      gi = val[r];
-      s = warp_dot(q_f32 + (int64_t)qi * d, g_f32 + (int64_t)gi * d, d, lane);
+  constexpr int RW = RS_THREADS / 32;
+  for (int r = warp; r < REID_RTOP; r += 2 * RW) {               // two rows per warp at a time: both gathers in flight
+    const int r2 = r + RW;
+    float s0 = REID_NEG_INF, s1 = REID_NEG_INF; int g0 = 0x7fffffff, g1 = 0x7fffffff;
+    if (r < R) g0 = val[r];
+    if (r2 < R) g1 = val[r2];
+    const float* qrow = q_f32 + (int64_t)qi * d;
+    if (d == 512 && r2 < R) {
+      warp_dot2_512(qrow, g_f32 + (int64_t)g0 * d, g_f32 + (int64_t)g1 * d, lane, s0, s1);
+    } else {
+      if (r < R) s0 = warp_dot(qrow, g_f32 + (int64_t)g0 * d, d, lane);
+      if (r2 < R) s1 = warp_dot(qrow, g_f32 + (int64_t)g1 * d, d, lane);
     }
-    if (lane == 0) { ex_s[r] = s; ex_i[r] = gi; }
+    if (lane == 0) { ex_s[r] = s0; ex_i[r] = g0; if (r2 < REID_RTOP) { ex_s[r2] = s1; ex_i[r2] = g1; } }
   }
   __syncthreads();
   if (warp == 0) {
@@ -266,10 +311,13 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
   const int np = min(n_pos[qi], Pmax);
   const int qcode = q_code[qi];
   const float bound = cut + eps;   // no local non-candidate row can score above this
+  __shared__ int s_neg[REID_RTOP];                             // re-scored row r is NOT a positive of the query
+  if (threadIdx.x < REID_RTOP) s_neg[threadIdx.x] = (threadIdx.x < R && g_code[ex_i[threadIdx.x]] != qcode) ? 1 : 0;
+  __syncthreads();
   for (int j = threadIdx.x; j < np; j += blockDim.x) {
     const float t = pos_thr[(int64_t)qi * Pmax + j];
     int lb = 0;
-    for (int r = 0; r < R; ++r) lb += (g_code[ex_i[r]] != qcode && ex_s[r] > t) ? 1 : 0;
+    for (int r = 0; r < R; ++r) lb += (s_neg[r] && ex_s[r] > t) ? 1 : 0;
     int32_t* dst = pos_above + (int64_t)qi * Pmax + j;
     if (t > bound || cut == REID_NEG_INF) *dst = lb;       // exact local count
     else {

@@ -702,8 +702,10 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
     // deep = the row sample is expected to hold >= 32 rows above the threshold OVER ALL CHUNKS OF ALL RANKS
     // (17.7% rank error at the boundary); never classify on fewer than 8 calibration hits
     const float scale = (float)p.rows_per_chunk / (float)CALIB_ROWS;
+    // (budget = 32 SAMPLE_W rows GALLERY-WIDE: a per-chunk budget would count 8 x 1024 rows exactly when a 100k-row
+    //  gallery is cut into 8 chunks -- 8 % of all rows as hits)
     const int tc_all = total_chunks > n_chunks ? total_chunks : n_chunks;
-    const float limit = fmaxf(32.f * (float)SAMPLE_W * (float)n_chunks / (float)tc_all, 8.f * scale);
+    const float limit = fmaxf(32.f * (float)SAMPLE_W / (float)tc_all, 8.f * scale);
     calib_split_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, scale, limit, p.n_exact);
   } else {
     fill_n_exact_kernel<<<aux_grid, 256, 0, st>>>(n_pos, Q, Pmax, p.n_exact);
