@@ -56,15 +56,30 @@ pos_scores_kernel(const float* __restrict__ q_f32, const float* __restrict__ g_f
   const int code = q_code[q];
   const int cnt = (code >= 0) ? min(q_count[q], Pmax) : 0;
   const float* qrow = q_f32 + q * (int64_t)d;
-  for (int s = warp; s < Pmax; s += 4) {
-    float val = REID_NEG_INF;
-    if (s < cnt) {
-      const int64_t gi = order[code + s];
-      bool ok = (gi >= g_offset) && (gi < g_offset + G_local);
-      for (int e = 0; e < E && ok; ++e) ok = (excl[q * E + e] != (int32_t)gi);
-      if (ok) val = warp_dot(qrow, g_f32 + (gi - g_offset) * (int64_t)d, d, lane);
+  // two slots per warp at a time: both row gathers in flight (results bit-identical to warp_dot)
+  for (int s = warp; s < Pmax; s += 8) {
+    const int s2 = s + 4;
+    int64_t g0 = -1, g1 = -1;
+    if (s < cnt) g0 = order[code + s];
+    if (s2 < cnt) g1 = order[code + s2];
+    bool ok0 = (g0 >= g_offset) && (g0 < g_offset + G_local);
+    bool ok1 = (g1 >= g_offset) && (g1 < g_offset + G_local);
+    for (int e = 0; e < E; ++e) {
+      const int32_t x = excl[q * E + e];
+      ok0 = ok0 && (x != (int32_t)g0);
+      ok1 = ok1 && (x != (int32_t)g1);
     }
-    if (lane == 0) pos_score[q * Pmax + s] = val;
+    float v0 = REID_NEG_INF, v1 = REID_NEG_INF;
+    if (d == 512 && ok0 && ok1) {
+      warp_dot2_512(qrow, g_f32 + (g0 - g_offset) * (int64_t)d, g_f32 + (g1 - g_offset) * (int64_t)d, lane, v0, v1);
+    } else {
+      if (ok0) v0 = warp_dot(qrow, g_f32 + (g0 - g_offset) * (int64_t)d, d, lane);
+      if (ok1) v1 = warp_dot(qrow, g_f32 + (g1 - g_offset) * (int64_t)d, d, lane);
+    }
+    if (lane == 0) {
+      pos_score[q * Pmax + s] = v0;
+      if (s2 < Pmax) pos_score[q * Pmax + s2] = v1;
+    }
   }
 }
 
