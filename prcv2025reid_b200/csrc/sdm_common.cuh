@@ -36,7 +36,7 @@ __device__ __forceinline__ void st_out(void* base, size_t i, float v) {
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---- tcgen05 path: layout of the per-pair `saved` buffer (offsets in floats unless noted) ----
-// [den_q N][den_g M][lse_r N][lse_c M][cnt_r N][cnt_c M][ce_r N][ce_c M][hdr 96][S N*M][St M*N] then, 128-byte
+// [den_q N][den_g M][lse_r N][lse_c M][cnt_r N][cnt_c M][ce_r N][ce_c M][hdr 128][S N*M][St M*N] then, 128-byte
 // aligned, the positive masks of y as bit rows (ybits [N][16] / ybitsT [M][16] 32-bit words) and four bf16 operand images in the UMMA K-major 128B-swizzle layout (8-row x 64-element atoms of 1024 bytes,
 // [k block][row group]) so that an operand tile is ONE contiguous cp.async.bulk:
 //   Qn  [Np rows][d]   Gn  [Mp rows][d]   QnT [d rows][Np]   GnT [d rows][Mp]      (Np, Mp = N, M rounded up to 128)
@@ -50,7 +50,7 @@ struct TcLayout {
   size_t qn, gn, qnt, gnt;         // byte offsets of the images
   size_t total_bytes;
 };
-constexpr int TC_HDR_FLOATS = 96;
+constexpr int TC_HDR_FLOATS = 128;    // (words 80..111: optional phase time stamps of REID_SDM_TIMING builds)
 __host__ __device__ inline TcLayout tc_layout(int N, int M, int d) {
   TcLayout L;
   L.N = N; L.M = M; L.d = d; L.Np = round_up(N, 128); L.Mp = round_up(M, 128);

@@ -524,6 +524,13 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
   if (PAIR) tc::cluster_sync_all(); else __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
+#ifdef REID_SDM_TIMING
+  const bool stamp = rb == 0 && side == 0;
+#define BSTAMP(cond, slot) do { if (cond) reinterpret_cast<unsigned long long*>(const_cast<int*>(hdr_i) + 80)[8 + (slot)] = gtime(); } while (0)
+#else
+#define BSTAMP(cond, slot) do { } while (0)
+#endif
+  BSTAMP(stamp && threadIdx.x == 64, 0);                     // prologue done
 
   if (warp == 0 && lane == 0) {
     if (PAIR) {
@@ -615,6 +622,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       }
     }
     named_bar(1, BWD_PROD_THREADS);
+    BSTAMP(stamp && t == 0, 1);                           // statistics staged
     // this side's view of S (side 0: S [N][M], side 1: St [M][N]) and of the positive mask: rows = tile rows, K contiguous
     const float* Sv = base + (side ? L.St : L.S);
     const uint32_t* bitsv = reinterpret_cast<const uint32_t*>(bytes + (side ? L.ybitsT : L.ybits));
@@ -676,6 +684,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
 #pragma unroll
       for (int u = 0; u < 4; ++u) { sa[u] = na[u]; sb[u] = nb[u]; bw[u] = nw[u]; }
     }
+    BSTAMP(stamp && t == 0, 2);                           // all dS tiles formed
     // ---------------------------------------------------------------- epilogue: two threads per output row (half the columns each)
     if (active) {
       const int quad = warp & 3, half = (warp - 2) >> 2;
@@ -692,6 +701,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       float* pdot = RL;                                  // the row statistics are dead now: reuse as [2][128] partial dots
       tc::mbar_wait(&accfull, 0);                        // every MMA has retired: the stage buffers are free
       tc::fence_after_sync();
+      BSTAMP(stamp && t == 0, 3);                     // accumulator complete
       // x^ of this row block (the values the forward multiplied): 128 rows x d of the K-major operand image,
       // one contiguous 16 KB bulk copy per 64-feature block, into the (now idle) stage buffers
       if (t == 0) {
@@ -703,6 +713,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       }
       named_bar(1, BWD_PROD_THREADS);                    // every producer is past its last read of RL / RW
       tc::mbar_wait(&xfull, 0);
+      BSTAMP(stamp && t == 0, 4);                     // x^ tile in shared memory
       const uint8_t* xrow = smem + (row >> 3) * 1024 + (row & 7) * 128;
       auto xchunk = [&](int c) -> uint4 {                // 8 consecutive features starting at c (multiple of 8)
         return *reinterpret_cast<const uint4*>(xrow + (c >> 6) * A_TILE + ((((c & 63) >> 3) ^ (row & 7)) << 4));
@@ -722,6 +733,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
           dot2 = fmaf(__uint_as_float(r[8 + e]), fb[e], dot2);
         }
       }
+      BSTAMP(stamp && t == 0, 5);                     // pass 1 (row dots) done
       pdot[half * 128 + row] = dot + dot2;
       named_bar(1, BWD_PROD_THREADS);
       dot = clamped ? 0.f : (pdot[row] + pdot[128 + row]);
@@ -743,6 +755,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
           *reinterpret_cast<uint4*>(orow + c0 + 8) = pack8(ob);
         }
       }
+      BSTAMP(stamp && t == 0, 6);                     // pass 2 (gradient rows written) done
     }
   }
   tc::fence_before_sync();

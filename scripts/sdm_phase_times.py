@@ -18,6 +18,7 @@ def fwd(ctx, *a):
 sdm_loss._SdmPairsFn.forward = staticmethod(fwd)
 for it in range(5):
     losses = sdm_loss.sdm_loss_pairs(qs, vs, [y] * 10, tau=0.2)
+    losses.sum().backward()
     torch.cuda.synchronize()
 L = _cabi.lib()
 names = ["prologue", "masks", "accfull", "columns", "rowstats"]
@@ -27,4 +28,7 @@ for i in (0, 5, 9):
     off = (base - sv.data_ptr()) // 4
     hdr = off + 8 * 512                                     # den_q..ce_c = 8 arrays of 512 floats
     t = sv[hdr + 80: hdr + 96].view(torch.int64).cpu().tolist()
-    print("pair %d:" % i, ", ".join("%s +%.1f us" % (n, (t[k] - t[0]) / 1e3) for k, n in enumerate(names)))
+    print("pair %d fwd:" % i, ", ".join("%s +%.1f us" % (n, (t[k] - t[0]) / 1e3) for k, n in enumerate(names)))
+    tb = sv[hdr + 96: hdr + 112].view(torch.int64).cpu().tolist()
+    bn = ["prologue", "stats staged", "dS tiles formed", "accfull", "x^ tile loaded", "pass 1", "pass 2"]
+    print("pair %d bwd:" % i, ", ".join("%s +%.1f us" % (n, (tb[k] - tb[0]) / 1e3) for k, n in enumerate(bn)))
