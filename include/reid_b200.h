@@ -119,8 +119,9 @@ int reid_rescore_topk(const float* q_f32, const float* g_f32, const int32_t* q_c
                       float eps, int32_t* pos_above, float* top_score, int32_t* top_idx,
                       int32_t* flag, void* stream);
 
-/* merge n_lists per-shard top lists [n_lists, Q, REID_RTOP] into out[Q, topk] (score desc, idx asc) */
-int reid_merge_topk(const float* scores, const int32_t* idx, int n_lists, int64_t Q, int topk,
+/* merge n_lists per-shard top lists [n_lists, Q, list_len] (each sorted; the global top-k is contained in the union of
+ * the shards' top-k, so list_len = topk suffices) into out[Q, topk] (score desc, idx asc) */
+int reid_merge_topk(const float* scores, const int32_t* idx, int n_lists, int64_t Q, int list_len, int topk,
                     float* out_score, int32_t* out_idx, void* stream);
 
 /* ---- metrics: eval_mm_protocol.py:435-469.  rank_j = 1 + pos_above[q,j] + j;

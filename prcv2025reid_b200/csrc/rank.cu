@@ -335,17 +335,17 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
 // merge per-shard top lists: one warp-multiple CTA per query, bitonic over n_lists*RTOP entries
 __global__ void __launch_bounds__(128)
 merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, int n_lists, int64_t Q,
-                  int topk, int n2, float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
+                  int list_len, int topk, int n2, float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* key = reinterpret_cast<float*>(smem_raw);
   int32_t* val = reinterpret_cast<int32_t*>(key + n2);
   const int64_t q = blockIdx.x;
-  const int n = n_lists * REID_RTOP;
+  const int n = n_lists * list_len;
   for (int i = threadIdx.x; i < n2; i += blockDim.x) {
     float s = REID_NEG_INF; int gi = 0x7fffffff;
     if (i < n) {
-      const int l = i / REID_RTOP, r = i % REID_RTOP;
-      const int64_t o = ((int64_t)l * Q + q) * REID_RTOP + r;
+      const int l = i / list_len, r = i % list_len;
+      const int64_t o = ((int64_t)l * Q + q) * list_len + r;
       gi = idx[o]; s = scores[o];
       if (gi < 0) { gi = 0x7fffffff; s = REID_NEG_INF; }
     }
@@ -464,14 +464,14 @@ extern "C" int reid_rescore_topk(const float* q_f32, const float* g_f32, const i
   return REID_OK;
 }
 
-extern "C" int reid_merge_topk(const float* scores, const int32_t* idx, int n_lists, int64_t Q, int topk,
+extern "C" int reid_merge_topk(const float* scores, const int32_t* idx, int n_lists, int64_t Q, int list_len, int topk,
                                float* out_score, int32_t* out_idx, void* stream) {
-  if (!scores || !idx || !out_score || !out_idx || n_lists <= 0 || topk <= 0 || n_lists * REID_RTOP > 8192)
+  if (!scores || !idx || !out_score || !out_idx || n_lists <= 0 || topk <= 0 || list_len <= 0 || n_lists * list_len > 8192)
     return REID_E_INVALID;
   if (Q <= 0) return REID_OK;
   int n2 = 32;
-  while (n2 < n_lists * REID_RTOP) n2 <<= 1;
-  merge_topk_kernel<<<(unsigned)Q, 128, (size_t)n2 * 8, (cudaStream_t)stream>>>(scores, idx, n_lists, Q, topk, n2,
+  while (n2 < n_lists * list_len) n2 <<= 1;
+  merge_topk_kernel<<<(unsigned)Q, 128, (size_t)n2 * 8, (cudaStream_t)stream>>>(scores, idx, n_lists, Q, list_len, topk, n2,
                                                                                  out_score, out_idx);
   REID_CHECK_LAUNCH();
   return REID_OK;

@@ -320,13 +320,13 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
 
     if world > 1:
         sharding.exchange_counts(pos_above, group)                      # counts are additive over shards
-        all_s, all_i = sharding.gather_top_lists(top_score, top_idx, group)
-        n_lists = world
+        # the global top-k is contained in the union of the shards' (exactly ordered) top-k lists
+        all_s, all_i = sharding.gather_top_lists(top_score[:, :topk].contiguous(), top_idx[:, :topk].contiguous(), group)
+        out_s = torch.empty(Q, topk, dtype=torch.float32, device=dev)
+        out_i = torch.empty(Q, topk, dtype=torch.int32, device=dev)
+        check(L.reid_merge_topk(ptr(all_s), ptr(all_i), world, Q, topk, topk, ptr(out_s), ptr(out_i), st), "reid_merge_topk")
     else:
-        all_s, all_i, n_lists = top_score, top_idx, 1
-    out_s = torch.empty(Q, topk, dtype=torch.float32, device=dev)
-    out_i = torch.empty(Q, topk, dtype=torch.int32, device=dev)
-    check(L.reid_merge_topk(ptr(all_s), ptr(all_i), n_lists, Q, topk, ptr(out_s), ptr(out_i), st), "reid_merge_topk")
+        out_s, out_i = top_score[:, :topk].contiguous(), top_idx[:, :topk].contiguous()   # one shard: already ordered
 
     out = torch.empty(5, dtype=torch.float64, device=dev)
     ap = torch.empty(Q, dtype=torch.float64, device=dev) if want_ap else None

@@ -566,3 +566,25 @@ def test_gallery_store_shards_match_direct_install(eng, tmp_path):
     assert sum(rows) == case.G
     shard, meta2, _ = gallery_store.load_shard(str(tmp_path))
     assert meta2 == meta and torch.equal(shard.g_f16, ref.g_f16)
+
+
+def test_merge_topk_of_shard_lists():
+    """The multi-GPU merge step on one GPU: per-shard sorted top-k lists [n_lists, Q, k] -> global top-k (score desc, idx asc)."""
+    from prcv2025reid_b200 import _cabi
+    from prcv2025reid_b200._cabi import check, ptr, stream_ptr
+    g = torch.Generator().manual_seed(4)
+    n_lists, Q, k = 3, 257, 10
+    sc = torch.randn(n_lists, Q, k, generator=g)
+    sc[1, :, 5:] = float("-inf")                                  # a shard with fewer than k rows: -inf / -1 padding
+    sc, _ = torch.sort(sc, dim=2, descending=True)
+    idx = torch.arange(n_lists * Q * k, dtype=torch.int32).view(n_lists, Q, k)
+    idx[1, :, 5:] = -1
+    sc[2, :, 0] = sc[0, :, 0]                                     # exact score ties across shards: the lower index wins
+    scd, idxd = sc.cuda().contiguous(), idx.cuda().contiguous()
+    out_s = torch.empty(Q, k, device="cuda"); out_i = torch.empty(Q, k, dtype=torch.int32, device="cuda")
+    check(_cabi.lib().reid_merge_topk(ptr(scd), ptr(idxd), n_lists, Q, k, k, ptr(out_s), ptr(out_i), stream_ptr()), "reid_merge_topk")
+    flat_s = sc.permute(1, 0, 2).reshape(Q, -1); flat_i = idx.permute(1, 0, 2).reshape(Q, -1)
+    for q in range(0, Q, 16):
+        items = sorted([(-float(s), int(i)) for s, i in zip(flat_s[q], flat_i[q]) if int(i) >= 0])[:k]
+        assert out_i[q].tolist() == [i for _, i in items]
+        assert out_s[q].tolist() == [-s for s, _ in items]
