@@ -305,7 +305,6 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
     const int i = rb * 128 + row;
     const bool live = i < R;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    float* Sout = base + (side ? L.St : L.S) + (size_t)(live ? i : 0) * C;     // side 0: S[i][:]  side 1: St[j][:]
     const int cstep = round_up((C + PARTS - 1) / PARTS, 32);
     const int c_begin = part * cstep < C ? part * cstep : C, c_end = (part + 1) * cstep < C ? (part + 1) * cstep : C;
     // positive mask of this thread's columns (<= 128 = 4 words), formed from y WHILE the MMAs run and kept in
@@ -342,46 +341,55 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
     tc::mbar_wait(&accfull, 0);
     tc::fence_after_sync();
     SDM_STAMP(stamp && et == 0, 2);                          // accumulator complete
+    // S (side 0) / St (side 1) leave through a per-warp staging tile in the (now idle) operand ring: a thread owns a
+    // row, so direct stores would touch 32 rows with 16 bytes each per instruction; staged, every store instruction
+    // writes 256 contiguous bytes of two rows (XOR-swizzled 16-byte chunks keep both directions conflict-free).
+    uint8_t* tile = smem + (warp - 2) * 8192;                  // [32 rows][64 columns] fp32
+    float* Sbase = base + (side ? L.St : L.S);
 #pragma unroll 1
-    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-      uint32_t r[16];
-      __syncwarp();                                          // tcgen05.ld is .sync.aligned: reconverge first
-      const int wsel = (c0 - c_begin) >> 5;
-      const uint32_t bw = (wsel == 0 ? mb[0] : wsel == 1 ? mb[1] : wsel == 2 ? mb[2] : mb[3]) >> ((c0 - c_begin) & 31);
-      tc::tmem_ld_x16(taddr + c0, r);
-      tc::tmem_wait_ld();
-      if (!live) continue;
-      float sv[16];
-      if (c_end - c0 >= 16) {
-        float se2 = 0.f;                                          // two accumulation chains
+    for (int cg = c_begin; cg < c_end; cg += 64) {
+#pragma unroll 1
+      for (int it = 0; it < 4; ++it) {
+        const int c0 = cg + 16 * it;
+        if (c0 >= c_end) break;                                // (warp-uniform)
+        uint32_t r[16];
+        __syncwarp();                                          // tcgen05.ld is .sync.aligned: reconverge first
+        const int wsel = (c0 - c_begin) >> 5;
+        const uint32_t bw = (wsel == 0 ? mb[0] : wsel == 1 ? mb[1] : wsel == 2 ? mb[2] : mb[3]) >> ((c0 - c_begin) & 31);
+        tc::tmem_ld_x16(taddr + c0, r);
+        tc::tmem_wait_ld();
+        const int nv = c_end - c0 < 16 ? c_end - c0 : 16;       // 16, or 8 in the ragged tail (C is a multiple of 8)
+        float sv[16];
+        float se2 = 0.f;                                        // two accumulation chains
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          float s = __uint_as_float(r[e]) * inv_tau;              // :86 (x 1/tau: <= 1 ulp from the reference's division)
-          bad |= !(fabsf(s) <= 3.0e38f);                          // :89-91 (NaN or Inf)
-          s = fminf(fmaxf(s, -20.f), 20.f);                       // :94 (and :46)
+          float s = __uint_as_float(r[e]) * inv_tau;            // :86 (x 1/tau: <= 1 ulp from the reference's division)
+          const bool in = live && e < nv;
+          bad |= in && !(fabsf(s) <= 3.0e38f);                  // :89-91 (NaN or Inf)
+          s = fminf(fmaxf(s, -20.f), 20.f);                     // :94 (and :46)
           sv[e] = s;
-          if (e & 1) se2 += fast_exp(s); else se += fast_exp(s);  // |s| <= 20: no overflow without max subtraction
-          if ((bw >> e) & 1u) { ps += s; pc += 1.f; }
-        }
-        se += se2;
-        float* sp = Sout + c0;
-#pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4)
-          *reinterpret_cast<float4*>(sp + 4 * e4) = make_float4(sv[4 * e4], sv[4 * e4 + 1], sv[4 * e4 + 2], sv[4 * e4 + 3]);
-      } else {
-        const int nv = c_end - c0;                                // ragged tail (C is a multiple of 8)
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          if (e < nv) {
-            float s = __uint_as_float(r[e]) * inv_tau;
-            bad |= !(fabsf(s) <= 3.0e38f);
-            s = fminf(fmaxf(s, -20.f), 20.f);
-            se += fast_exp(s);
+          if (in) {
+            if (e & 1) se2 += fast_exp(s); else se += fast_exp(s);   // |s| <= 20: no overflow without max subtraction
             if ((bw >> e) & 1u) { ps += s; pc += 1.f; }
-            Sout[c0 + e] = s;
           }
         }
+        se += se2;
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4)
+          *reinterpret_cast<float4*>(tile + lane * 256 + (((it * 4 + e4) ^ (lane & 15)) << 4)) =
+              make_float4(sv[4 * e4], sv[4 * e4 + 1], sv[4 * e4 + 2], sv[4 * e4 + 3]);
       }
+      __syncwarp();
+#pragma unroll 4
+      for (int rr = 0; rr < 32; rr += 2) {
+        const int rw = rr + (lane >> 4), lc = lane & 15;
+        const int col = cg + lc * 4;
+        const int gi = rb * 128 + quad * 32 + rw;
+        if (col < c_end && gi < R)
+          *reinterpret_cast<float4*>(Sbase + (size_t)gi * C + col) =
+              *reinterpret_cast<const float4*>(tile + rw * 256 + ((lc ^ (rw & 15)) << 4));
+      }
+      __syncwarp();
     }
     SDM_STAMP(stamp && et == 0, 3);                          // column loop done
     if (part > 0) { s_part[part - 1][0][row] = se; s_part[part - 1][1][row] = ps; s_part[part - 1][2][row] = pc; }
@@ -695,7 +703,6 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       const float den = (base + (side ? L.den_g : L.den_q))[gl];
       const float rden = 1.f / den;
       const bool clamped = !(den > bf16r(eps));          // norm <= eps: the denominator is the constant eps
-      bf16* orow = out + (size_t)gl * d;
       const int dh = d >> 1;
       const int c_begin = half * dh, c_end = c_begin + dh;
       float* pdot = RL;                                  // the row statistics are dead now: reuse as [2][128] partial dots
@@ -737,23 +744,41 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       pdot[half * 128 + row] = dot + dot2;
       named_bar(1, BWD_PROD_THREADS);
       dot = clamped ? 0.f : (pdot[row] + pdot[128 + row]);
+      // the gradient rows leave through a per-warp staging tile (free ring space above the x^ tile): a thread owns a
+      // row, so direct stores would write 32 bytes to each of 32 rows per step; staged, every store instruction writes
+      // 128 contiguous bytes of four rows (d/2 is a multiple of 32: groups of 64 columns, the last may hold 32)
+      uint8_t* otile = smem + (size_t)(d >> 6) * A_TILE + (warp - 2) * 4096;   // [32 rows][64 columns] bf16
+      const int wrow0 = row0 + quad * 32;
 #pragma unroll 1
-      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-        uint32_t r[16];
-        __syncwarp();
-        tc::tmem_ld_x16(taddr + c0, r);
-        float fa[8], fb[8], oa[8], ob[8];
-        unpack8(xchunk(c0), fa); unpack8(xchunk(c0 + 8), fb);
-        tc::tmem_wait_ld();
+      for (int cg = c_begin; cg < c_end; cg += 64) {
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+          const int c0 = cg + 16 * it;
+          if (c0 >= c_end) break;                            // (warp-uniform)
+          uint32_t r[16];
+          __syncwarp();
+          tc::tmem_ld_x16(taddr + c0, r);
+          float fa[8], fb[8], oa[8], ob[8];
+          unpack8(xchunk(c0), fa); unpack8(xchunk(c0 + 8), fb);
+          tc::tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          oa[e] = (__uint_as_float(r[e]) - fa[e] * dot) * rden;
-          ob[e] = (__uint_as_float(r[8 + e]) - fb[e] * dot) * rden;
+          for (int e = 0; e < 8; ++e) {
+            oa[e] = (__uint_as_float(r[e]) - fa[e] * dot) * rden;
+            ob[e] = (__uint_as_float(r[8 + e]) - fb[e] * dot) * rden;
+          }
+          *reinterpret_cast<uint4*>(otile + lane * 128 + (((2 * it) ^ (lane & 7)) << 4)) = pack8(oa);
+          *reinterpret_cast<uint4*>(otile + lane * 128 + (((2 * it + 1) ^ (lane & 7)) << 4)) = pack8(ob);
         }
-        if (live) {
-          *reinterpret_cast<uint4*>(orow + c0) = pack8(oa);
-          *reinterpret_cast<uint4*>(orow + c0 + 8) = pack8(ob);
+        __syncwarp();
+#pragma unroll 4
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int rw = rr + (lane >> 3), lc = lane & 7;
+          const int col = cg + lc * 8;
+          if (col < c_end && wrow0 + rw < R)
+            *reinterpret_cast<uint4*>(out + (size_t)(wrow0 + rw) * d + col) =
+                *reinterpret_cast<const uint4*>(otile + rw * 128 + ((lc ^ (rw & 7)) << 4));
         }
+        __syncwarp();
       }
       BSTAMP(stamp && t == 0, 6);                     // pass 2 (gradient rows written) done
     }
