@@ -3,32 +3,33 @@
 // Replaces the per-query loop body of rank_and_metrics, eval_mm_protocol.py:401-455 (cosine_sim,
 // same-image mask, argsort, CMC, AP walk) for one gallery shard, without materialising S or a sort.
 //
-// Work item = (block of NQ=128 queries, gallery chunk).  A persistent CTA per SM loops over items:
-//   * the query block (B operand, 128 x d fp16 = up to 128 KB) is TMA-loaded once per item and stays
-//     resident in shared memory; gallery tiles (A operand, 128 rows) stream through a TMA ring;
-//   * one thread issues tcgen05.mma (M=128 gallery rows -> TMEM lanes, N=128 queries -> TMEM columns,
-//     fp16 x fp16 -> fp32) into one of four 128-column TMEM accumulators (the epilogue may lag 3 tiles);
-//   * eight epilogue warps (two per TMEM lane quadrant) read the accumulator with tcgen05.ld: lane l owns gallery row
-//     32w+l, a column is a query, so every per-query quantity is WARP-UNIFORM and a whole column
-//     of 32 scores is tested with one compare + ballot against min(top-list threshold, lowest
-//     positive threshold).  Hits are compacted into a per-warp queue in shared memory and drained
-//     lane-parallel:
+// Two layouts of the same kernel (template PAIR; the kernel comment further down has the MMA shapes):
+//   PAIR = true (default)  "R layout": a cta_group::2 pair of a 2-CTA cluster per work item = (256 queries, gallery
+//     chunk); each CTA keeps its 128 queries resident in shared memory (A operand, 128 KB) and streams its half of
+//     every 256-row gallery tile through a 3-stage TMA ring; the leader issues M256 x N256 MMAs into one of two
+//     256-column TMEM accumulators.  TMEM lane = query, column = gallery row.
+//   PAIR = false "T layout": one CTA per work item = (128 queries, gallery chunk), M128 (gallery rows) x N128 (queries)
+//     MMAs into one of four 128-column accumulators; TMEM lane = gallery row, column = query.
+// Epilogue (16 warps, four per TMEM lane quadrant, tcgen05.ld 32x32b.x16): every score is compared with
+// min(candidate threshold, lowest exactly-counted positive threshold) of its query (R: per-lane registers, T:
+// warp-uniform shared values); ONE redux.or per 16-column step tells whether the warp has a hit at all.  Hits are
+// compacted round by round (n-th hit of every lane: register select tree + ballot / popc) into a per-warp queue in
+// shared memory and drained 32 at a time, lane-parallel, mostly after the accumulator has been handed back:
 //       (a) counting: a binary search over the query's positive thresholds (sorted descending, in
 //           shared memory) gives the bucket b = #thresholds >= score; hist[q][b]++ (packed 16-bit
-//           counters in shared memory, spilled to a global histogram every 256 tiles); the count of
-//           rows ranked above positive j is the prefix sum over buckets <= j;
+//           counters in shared memory, spilled to a global histogram every 128 tiles); the count of
+//           rows ranked above positive j is the prefix sum over buckets <= j.
 //           Thresholds whose rank inside the chunk is estimated (calibration pre-pass over a strided
-//           2048-row sample) to exceed 32*SAMPLE_W rows are "deep": they are counted on a fixed
-//           1/SAMPLE_W stratified row sample with weight SAMPLE_W (>= 32 sampled rows above such a
-//           threshold: <= 18% unbiased error on a rank > 1000, which moves a query's AP by ~1e-5 and
-//           mAP by ~1e-6); all shallower thresholds are counted exactly on every row;
+//           2048-row sample) to exceed max(32*SAMPLE_W / total_chunks, 8 calibration hits) rows are "deep":
+//           they are counted on a fixed 1/SAMPLE_W stratified row sample with weight SAMPLE_W (>= 32 sampled
+//           rows above such a threshold gallery-wide: <= 18% unbiased error on a rank > 1000, which moves a
+//           query's AP by ~1e-5 and mAP by ~1e-6); all shallower thresholds are counted exactly on every row;
 //       (b) candidates: rows above the query's running threshold are appended (lane-parallel) to its
-//           candidate buffer in global memory; every 64 appends the threshold is raised to the 32nd
-//           largest of the last 64 appended scores, so >= 32 appended rows always lie above it.
-//     The warp pairs walk the four 32-column groups of a tile in rotated order (each warp of a pair
-//     takes 16 columns) with a named barrier between phases, so a query's shared state is owned by
-//     exactly one warp at a time.  The top-list threshold reached by one gallery chunk is published
-//     (atomicMax) and warm-starts the later chunks of the same query.
+//           candidate buffer in global memory (slots pre-filled with -inf); at tile boundaries the owning warp
+//           raises the threshold to the 32nd largest of the last 64 appended scores, so >= 32 appended rows
+//           always lie above it.  The threshold reached by one gallery chunk is published (atomicMax) and
+//           warm-starts the later chunks of the same query.
+//     The epilogue has no CTA barrier inside an item: every shared structure is atomic-safe.
 // Roofline: tensor cores, 2*Q*G*d flop; algorithmic HBM bytes are only operands + outputs.
 #include "common.cuh"
 #include "tc_common.cuh"
