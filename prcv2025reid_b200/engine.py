@@ -125,6 +125,8 @@ def prepare_gallery(gallery: torch.Tensor, g_pid_all: torch.Tensor, g_offset: in
 
 def _pick_chunks(n_qblocks: int, G_local: int, sms: int) -> int:
     """Gallery chunks per query block: the smallest split whose last wave is >= 95% full."""
+    if os.environ.get("REID_CHUNKS"):                      # tuning experiments
+        return max(1, int(os.environ["REID_CHUNKS"]))
     best, best_eff = 1, 0.0
     max_chunks = max(1, min(8, G_local // (128 * 32)))
     for c in range(1, max_chunks + 1):
