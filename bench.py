@@ -187,6 +187,41 @@ def time_sdm(torch, synth, sdm_loss_pairs, P, K, n_pairs, dtype, iters=50):
     return us, alg_bytes, len(pairs), graph_us
 
 
+def torch_gpu_baseline(torch, engine, shard, case, weights, nq, iters=3):
+    """The reference ALGORITHM (fp32 similarity rows, same-image mask, full argsort, AP over the full ranking;
+    eval_mm_protocol.py:401-455, vectorised over a block of queries) with plain torch CUDA ops on the same GPU: a
+    second, stronger baseline next to the CPU arm.  Not the product path and not timed into `value`."""
+    q32, _ = engine.fuse_queries(case.query_raw[:nq], case.mod_id[:nq], weights)
+    g32, g_pid, q_pid, excl = shard.g_f32, case.g_pid, case.q_pid[:nq], case.excl[:nq]
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rows = torch.arange(nq, device=q32.device)[:, None].expand_as(excl)
+
+    def run():
+        S = q32 @ g32.T                                                     # :401
+        ok = excl >= 0
+        S[rows[ok], excl[ok].long()] = -1e9                                 # :421-422
+        order = torch.argsort(S, dim=1, descending=True)                    # :423
+        match = (g_pid[order] == q_pid[:, None]) & (S.gather(1, order) > -1e8)   # :427
+        npos = match.sum(1)
+        prec = match.cumsum(1) / torch.arange(1, S.shape[1] + 1, device=S.device)
+        ap = (prec * match).sum(1) / npos.clamp_min(1)                      # :444-455
+        valid = npos > 0
+        return float(ap[valid].double().mean()), float(match[:, :1].any(1)[valid].float().mean())
+    run()
+    torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        m = run()
+    e.record()
+    torch.cuda.synchronize()
+    torch.backends.cuda.matmul.allow_tf32 = old
+    ms = s.elapsed_time(e) / iters
+    return {"value": nq / (ms * 1e-3), "unit": "queries/s", "kind": "reference algorithm, torch CUDA ops (fp32 matmul, full argsort), same GPU",
+            "sample": "first %d queries of the workload against the full gallery shard" % nq, "mAP_on_sample": m[0], "R@1_on_sample": m[1]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -376,6 +411,11 @@ def main():
                                             "kernels": "tc_prep + tc_fwd + tc_bwd (tcgen05, bf16)"}
             line["sdm"] = sdm
         if not args.no_cpu_baseline:
+            try:
+                line["torch_gpu_baseline"] = torch_gpu_baseline(torch, engine, shard, case, weights, 128 if G > 200000 else 1024)
+            except Exception as ex:                                          # (never let the optional arm break the bench line)
+                line["torch_gpu_baseline"] = {"unavailable": str(ex)[:200]}
+            torch.cuda.empty_cache()
             from oracle import retrieval as orc
             nq = args.cpu_baseline_queries
             g_cpu = shard.g_f32.cpu()
