@@ -482,6 +482,9 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         const int myq = quad * 32 + lane;                               // R: query column id of this lane
         float minA = 0.f, minS = 0.f;
         if (PAIR) { minA = es->s_min[myq]; minS = es->s_minS[myq]; }   // refreshed thresholds, once per tile
+        // fp16 images of the thresholds for the packed fast-path test (rounded DOWN after subtracting the rounding bound)
+        const __half lowA = __float2half_rd(minA - 5e-4f), lowS = __float2half_rd(minS - 5e-4f);
+        const __half2 hAA = __halves2half2(lowA, lowA), hAS = __halves2half2(lowA, lowS);
         const long long te0 = (p.debug & 8192) ? clock64() : 0;
         tc::mbar_wait(&tfull[buf], bph);
         tc::fence_after_sync();
@@ -503,33 +506,43 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
             }
           }
           tc::tmem_wait_ld();
-          // fast path: one compare per column into a per-lane bit mask, ONE warp-wide OR per step
-          // (16 votes per step serialise at ~20 cycles each); bit i of colmask = column c0+i has a hit
+          // fast path: a per-lane bit mask of the columns that MAY hit, ONE warp-wide OR per step.
+          // R layout: the 16 scores are packed to half2 (one F2FP per pair) and compared pairwise against the
+          // thresholds lowered by the fp16 rounding bound (5e-4 >= half an ulp of any |score| <= 1, rounded down), so
+          // the mask is a superset of the exact hits (a few % more); the slow path re-tests exactly in fp32.
+          // Mask bit p / 16 + p = column 2p / 2p + 1.
           unsigned colmask = 0, bits = 0;
           if (!(p.debug & 32)) {
+            if (PAIR) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float s = __uint_as_float(r[i]);
-              // R: column c0+i is gallery row tile_row0+c0+i.  Only column 5 of a 16-column step can be a
-              // sampled row (rows = 5 mod SAMPLE_W); rows beyond the shard end are dropped by the drain.
-              const bool hit = PAIR ? (s > ((i == 5 && step_sampled) ? minS : minA)) : (valid && s > mm[i]);
-              bits |= hit ? (1u << i) : 0u;
+              for (int pr = 0; pr < 8; ++pr) {
+                const __half2 h = __floats2half2_rn(__uint_as_float(r[2 * pr]), __uint_as_float(r[2 * pr + 1]));
+                // only column 5 of a 16-column step can be a sampled row (rows = 5 mod SAMPLE_W)
+                const __half2 thr = (pr == 2 && step_sampled) ? hAS : hAA;
+                bits |= __hgt2_mask(h, thr) & ((1u << pr) | (1u << (16 + pr)));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool hit = valid && __uint_as_float(r[i]) > mm[i];
+                bits |= hit ? (1u << (i >> 1) << ((i & 1) * 16)) : 0u;
+              }
             }
             colmask = __reduce_or_sync(0xffffffffu, bits);
           }
           // slow path (single copy of the code: the kernel must fit the instruction cache).  Round n takes
-          // the n-th hit of EVERY lane at once: per-lane select tree for the score, one ballot + prefix
-          // popc to compact the round into the dense warp queue.  Rounds per step = max hits per lane
-          // (usually 1), not the number of hit columns.
+          // the n-th flagged column of EVERY lane at once: per-lane select tree for the score, exact fp32 test, one
+          // ballot + prefix popc to compact the round into the dense warp queue.  Rounds per step = max flagged
+          // columns per lane (usually 1), not the number of hit columns.
           if (p.debug & 4096) colmask = 0;               // debug: fast path only (hits ignored)
           if (colmask) {
             unsigned b = bits;
 #pragma unroll 1
             while (true) {
               const bool has = b != 0;
-              const unsigned c = __ballot_sync(0xffffffffu, has);
-              if (!c) break;
-              const int i = has ? (__ffs(b) - 1) : 0;
+              if (!__any_sync(0xffffffffu, has)) break;
+              const int bp = has ? (__ffs(b) - 1) : 0;
+              const int i = ((bp & 15) << 1) | (bp >> 4);
               b &= b - 1;                                // (0 stays 0)
               // the lane's score of column i: 4-level select tree over the 16 registers (no memory)
               uint32_t t8[8], t4[4], t2[2];
@@ -539,10 +552,14 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
               for (int u = 0; u < 4; ++u) t4[u] = (i & 2) ? t8[2 * u + 1] : t8[2 * u];
 #pragma unroll
               for (int u = 0; u < 2; ++u) t2[u] = (i & 4) ? t4[2 * u + 1] : t4[2 * u];
-              if (has) {
+              const float sc = __uint_as_float((i & 8) ? t2[1] : t2[0]);
+              const bool smp_col = PAIR && i == 5 && step_sampled;
+              const bool hit = has && (!PAIR || sc > (smp_col ? minS : minA));     // exact test (T layout: already exact)
+              const unsigned c = __ballot_sync(0xffffffffu, hit);
+              if (hit) {
                 const int pos = qn + __popc(c & lt_mask);
-                my_qs[pos] = __uint_as_float((i & 8) ? t2[1] : t2[0]);
-                my_qm[pos] = PAIR ? ((uint32_t)myq | ((i == 5 && step_sampled) ? M_SAMPLED : 0u) |
+                my_qs[pos] = sc;
+                my_qm[pos] = PAIR ? ((uint32_t)myq | (smp_col ? M_SAMPLED : 0u) |
                                      ((uint32_t)(tile_row0 + c0 + i) << M_ROW_SHIFT))
                                   : ((uint32_t)(c0 + i) | lane_bits | ((uint32_t)grow_local << M_ROW_SHIFT));
               }
