@@ -351,7 +351,7 @@ def main():
             peak, which = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
         traffic, traffic_src = None, None
         try:      # DRAM bytes per launch from the committed ncu --set full capture of this exact configuration
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01c_traffic.json")))[dom]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01e_traffic.json")))[dom]
             if tr["workload"] == args.workload and tr["n_gpus"] == world:
                 traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
         except Exception:
