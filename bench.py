@@ -399,10 +399,11 @@ def main():
         if not args.no_sdm:
             sdm = {}
             note = ("us_per_step_eager = autograd step on the stream (host-bound: Python + launches); "
-                    "us_per_step_graph = the same forward+backward replayed as one CUDA graph (device time)")
+                    "us_per_step_graph = the same forward+backward (reid_sdm_step, objective = sum of the pair losses) "
+                    "replayed as one CUDA graph (device time)")
             us, ab, npairs, gu = time_sdm(torch, synth, sdm_loss_pairs, 4, 2, 4, torch.float32)
             sdm["c2_p4k2_fp32_4pairs"] = {"us_per_step_eager": us, "us_per_step_graph": gu, "algorithmic_bytes": ab,
-                                          "hbm_gbs_graph": ab / (gu * 1e-6) / 1e9, "kernels": "sdm_small_fwd/bwd (fp32 SIMT, 1 CTA per pair)",
+                                          "hbm_gbs_graph": ab / (gu * 1e-6) / 1e9, "kernels": "graph: sdm_small_step (forward + backward in ONE launch, fp32 SIMT, 1 CTA per pair); eager: sdm_small_fwd + sdm_small_bwd",
                                           "note": note}
             us, ab, npairs, gu = time_sdm(torch, synth, sdm_loss_pairs, 64, 8, 10, torch.bfloat16)
             sdm["c5_p64k8_bf16_10pairs"] = {"us_per_step_eager": us, "us_per_step_graph": gu, "algorithmic_bytes": ab,

@@ -158,6 +158,13 @@ int reid_sdm_fwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, floa
                  void* stream);
 int reid_sdm_bwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps,
                  void* stream);
+/* One training step = forward + backward (the autograd pass train.py:969-972 triggers) with the upstream gradient
+ * grad_out[p] of every pair known up front (the weight of loss p in the objective): one launch for small pairs
+ * (N, M <= 32: rows, S and statistics never leave shared memory), otherwise reid_sdm_fwd followed by reid_sdm_bwd. */
+int reid_sdm_step(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps,
+                  void* stream);
+/* kernel launches reid_sdm_step issues for this batch: 1 (small pairs), 3 (tcgen05: pack + forward + backward), 2 (general) */
+int reid_sdm_step_launches(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d);
 
 /* scratch sizes.  which: 0 = reid_pid_index_build(G), 1 = reid_retrieve_fused */
 size_t reid_workspace_bytes(int which, int64_t Q, int64_t G, int d);

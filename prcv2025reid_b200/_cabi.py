@@ -52,6 +52,8 @@ _SIGS = {
     "reid_sdm_uses_tensor_cores": (c_int, [c_void_p, c_int, c_int, c_int]),
     "reid_sdm_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "reid_sdm_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "reid_sdm_step": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "reid_sdm_step_launches": (c_int, [c_void_p, c_int, c_int, c_int]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGS)
@@ -63,6 +65,7 @@ _LAUNCHES_PER_CALL = {
     "reid_pid_lookup": 1, "reid_pos_scores": 1, "reid_pos_sort": 1, "reid_retrieve_fused": 4,
     "reid_retrieve_exact": 1, "reid_rescore_topk": 1, "reid_merge_topk": 1, "reid_metrics_reduce": 2,
     "reid_topk_label_metrics": 1, "reid_sdm_fwd": 1, "reid_sdm_bwd": 1,   # (tcgen05 path: fwd = 2 launches, counted in sdm_loss.py)
+    "reid_sdm_step": 0,                                                   # (counted in sdm_loss.py: reid_sdm_step_launches)
 }
 LAUNCH_COUNT = {"n": 0}
 # optional per-kernel device timing: set PROFILE = [] and every kernel call appends (name, start, end) events

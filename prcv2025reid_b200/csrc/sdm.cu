@@ -550,6 +550,170 @@ sdm_small_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   }
 }
 
+// Forward AND backward of a small pair in ONE launch (reid_sdm_step): the normalised rows, S and the row / column
+// statistics stay in shared memory between the two halves, so the step reads the features once and takes one launch
+// instead of two dependent ones (the step is pure latency at C2).  The arithmetic is the two kernels' above, operation
+// for operation (tests compare the results bit for bit); `saved` still receives the statistics a later
+// reid_sdm_bwd call would need.  grad_out[p] (the weight of loss p in the step's objective) is read up front.
+template <bool BF16>
+__global__ void __launch_bounds__(TB)
+sdm_small_step_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
+  extern __shared__ __align__(16) float small_smem[];
+  const reid_sdm_pair& P = batch.p[blockIdx.x];
+  const int N = P.N, M = P.M;
+  Saved sv = carve(P.saved, N, M, d);
+  float* xs = small_smem;                              // [N + M][d] normalised rows
+  float* Ss = xs + (size_t)(N + M) * d;                // [N][M + 1]  S, then dL/dS
+  float* st_r = Ss + N * (M + 1);                      // [N + M][4]  cnt, ce, lse, den per row, then per column
+  __shared__ int s_flags, s_status;
+  __shared__ float s_nR, s_nC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float gout = *P.grad_out;
+  if (threadIdx.x == 0) s_flags = 0;
+  __syncthreads();
+  for (int r = warp; r < N + M; r += TB / 32) {
+    const bool isq = r < N;
+    const int row = isq ? r : r - N;
+    const void* x = isq ? P.qry : P.gal;
+    float v[16];
+    small_load_row<BF16>(x, (size_t)row, d, lane, v);
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) ss = fmaf(v[c], v[c], ss);
+    ss = warp_sum(ss);
+    float nrm = sqrtf(ss), e = eps;
+    if (BF16) { nrm = __bfloat162float(__float2bfloat16_rn(nrm)); e = __bfloat162float(__float2bfloat16_rn(eps)); }
+    const float dn = fmaxf(nrm, e);
+    const bool bad = !small_store_norm<BF16>(v, dn, xs + (size_t)r * d, d, lane);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_flags, 2);
+    if (lane == 0) { (isq ? sv.den_q : sv.den_g)[row] = dn; st_r[4 * r + 3] = dn; }
+  }
+  __syncthreads();
+  for (int idx = warp; idx < N * M; idx += TB / 32) {
+    const int i = idx / M, j = idx % M;
+    const float dot = warp_dot(xs + (size_t)i * d, xs + (size_t)(N + j) * d, d, lane);
+    if (lane == 0) {
+      const float s = __fdiv_rn(dot, tau_eff);
+      if (!isfinite(s)) atomicOr(&s_flags, 4);
+      const float sc = fminf(fmaxf(s, -20.f), 20.f);
+      Ss[i * (M + 1) + j] = sc;
+      sv.S[(size_t)i * M + j] = sc;
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < N + M; r += TB / 32) {
+    const bool isrow = r < N;
+    const int a = isrow ? r : r - N, len = isrow ? M : N;
+    const bool in = lane < len;
+    const float s = in ? (isrow ? Ss[a * (M + 1) + lane] : Ss[lane * (M + 1) + a]) : -INFINITY;
+    const float yv = in ? (isrow ? P.y[(size_t)a * M + lane] : P.y[(size_t)lane * M + a]) : 0.f;
+    const float mx = warp_max(s);
+    const float se = warp_sum(in ? expf(s - mx) : 0.f);
+    const float ps = warp_sum(yv > 0.f ? s : 0.f), pc = warp_sum(yv > 0.f ? 1.f : 0.f);
+    if (lane == 0) {
+      const float lse = mx + logf(se);
+      const float ce = pc > 0.f ? (lse - ps / pc) : 0.f;
+      (isrow ? sv.lse_r : sv.lse_c)[a] = lse;
+      (isrow ? sv.cnt_r : sv.cnt_c)[a] = pc;
+      (isrow ? sv.ce_r : sv.ce_c)[a] = ce;
+      st_r[4 * r] = pc; st_r[4 * r + 1] = ce; st_r[4 * r + 2] = lse;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[4] = {0, 0, 0, 0};
+    int anypos = 0;
+    for (int r = 0; r < N; ++r) {
+      const float pc = st_r[4 * r], ce = st_r[4 * r + 1];
+      if (pc > 0.f) { anypos = 1; if (isfinite(ce)) { t[0] += ce; t[1] += 1.0; } }
+    }
+    for (int r = N; r < N + M; ++r) {
+      const float pc = st_r[4 * r], ce = st_r[4 * r + 1];
+      if (pc > 0.f && isfinite(ce)) { t[2] += ce; t[3] += 1.0; }
+    }
+    int st = s_flags;
+    if (!anypos) st |= 8;
+    const float lr = t[1] > 0 ? (float)(t[0] / t[1]) : 0.f;
+    const float lc = t[3] > 0 ? (float)(t[2] / t[3]) : 0.f;
+    float loss = 0.5f * (lr + lc);
+    if (!(st & (2 | 4 | 8)) && (isnan(loss) || isinf(loss) || loss < 0.f)) st |= 16;
+    if (st & (2 | 4 | 8 | 16)) { st |= 1; loss = 0.f; }
+    sv.hdr[0] = (float)t[1]; sv.hdr[1] = (float)t[3]; sv.hdr[3] = loss;
+    *reinterpret_cast<int*>(sv.hdr + 2) = st;
+    *P.loss = loss;
+    *P.status = st;
+    s_status = st; s_nR = (float)t[1]; s_nC = (float)t[3];
+  }
+  __syncthreads();
+  // ---------------------------------------------------------------- backward half (sdm_small_bwd_kernel)
+  if (s_status & 1) {
+    for (int idx = threadIdx.x; idx < (N + M) * d; idx += TB) {
+      const bool isq = idx < N * d;
+      st_out<BF16>(isq ? P.dqry : P.dgal, isq ? idx : idx - N * d, 0.f);
+    }
+    return;
+  }
+  const float nR = s_nR, nC = s_nC;
+  const float gscale = gout * 0.5f / tau_eff;
+  const float wr = nR > 0.f ? gscale / nR : 0.f, wc = nC > 0.f ? gscale / nC : 0.f;
+  for (int idx = threadIdx.x; idx < N * M; idx += TB) {
+    const int i = idx / M, j = idx % M;
+    const float s = Ss[i * (M + 1) + j];
+    float g = 0.f;
+    if (s < 20.f && s > -20.f) {
+      const float pos = P.y[idx] > 0.f ? 1.f : 0.f;
+      const float cr = st_r[4 * i], cc = st_r[4 * (N + j)];
+      if (cr > 0.f && isfinite(st_r[4 * i + 1])) g += wr * (expf(s - st_r[4 * i + 2]) - pos / cr);
+      if (cc > 0.f && isfinite(st_r[4 * (N + j) + 1])) g += wc * (expf(s - st_r[4 * (N + j) + 2]) - pos / cc);
+    }
+    Ss[i * (M + 1) + j] = g;                              // (each element is read and rewritten by one thread)
+  }
+  __syncthreads();
+  const int nchunk = d >> 7;
+  float e = eps;
+  if (BF16) e = __bfloat162float(__float2bfloat16_rn(eps));
+  for (int r = warp; r < N + M; r += TB / 32) {
+    const bool isq = r < N;
+    const int row = isq ? r : r - N, len = isq ? M : N;
+    const float* other = xs + (size_t)(isq ? N : 0) * d;
+    float4 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k2 = 0; k2 < len; ++k2) {
+      const float w = isq ? Ss[row * (M + 1) + k2] : Ss[k2 * (M + 1) + row];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < nchunk) {
+          const float4 v = *reinterpret_cast<const float4*>(other + (size_t)k2 * d + k * 128 + lane * 4);
+          acc[k].x = fmaf(w, v.x, acc[k].x); acc[k].y = fmaf(w, v.y, acc[k].y);
+          acc[k].z = fmaf(w, v.z, acc[k].z); acc[k].w = fmaf(w, v.w, acc[k].w);
+        }
+    }
+    const float den = st_r[4 * r + 3];
+    float dot = 0.f;
+    float4 xh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < nchunk) {
+        xh[k] = *reinterpret_cast<const float4*>(xs + (size_t)r * d + k * 128 + lane * 4);
+        dot = fmaf(acc[k].x, xh[k].x, dot); dot = fmaf(acc[k].y, xh[k].y, dot);
+        dot = fmaf(acc[k].z, xh[k].z, dot); dot = fmaf(acc[k].w, xh[k].w, dot);
+      }
+    dot = warp_sum(dot);
+    if (!(den > e)) dot = 0.f;
+    void* out = isq ? P.dqry : P.dgal;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < nchunk) {
+        const size_t o = (size_t)row * d + k * 128 + lane * 4;
+        st_out<BF16>(out, o, (acc[k].x - xh[k].x * dot) / den);
+        st_out<BF16>(out, o + 1, (acc[k].y - xh[k].y * dot) / den);
+        st_out<BF16>(out, o + 2, (acc[k].z - xh[k].z * dot) / den);
+        st_out<BF16>(out, o + 3, (acc[k].w - xh[k].w * dot) / den);
+      }
+  }
+}
+
 bool small_eligible(const reid_sdm_pair* pairs, int n_pairs, int d) {
   if (!pairs || n_pairs <= 0 || n_pairs > REID_SDM_MAX_PAIRS || d % 128 != 0 || d > 512) return false;
   for (int i = 0; i < n_pairs; ++i) {
@@ -569,7 +733,7 @@ int launch_small(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float
     if (!p.qry || !p.gal || !p.y || !p.loss || !p.status || !p.saved) return REID_E_INVALID;
     if (bwd && (!p.grad_out || !p.dqry || !p.dgal)) return REID_E_INVALID;
     b.p[i] = p;
-    const size_t need = ((size_t)(p.N + p.M) * d + (size_t)p.N * (p.M + 1) + 2 * (size_t)(p.N + p.M)) * sizeof(float);
+    const size_t need = ((size_t)(p.N + p.M) * d + (size_t)p.N * (p.M + 1) + 4 * (size_t)(p.N + p.M)) * sizeof(float);
     if (need > smem) smem = need;
   }
   const float tau_eff = fmaxf(0.15f, fminf(0.5f, tau));                    // sdm_loss.py:28
@@ -650,4 +814,21 @@ extern "C" int reid_sdm_bwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, 
   if (sdm::tc_eligible(pairs, n_pairs, dtype, d)) return sdm::tc_backward(pairs, n_pairs, d, tau, eps, (cudaStream_t)stream);
   if (dtype == REID_DTYPE_BF16) return launch_sdm(sdm_bwd_kernel<true>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
   return REID_E_UNSUPPORTED;
+}
+
+// Forward + backward of a step in as few launches as the path allows: one for small pairs, otherwise the two calls above.
+// Every pair carries its backward slots (grad_out = the weight of loss p in the objective, dqry, dgal).
+extern "C" int reid_sdm_step(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps, void* stream) {
+  if (small_eligible(pairs, n_pairs, d)) {
+    if (dtype == REID_DTYPE_F32) return launch_small(sdm_small_step_kernel<false>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
+    if (dtype == REID_DTYPE_BF16) return launch_small(sdm_small_step_kernel<true>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
+  }
+  const int rc = reid_sdm_fwd(pairs, n_pairs, dtype, d, tau, eps, stream);
+  return rc != REID_OK ? rc : reid_sdm_bwd(pairs, n_pairs, dtype, d, tau, eps, stream);
+}
+
+// kernel launches reid_sdm_step issues for this batch (1 small / 3 tcgen05: pack + forward + backward / 2 general)
+extern "C" int reid_sdm_step_launches(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d) {
+  if (small_eligible(pairs, n_pairs, d) && (dtype == REID_DTYPE_F32 || dtype == REID_DTYPE_BF16)) return 1;
+  return (dtype == REID_DTYPE_BF16 && sdm::tc_eligible(pairs, n_pairs, dtype, d)) ? 3 : 2;
 }

@@ -273,7 +273,7 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
             n_chunks = _pick_chunks(-(-nb // 128), shard.G_local, sms)
         else:
             n_chunks = max(1, min(16, (2 * sms) // max(1, -(-nb // 8)), shard.G_local // 1024 or 1))
-        cap = max(cand_cap, 64)
+        cap = max(int(os.environ.get("REID_CAND_CAP") or cand_cap), 64) // 4 * 4      # (env: tuning experiments)
         cand_score = shard.buf("cand_score", (nb, n_chunks, cap), torch.float32)
         cand_idx = shard.buf("cand_idx", (nb, n_chunks, cap), torch.int32)
         cand_count = shard.buf("cand_count", (nb, n_chunks), torch.int32, zero=True)

@@ -130,33 +130,72 @@ class _SdmPairsFn(torch.autograd.Function):
         return (None, None, None) + tuple(dq) + tuple(dg) + (None,) * n
 
 
+class SdmStep:
+    """Forward + backward of all pairs of a training step through ONE C call (`reid_sdm_step`), without autograd.
+
+    The objective is `sum_p weights[p] * loss[p]` (weights default to 1: the `losses.sum()` of a step; the mean of
+    models/model.py:622 is weights = 1/n).  Buffers are allocated once: `losses` [n] fp32, `dq[p]` / `dg[p]` in the
+    input dtype hold the step's results after `run()`.  On the small-batch path the step is a single kernel launch;
+    on the tcgen05 path three (pack, forward, backward)."""
+
+    def __init__(self, qrys, gals, ys, tau=0.2, eps=1e-8, weights=None):
+        n = len(qrys)
+        if not (n == len(gals) == len(ys)) or n == 0 or n > _cabi.SDM_MAX_PAIRS:
+            raise ValueError("SdmStep: need equally long lists of 1..%d pairs" % _cabi.SDM_MAX_PAIRS)
+        L = _cabi.lib()
+        dev, dt, d = qrys[0].device, qrys[0].dtype, qrys[0].shape[1]
+        self.code = _dtype_code(qrys[0])
+        self.q = [q.detach().contiguous() for q in qrys]
+        self.g = [g.detach().contiguous() for g in gals]
+        self.y = [y.detach().to(torch.float32).contiguous() for y in ys]
+        for q, g, y in zip(self.q, self.g, self.y):
+            if q.dtype != dt or g.dtype != dt or q.shape[1] != d or g.shape[1] != d:
+                raise TypeError("sdm_loss: all features of a batch must share dtype and width")
+            if y.shape[0] != q.shape[0] or y.shape[1] != g.shape[0]:
+                raise ValueError("sdm_loss: y must be [N, M]")
+        self.n, self.d, self.tau, self.eps = n, d, float(tau), float(eps)
+        self.losses = torch.empty(n, dtype=torch.float32, device=dev)
+        self.status = torch.empty(n, dtype=torch.int32, device=dev)
+        self.weights = (torch.ones(n, dtype=torch.float32, device=dev) if weights is None
+                        else weights.detach().to(device=dev, dtype=torch.float32).contiguous().clone())
+        sizes = [_saved_floats(L, q.shape[0], g.shape[0], d) for q, g in zip(self.q, self.g)]
+        self.saved = torch.empty(sum(sizes), dtype=torch.float32, device=dev).split(sizes)
+        self.dq = [torch.empty_like(q) for q in self.q]
+        self.dg = [torch.empty_like(g) for g in self.g]
+        self.table = _pair_table(self.q, self.g, self.y, self.losses, self.status, self.saved, self.weights, self.dq, self.dg)
+        self.launches = L.reid_sdm_step_launches(self.table, n, self.code, d)
+
+    def run(self):
+        """Enqueue the step on the current stream; returns `losses` (results are stream-ordered, no host sync)."""
+        _cabi.LAUNCH_COUNT["n"] += self.launches
+        check(_cabi.lib().reid_sdm_step(self.table, self.n, self.code, self.d, self.tau, self.eps, _raw_stream(self.losses.device)),
+              "reid_sdm_step")
+        return self.losses
+
+
 class SdmGraphStep:
-    """One SDM training step (all pairs: forward, loss sum, backward) captured in a CUDA graph.
+    """One SDM training step (all pairs: forward, objective = sum of the pair losses, backward) as a CUDA graph.
 
-    The step is launch-bound at the reference's batch sizes (P x K = 4 x 2: a few KB of data), so the
-    whole forward + backward is recorded once and replayed with a single graph launch.  Inputs are
-    copied into the graph's static buffers (`load`), gradients are read from `dq` / `dg`.
-    """
+    The step is launch-bound at the reference's batch sizes (P x K = 4 x 2: a few KB of data), so the whole
+    forward + backward (`SdmStep`: one kernel for small pairs, pack + forward + backward on the tcgen05 path; no
+    autograd glue kernels) is recorded once and replayed with a single graph launch.  Inputs are copied into the
+    graph's static buffers (`load`), gradients are read from `dq` / `dg`."""
 
-    def __init__(self, qrys, gals, ys, tau=0.2, eps=1e-8, warmup=3):
-        self.q = [q.detach().clone().requires_grad_(True) for q in qrys]
-        self.g = [g.detach().clone().requires_grad_(True) for g in gals]
-        self.y = [y.detach().clone() for y in ys]
+    def __init__(self, qrys, gals, ys, tau=0.2, eps=1e-8, warmup=3, weights=None):
+        self.step = SdmStep([q.detach().clone() for q in qrys], [g.detach().clone() for g in gals],
+                            [y.detach().clone() for y in ys], tau, eps, weights)
+        self.q, self.g, self.y = self.step.q, self.step.g, self.step.y
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._eager(tau, eps)
+                self.step.run()
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.losses, grads = self._eager(tau, eps)
-        self.dq, self.dg = grads[:len(self.q)], grads[len(self.q):]
-
-    def _eager(self, tau, eps):
-        losses = sdm_loss_pairs(self.q, self.g, self.y, tau, eps)
-        grads = torch.autograd.grad(losses.sum(), self.q + self.g)
-        return losses, grads
+            self.losses = self.step.run()
+        self.dq, self.dg = self.step.dq, self.step.dg
+        self.launches = self.step.launches
 
     def load(self, qrys, gals, ys=None):
         with torch.no_grad():
@@ -167,6 +206,7 @@ class SdmGraphStep:
                     dst.copy_(src)
 
     def replay(self):
+        _cabi.LAUNCH_COUNT["n"] += self.launches
         self.graph.replay()
         return self.losses
 

@@ -474,6 +474,36 @@ def test_sdm_graph_step_matches_eager():
             assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("N,M,dtype", [(8, 8, torch.float32), (32, 20, torch.float32), (24, 24, torch.bfloat16),
+                                       (33, 8, torch.float32), (128, 64, torch.bfloat16)])
+def test_sdm_step_single_call_matches_autograd(N, M, dtype):
+    """`reid_sdm_step` (forward + backward in one C call; ONE kernel launch for small pairs) reproduces the autograd path
+    bit for bit, with per-pair objective weights, and a pair without positives yields the zero loss / zero gradients."""
+    from prcv2025reid_b200.sdm_loss import SdmStep, sdm_loss_pairs
+    gen = torch.Generator().manual_seed(7 * N + M)
+    qs, vs, ys = [], [], []
+    for p in range(3):
+        lq = torch.randint(0, 5, (N,), generator=gen); lv = torch.randint(0, 5, (M,), generator=gen)
+        lv[0] = lq[0]
+        y = (lq[:, None] == lv[None, :]).float()
+        if p == 2:
+            y.zero_()                                                  # guard path (sdm_loss.py:105-106)
+        qs.append(torch.randn(N, 512, generator=gen).to(dtype).cuda().requires_grad_(True))
+        vs.append(torch.randn(M, 512, generator=gen).to(dtype).cuda().requires_grad_(True))
+        ys.append(y.cuda())
+    w = torch.tensor([1.0, 0.25, 2.0], device="cuda")
+    losses = sdm_loss_pairs(qs, vs, ys, tau=0.2)
+    grads = torch.autograd.grad((losses * w).sum(), qs + vs)
+    step = SdmStep(qs, vs, ys, tau=0.2, weights=w)
+    assert step.launches == (1 if max(N, M) <= 32 else 3 if dtype == torch.bfloat16 else 2)
+    got = step.run()
+    torch.cuda.synchronize()
+    assert torch.equal(got, losses) and float(got[2]) == 0.0 and int(step.status[2]) & 1
+    for a, b in zip(step.dq + step.dg, grads):
+        assert torch.equal(a, b)
+    assert not step.dq[2].any() and not step.dg[2].any()
+
+
 @pytest.mark.parametrize("N,M,d,dtype", [(32, 20, 512, torch.float32), (5, 32, 256, torch.float32), (1, 1, 128, torch.float32),
                                           (33, 8, 512, torch.float32), (24, 24, 512, torch.bfloat16)])
 def test_sdm_small_and_general_paths_match_oracle(N, M, d, dtype):
