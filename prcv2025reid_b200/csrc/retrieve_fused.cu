@@ -66,7 +66,10 @@ constexpr int FLUSH_TILES = 128;         // 16-bit counters: <= 240 weighted inc
 #endif
 constexpr int SAMPLE_W = REID_SAMPLE_W;  // deep thresholds: rows with (row % SAMPLE_W) == 5, weight SAMPLE_W
 static_assert(SAMPLE_W >= 16 && SAMPLE_W % 16 == 0, "sampled rows are column 5 of a 16-column step");
-constexpr int CALIB_ROWS = 2048;         // strided gallery sample of the calibration pre-pass
+#ifndef REID_CALIB_ROWS
+#define REID_CALIB_ROWS 2048
+#endif
+constexpr int CALIB_ROWS = REID_CALIB_ROWS;   // strided gallery sample of the calibration pre-pass
 // queue meta word: bits 0-6 query column, 7 SAMPLED, 10-31 local gallery row (< 2^22)
 constexpr uint32_t M_SAMPLED = 1u << 7;
 constexpr int M_ROW_SHIFT = 10;

@@ -550,28 +550,41 @@ sdm_small_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   }
 }
 
-// Forward AND backward of a small pair in ONE launch (reid_sdm_step): the normalised rows, S and the row / column
-// statistics stay in shared memory between the two halves, so the step reads the features once and takes one launch
+// Forward AND backward of a small pair in ONE launch (reid_sdm_step): the normalised rows, S, y and the row / column
+// statistics stay in shared memory between the two halves, so the step reads every input once and takes one launch
 // instead of two dependent ones (the step is pure latency at C2).  The arithmetic is the two kernels' above, operation
 // for operation (tests compare the results bit for bit); `saved` still receives the statistics a later
-// reid_sdm_bwd call would need.  grad_out[p] (the weight of loss p in the step's objective) is read up front.
+// reid_sdm_bwd call would need.  grad_out[p] (the weight of loss p in the objective) and y are fetched up front, so
+// their latency hides behind the feature rows.  16 warps: at C2 (N = M = 8) every phase is ONE pass -- a row per warp,
+// four independent dots per warp in flight, a row / column statistic per warp, an output row per warp.
+constexpr int STB = 512;
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 template <bool BF16>
-__global__ void __launch_bounds__(TB)
+__global__ void __launch_bounds__(STB, 1)
 sdm_small_step_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   extern __shared__ __align__(16) float small_smem[];
+  constexpr int NW = STB / 32;
   const reid_sdm_pair& P = batch.p[blockIdx.x];
   const int N = P.N, M = P.M;
   Saved sv = carve(P.saved, N, M, d);
   float* xs = small_smem;                              // [N + M][d] normalised rows
   float* Ss = xs + (size_t)(N + M) * d;                // [N][M + 1]  S, then dL/dS
   float* st_r = Ss + N * (M + 1);                      // [N + M][4]  cnt, ce, lse, den per row, then per column
+  float* Ys = st_r + 4 * (N + M);                      // [N][M]      y
   __shared__ int s_flags, s_status;
   __shared__ float s_nR, s_nC;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float gout = *P.grad_out;
+  float yreg[2];                                        // N * M <= 1024 = 2 per thread
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { const int i = threadIdx.x + u * STB; yreg[u] = i < N * M ? P.y[i] : 0.f; }
   if (threadIdx.x == 0) s_flags = 0;
   __syncthreads();
-  for (int r = warp; r < N + M; r += TB / 32) {
+  for (int r = warp; r < N + M; r += NW) {
     const bool isq = r < N;
     const int row = isq ? r : r - N;
     const void* x = isq ? P.qry : P.gal;
@@ -588,28 +601,38 @@ sdm_small_step_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_flags, 2);
     if (lane == 0) { (isq ? sv.den_q : sv.den_g)[row] = dn; st_r[4 * r + 3] = dn; }
   }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { const int i = threadIdx.x + u * STB; if (i < N * M) Ys[i] = yreg[u]; }
   __syncthreads();
-  for (int idx = warp; idx < N * M; idx += TB / 32) {
-    const int i = idx / M, j = idx % M;
-    const float dot = warp_dot(xs + (size_t)i * d, xs + (size_t)(N + j) * d, d, lane);
-    if (lane == 0) {
-      const float s = __fdiv_rn(dot, tau_eff);
-      if (!isfinite(s)) atomicOr(&s_flags, 4);
-      const float sc = fminf(fmaxf(s, -20.f), 20.f);
-      Ss[i * (M + 1) + j] = sc;
-      sv.S[(size_t)i * M + j] = sc;
+  // S: four independent dots per warp and pass (indices past the end are clamped and discarded)
+  const int nm = N * M;
+  for (int idx0 = warp; idx0 < nm; idx0 += 4 * NW) {
+    float dots[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = min(idx0 + u * NW, nm - 1);
+      dots[u] = warp_dot(xs + (size_t)(idx / M) * d, xs + (size_t)(N + idx % M) * d, d, lane);
+    }
+    if (lane < 4 && idx0 + lane * NW < nm) {
+      const int idx = idx0 + lane * NW;
+      const float dot = lane == 0 ? dots[0] : lane == 1 ? dots[1] : lane == 2 ? dots[2] : dots[3];
+      const float sc0 = __fdiv_rn(dot, tau_eff);
+      if (!isfinite(sc0)) atomicOr(&s_flags, 4);
+      const float sc = fminf(fmaxf(sc0, -20.f), 20.f);
+      Ss[(idx / M) * (M + 1) + idx % M] = sc;
+      sv.S[idx] = sc;
     }
   }
   __syncthreads();
-  for (int r = warp; r < N + M; r += TB / 32) {
+  for (int r = warp; r < N + M; r += NW) {
     const bool isrow = r < N;
     const int a = isrow ? r : r - N, len = isrow ? M : N;
     const bool in = lane < len;
-    const float s = in ? (isrow ? Ss[a * (M + 1) + lane] : Ss[lane * (M + 1) + a]) : -INFINITY;
-    const float yv = in ? (isrow ? P.y[(size_t)a * M + lane] : P.y[(size_t)lane * M + a]) : 0.f;
-    const float mx = warp_max(s);
-    const float se = warp_sum(in ? expf(s - mx) : 0.f);
-    const float ps = warp_sum(yv > 0.f ? s : 0.f), pc = warp_sum(yv > 0.f ? 1.f : 0.f);
+    const float sv_ = in ? (isrow ? Ss[a * (M + 1) + lane] : Ss[lane * (M + 1) + a]) : -INFINITY;
+    const float yv = in ? (isrow ? Ys[a * M + lane] : Ys[lane * M + a]) : 0.f;
+    const float mx = warp_max(sv_);
+    const float se = warp_sum(in ? expf(sv_ - mx) : 0.f);
+    const float ps = warp_sum(yv > 0.f ? sv_ : 0.f), pc = warp_sum(yv > 0.f ? 1.f : 0.f);
     if (lane == 0) {
       const float lse = mx + logf(se);
       const float ce = pc > 0.f ? (lse - ps / pc) : 0.f;
@@ -620,34 +643,40 @@ sdm_small_step_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double t[4] = {0, 0, 0, 0};
+  // means over valid rows / columns and the guards: one warp, a row and a column per lane.  The float64 sums of <= 32
+  // fp32 terms are exact, so their order does not matter (same value as the serial loop of sdm_small_fwd_kernel).
+  if (warp == 0) {
+    double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     int anypos = 0;
-    for (int r = 0; r < N; ++r) {
-      const float pc = st_r[4 * r], ce = st_r[4 * r + 1];
-      if (pc > 0.f) { anypos = 1; if (isfinite(ce)) { t[0] += ce; t[1] += 1.0; } }
+    if (lane < N) {
+      const float pc = st_r[4 * lane], ce = st_r[4 * lane + 1];
+      if (pc > 0.f) { anypos = 1; if (isfinite(ce)) { t0 = ce; t1 = 1.0; } }
     }
-    for (int r = N; r < N + M; ++r) {
-      const float pc = st_r[4 * r], ce = st_r[4 * r + 1];
-      if (pc > 0.f && isfinite(ce)) { t[2] += ce; t[3] += 1.0; }
+    if (lane < M) {
+      const float pc = st_r[4 * (N + lane)], ce = st_r[4 * (N + lane) + 1];
+      if (pc > 0.f && isfinite(ce)) { t2 = ce; t3 = 1.0; }
     }
-    int st = s_flags;
-    if (!anypos) st |= 8;
-    const float lr = t[1] > 0 ? (float)(t[0] / t[1]) : 0.f;
-    const float lc = t[3] > 0 ? (float)(t[2] / t[3]) : 0.f;
-    float loss = 0.5f * (lr + lc);
-    if (!(st & (2 | 4 | 8)) && (isnan(loss) || isinf(loss) || loss < 0.f)) st |= 16;
-    if (st & (2 | 4 | 8 | 16)) { st |= 1; loss = 0.f; }
-    sv.hdr[0] = (float)t[1]; sv.hdr[1] = (float)t[3]; sv.hdr[3] = loss;
-    *reinterpret_cast<int*>(sv.hdr + 2) = st;
-    *P.loss = loss;
-    *P.status = st;
-    s_status = st; s_nR = (float)t[1]; s_nC = (float)t[3];
+    t0 = warp_sum_f64(t0); t1 = warp_sum_f64(t1); t2 = warp_sum_f64(t2); t3 = warp_sum_f64(t3);
+    anypos = __any_sync(0xffffffffu, anypos);
+    if (lane == 0) {
+      int st = s_flags;
+      if (!anypos) st |= 8;
+      const float lr = t1 > 0 ? (float)(t0 / t1) : 0.f;
+      const float lc = t3 > 0 ? (float)(t2 / t3) : 0.f;
+      float loss = 0.5f * (lr + lc);
+      if (!(st & (2 | 4 | 8)) && (isnan(loss) || isinf(loss) || loss < 0.f)) st |= 16;
+      if (st & (2 | 4 | 8 | 16)) { st |= 1; loss = 0.f; }
+      sv.hdr[0] = (float)t1; sv.hdr[1] = (float)t3; sv.hdr[3] = loss;
+      *reinterpret_cast<int*>(sv.hdr + 2) = st;
+      *P.loss = loss;
+      *P.status = st;
+      s_status = st; s_nR = (float)t1; s_nC = (float)t3;
+    }
   }
   __syncthreads();
   // ---------------------------------------------------------------- backward half (sdm_small_bwd_kernel)
   if (s_status & 1) {
-    for (int idx = threadIdx.x; idx < (N + M) * d; idx += TB) {
+    for (int idx = threadIdx.x; idx < (N + M) * d; idx += STB) {
       const bool isq = idx < N * d;
       st_out<BF16>(isq ? P.dqry : P.dgal, isq ? idx : idx - N * d, 0.f);
     }
@@ -656,12 +685,12 @@ sdm_small_step_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   const float nR = s_nR, nC = s_nC;
   const float gscale = gout * 0.5f / tau_eff;
   const float wr = nR > 0.f ? gscale / nR : 0.f, wc = nC > 0.f ? gscale / nC : 0.f;
-  for (int idx = threadIdx.x; idx < N * M; idx += TB) {
+  for (int idx = threadIdx.x; idx < nm; idx += STB) {
     const int i = idx / M, j = idx % M;
     const float s = Ss[i * (M + 1) + j];
     float g = 0.f;
     if (s < 20.f && s > -20.f) {
-      const float pos = P.y[idx] > 0.f ? 1.f : 0.f;
+      const float pos = Ys[idx] > 0.f ? 1.f : 0.f;
       const float cr = st_r[4 * i], cc = st_r[4 * (N + j)];
       if (cr > 0.f && isfinite(st_r[4 * i + 1])) g += wr * (expf(s - st_r[4 * i + 2]) - pos / cr);
       if (cc > 0.f && isfinite(st_r[4 * (N + j) + 1])) g += wc * (expf(s - st_r[4 * (N + j) + 2]) - pos / cc);
@@ -672,7 +701,7 @@ sdm_small_step_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   const int nchunk = d >> 7;
   float e = eps;
   if (BF16) e = __bfloat162float(__float2bfloat16_rn(eps));
-  for (int r = warp; r < N + M; r += TB / 32) {
+  for (int r = warp; r < N + M; r += NW) {
     const bool isq = r < N;
     const int row = isq ? r : r - N, len = isq ? M : N;
     const float* other = xs + (size_t)(isq ? N : 0) * d;
@@ -724,7 +753,8 @@ bool small_eligible(const reid_sdm_pair* pairs, int n_pairs, int d) {
 }
 
 template <class K>
-int launch_small(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float eps, bool bwd, cudaStream_t st) {
+int launch_small(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float eps, bool bwd, cudaStream_t st,
+                 int threads = TB) {
   SdmBatch b;
   b.n_pairs = n_pairs;
   size_t smem = 0;
@@ -733,13 +763,13 @@ int launch_small(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float
     if (!p.qry || !p.gal || !p.y || !p.loss || !p.status || !p.saved) return REID_E_INVALID;
     if (bwd && (!p.grad_out || !p.dqry || !p.dgal)) return REID_E_INVALID;
     b.p[i] = p;
-    const size_t need = ((size_t)(p.N + p.M) * d + (size_t)p.N * (p.M + 1) + 4 * (size_t)(p.N + p.M)) * sizeof(float);
+    const size_t need = ((size_t)(p.N + p.M) * d + (size_t)p.N * (p.M + 1) + 4 * (size_t)(p.N + p.M) + (size_t)p.N * p.M) * sizeof(float);
     if (need > smem) smem = need;
   }
   const float tau_eff = fmaxf(0.15f, fminf(0.5f, tau));                    // sdm_loss.py:28
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return REID_E_CUDA;
-  kernel<<<n_pairs, TB, smem, st>>>(b, d, tau_eff, eps);
+  kernel<<<n_pairs, threads, smem, st>>>(b, d, tau_eff, eps);
   REID_CHECK_LAUNCH();
   return REID_OK;
 }
@@ -820,8 +850,8 @@ extern "C" int reid_sdm_bwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, 
 // Every pair carries its backward slots (grad_out = the weight of loss p in the objective, dqry, dgal).
 extern "C" int reid_sdm_step(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps, void* stream) {
   if (small_eligible(pairs, n_pairs, d)) {
-    if (dtype == REID_DTYPE_F32) return launch_small(sdm_small_step_kernel<false>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
-    if (dtype == REID_DTYPE_BF16) return launch_small(sdm_small_step_kernel<true>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
+    if (dtype == REID_DTYPE_F32) return launch_small(sdm_small_step_kernel<false>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream, STB);
+    if (dtype == REID_DTYPE_BF16) return launch_small(sdm_small_step_kernel<true>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream, STB);
   }
   const int rc = reid_sdm_fwd(pairs, n_pairs, dtype, d, tau, eps, stream);
   return rc != REID_OK ? rc : reid_sdm_bwd(pairs, n_pairs, dtype, d, tau, eps, stream);
