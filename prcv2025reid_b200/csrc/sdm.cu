@@ -563,11 +563,12 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-template <bool BF16>
+template <bool BF16, bool D512>                        // D512: the reference's feature width as a compile-time constant
 __global__ void __launch_bounds__(STB, 1)
-sdm_small_step_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
+sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
   extern __shared__ __align__(16) float small_smem[];
   constexpr int NW = STB / 32;
+  const int d = D512 ? 512 : d_arg;                    // (halves the code of this run-once kernel: no chunk predicates)
   const reid_sdm_pair& P = batch.p[blockIdx.x];
   const int N = P.N, M = P.M;
   Saved sv = carve(P.saved, N, M, d);
@@ -850,8 +851,13 @@ extern "C" int reid_sdm_bwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, 
 // Every pair carries its backward slots (grad_out = the weight of loss p in the objective, dqry, dgal).
 extern "C" int reid_sdm_step(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps, void* stream) {
   if (small_eligible(pairs, n_pairs, d)) {
-    if (dtype == REID_DTYPE_F32) return launch_small(sdm_small_step_kernel<false>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream, STB);
-    if (dtype == REID_DTYPE_BF16) return launch_small(sdm_small_step_kernel<true>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream, STB);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == REID_DTYPE_F32)
+      return d == 512 ? launch_small(sdm_small_step_kernel<false, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
+                      : launch_small(sdm_small_step_kernel<false, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
+    if (dtype == REID_DTYPE_BF16)
+      return d == 512 ? launch_small(sdm_small_step_kernel<true, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
+                      : launch_small(sdm_small_step_kernel<true, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
   }
   const int rc = reid_sdm_fwd(pairs, n_pairs, dtype, d, tau, eps, stream);
   return rc != REID_OK ? rc : reid_sdm_bwd(pairs, n_pairs, dtype, d, tau, eps, stream);

@@ -474,9 +474,10 @@ def test_sdm_graph_step_matches_eager():
             assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("N,M,dtype", [(8, 8, torch.float32), (32, 20, torch.float32), (24, 24, torch.bfloat16),
-                                       (33, 8, torch.float32), (128, 64, torch.bfloat16)])
-def test_sdm_step_single_call_matches_autograd(N, M, dtype):
+@pytest.mark.parametrize("N,M,dtype,d", [(8, 8, torch.float32, 512), (32, 20, torch.float32, 512), (24, 24, torch.bfloat16, 512),
+                                         (33, 8, torch.float32, 512), (128, 64, torch.bfloat16, 512),
+                                         (8, 5, torch.float32, 256), (16, 32, torch.bfloat16, 128)])
+def test_sdm_step_single_call_matches_autograd(N, M, dtype, d):
     """`reid_sdm_step` (forward + backward in one C call; ONE kernel launch for small pairs) reproduces the autograd path
     bit for bit, with per-pair objective weights, and a pair without positives yields the zero loss / zero gradients."""
     from prcv2025reid_b200.sdm_loss import SdmStep, sdm_loss_pairs
@@ -488,8 +489,8 @@ def test_sdm_step_single_call_matches_autograd(N, M, dtype):
         y = (lq[:, None] == lv[None, :]).float()
         if p == 2:
             y.zero_()                                                  # guard path (sdm_loss.py:105-106)
-        qs.append(torch.randn(N, 512, generator=gen).to(dtype).cuda().requires_grad_(True))
-        vs.append(torch.randn(M, 512, generator=gen).to(dtype).cuda().requires_grad_(True))
+        qs.append(torch.randn(N, d, generator=gen).to(dtype).cuda().requires_grad_(True))
+        vs.append(torch.randn(M, d, generator=gen).to(dtype).cuda().requires_grad_(True))
         ys.append(y.cuda())
     w = torch.tensor([1.0, 0.25, 2.0], device="cuda")
     losses = sdm_loss_pairs(qs, vs, ys, tau=0.2)
