@@ -61,3 +61,77 @@ def test_product_path_fails_loudly_without_a_gpu():
         sdm_loss_stable(torch.randn(4, 8), torch.randn(4, 8), torch.eye(4))
     with pytest.raises(RuntimeError):
         train_eval.compute_cmc(torch.randn(4, 8), torch.randn(6, 8), torch.arange(4), torch.arange(6))
+
+
+def _prototypes():
+    """{name: (return type, [parameter types])} parsed from the header's declarations."""
+    src = open(HEADER, encoding="utf-8").read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(reid_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, params = m.group(1).strip(), m.group(2), m.group(3).strip()
+        plist = [] if params in ("", "void") else [" ".join(p.split()) for p in params.split(",")]
+        out[name] = (ret, plist)
+    return out
+
+
+def _ctype_of(decl):
+    """ctypes class a C parameter / return declaration must be bound as."""
+    d = decl.replace("const ", "").strip()
+    if "*" in d:
+        return ctypes.c_char_p if d.startswith("char") else ctypes.c_void_p
+    base = d.split()[0] if " " in d else d
+    return {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
+            "float": ctypes.c_float, "double": ctypes.c_double}[base]
+
+
+def test_binding_signatures_match_the_header():
+    """Every ctypes signature in _cabi._SIGS has the parameter count, order and scalar widths the header declares
+    (an int64_t bound as c_int, or a dropped argument, would corrupt the call silently)."""
+    from prcv2025reid_b200 import _cabi
+    protos = _prototypes()
+    assert set(protos) == set(_cabi._SIGS), set(protos) ^ set(_cabi._SIGS)
+    for name, (ret, params) in protos.items():
+        res, args = _cabi._SIGS[name]
+        assert ctypes.sizeof(res) == ctypes.sizeof(_ctype_of(ret)), (name, ret)
+        assert len(args) == len(params), (name, len(args), params)
+        for i, (a, p) in enumerate(zip(args, params)):
+            want = _ctype_of(p)
+            if want is ctypes.c_void_p:
+                assert a in (ctypes.c_void_p, ctypes.c_char_p), (name, i, p, a)
+            else:
+                assert a is want or (ctypes.sizeof(a) == ctypes.sizeof(want) and a._type_ == want._type_), (name, i, p, a)
+
+
+def test_sdm_pair_struct_matches_the_header():
+    from prcv2025reid_b200 import _cabi
+    src = open(HEADER, encoding="utf-8").read()
+    body = re.search(r"typedef struct \{(.*?)\} reid_sdm_pair;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", " ", body, flags=re.S)
+    fields = [f.strip() for f in body.split(";") if f.strip()]
+    names = [re.split(r"[\s\*]+", f)[-1] for f in fields]
+    assert names == [n for n, _ in _cabi.SdmPair._fields_]
+    for f, (n, t) in zip(fields, _cabi.SdmPair._fields_):
+        assert ctypes.sizeof(t) == ctypes.sizeof(_ctype_of(f.rsplit(n, 1)[0])), (f, t)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 (no C++ / CUDA / torch types in any signature)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include "reid_b200.h"\nint main(void) { reid_sdm_pair p; (void)p; return REID_OK; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.dirname(HEADER), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_error_strings_cover_every_code(lib):
+    lib.reid_strerror.restype = ctypes.c_char_p
+    texts = {c: lib.reid_strerror(c).decode() for c in (0, -1, -2, -3, -4, -99)}
+    assert all(texts.values())
+    assert len({texts[c] for c in (0, -1, -2, -3, -4)}) == 5     # distinct messages for the declared codes
