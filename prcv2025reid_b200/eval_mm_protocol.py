@@ -8,7 +8,9 @@ device, metrics as Python floats).  Importing this module without the built libr
 GPU and calling into it raises -- there is no CPU fallback.
 """
 import csv
-from typing import Dict, List, Optional
+import itertools
+import random
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -22,6 +24,46 @@ def _dev():
     if not torch.cuda.is_available():
         raise RuntimeError("prcv2025reid_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     return torch.device("cuda", torch.cuda.current_device())
+
+
+def pick_one(items: List[dict], rng: random.Random) -> dict:
+    """eval_mm_protocol.py:37-39 -- one uniformly drawn sample (one `rng.choice` call, so the stream of a seeded
+    `random.Random` is consumed exactly like the reference does)."""
+    return rng.choice(items)
+
+
+def combos(mods: List[str], k: int) -> List[Tuple[str, ...]]:
+    """eval_mm_protocol.py:41-44 -- all k-subsets of `mods` in itertools.combinations order."""
+    return list(itertools.combinations(mods, k))
+
+
+def build_queries(index: Dict[int, Dict[str, List[dict]]], mode_k: int, rng: random.Random,
+                  main_mod_choice="lexi_first") -> List[dict]:
+    """eval_mm_protocol.py:223-276 -- the MM-k query list of an identity index (host-side combinatorics, row N4).
+
+    For every identity (index order) and every k-subset of the non-RGB modalities it HAS samples for (subsets in
+    combinations order over ALL_NON_RGB, each sorted by name): one query {"pid", "modalities", "samples"} whose
+    `samples` dict holds one drawn sample per modality, main modality first.  The main modality is the
+    alphabetically first one ("lexi_first") or one `rng.choice`; draws happen main first, then the rest in
+    sorted order -- the same number and order of `rng` calls as the reference, so a seeded rng yields the same
+    queries.  Identities with fewer than k populated modalities contribute nothing."""
+    out: List[dict] = []
+    for pid, by_mod in index.items():
+        have = [m for m in ALL_NON_RGB if len(by_mod.get(m, ())) > 0]           # :240 (a missing key is not created)
+        for subset in itertools.combinations(have, mode_k):                     # :243
+            mods = tuple(sorted(subset))                                        # :244
+            main = mods[0] if main_mod_choice == "lexi_first" else rng.choice(mods)   # :247-250
+            picked = {main: pick_one(by_mod[main], rng)}                        # :257
+            for m in mods:                                                      # :261-267 (every m in `have` is populated)
+                if m != main:
+                    picked[m] = pick_one(by_mod[m], rng)
+            out.append({"pid": pid, "modalities": mods, "samples": picked})     # :270-274
+    return out
+
+
+def build_gallery(index: Dict[int, Dict[str, List[dict]]]) -> List[dict]:
+    """eval_mm_protocol.py:280-287 -- every RGB sample of every identity, in index order."""
+    return [s for by_mod in index.values() for s in by_mod.get("rgb", [])]
 
 
 def l2n(x: torch.Tensor) -> torch.Tensor:
@@ -140,25 +182,65 @@ def _exclusions(queries, g_imgid, ignore_same_img: bool, dev) -> Optional[torch.
     return ex.to(dev)
 
 
+def install_gallery(gallery_feats: torch.Tensor, gallery_meta: List[dict]) -> engine.GalleryShard:
+    """The gallery side of rank_and_metrics (eval_mm_protocol.py:390 `g_pids`, :546 `l2n(g_feats)`) installed once
+    on the device: normalised fp32 rows, the fp16 tensor-core copy and the identity index.  Pass the result as
+    `shard=` to rank_and_metrics when several query sets run against the same gallery (run_eval's MM-1..4 loop)."""
+    dev = _dev()
+    g_pids = torch.tensor([m["pid"] for m in gallery_meta], dtype=torch.long)                 # :390
+    return engine.prepare_gallery(gallery_feats.to(dev), g_pids.to(dev))
+
+
 def rank_and_metrics(queries: List[dict], gallery_feats: torch.Tensor, gallery_meta: List[dict], extractor,
                      weight_cfg: Dict[str, float], ignore_same_img=True, cross_camera=False,
-                     mode: str = "fused") -> Dict[str, float]:
+                     mode: str = "fused", shard: Optional[engine.GalleryShard] = None) -> Dict[str, float]:
     """eval_mm_protocol.py:369-469.  `cross_camera` is accepted and ignored like the reference (:375,392).
 
     Returns {"mAP","R@1","R@5","R@10","num_queries"}; queries without a positive are skipped (:430-432),
-    an empty result gives 0.0 metrics (:458-461)."""
+    an empty result gives 0.0 metrics (:458-461).  `shard` (optional, from install_gallery on the same
+    gallery_feats / gallery_meta) skips the per-call gallery installation."""
     dev = _dev()
     if len(queries) == 0 or len(gallery_meta) == 0:
         return {"mAP": 0.0, "R@1": 0.0, "R@5": 0.0, "R@10": 0.0, "num_queries": 0}
-    g_pids = torch.tensor([m["pid"] for m in gallery_meta], dtype=torch.long)                 # :390
     g_imgid = [m.get("img_id", None) for m in gallery_meta]                                   # :391
-    shard = engine.prepare_gallery(gallery_feats.to(dev), g_pids.to(dev))
+    if shard is None:
+        shard = install_gallery(gallery_feats, gallery_meta)
+    elif shard.G_total != len(gallery_meta):
+        raise ValueError("shard was installed for a gallery of %d rows, gallery_meta has %d" % (shard.G_total, len(gallery_meta)))
     q32 = _fuse_batch(queries, extractor, weight_cfg)
     q16 = q32.to(torch.float16)
     q_pid = torch.tensor([int(q["pid"]) for q in queries], dtype=torch.long, device=dev)
     excl = _exclusions(queries, g_imgid, ignore_same_img, dev)
     res = engine.retrieve(shard, q32, q16, q_pid, excl, topk=10, mode=mode)
     return res.metrics
+
+
+def run_eval_features(index: Dict[int, Dict[str, List[dict]]], gallery_feats: torch.Tensor, gallery_meta: List[dict],
+                      extractor, seed: int = 42, weight_cfg: Optional[Dict[str, float]] = None, ignore_same_img=True,
+                      cross_camera=False, mode: str = "fused") -> Dict[str, Dict[str, float]]:
+    """The evaluation loop of run_eval (eval_mm_protocol.py:497-590) from pre-extracted features: the part of
+    run_eval after the model / dataset / gallery cache have been loaded (:508-546 are out of scope: they need the
+    CLIP weights and the image files).  Seeds `random.Random(seed)` (:498), default weights (:503-504), then for
+    k = 1..4 build_queries(index, k, rng, "lexi_first") (:556) and rank_and_metrics (:566-569); MM-k without
+    queries gives zero metrics (:559-562); "AVG(1-4)" is the plain mean over the MM-k that had queries (:576-586).
+    The gallery is installed on the device once for the four passes."""
+    rng = random.Random(seed)                                                                 # :498
+    if weight_cfg is None:
+        weight_cfg = {"ir": 1.0, "cpencil": 1.0, "sketch": 1.0, "text": 1.2}                  # :504
+    shard = install_gallery(gallery_feats, gallery_meta) if len(gallery_meta) else None       # :545-546, once
+    results: Dict[str, Dict[str, float]] = {}
+    for k in (1, 2, 3, 4):                                                                    # :553
+        queries = build_queries(index, mode_k=k, rng=rng, main_mod_choice="lexi_first")       # :556
+        if len(queries) == 0:                                                                 # :559-562
+            results["MM-%d" % k] = {"mAP": 0.0, "R@1": 0.0, "R@5": 0.0, "R@10": 0.0, "num_queries": 0}
+            continue
+        results["MM-%d" % k] = rank_and_metrics(queries, gallery_feats, gallery_meta, extractor, weight_cfg,
+                                                ignore_same_img=ignore_same_img, cross_camera=cross_camera,
+                                                mode=mode, shard=shard)
+    valid = [results["MM-%d" % k] for k in (1, 2, 3, 4) if results["MM-%d" % k]["num_queries"] > 0]   # :576
+    results["AVG(1-4)"] = {key: (sum(r[key] for r in valid) / len(valid) if valid else 0.0)
+                           for key in ("mAP", "R@1", "R@5", "R@10")}                          # :577-586
+    return results
 
 
 def export_submission_csv(queries: List[dict], gallery_feats: torch.Tensor, gallery_meta: List[dict], extractor,

@@ -204,3 +204,51 @@ def make_sdm_batch(seed: int, P: int, K: int, n_modalities: int = 5, dim: int = 
         f = centres[labels] + 1.5 * torch.randn(P * K, dim, generator=gen, device=device)
         feats.append(f.to(dtype))
     return feats, labels
+
+
+# ---------------------------------------------------------------------------------------------
+# An identity index in the reference's own format (eval_mm_protocol.py:58-130 `build_index`):
+# {pid: {"rgb": [sample, ...], "ir": [...], "cpencil": [...], "sketch": [...], "text": [...]}}
+# ---------------------------------------------------------------------------------------------
+def make_protocol_index(seed: int, n_ids: int, rgb_per_id: int = 4, max_per_mod: int = 3, drop_frac: float = 0.25,
+                        dim: int = FEAT_DIM):
+    """-> (index, gallery_feats [G, D] un-normalised, gallery_meta, extractor) for the MM-1..4 protocol loop.
+
+    Every identity has `rgb_per_id` gallery images and 0..max_per_mod samples of each non-RGB modality (a modality
+    is absent with probability drop_frac, so identities contribute different numbers of MM-k combinations, some
+    none at all).  A non-RGB sample shares its img_id with one of the identity's RGB images with probability 1/3
+    (the same-image rule of rank_and_metrics, :408-418).  Features follow the recipe at the top of this file."""
+    import random as _random
+    rnd = _random.Random(seed)
+    gen = torch.Generator().manual_seed(seed)
+    centres = torch.randn(n_ids, dim, generator=gen)
+    bias = {m: BIAS_SCALE * torch.randn(dim, generator=gen) for m in ("rgb",) + MODALITIES}
+    index: Dict[int, Dict[str, List[dict]]] = {}
+    table: Dict[str, torch.Tensor] = {}
+    gallery_rows, gallery_meta = [], []
+    for i in range(n_ids):
+        pid = 1000 + 3 * i                       # non-contiguous person ids
+        by_mod: Dict[str, List[dict]] = {"rgb": []}
+        for j in range(rgb_per_id):
+            img_id = "p%d_rgb%d" % (pid, j)
+            f = centres[i] + bias["rgb"] + SIGMA_RGB * torch.randn(dim, generator=gen)
+            table["rgb/" + img_id] = f
+            by_mod["rgb"].append({"img_path": "rgb/" + img_id, "pid": pid, "img_id": img_id, "camid": None})
+            gallery_rows.append(f)
+            gallery_meta.append({"img_id": img_id, "pid": pid, "camid": None})
+        for m in MODALITIES:
+            n = 0 if rnd.random() < drop_frac else rnd.randint(1, max_per_mod)
+            if n == 0:
+                if rnd.random() < 0.5:
+                    by_mod[m] = []               # present but empty (build_queries must treat it like a missing key)
+                continue
+            by_mod[m] = []
+            for j in range(n):
+                own = "p%d_%s%d" % (pid, m, j)
+                img_id = "p%d_rgb%d" % (pid, rnd.randrange(rgb_per_id)) if rnd.random() < 1.0 / 3 else own
+                key = "%s/%s" % (m, own)
+                table[key] = centres[i] + bias[m] + SIGMA[m] * torch.randn(dim, generator=gen)
+                by_mod[m].append({"text": key, "pid": pid, "img_id": img_id} if m == "text" else
+                                 {"img_path": key, "pid": pid, "img_id": img_id, "camid": None})
+        index[pid] = by_mod
+    return index, torch.stack(gallery_rows), gallery_meta, TensorExtractor(table)

@@ -1,0 +1,155 @@
+"""Host side of the evaluation protocol (row N4): `build_queries` / `build_gallery` and the MM-1..4 loop of
+`run_eval`, against fixtures generated from the UNMODIFIED reference (oracle/make_golden_protocol.py ->
+tests/golden/protocol.json) and against the live reference when it is mounted.
+
+The list-of-dicts plumbing of the drop-in module (`_fuse_batch`, `_exclusions`, `rank_and_metrics`,
+`run_eval_features`) is exercised here WITHOUT a GPU by swapping the device engine for an oracle-backed stand-in:
+what is under test is the host logic (query order, modality ids, weights, same-image exclusion lists, skipped
+MM-k, the average), not the kernels -- those are compared with the same fixture in the -m gpu tests."""
+import json
+import os
+import random
+import types
+
+import pytest
+import torch
+
+from oracle import ref_loader
+from oracle import retrieval as orc
+from oracle.make_golden_protocol import query_digest
+from prcv2025reid_b200 import eval_mm_protocol as emp
+from prcv2025reid_b200 import synth
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "protocol.json"), encoding="utf-8"))
+
+
+@pytest.fixture(scope="module")
+def world():
+    index, g_feats, g_meta, ext = synth.make_protocol_index(**GOLDEN["index_args"])
+    cs = float(g_feats.double().abs().sum()) + float(sum(float(v.double().abs().sum()) for v in ext.table.values()))
+    if abs(cs - GOLDEN["checksum"]) > 1e-6 * abs(cs):
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    return index, g_feats, g_meta, ext
+
+
+@pytest.mark.parametrize("mode", ["lexi_first", "random"])
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_build_queries_matches_reference_golden(world, mode, k):
+    index = world[0]
+    qs = emp.build_queries(index, mode_k=k, rng=random.Random(1000 + k), main_mod_choice=mode)
+    want = GOLDEN["build_queries"]["%s/k%d" % (mode, k)]
+    sha, rows = query_digest(qs)
+    assert len(qs) == want["n"]
+    assert rows[:3] == want["first"]
+    assert sha == want["sha256"]
+    for q in qs:                                   # shape of a query (eval_mm_protocol.py:270-274)
+        assert isinstance(q["modalities"], tuple) and list(q["modalities"]) == sorted(q["modalities"])
+        assert set(q["samples"]) == set(q["modalities"]) and len(q["modalities"]) == k
+        if mode == "lexi_first":
+            assert next(iter(q["samples"])) == q["modalities"][0]       # main modality first
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_build_queries_matches_live_reference():
+    from collections import defaultdict
+    ref = ref_loader.load_reference_eval()
+    index, _, _, _ = synth.make_protocol_index(seed=77, n_ids=25, max_per_mod=4, drop_frac=0.4)
+    dd = defaultdict(lambda: defaultdict(list))     # the reference's own container type (build_index :71)
+    for pid, by in index.items():
+        for m, v in by.items():
+            dd[pid][m].extend(v)
+    for container in (index, dd):
+        for mode in ("lexi_first", "random"):
+            for k in (1, 2, 3, 4, 5):
+                a = emp.build_queries(container, k, random.Random(3), mode)
+                b = ref.build_queries(container, k, random.Random(3), mode)
+                assert a == b and [list(x["samples"]) for x in a] == [list(x["samples"]) for x in b]
+    assert {m for by in dd.values() for m in by} <= {"rgb", "ir", "cpencil", "sketch", "text"}   # no key was created
+    assert emp.build_gallery(index) == ref.build_gallery(index)
+    assert emp.combos(list("abcd"), 3) == ref.combos(list("abcd"), 3)
+    assert emp.pick_one([1, 2, 3], random.Random(9)) == ref.pick_one([1, 2, 3], random.Random(9))
+
+
+def test_build_queries_edge_cases():
+    assert emp.build_queries({}, 2, random.Random(0)) == []
+    idx = {5: {"rgb": [{"img_id": "a"}], "ir": [], "text": [{"text": "t", "img_id": "x"}]}}
+    assert emp.build_queries(idx, 2, random.Random(0)) == []                        # only one populated modality
+    one = emp.build_queries(idx, 1, random.Random(0))
+    assert [q["modalities"] for q in one] == [("text",)] and one[0]["pid"] == 5
+    assert emp.build_gallery({1: {"ir": [{}]}, 2: {"rgb": [{"img_id": "r"}]}}) == [{"img_id": "r"}]
+
+
+class _OracleEngine:
+    """Stand-in for prcv2025reid_b200.engine with the oracle's CPU arithmetic (TEST ONLY)."""
+    GalleryShard = object
+
+    def __init__(self):
+        self.installs = 0
+
+    def l2norm_rows(self, x, want_f16=False, eps=1e-12):
+        return orc.l2n(x.float()), None
+
+    def fuse_queries(self, rows, mid, w):
+        Q, k, D = rows.shape
+        f = orc.l2n(rows.float())
+        acc = torch.zeros(Q, D)
+        for j in range(k):                                    # slots with mod_id < 0 are skipped (reid_b200.h K2)
+            use = (mid[:, j] >= 0)
+            wj = torch.where(use, w[mid[:, j].clamp(min=0).long()], torch.zeros(Q))
+            acc = acc + f[:, j] * wj[:, None] if j else f[:, j] * wj[:, None]
+        return orc.l2n(acc), None
+
+    def prepare_gallery(self, gallery, g_pid_all, g_offset=0):
+        self.installs += 1
+        return types.SimpleNamespace(g_f32=orc.l2n(gallery.float()), g_pid=g_pid_all, G_total=int(g_pid_all.numel()))
+
+    def retrieve(self, shard, q32, q16, q_pid, excl, topk=10, mode="fused"):
+        return types.SimpleNamespace(metrics=orc.rank_and_metrics_loop(q32, shard.g_f32, q_pid, shard.g_pid, excl))
+
+
+@pytest.fixture()
+def cpu_engine(monkeypatch):
+    eng = _OracleEngine()
+    monkeypatch.setattr(emp, "engine", eng)
+    monkeypatch.setattr(emp, "_dev", lambda: torch.device("cpu"))
+    return eng
+
+
+@pytest.mark.parametrize("mask", [True, False])
+def test_protocol_loop_host_logic_matches_reference_golden(world, cpu_engine, mask):
+    index, g_feats, g_meta, ext = world
+    want = GOLDEN["run_eval/ignore_same_img=%s" % mask]["results"]
+    got = emp.run_eval_features(index, g_feats, g_meta, ext, seed=GOLDEN["run_seed"], ignore_same_img=mask)
+    assert cpu_engine.installs == 1                            # the gallery is installed once for the four passes
+    assert list(got) == ["MM-1", "MM-2", "MM-3", "MM-4", "AVG(1-4)"]
+    for name, w in want.items():
+        assert got[name].get("num_queries") == w.get("num_queries"), name
+        for key in ("mAP", "R@1", "R@5", "R@10"):
+            assert got[name][key] == pytest.approx(w[key], abs=1e-12), (name, key)
+
+
+def test_protocol_loop_skips_empty_mm_k(world, cpu_engine):
+    index, g_feats, g_meta, ext = world
+    sparse = {pid: {m: v for m, v in by.items() if m != "text"} for pid, by in index.items()}
+    want = GOLDEN["run_eval/no_text"]["results"]
+    got = emp.run_eval_features(sparse, g_feats, g_meta, ext, seed=GOLDEN["run_seed"])
+    assert got["MM-4"] == {"mAP": 0.0, "R@1": 0.0, "R@5": 0.0, "R@10": 0.0, "num_queries": 0} == want["MM-4"]
+    for key in ("mAP", "R@1", "R@5", "R@10"):                  # the average leaves MM-4 out (:576)
+        assert got["AVG(1-4)"][key] == pytest.approx(want["AVG(1-4)"][key], abs=1e-12)
+    empty = emp.run_eval_features({}, g_feats, g_meta, ext)
+    assert all(v == 0.0 for v in empty["AVG(1-4)"].values()) and empty["MM-1"]["num_queries"] == 0
+
+
+def test_rank_and_metrics_rejects_a_shard_of_another_gallery(world, cpu_engine):
+    index, g_feats, g_meta, ext = world
+    shard = emp.install_gallery(g_feats[:8], g_meta[:8])
+    qs = emp.build_queries(index, 2, random.Random(0))
+    with pytest.raises(ValueError):
+        emp.rank_and_metrics(qs, g_feats, g_meta, ext, dict(synth.DEFAULT_WEIGHTS), shard=shard)
+
+
+def test_unknown_modality_raises_like_the_reference(world, cpu_engine):
+    _, g_feats, g_meta, ext = world
+    q = {"pid": 1000, "modalities": ("thermal",), "samples": {"thermal": {"img_path": "x", "img_id": "y"}}}
+    with pytest.raises(ValueError):                            # eval_mm_protocol.py:351
+        emp.extract_query_feat(q, ext, {})

@@ -1,0 +1,54 @@
+"""The MM-1..4 protocol loop (run_eval :553-586, row N4) through the CUDA path against the fixture generated from
+the unmodified reference (tests/golden/protocol.json).  Kept in its own file, collected after the kernel tests."""
+import json
+import os
+import random
+
+import pytest
+import torch
+
+from prcv2025reid_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "protocol.json"), encoding="utf-8"))
+
+
+@pytest.fixture(scope="module")
+def world():
+    index, g_feats, g_meta, ext = synth.make_protocol_index(**GOLDEN["index_args"])
+    cs = float(g_feats.double().abs().sum()) + float(sum(float(v.double().abs().sum()) for v in ext.table.values()))
+    if abs(cs - GOLDEN["checksum"]) > 1e-6 * abs(cs):
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    return index, g_feats, g_meta, ext
+
+
+def _check(got, want):
+    for name, w in want.items():
+        assert got[name].get("num_queries") == w.get("num_queries"), name
+        assert abs(got[name]["mAP"] - w["mAP"]) <= 1e-4, (name, got[name], w)        # north star: mAP within 1e-4
+        if name == "AVG(1-4)":
+            for key in ("R@1", "R@5", "R@10"):
+                assert abs(got[name][key] - w[key]) <= 1e-12, (name, key)
+        else:
+            assert [got[name][k] for k in ("R@1", "R@5", "R@10")] == [w[k] for k in ("R@1", "R@5", "R@10")], (name, got[name], w)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fused"])
+@pytest.mark.parametrize("mask", [True, False])
+def test_protocol_loop_matches_reference_golden(world, mode, mask):
+    from prcv2025reid_b200 import eval_mm_protocol as emp
+    index, g_feats, g_meta, ext = world
+    got = emp.run_eval_features(index, g_feats, g_meta, ext, seed=GOLDEN["run_seed"], ignore_same_img=mask, mode=mode)
+    _check(got, GOLDEN["run_eval/ignore_same_img=%s" % mask]["results"])
+
+
+def test_installed_gallery_is_reusable_across_query_sets(world):
+    from prcv2025reid_b200 import eval_mm_protocol as emp
+    index, g_feats, g_meta, ext = world
+    w = dict(synth.DEFAULT_WEIGHTS)
+    shard = emp.install_gallery(g_feats, g_meta)
+    for k in (3, 1, 4, 2):                                   # growing and shrinking query sets over one shard's scratch
+        qs = emp.build_queries(index, k, random.Random(k))
+        a = emp.rank_and_metrics(qs, g_feats, g_meta, ext, w, shard=shard)
+        b = emp.rank_and_metrics(qs, g_feats, g_meta, ext, w)
+        assert a == b, (k, a, b)
