@@ -77,9 +77,11 @@ def quiet(fn, *a, **kw):
 
 
 def load_reference_train_eval():
-    """The UNMODIFIED `compute_map`, `compute_cmc` and `_reid_map` of train.py (:101-138, :451-479).  train.py cannot
-    be imported (dataset / model / CLIP imports at module level), so the three function definitions are cut out of
-    its source with `ast` and executed as they stand in a namespace that holds what they use (torch, F, np)."""
+    """The UNMODIFIED `compute_map`, `compute_cmc`, `_reid_map`, `_flatten_loaders`, `evaluate_one_query` and
+    `validate_competition_style` of train.py (:101-138, :402-424, :451-631).  train.py cannot be imported (dataset /
+    model / CLIP imports at module level), so the function definitions are cut out of its source with `ast` and
+    executed as they stand in a namespace that holds what they use (torch, F, np, os, hashlib, pickle, DataLoader,
+    Subset); `_extract_feats_and_ids` -- the model forward -- is the only stub."""
     if "train_eval" in _cache:
         return _cache["train_eval"]
     import ast
@@ -91,9 +93,22 @@ def load_reference_train_eval():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
     src = open(path, encoding="utf-8").read()
     tree = ast.parse(src)
-    ns = {"torch": torch, "F": F, "np": np}
+    import hashlib
+    import pickle
+    from torch.utils.data import DataLoader, Subset
+
+    def _extract_feats_and_ids(model, loader, device):
+        """STUB of train.py:428-449 (the one step that needs the model): serves the pre-extracted (feature, id) items the
+        loader's dataset holds, for the unmodified evaluate_one_query / validate_competition_style below."""
+        ds = loader.dataset
+        items = [ds[i] for i in range(len(ds))]
+        return torch.stack([f for f, _ in items]), torch.stack([torch.as_tensor(i) for _, i in items])
+
+    ns = {"torch": torch, "F": F, "np": np, "os": os, "hashlib": hashlib, "pickle": pickle, "DataLoader": DataLoader,
+          "Subset": Subset, "_extract_feats_and_ids": _extract_feats_and_ids}
+    wanted = ("compute_map", "compute_cmc", "_reid_map", "_flatten_loaders", "evaluate_one_query", "validate_competition_style")
     for node in tree.body:
-        if isinstance(node, ast.FunctionDef) and node.name in ("compute_map", "compute_cmc", "_reid_map"):
+        if isinstance(node, ast.FunctionDef) and node.name in wanted:
             exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
     _cache["train_eval"] = ns
     return ns

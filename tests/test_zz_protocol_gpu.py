@@ -53,3 +53,32 @@ def test_installed_gallery_is_reusable_across_query_sets(world):
         b = emp.rank_and_metrics(qs, g_feats, g_meta, ext, w)
         assert {x: a[x] for x in a if x != "mAP"} == {x: b[x] for x in b if x != "mAP"}, (k, a, b)
         assert abs(a["mAP"] - b["mAP"]) <= 1e-12, (k, a, b)
+
+
+# ---------------------------------------------------------------- train-time evaluation loop (row N2)
+VGOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_validate.json"), encoding="utf-8"))
+
+
+@pytest.mark.parametrize("case", ["default", "cpencil_name", "sampled", "include_all", "no_quad", "first_unmatched"])
+def test_validate_competition_style_matches_reference_golden(case):
+    import types
+    from oracle.make_golden_validate import ARGS, CASES, make_world, nest
+    from prcv2025reid_b200 import train_eval as te
+    kw = dict(CASES[case])
+    g_feat, g_id, sets = make_world(**ARGS, rename=kw.pop("rename", None), first_unmatched=kw.pop("first_unmatched", False))
+    if case == "default":
+        cs = float(g_feat.double().abs().sum()) + float(sum(float(v[0].double().abs().sum()) for v in sets.values()))
+        if abs(cs - VGOLD["checksum"]) > 1e-6 * abs(cs):
+            pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    cfg = types.SimpleNamespace(eval_include_patterns=kw["include"]) if "include" in kw else None
+    if "torch_seed" in kw:
+        torch.manual_seed(kw["torch_seed"])
+    got = te.validate_competition_style_features(g_feat, g_id, nest(sets), sample_ratio=kw.get("sample_ratio", 1.0), cfg=cfg)
+    want = VGOLD["cases"][case]
+    assert list(got["detail"]) == list(want["detail"])
+    for name, w in want["detail"].items():
+        assert abs(got["detail"][name]["mAP"] - w["mAP"]) <= 1e-4, (name, got["detail"][name], w)
+        assert abs(got["detail"][name]["Top1"] - w["Top1"]) <= 1e-12, (name, got["detail"][name], w)
+    for key in ("map_single", "map_quad", "map_avg2"):
+        assert abs(got[key] - want[key]) <= 1e-4, (key, got[key], want[key])
+    assert (got["cmc1"], got["cmc5"], got["cmc10"]) == (want["cmc1"], want["cmc5"], want["cmc10"])
