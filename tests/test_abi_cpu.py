@@ -135,3 +135,47 @@ def test_error_strings_cover_every_code(lib):
     texts = {c: lib.reid_strerror(c).decode() for c in (0, -1, -2, -3, -4, -99)}
     assert all(texts.values())
     assert len({texts[c] for c in (0, -1, -2, -3, -4)}) == 5     # distinct messages for the declared codes
+
+
+def test_entry_points_reject_invalid_arguments_before_touching_the_device():
+    """Error behaviour of the C ABI (reid_b200.h: "return 0 = OK, negative = REID_E_*; never throws"): null pointers and
+    unsupported sizes are refused with REID_E_INVALID by the argument checks, i.e. before any CUDA call -- which is
+    why this runs on a machine without a GPU (no kernel is launched by any of these calls)."""
+    from prcv2025reid_b200 import _cabi
+    L = _cabi.lib()
+    N = None
+    one = ctypes.c_void_p(0x1000)                  # a non-null (never dereferenced) pointer
+    bad = {
+        "l2norm null x": L.reid_l2norm_rows(N, one, N, 10, 512, 1e-12, N),
+        "l2norm no output": L.reid_l2norm_rows(one, N, N, 10, 512, 1e-12, N),
+        "l2norm negative rows": L.reid_l2norm_rows(one, one, N, -1, 512, 1e-12, N),
+        "fuse null feats": L.reid_mm_fuse_normalize(N, one, one, 4, one, one, 10, 4, 512, N),
+        "fuse k = 0": L.reid_mm_fuse_normalize(one, one, one, 4, one, one, 10, 0, 512, N),
+        "sim_gemm null": L.reid_sim_gemm(N, N, N, 1, 1, 512, 1, N),
+        "sim_gemm ldS < G": L.reid_sim_gemm(one, one, one, 4, 100, 512, 50, N),
+        "pid_index null": L.reid_pid_index_build(N, 10, N, N, N, N, 0, N),
+        "pid_lookup null": L.reid_pid_lookup(N, 10, N, 1, N, N, N),
+        "pos_scores null": L.reid_pos_scores(N, N, N, N, N, N, 0, 1, 1, 0, 512, 4, N, N),
+        "pos_scores excl missing": L.reid_pos_scores(one, one, one, one, one, N, 2, 1, 1, 0, 512, 4, one, N),
+        "pos_sort null": L.reid_pos_sort(N, N, 1, 4, N),
+        "fused null": L.reid_retrieve_fused(N, N, N, N, N, 0, N, N, 1, 1, 0, 512, 4, 1, 1, 64, N, N, N, N, N, N, 0, N),
+        "exact null": L.reid_retrieve_exact(N, N, N, N, N, 0, N, N, N, 0, 1, 1, 0, 512, 4, 1, 64, N, N, N, N, N),
+        "rescore null": L.reid_rescore_topk(N, N, N, N, N, N, N, N, N, N, N, 0, 1, 1, 0, 512, 4, 1, 64, 10, 0.0, N, N, N, N, N),
+        "merge null": L.reid_merge_topk(N, N, 1, 1, 10, 10, N, N, N),
+        "metrics null": L.reid_metrics_reduce(N, N, 1, 4, N, N, N),
+        "label_metrics null": L.reid_topk_label_metrics(N, N, N, 1, 10, 10, N, N, N),
+        "label_metrics k > list": L.reid_topk_label_metrics(one, one, one, 1, 10, 11, one, one, N),
+        "sdm_fwd null": L.reid_sdm_fwd(N, 1, 0, 512, 0.2, 1e-8, N),
+        "sdm_bwd null": L.reid_sdm_bwd(N, 1, 0, 512, 0.2, 1e-8, N),
+        "sdm_step null": L.reid_sdm_step(N, 1, 0, 512, 0.2, 1e-8, N),
+    }
+    pairs = (_cabi.SdmPair * 1)()
+    pairs[0].qry = pairs[0].gal = pairs[0].y = pairs[0].loss = pairs[0].status = pairs[0].saved = 0x1000
+    pairs[0].N, pairs[0].M = 8, 8
+    bad["sdm_fwd too many pairs"] = L.reid_sdm_fwd(pairs, _cabi.SDM_MAX_PAIRS + 1, 0, 512, 0.2, 1e-8, N)
+    bad["sdm_fwd zero pairs"] = L.reid_sdm_fwd(pairs, 0, 0, 512, 0.2, 1e-8, N)
+    assert L.reid_sdm_fwd(pairs, 1, 7, 512, 0.2, 1e-8, N) == -4          # unknown dtype: REID_E_UNSUPPORTED
+    pairs[0].N = 0
+    bad["sdm_fwd empty pair"] = L.reid_sdm_fwd(pairs, 1, 0, 512, 0.2, 1e-8, N)
+    wrong = {k: v for k, v in bad.items() if v != -1}
+    assert not wrong, wrong
