@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the hot path (see BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3b|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3a|c3b|c1]
 
 Metric: queries/sec for MM-4 retrieval + evaluation, 512-d features, 100k queries x 1M gallery
 (BASELINE config C4).  One "step" = one pass of the hot path over the whole
@@ -32,6 +32,7 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # name: (seed, n_ids, gal_per_id, k, queries_per_id)   SURVEY.md section 8d
     "c4": (1005, 25000, 40, 4, 4),      # MM-4, Q=100k, G=1M
+    "c3a": (1003, 5000, 20, 3, 4),      # MM-3, Q=20k,  G=100k
     "c3b": (1004, 5000, 20, 4, 4),      # MM-4, Q=20k,  G=100k
     "c1": (1001, 500, 20, 2, 6),        # MM-2, Q=3k,   G=10k
 }
