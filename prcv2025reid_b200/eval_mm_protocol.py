@@ -66,6 +66,28 @@ def build_gallery(index: Dict[int, Dict[str, List[dict]]]) -> List[dict]:
     return [s for by_mod in index.values() for s in by_mod.get("rgb", [])]
 
 
+def extract_gallery_feats(gallery: List[dict], extractor, cache_dir: str):
+    """eval_mm_protocol.py:291-325 -- the gallery feature cache: `rgb_feats.npy` (fp32 [G, D], rows L2-normalised) +
+    `rgb_meta.json` ([{"img_id", "pid", "camid"}]) under cache_dir.  A complete cache is returned as it is (:296-302,
+    no device involved); otherwise every item is encoded with `extractor.encode_rgb(item["img_path"])` (the model
+    forward, not part of this library), all rows are normalised in ONE K1 pass instead of one `l2n` call per image
+    (:310), and both files are written in the reference's format.  -> (feats fp32 CPU tensor [G, D], meta)."""
+    import os
+    import numpy as np
+    from . import gallery_store
+    feat_path = os.path.join(cache_dir, gallery_store.FEATS)
+    meta_path = os.path.join(cache_dir, gallery_store.META)
+    os.makedirs(cache_dir, exist_ok=True)                                                     # :293
+    if os.path.exists(feat_path) and os.path.exists(meta_path):                               # :297
+        return torch.from_numpy(np.load(feat_path)).float(), gallery_store.load_meta(cache_dir)
+    raw = torch.stack([extractor.encode_rgb(item["img_path"]).float().view(-1) for item in gallery])   # :309, :310 (.float().view)
+    feats = l2n(raw).cpu()                                                                    # :310, batched
+    meta = [{"img_id": item.get("img_id", None), "pid": int(item["pid"]), "camid": item.get("camid", None)}
+            for item in gallery]                                                              # :314-318
+    gallery_store.save_cache(cache_dir, feats, meta)                                          # :321-323
+    return feats.float(), meta
+
+
 def l2n(x: torch.Tensor) -> torch.Tensor:
     """eval_mm_protocol.py:46-48 -- F.normalize(x, dim=-1) (p=2, eps=1e-12)."""
     src = x.device

@@ -153,3 +153,32 @@ def test_unknown_modality_raises_like_the_reference(world, cpu_engine):
     q = {"pid": 1000, "modalities": ("thermal",), "samples": {"thermal": {"img_path": "x", "img_id": "y"}}}
     with pytest.raises(ValueError):                            # eval_mm_protocol.py:351
         emp.extract_query_feat(q, ext, {})
+
+
+def test_extract_gallery_feats_cache_hit_and_miss(world, cpu_engine, tmp_path):
+    """eval_mm_protocol.py:291-325: a complete cache is returned untouched; a miss encodes, normalises, writes both
+    files in the reference's format -- which the unmodified reference then reads back as a cache hit."""
+    import numpy as np
+    index, g_feats, g_meta, ext = world
+    gallery = emp.build_gallery(index)
+    calls = []
+    orig = ext.encode_rgb
+    ext.encode_rgb = lambda key: (calls.append(key), orig(key))[1]
+    try:
+        feats, meta = emp.extract_gallery_feats(gallery, ext, str(tmp_path / "c"))
+        assert len(calls) == len(gallery) and meta == g_meta
+        assert torch.equal(feats, orc.l2n(g_feats))                     # (stand-in engine: the oracle's own arithmetic)
+        assert sorted(os.listdir(str(tmp_path / "c"))) == ["rgb_feats.npy", "rgb_meta.json"]
+        feats2, meta2 = emp.extract_gallery_feats(gallery, ext, str(tmp_path / "c"))    # hit: no encoder call
+        assert len(calls) == len(gallery) and torch.equal(feats2, feats) and meta2 == meta
+        assert feats2.dtype == torch.float32 and np.load(str(tmp_path / "c" / "rgb_feats.npy")).dtype == np.float32
+        if ref_loader.reference_available():
+            ref = ref_loader.load_reference_eval()
+            rf, rm = ref_loader.quiet(ref.extract_gallery_feats, gallery, ext, str(tmp_path / "c"))   # reads OUR cache
+            assert len(calls) == len(gallery) and torch.equal(rf, feats) and rm == meta
+            rf2, rm2 = ref_loader.quiet(ref.extract_gallery_feats, gallery, ext, str(tmp_path / "r"))  # writes ITS cache
+            f3, m3 = emp.extract_gallery_feats(gallery, ext, str(tmp_path / "r"))                     # we read it
+            assert torch.equal(f3, rf2) and m3 == rm2 == meta
+            assert torch.equal(rf2, feats)                              # per-image l2n == batched l2n, bit for bit
+    finally:
+        ext.encode_rgb = orig

@@ -82,3 +82,18 @@ def test_validate_competition_style_matches_reference_golden(case):
     for key in ("map_single", "map_quad", "map_avg2"):
         assert abs(got[key] - want[key]) <= 1e-4, (key, got[key], want[key])
     assert (got["cmc1"], got["cmc5"], got["cmc10"]) == (want["cmc1"], want["cmc5"], want["cmc10"])
+
+
+def test_extract_gallery_feats_writes_the_reference_cache(world, tmp_path):
+    """eval_mm_protocol.py:291-325 on the CUDA path: one K1 pass over all gallery rows, cache files in the reference's format."""
+    import numpy as np
+    from oracle import retrieval as orc
+    from prcv2025reid_b200 import eval_mm_protocol as emp
+    index, g_feats, g_meta, ext = world
+    gallery = emp.build_gallery(index)
+    feats, meta = emp.extract_gallery_feats(gallery, ext, str(tmp_path / "cache"))
+    assert meta == g_meta and feats.device.type == "cpu" and feats.dtype == torch.float32
+    assert (feats - orc.l2n(g_feats)).abs().max() <= 4e-7                      # K1 bar (DESIGN.md section 2)
+    assert np.array_equal(np.load(str(tmp_path / "cache" / "rgb_feats.npy")), feats.numpy())
+    feats2, meta2 = emp.extract_gallery_feats(gallery, ext, str(tmp_path / "cache"))     # cache hit
+    assert torch.equal(feats2, feats) and meta2 == meta
