@@ -1,0 +1,140 @@
+"""CPU model of the COUNTING RULE of the fused retrieval kernel (csrc/retrieve_fused.cu).  TEST INFRASTRUCTURE ONLY.
+
+The reference computes AP from a full argsort (tools/eval_mm_protocol.py:423, :444-455).  The fused kernel replaces
+the sort by counts -- rank_j = 1 + #{valid non-positive rows scoring above positive j} + j -- and, for a query's DEEP
+positives only, estimates that count from a fixed 1/32 row sample (DESIGN.md section 4.1 "Deep-rank sampling").  This
+file restates that rule in numpy so that its error against the exact oracle can be measured without a GPU, and so
+that a change of its parameters (calibration rows, sample width, exact-count budget) can be assessed before it is
+built.  It follows the kernel, not the reference:
+
+  scores             fp32 accumulation of fp16-rounded operands                       retrieve_fused.cu kernel comment (kind::f16 MMA)
+  thresholds t_j     the positives' EXACT fp32 scores, sorted descending              reid_pos_scores / reid_pos_sort
+  calibration        strided sample of CALIB_ROWS rows, every threshold exact         reid_retrieve_fused host code (`sample_deep`)
+  exact / deep split calib_split_kernel: threshold j is exact while the estimated     retrieve_fused.cu:237-255
+                     in-chunk rank of thresholds 0..j stays <= limit,
+                     limit = max(32 * SAMPLE_W / total_chunks, 8 * scale)
+  main pass          ordinary rows see thresholds [0, n_exact); rows with             epi_drain32, retrieve_fused.cu:159-176
+                     local_row % SAMPLE_W == 5 see all of them and weigh SAMPLE_W
+                     in the deep buckets; positives of the query and masked rows
+                     are skipped; rows >= G_local are no rows
+  pos_above[j]       prefix sum of the bucket histogram                               hist_to_above_kernel
+
+Not modelled: the candidate / re-scoring side (top-k and CMC are exact by construction there, and positives inside
+the re-scored top list get their exact rank from it, which only removes error).
+"""
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+SAMPLE_W = 32        # REID_SAMPLE_W
+CALIB_ROWS = 2048    # REID_CALIB_ROWS
+SAMPLE_PHASE = 5     # rows with (row % SAMPLE_W) == 5
+
+
+def positive_thresholds(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, g_pid: torch.Tensor,
+                        excl: Optional[torch.Tensor] = None):
+    """reid_pos_scores + reid_pos_sort over the WHOLE gallery (after the all-reduce MAX of sharding.exchange_pos_scores):
+    -> (thr [Q, Pmax] fp32 exact scores of the unmasked positives, sorted descending, -inf pad; n_pos [Q])."""
+    Q, G = q_f32.shape[0], g_f32.shape[0]
+    S32 = (q_f32 @ g_f32.T).numpy()
+    gp, qp = g_pid.numpy(), q_pid.numpy()
+    is_pos = gp[None, :] == qp[:, None]
+    if excl is not None:
+        ex = excl.numpy()
+        for q in range(Q):
+            is_pos[q, ex[q][ex[q] >= 0]] = False
+    n_pos = is_pos.sum(1)
+    thr = np.full((Q, max(1, int(n_pos.max()))), -np.inf, dtype=np.float32)
+    for q in range(Q):
+        thr[q, :n_pos[q]] = np.sort(S32[q, is_pos[q]])[::-1]
+    return thr, n_pos
+
+
+def fused_counts(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, g_pid: torch.Tensor,
+                 excl: Optional[torch.Tensor] = None, n_chunks: int = 1, total_chunks: int = 0, exact_all: bool = False,
+                 sample_w: int = SAMPLE_W, calib_rows: int = CALIB_ROWS, thr: Optional[np.ndarray] = None,
+                 n_pos: Optional[np.ndarray] = None, g_offset: int = 0) -> Dict[str, np.ndarray]:
+    """One rank's reid_retrieve_fused -> {"pos_above" [Q, Pmax] int64 (modelled LOCAL counts, additive over ranks),
+    "n_pos" [Q], "n_exact" [Q], "thr" [Q, Pmax]}.
+
+    q_f32 [Q, D] fused + normalised queries; g_f32 [G_local, D] / g_pid [G_local] this rank's normalised gallery rows,
+    which are rows [g_offset, g_offset + G_local) of the whole gallery; excl [Q, E] GLOBAL gallery rows masked per query
+    (-1 pad); thr / n_pos: the gallery-wide positive thresholds (positive_thresholds; default: computed from this shard,
+    i.e. a one-rank job).  exact_all = the kernel with REID_FUSED_DEBUG=64 (no deep sampling)."""
+    Q, G = q_f32.shape[0], g_f32.shape[0]
+    S16 = (q_f32.half().float() @ g_f32.half().float().T).numpy()          # what the tensor cores score with
+    gp, qp = g_pid.numpy(), q_pid.numpy()
+    masked = np.zeros((Q, G), dtype=bool)
+    if excl is not None:
+        ex = excl.numpy().astype(np.int64) - g_offset
+        for q in range(Q):
+            e = ex[q][(excl.numpy()[q] >= 0) & (ex[q] >= 0) & (ex[q] < G)]
+            masked[q, e] = True
+    if thr is None:
+        thr, n_pos = positive_thresholds(q_f32, g_f32, q_pid, g_pid,
+                                         None if excl is None else torch.from_numpy(np.where(excl.numpy() >= 0, excl.numpy() - g_offset, -1)))
+    Pmax = thr.shape[1]
+    rows_per_chunk = -(-G // n_chunks)
+    rows_per_chunk = -(-rows_per_chunk // 256) * 256                       # tiles of 256 rows (pair layout)
+    sample_deep = (G >= 16 * calib_rows) and not exact_all
+    tc_all = max(total_chunks, n_chunks)
+    pos_above = np.zeros((Q, Pmax), dtype=np.int64)
+    n_exact = np.zeros(Q, dtype=np.int64)
+    countable = ~masked & (gp[None, :] != qp[:, None])                      # neither masked nor a positive of the query
+    if sample_deep:
+        stride = G // calib_rows
+        cal_rows = np.arange(calib_rows) * stride
+        scale = rows_per_chunk / calib_rows
+        limit = max(32.0 * sample_w / tc_all, 8.0 * scale)
+    rows = np.arange(G)
+    sampled = (rows % sample_w) == SAMPLE_PHASE                            # chunk starts are multiples of 256: local row % W
+    for q in range(Q):
+        npq = int(n_pos[q])
+        if npq == 0:
+            continue
+        t = thr[q, :npq]
+        ne = npq
+        if sample_deep:
+            # calibration pass: bucket histogram of the strided sample, every threshold exact
+            cs = S16[q, cal_rows][countable[q, cal_rows]]
+            acc = np.array([(cs > tj).sum() for tj in t])                  # prefix sums over buckets <= j
+            ok = acc.astype(np.float32) * np.float32(scale) <= np.float32(limit)
+            ne = npq if ok.all() else int(np.argmin(ok))                  # the first threshold over the limit closes the prefix
+        n_exact[q] = ne
+        s, use = S16[q], countable[q]
+        # (the chunk structure does not change the counts: every chunk of a rank uses the same n_exact and the same
+        #  row sample, and counts are additive over chunks)
+        top = int((use & (s > t[ne - 1])).sum()) if ne > 0 else 0
+        for j in range(npq):
+            if j < ne:
+                pos_above[q, j] = int((use & (s > t[j])).sum())            # exact on every row
+            else:
+                # rows above the lowest exact threshold are counted exactly (buckets < n_exact), the rest of the way
+                # down to t_j on the row sample with weight sample_w
+                lo_mask = use & sampled & (s > t[j])
+                if ne > 0:
+                    lo_mask &= ~(s > t[ne - 1])
+                pos_above[q, j] = top + sample_w * int(lo_mask.sum())
+    return {"pos_above": pos_above, "n_pos": n_pos, "n_exact": n_exact, "thr": thr}
+
+
+def metrics_from_counts(pos_above: np.ndarray, n_pos: np.ndarray) -> Dict[str, object]:
+    """reid_metrics_reduce (rank.cu metrics_kernel): rank_j = 1 + pos_above[j] + j, AP in float64, queries without
+    a positive skipped (eval_mm_protocol.py:430-432, :444-461)."""
+    Q = pos_above.shape[0]
+    ap = np.full(Q, -1.0)
+    first = np.zeros(Q, dtype=np.int64)
+    for q in range(Q):
+        npq = int(n_pos[q])
+        if npq == 0:
+            continue
+        j = np.arange(npq)
+        ap[q] = float(np.sum((j + 1) / (pos_above[q, :npq] + j + 1.0)) / npq)
+        first[q] = pos_above[q, 0] + 1
+    v = ap >= 0
+    return {"mAP": float(ap[v].mean()) if v.any() else 0.0,
+            "R@1": float((first[v] <= 1).mean()) if v.any() else 0.0,
+            "R@5": float((first[v] <= 5).mean()) if v.any() else 0.0,
+            "R@10": float((first[v] <= 10).mean()) if v.any() else 0.0,
+            "num_queries": int(v.sum()), "_ap": ap}
