@@ -1,0 +1,358 @@
+// abi_host.cpp -- a NATIVE host of libreid_b200.so: plain C++ + the CUDA runtime, no Python, no torch.
+//
+// Shows (and checks) what INTEGRATION.md section 2 says: the boundary is a C ABI (include/reid_b200.h) that any host
+// can bind -- device pointers from cudaMalloc, a cudaStream_t, int status codes.  The program drives the same call
+// sequence as prcv2025reid_b200/engine.py for one gallery shard
+//     K1 normalise -> identity index -> positives' scores -> fused tcgen05 pass (and the all-fp32 pass) ->
+//     candidate re-scoring -> metric reduction                     (tools/eval_mm_protocol.py:46-48, :401-469)
+// plus K2 query fusion (:328-365), the K3 similarity GEMM (:50-53) and one SDM forward + backward
+// (models/sdm_loss.py:13-149), and compares every result with a straightforward double-precision host computation
+// of the reference's formulas.  Exit code 0 and a last line "ALL OK" mean every check passed.
+//
+// Build (done by __graft_entry__.build()):
+//   nvcc -O2 -std=c++17 -Iinclude examples/abi_host.cpp -o examples/abi_host -Lprcv2025reid_b200 -lreid_b200 \
+//        -Xlinker -rpath -Xlinker '$ORIGIN/../prcv2025reid_b200'
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "reid_b200.h"
+
+namespace {
+
+int g_fail = 0;
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    const int rc_ = (call);                                                                         \
+    if (rc_ != 0) { std::printf("FAIL %s -> %d (%s)\n", #call, rc_, reid_strerror(rc_)); std::fflush(stdout); std::exit(2); } \
+  } while (0)
+#define CU(call)                                                                                    \
+  do {                                                                                              \
+    const cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) { std::printf("FAIL %s -> %s\n", #call, cudaGetErrorString(e_)); std::fflush(stdout); std::exit(3); } \
+  } while (0)
+
+void expect(bool ok, const char* what, double got, double bound) {
+  std::printf("%s %-58s %.3e (bound %.1e)\n", ok ? "ok  " : "FAIL", what, got, bound);
+  std::fflush(stdout);
+  if (!ok) ++g_fail;
+}
+
+// deterministic N(0,1) stream (LCG + Box-Muller)
+struct Rng {
+  uint64_t s;
+  explicit Rng(uint64_t seed) : s(seed * 6364136223846793005ull + 1442695040888963407ull) {}
+  double uni() { s = s * 6364136223846793005ull + 1442695040888963407ull; return ((s >> 11) + 0.5) / 9007199254740992.0; }
+  float normal() { const double u = uni(), v = uni(); return (float)(std::sqrt(-2.0 * std::log(u)) * std::cos(6.283185307179586 * v)); }
+};
+
+template <typename T>
+struct Dev {
+  T* p = nullptr;
+  size_t n = 0;
+  explicit Dev(size_t count) : n(count) { CU(cudaMalloc((void**)&p, std::max<size_t>(1, count) * sizeof(T))); CU(cudaMemset(p, 0, std::max<size_t>(1, count) * sizeof(T))); }
+  explicit Dev(const std::vector<T>& h) : Dev(h.size()) { CU(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice)); }
+  ~Dev() { cudaFree(p); }
+  Dev(const Dev&) = delete;
+  Dev& operator=(const Dev&) = delete;
+  std::vector<T> host() const { std::vector<T> h(n); CU(cudaMemcpy(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost)); return h; }
+  void zero() { CU(cudaMemset(p, 0, std::max<size_t>(1, n) * sizeof(T))); }
+};
+
+constexpr int D = 512;
+
+// F.normalize(x, dim=-1): x / max(||x||2, eps)       (eval_mm_protocol.py:46-48)
+std::vector<double> l2n_rows(const std::vector<float>& x, int64_t rows, int d, double eps) {
+  std::vector<double> out((size_t)rows * d);
+  for (int64_t r = 0; r < rows; ++r) {
+    double ss = 0;
+    for (int i = 0; i < d; ++i) ss += (double)x[r * d + i] * x[r * d + i];
+    const double den = std::max(std::sqrt(ss), eps);
+    for (int i = 0; i < d; ++i) out[r * d + i] = x[r * d + i] / den;
+  }
+  return out;
+}
+
+// sdm_loss_stable in double (models/sdm_loss.py:28-32, :34-70, :86-94, :121-123)
+double sdm_loss_host(const std::vector<double>& q, const std::vector<double>& g, const std::vector<float>& y, int N, int M, int d,
+                     double tau, double eps) {
+  const double te = std::max(0.15, std::min(0.5, tau));
+  std::vector<double> qn((size_t)N * d), gn((size_t)M * d), S((size_t)N * M);
+  auto norm = [&](const std::vector<double>& x, std::vector<double>& o, int R) {
+    for (int r = 0; r < R; ++r) {
+      double ss = 0;
+      for (int i = 0; i < d; ++i) ss += x[(size_t)r * d + i] * x[(size_t)r * d + i];
+      const double den = std::max(std::sqrt(ss), eps);
+      for (int i = 0; i < d; ++i) o[(size_t)r * d + i] = x[(size_t)r * d + i] / den;
+    }
+  };
+  norm(q, qn, N); norm(g, gn, M);
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < M; ++j) {
+      double s = 0;
+      for (int k = 0; k < d; ++k) s += qn[(size_t)i * d + k] * gn[(size_t)j * d + k];
+      S[(size_t)i * M + j] = std::max(-20.0, std::min(20.0, s / te));
+    }
+  auto side = [&](bool transposed) {
+    const int R = transposed ? M : N, C = transposed ? N : M;
+    double sum = 0; int valid = 0;
+    for (int r = 0; r < R; ++r) {
+      double mx = -1e300, npos = 0;
+      for (int c = 0; c < C; ++c) {
+        const double s = transposed ? S[(size_t)c * M + r] : S[(size_t)r * M + c];
+        mx = std::max(mx, s);
+        npos += (transposed ? y[(size_t)c * M + r] : y[(size_t)r * M + c]) > 0.f;
+      }
+      if (npos == 0) continue;
+      double se = 0, ps = 0;
+      for (int c = 0; c < C; ++c) {
+        const double s = transposed ? S[(size_t)c * M + r] : S[(size_t)r * M + c];
+        se += std::exp(s - mx);
+        if ((transposed ? y[(size_t)c * M + r] : y[(size_t)r * M + c]) > 0.f) ps += s;
+      }
+      sum += (mx + std::log(se)) - ps / npos;      // -sum_j q_j log_softmax_j, q uniform over the positives
+      ++valid;
+    }
+    return valid ? sum / valid : 0.0;
+  };
+  return 0.5 * (side(false) + side(true));
+}
+
+}  // namespace
+
+int main() {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { std::printf("no CUDA device: this example needs a B200\n"); return 77; }
+  CU(cudaSetDevice(0));
+  cudaStream_t st;
+  CU(cudaStreamCreate(&st));
+  std::printf("libreid_b200 ABI v%d, %d SMs\n", reid_abi_version(), reid_device_sm_count());
+
+  // ------------------------------------------------------------------ synthetic identities: gallery + queries
+  const int n_ids = 512, per_id = 8, G = n_ids * per_id, Q = 256, K = 4;
+  Rng rng(20251018);
+  std::vector<float> centres((size_t)n_ids * D), gal((size_t)G * D), qraw((size_t)Q * K * D);
+  for (auto& v : centres) v = rng.normal();
+  std::vector<int64_t> g_pid(G), q_pid(Q);
+  for (int g = 0; g < G; ++g) {
+    g_pid[g] = 7000 + 3 * (g / per_id);                              // non-contiguous person ids
+    for (int i = 0; i < D; ++i) gal[(size_t)g * D + i] = centres[(size_t)(g / per_id) * D + i] + 2.5f * rng.normal();
+  }
+  const float sigma[K] = {3.5f, 3.5f, 4.5f, 5.5f};                   // ir, cpencil, sketch, text
+  for (int q = 0; q < Q; ++q) {
+    const int id = (q * 37) % n_ids;
+    q_pid[q] = (q % 29 == 28) ? 99 : 7000 + 3 * id;                   // a few queries without any positive (:430-432)
+    for (int k = 0; k < K; ++k)
+      for (int i = 0; i < D; ++i) qraw[((size_t)q * K + k) * D + i] = centres[(size_t)id * D + i] + sigma[k] * rng.normal();
+  }
+
+  // ------------------------------------------------------------------ K1: gallery normalisation
+  Dev<float> d_gal(gal), d_g32((size_t)G * D);
+  Dev<__half> d_g16((size_t)G * D);
+  CK(reid_l2norm_rows(d_gal.p, d_g32.p, d_g16.p, G, D, 1e-12f, st));
+  CU(cudaStreamSynchronize(st));
+  const std::vector<float> g32 = d_g32.host();
+  {
+    const std::vector<double> ref = l2n_rows(gal, G, D, 1e-12);
+    double e = 0;
+    for (size_t i = 0; i < ref.size(); ++i) e = std::max(e, std::fabs(ref[i] - g32[i]));
+    expect(e <= 4e-7, "K1 reid_l2norm_rows vs F.normalize (max abs)", e, 4e-7);
+  }
+
+  // ------------------------------------------------------------------ K2: MM-4 query fusion
+  std::vector<int32_t> mod_id((size_t)Q * K);
+  for (int q = 0; q < Q; ++q) for (int k = 0; k < K; ++k) mod_id[(size_t)q * K + k] = k;
+  const std::vector<float> w = {1.0f, 1.0f, 1.0f, 1.2f};             // run_eval's default weight_cfg (:504)
+  Dev<float> d_qraw(qraw), d_w(w), d_q32((size_t)Q * D);
+  Dev<int32_t> d_mod(mod_id);
+  Dev<__half> d_q16((size_t)Q * D);
+  CK(reid_mm_fuse_normalize(d_qraw.p, d_mod.p, d_w.p, K, d_q32.p, d_q16.p, Q, K, D, st));
+  CU(cudaStreamSynchronize(st));
+  const std::vector<float> q32 = d_q32.host();
+  {
+    const std::vector<double> fn = l2n_rows(qraw, (int64_t)Q * K, D, 1e-12);     // :353
+    double e = 0;
+    for (int q = 0; q < Q; ++q) {
+      std::vector<float> acc(D);
+      for (int i = 0; i < D; ++i) {
+        double a = 0;
+        for (int k = 0; k < K; ++k) a += (double)w[k] * fn[((size_t)q * K + k) * D + i];   // :362-364
+        acc[i] = (float)a;
+      }
+      const std::vector<double> r = l2n_rows(acc, 1, D, 1e-12);                     // :365
+      for (int i = 0; i < D; ++i) e = std::max(e, std::fabs(r[i] - q32[(size_t)q * D + i]));
+    }
+    expect(e <= 1e-6, "K2 reid_mm_fuse_normalize vs extract_query_feat (max abs)", e, 1e-6);
+  }
+
+  // ------------------------------------------------------------------ K3: similarity GEMM (tcgen05)
+  {
+    const int Qs = 128, Gs = 1000;
+    Dev<float> d_S((size_t)Qs * Gs);
+    CK(reid_sim_gemm(d_q16.p, d_g16.p, d_S.p, Qs, Gs, D, Gs, st));
+    CU(cudaStreamSynchronize(st));
+    const std::vector<float> S = d_S.host();
+    const std::vector<__half> q16 = d_q16.host(), g16 = d_g16.host();
+    double e = 0;
+    for (int q = 0; q < Qs; q += 9)
+      for (int g = 0; g < Gs; g += 7) {
+        double s = 0;
+        for (int i = 0; i < D; ++i) s += (double)__half2float(q16[(size_t)q * D + i]) * (double)__half2float(g16[(size_t)g * D + i]);
+        e = std::max(e, std::fabs(s - S[(size_t)q * Gs + g]));
+      }
+    expect(e <= 2e-6, "K3 reid_sim_gemm vs the product of the same fp16 operands", e, 2e-6);
+  }
+
+  // ------------------------------------------------------------------ gallery identity index + positives' thresholds
+  Dev<int64_t> d_gpid(g_pid), d_sorted(G), d_qpid(q_pid);
+  Dev<int32_t> d_order(G), d_maxrun(1), d_gcode(G), d_qcode(Q), d_qcount(Q), d_npos(Q);
+  {
+    const size_t wsb = reid_workspace_bytes(0, 0, G, 0);
+    Dev<uint8_t> ws(wsb);
+    CK(reid_pid_index_build(d_gpid.p, G, d_sorted.p, d_order.p, d_maxrun.p, ws.p, wsb, st));
+    CK(reid_pid_lookup(d_sorted.p, G, d_gpid.p, G, d_gcode.p, nullptr, st));
+    CK(reid_pid_lookup(d_sorted.p, G, d_qpid.p, Q, d_qcode.p, d_qcount.p, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  const int Pmax = d_maxrun.host()[0];
+  expect(Pmax == per_id, "reid_pid_index_build: largest identity run", Pmax, per_id);
+  Dev<float> d_thr((size_t)Q * Pmax);
+  CK(reid_pos_scores(d_q32.p, d_g32.p, d_order.p, d_qcode.p, d_qcount.p, nullptr, 0, Q, G, 0, D, Pmax, d_thr.p, st));
+  CK(reid_pos_sort(d_thr.p, d_npos.p, Q, Pmax, st));
+
+  // ------------------------------------------------------------------ host ranking: full sort per query (:423-455)
+  double ref_map = 0, ref_r1 = 0, ref_r5 = 0, ref_r10 = 0; int ref_n = 0;
+  std::vector<int> ref_top1(Q, -1);
+  {
+    std::vector<double> s(G);
+    std::vector<int> idx(G);
+    for (int q = 0; q < Q; ++q) {
+      for (int g = 0; g < G; ++g) {
+        double a = 0;
+        for (int i = 0; i < D; ++i) a += (double)q32[(size_t)q * D + i] * g32[(size_t)g * D + i];
+        s[g] = a; idx[g] = g;
+      }
+      std::sort(idx.begin(), idx.end(), [&](int a, int b) { return s[a] > s[b]; });
+      ref_top1[q] = idx[0];
+      int hits = 0, first = 0; double prec = 0;
+      for (int r = 0; r < G; ++r)
+        if (g_pid[idx[r]] == q_pid[q]) { ++hits; prec += (double)hits / (r + 1); if (!first) first = r + 1; }
+      if (!hits) continue;
+      ref_map += prec / hits; ref_r1 += first <= 1; ref_r5 += first <= 5; ref_r10 += first <= 10; ++ref_n;
+    }
+    ref_map /= ref_n; ref_r1 /= ref_n; ref_r5 /= ref_n; ref_r10 /= ref_n;
+  }
+
+  // ------------------------------------------------------------------ the ranking step: fused tcgen05 pass, then all-fp32 pass
+  const int cap = 2048, topk = 10;
+  const float eps16 = 0.0009765625f + 0.0001220703125f;              // 2^-10 + 2^-13: fp16 rounding bound for unit rows
+  for (int mode = 0; mode < 2; ++mode) {
+    const bool fused = mode == 0;
+    const int n_chunks = fused ? 1 : 4;
+    Dev<int32_t> d_above((size_t)Q * Pmax), d_cidx((size_t)Q * n_chunks * cap), d_ccnt((size_t)Q * n_chunks), d_topi((size_t)Q * REID_RTOP), d_flag(Q);
+    Dev<float> d_cs((size_t)Q * n_chunks * cap), d_cthr(Q), d_tops((size_t)Q * REID_RTOP);
+    if (fused) {
+      const size_t wsb = reid_workspace_bytes(1, Q, G, D);
+      Dev<uint8_t> ws(wsb);
+      CK(reid_retrieve_fused(d_q16.p, d_g16.p, d_qcode.p, d_gcode.p, nullptr, 0, d_thr.p, d_npos.p, Q, G, 0, D, Pmax, n_chunks,
+                             n_chunks, cap, d_above.p, d_cs.p, d_cidx.p, d_ccnt.p, d_cthr.p, ws.p, wsb, st));
+      CK(reid_rescore_topk(d_q32.p, d_g32.p, d_qcode.p, d_gcode.p, d_thr.p, d_npos.p, d_cs.p, d_cidx.p, d_ccnt.p, d_cthr.p, nullptr, Q,
+                           Q, G, 0, D, Pmax, n_chunks, cap, topk, eps16, d_above.p, d_tops.p, d_topi.p, d_flag.p, st));
+      CU(cudaStreamSynchronize(st));                                  // (ws must outlive the kernels)
+    } else {
+      CK(reid_retrieve_exact(d_q32.p, d_g32.p, d_qcode.p, d_gcode.p, nullptr, 0, d_thr.p, d_npos.p, nullptr, Q, Q, G, 0, D, Pmax,
+                             n_chunks, cap, d_above.p, d_cs.p, d_cidx.p, d_ccnt.p, st));
+      CK(reid_rescore_topk(d_q32.p, d_g32.p, d_qcode.p, d_gcode.p, d_thr.p, d_npos.p, d_cs.p, d_cidx.p, d_ccnt.p, nullptr, nullptr, Q,
+                           Q, G, 0, D, Pmax, n_chunks, cap, topk, 0.0f, d_above.p, d_tops.p, d_topi.p, d_flag.p, st));
+    }
+    Dev<double> d_out(5);
+    CK(reid_metrics_reduce(d_above.p, d_npos.p, Q, Pmax, d_out.p, nullptr, st));
+    CU(cudaStreamSynchronize(st));
+    const std::vector<double> m = d_out.host();
+    const std::vector<int32_t> flag = d_flag.host(), topi = d_topi.host();
+    int n_flag = 0, top1_diff = 0;
+    for (int q = 0; q < Q; ++q) {
+      n_flag += flag[q] != 0;
+      const int got = topi[(size_t)q * REID_RTOP];
+      if (flag[q] || got == ref_top1[q]) continue;
+      // a different row only counts when its score is really lower (ties within fp32 round-off may order either way)
+      double a = 0, b = 0;
+      for (int i = 0; i < D && got >= 0; ++i) {
+        a += (double)q32[(size_t)q * D + i] * g32[(size_t)got * D + i];
+        b += (double)q32[(size_t)q * D + i] * g32[(size_t)ref_top1[q] * D + i];
+      }
+      top1_diff += (got < 0 || b - a > 1e-6);
+    }
+    const char* name = fused ? "fused" : "exact";
+    std::printf("%s: mAP %.6f R@1 %.4f R@5 %.4f R@10 %.4f valid %d flagged %d | host sort: mAP %.6f R@1 %.4f R@5 %.4f R@10 %.4f valid %d\n",
+                name, m[0], m[1], m[2], m[3], (int)m[4], n_flag, ref_map, ref_r1, ref_r5, ref_r10, ref_n);
+    // queries the fused pass flags are re-run through the exact pass by the host side (engine.retrieve); with none
+    // flagged the fused metrics are final
+    if (!fused || n_flag == 0) {
+      expect(std::fabs(m[0] - ref_map) <= 1e-4, fused ? "fused: mAP vs full sort" : "exact: mAP vs full sort", std::fabs(m[0] - ref_map), 1e-4);
+      const double dc = std::fabs(m[1] - ref_r1) + std::fabs(m[2] - ref_r5) + std::fabs(m[3] - ref_r10);
+      expect(dc <= 1e-12, fused ? "fused: CMC@1/5/10 vs full sort" : "exact: CMC@1/5/10 vs full sort", dc, 1e-12);
+      expect((int)m[4] == ref_n, fused ? "fused: number of valid queries" : "exact: number of valid queries", m[4], ref_n);
+    }
+    expect(top1_diff == 0, fused ? "fused: top-1 gallery row of every unflagged query" : "exact: top-1 gallery row of every query", top1_diff, 0);
+    expect(n_flag <= (fused ? Q / 4 : 0), fused ? "fused: flagged queries (re-run through the exact pass by the host)" : "exact: flagged queries", n_flag, fused ? Q / 4 : 0);
+  }
+
+  // ------------------------------------------------------------------ SDM forward + backward (P x K = 4 x 2, fp32)
+  {
+    const int N = 8, M = 8;
+    std::vector<float> fq((size_t)N * D), fg((size_t)M * D), y((size_t)N * M);
+    for (int i = 0; i < N; ++i)
+      for (int k = 0; k < D; ++k) {
+        fq[(size_t)i * D + k] = centres[(size_t)(i / 2) * D + k] + 1.5f * rng.normal();
+        fg[(size_t)i * D + k] = centres[(size_t)(i / 2) * D + k] + 1.5f * rng.normal();
+      }
+    for (int i = 0; i < N; ++i) for (int j = 0; j < M; ++j) y[(size_t)i * M + j] = (i / 2 == j / 2) ? 1.f : 0.f;
+    Dev<float> d_fq(fq), d_fg(fg), d_y(y), d_loss(1), d_saved(reid_sdm_saved_floats(N, M, D)), d_go(std::vector<float>{1.0f}), d_dq((size_t)N * D), d_dg((size_t)M * D);
+    Dev<int32_t> d_status(1);
+    reid_sdm_pair pr;
+    pr.qry = d_fq.p; pr.gal = d_fg.p; pr.y = d_y.p; pr.N = N; pr.M = M; pr.loss = d_loss.p; pr.status = d_status.p; pr.saved = d_saved.p;
+    pr.grad_out = d_go.p; pr.dqry = d_dq.p; pr.dgal = d_dg.p;
+    CK(reid_sdm_fwd(&pr, 1, REID_DTYPE_F32, D, 0.2f, 1e-8f, st));
+    CK(reid_sdm_bwd(&pr, 1, REID_DTYPE_F32, D, 0.2f, 1e-8f, st));
+    CU(cudaStreamSynchronize(st));
+    const float loss = d_loss.host()[0];
+    const std::vector<float> dq = d_dq.host(), dg = d_dg.host();
+    std::vector<double> q64(fq.begin(), fq.end()), g64(fg.begin(), fg.end());
+    const double ref = sdm_loss_host(q64, g64, y, N, M, D, 0.2, 1e-8);
+    expect(std::fabs(loss - ref) <= 1e-5 * ref, "SDM forward: loss vs the closed form (relative)", std::fabs(loss - ref) / ref, 1e-5);
+    expect(d_status.host()[0] == 0, "SDM forward: status bits", d_status.host()[0], 0);
+    // backward: directional derivative of the host loss along a random direction vs <grad, direction>
+    std::vector<double> dirq((size_t)N * D), dirg((size_t)M * D);
+    double dot = 0;
+    for (size_t i = 0; i < dirq.size(); ++i) { dirq[i] = rng.normal(); dot += dirq[i] * dq[i]; }
+    for (size_t i = 0; i < dirg.size(); ++i) { dirg[i] = rng.normal(); dot += dirg[i] * dg[i]; }
+    const double h = 1e-4;
+    std::vector<double> qp(q64), qm(q64), gp(g64), gm(g64);
+    for (size_t i = 0; i < qp.size(); ++i) { qp[i] += h * dirq[i]; qm[i] -= h * dirq[i]; }
+    for (size_t i = 0; i < gp.size(); ++i) { gp[i] += h * dirg[i]; gm[i] -= h * dirg[i]; }
+    const double fd = (sdm_loss_host(qp, gp, y, N, M, D, 0.2, 1e-8) - sdm_loss_host(qm, gm, y, N, M, D, 0.2, 1e-8)) / (2 * h);
+    const double gtol = 1e-3 * std::max(1e-2, std::fabs(fd));
+    expect(std::fabs(fd - dot) <= gtol, "SDM backward: <grad, dir> vs central difference of the loss", std::fabs(fd - dot), gtol);
+    // one-call step: the same loss and gradients (reid_sdm_step)
+    Dev<float> d_dq2((size_t)N * D), d_dg2((size_t)M * D), d_loss2(1);
+    pr.loss = d_loss2.p; pr.dqry = d_dq2.p; pr.dgal = d_dg2.p;
+    CK(reid_sdm_step(&pr, 1, REID_DTYPE_F32, D, 0.2f, 1e-8f, st));
+    CU(cudaStreamSynchronize(st));
+    const std::vector<float> dq2 = d_dq2.host();
+    double e = std::fabs(d_loss2.host()[0] - loss);
+    for (size_t i = 0; i < dq.size(); ++i) e = std::max(e, (double)std::fabs(dq[i] - dq2[i]));
+    expect(e <= 1e-7, "SDM single-call step vs forward + backward (max abs)", e, 1e-7);
+  }
+
+  CU(cudaStreamDestroy(st));
+  if (g_fail) { std::printf("%d CHECK(S) FAILED\n", g_fail); return 1; }
+  std::printf("ALL OK\n");
+  return 0;
+}

@@ -54,5 +54,21 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def build_native_host(force=False):
+    """examples/abi_host: a plain C++ host of the C ABI (device memory from cudaMalloc, no torch), linked against the
+    in-tree library with a relative rpath so that it runs from the repository copy on the GPU box."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "examples", "abi_host.cpp")
+    out = os.path.join(root, "examples", "abi_host")
+    lib = build_library()
+    if force or _stale(out, [src, lib, os.path.join(root, "include", "reid_b200.h")]):
+        cmd = [_nvcc(), "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(root, "include"), src, "-o", out,
+               "-L", HERE, "-lreid_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../prcv2025reid_b200"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
