@@ -182,3 +182,40 @@ def test_extract_gallery_feats_cache_hit_and_miss(world, cpu_engine, tmp_path):
             assert torch.equal(rf2, feats)                              # per-image l2n == batched l2n, bit for bit
     finally:
         ext.encode_rgb = orig
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_build_queries_property_vs_live_reference():
+    """Random identity indices (missing / empty modalities, any k, both main-modality policies, any seed): the query
+    list, the order of the `samples` dicts and the state of the rng afterwards equal the unmodified reference's."""
+    from hypothesis import given, settings, strategies as st
+    ref = ref_loader.load_reference_eval()
+    mods = ["rgb", "ir", "cpencil", "sketch", "text", "thermal"]        # one modality the protocol does not know
+
+    @st.composite
+    def indices(draw):
+        index = {}
+        for pid in draw(st.lists(st.integers(0, 50), unique=True, max_size=6)):
+            by = {}
+            for m in draw(st.lists(st.sampled_from(mods), unique=True)):
+                n = draw(st.integers(0, 3))
+                by[m] = [{"img_path": "%s/%d/%d" % (m, pid, j), "img_id": "%d_%d" % (pid, j), "pid": pid} for j in range(n)]
+            index[pid] = by
+        return index
+
+    @settings(max_examples=150, deadline=None)
+    @given(indices(), st.integers(1, 6), st.sampled_from(["lexi_first", "random"]), st.integers(0, 2 ** 20))
+    def check(index, k, policy, seed):
+        ra, rb = random.Random(seed), random.Random(seed)
+        a = emp.build_queries(index, k, ra, policy)
+        b = ref.build_queries(index, k, rb, policy)
+        assert a == b
+        assert [list(q["samples"]) for q in a] == [list(q["samples"]) for q in b]
+        assert ra.getstate() == rb.getstate()
+
+    check()
+    for policy in ("lexi_first", "random"):             # mode_k = 0 is outside the protocol: same error as the reference
+        with pytest.raises(IndexError):
+            ref.build_queries({0: {}}, 0, random.Random(0), policy)
+        with pytest.raises(IndexError):
+            emp.build_queries({0: {}}, 0, random.Random(0), policy)
