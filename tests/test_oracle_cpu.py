@@ -168,3 +168,40 @@ def test_gallery_store_reads_the_reference_cache_format(tmp_path):
         pickle.dump({"g_feat": feats, "g_id": torch.arange(37)}, f)
     gf, gi = gallery_store.load_pickle_cache(str(tmp_path / "c.pkl"))
     assert gf.dtype == np.float32 and gi.dtype == np.int64 and np.array_equal(gf, feats.numpy())
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_retrieval_oracle_property_vs_live_reference():
+    """Random tiny jobs -- duplicated gallery rows (exact score ties), zero rows, masked positives, queries without a
+    positive, every k: the restatement returns exactly the dict the unmodified rank_and_metrics returns."""
+    from hypothesis import given, settings, strategies as st
+    ref = ref_loader.load_reference_eval()
+    wcfg = dict(synth.DEFAULT_WEIGHTS)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(1, 4), st.integers(2, 24), st.integers(1, 10), st.booleans())
+    def check(seed, k, G, Q, mask):
+        g = torch.Generator().manual_seed(seed)
+        d = 16
+        n_ids = max(1, G // 3)
+        gallery = torch.randn(G, d, generator=g)
+        dup = torch.randint(0, G, (G,), generator=g)
+        take = torch.rand(G, generator=g) < 0.3
+        gallery = torch.where(take[:, None], gallery[dup], gallery)              # exact duplicates -> tied scores
+        if G > 4:
+            gallery[int(torch.randint(0, G, (1,), generator=g))] = 0.0            # a zero row (l2n keeps it zero)
+        g_pid = torch.randint(0, n_ids, (G,), generator=g)
+        q_pid = torch.randint(0, n_ids + 1, (Q,), generator=g)                    # id n_ids: no positive in the gallery
+        query = torch.randn(Q, k, d, generator=g)
+        mod_id = torch.stack([torch.randperm(4, generator=g)[:k].sort().values for _ in range(Q)]).to(torch.int32)
+        E = min(2, k)                                                             # one same-image row per query sample at most
+        excl = torch.where(torch.rand(Q, E, generator=g) < 0.4, torch.randint(0, G, (Q, E), generator=g), torch.tensor(-1)).to(torch.int32)
+        case = synth.RetrievalCase(gallery, g_pid, query, mod_id, q_pid, excl, k)
+        queries, gmeta, ext = synth.case_to_reference_inputs(case)
+        gn = ref.l2n(gallery)
+        want = ref_loader.quiet(ref.rank_and_metrics, queries, gn, gmeta, ext, wcfg, ignore_same_img=mask)
+        qf = orc.fuse_queries(query, mod_id, synth.weights_tensor())
+        got = orc.rank_and_metrics_loop(qf, orc.l2n(gallery), q_pid, g_pid, excl if mask else None)
+        assert got == want
+
+    check()
