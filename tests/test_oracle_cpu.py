@@ -112,6 +112,41 @@ def test_sdm_oracle_matches_live_reference():
     assert float(a) == float(b)
 
 
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_sdm_oracle_property_vs_live_reference():
+    """Random shapes, label layouts (rows / columns without a positive, no positive at all), temperatures outside the
+    clamp range, bf16 inputs and a non-finite feature: loss value, result dtype, differentiability and the autograd
+    gradients of the restatement are bit-equal to the unmodified sdm_loss_stable's."""
+    from hypothesis import given, settings, strategies as st
+    sdm = ref_loader.load_reference_sdm().sdm_loss_stable
+
+    @settings(max_examples=80, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(1, 12), st.integers(1, 12), st.sampled_from([8, 48]),
+           st.sampled_from([0.05, 0.15, 0.2, 0.37, 0.5, 0.9]), st.sampled_from(["f32", "bf16", "nan", "nopos"]))
+    def check(seed, N, M, d, tau, kind):
+        g = torch.Generator().manual_seed(seed)
+        q = torch.randn(N, d, generator=g); v = torch.randn(M, d, generator=g)
+        lq = torch.randint(0, 4, (N,), generator=g); lv = torch.randint(0, 5, (M,), generator=g)
+        y = (lq[:, None] == lv[None, :]).float()
+        if kind == "nopos":
+            y = torch.zeros_like(y)
+        if kind == "nan":
+            q[0, 0] = float("nan")
+        if kind == "bf16":
+            q, v = q.bfloat16(), v.bfloat16()
+        qa, va = q.clone().requires_grad_(True), v.clone().requires_grad_(True)
+        qb, vb = q.clone().requires_grad_(True), v.clone().requires_grad_(True)
+        a = ref_loader.quiet(sdm, qa, va, y, tau=tau)
+        b = osdm.sdm_loss_oracle(qb, vb, y, tau=tau)
+        assert a.dtype == b.dtype and a.shape == b.shape and a.requires_grad == b.requires_grad
+        assert torch.equal(a.detach(), b.detach()) or (torch.isnan(a) and torch.isnan(b))
+        if a.requires_grad:
+            a.backward(); b.backward()
+            assert torch.equal(qa.grad, qb.grad) and torch.equal(va.grad, vb.grad)
+
+    check()
+
+
 # ---------------------------------------------------------------- train-time evaluator (SURVEY 8f N2)
 def _train_eval_case():
     import os
