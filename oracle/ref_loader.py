@@ -112,3 +112,51 @@ def load_reference_train_eval():
             exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
     _cache["train_eval"] = ns
     return ns
+
+
+def load_reference_compute_loss():
+    """The UNMODIFIED `CLIPBasedMultiModalReIDModel.compute_loss` (models/model.py:512-659) as a plain function
+    `compute_loss(self, outputs, labels)`.  models/model.py cannot be imported (its CLIP backbone needs the network), so
+    the method definition is cut out of the class with `ast` and executed as it stands; its function-local
+    `from .sdm_loss import sdm_loss_stable` (:556) resolves to the reference's own models/sdm_loss.py.  `self` only needs
+    the attributes the method reads: ce_loss, current_epoch, config.sdm_weight_warmup_epochs, contrastive_weight,
+    ce_weight, sdm_temperature, training."""
+    if "compute_loss" in _cache:
+        return _cache["compute_loss"]
+    import ast
+    import logging
+    import typing
+    import torch
+    path = os.path.join(REFERENCE_ROOT, "models", "model.py")
+    if not os.path.isfile(path):
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    tree = ast.parse(open(path, encoding="utf-8").read())
+    node = None
+    for cls in tree.body:
+        if isinstance(cls, ast.ClassDef) and cls.name == "CLIPBasedMultiModalReIDModel":
+            for item in cls.body:
+                if isinstance(item, ast.FunctionDef) and item.name == "compute_loss":
+                    node = item
+    if node is None:
+        raise RuntimeError("compute_loss not found in %s" % path)
+    sdm_mod = load_reference_sdm()
+    pkg = types.ModuleType("refmodels"); pkg.__path__ = []
+    ns = {"torch": torch, "logger": logging.getLogger("reference.models.model"), "Dict": typing.Dict, "List": typing.List,
+          "Any": typing.Any, "Optional": typing.Optional, "__name__": "refmodels.model", "__package__": "refmodels"}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    fn = ns["compute_loss"]
+
+    def call(self, outputs, labels):
+        saved = {k: sys.modules.get(k) for k in ("refmodels", "refmodels.sdm_loss")}
+        sys.modules["refmodels"] = pkg
+        sys.modules["refmodels.sdm_loss"] = sdm_mod
+        try:
+            return quiet(fn, self, outputs, labels)
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+    _cache["compute_loss"] = call
+    return call

@@ -240,3 +240,51 @@ def test_retrieval_oracle_property_vs_live_reference():
         assert got == want
 
     check()
+
+
+# ---------------------------------------------------------------- compute_loss SDM section
+ALIGN_CASES = ["full", "ragged", "no_vis", "no_pairs", "missing"]
+
+
+def _align_case(name):
+    import os
+    from oracle.make_golden_alignment import CASES, make_inputs
+    z = np.load(os.path.join(_golden.GOLDEN, "sdm_alignment.npz"))
+    seed, B, d, n_ids, kind, tau = CASES[name]
+    feats, masks, labels = make_inputs(seed, B, d, n_ids, kind)
+    cs = sum(float(f.double().abs().sum()) for f in feats.values() if f is not None)
+    if abs(cs - float(z[name + "/checksum"])) > 1e-6 * abs(cs):
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    grads = {k.split("grad_")[1]: z[k] for k in z.files if k.startswith(name + "/grad_")}
+    return feats, masks, labels, tau, float(z[name + "/loss"]), grads
+
+
+@pytest.mark.parametrize("name", ALIGN_CASES)
+def test_alignment_oracle_matches_compute_loss_golden(name):
+    """sdm_alignment_oracle vs the fixture produced by the UNMODIFIED compute_loss (models/model.py:512-659)."""
+    feats, masks, labels, tau, loss, grads = _align_case(name)
+    leaves = {m: (f.clone().requires_grad_(True) if f is not None else None) for m, f in feats.items()}
+    got = osdm.sdm_alignment_oracle(leaves, masks, labels, tau=tau)
+    assert float(got.detach()) == loss
+    if got.requires_grad:
+        got.backward()
+    have = {m: t.grad.numpy() for m, t in leaves.items() if t is not None and t.grad is not None}
+    assert sorted(have) == sorted(grads)
+    for m in grads:
+        assert np.array_equal(have[m], grads[m]), m
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_alignment_oracle_matches_live_compute_loss():
+    from oracle.make_golden_alignment import make_inputs, run_reference
+    for seed, kind in ((11, "full"), (12, "ragged"), (13, "missing"), (14, "no_pairs")):
+        feats, masks, labels = make_inputs(seed, 10, 96, 3, kind)
+        want, grads, out = run_reference(feats, masks, labels, 0.25)
+        leaves = {m: (f.clone().requires_grad_(True) if f is not None else None) for m, f in feats.items()}
+        got = osdm.sdm_alignment_oracle(leaves, masks, labels, tau=0.25)
+        assert float(got.detach()) == float(want)
+        assert float(out["total_loss"].detach()) == pytest.approx(0.3 * float(want) + float(out["ce_loss"].detach()))   # :651
+        if got.requires_grad:
+            got.backward()
+            for m, gr in grads.items():
+                assert torch.equal(leaves[m].grad, gr), m

@@ -97,3 +97,31 @@ def test_extract_gallery_feats_writes_the_reference_cache(world, tmp_path):
     assert np.array_equal(np.load(str(tmp_path / "cache" / "rgb_feats.npy")), feats.numpy())
     feats2, meta2 = emp.extract_gallery_feats(gallery, ext, str(tmp_path / "cache"))     # cache hit
     assert torch.equal(feats2, feats) and meta2 == meta
+
+
+# ---------------------------------------------------------------- compute_loss SDM section (row N1) vs the unmodified compute_loss
+@pytest.mark.parametrize("name", ["full", "ragged", "no_vis", "no_pairs", "missing"])
+def test_sdm_alignment_loss_matches_compute_loss_golden(name):
+    import numpy as np
+    from oracle.make_golden_alignment import CASES, make_inputs
+    from prcv2025reid_b200.sdm_loss import sdm_alignment_loss
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdm_alignment.npz"))
+    seed, B, d, n_ids, kind, tau = CASES[name]
+    feats, masks, labels = make_inputs(seed, B, d, n_ids, kind)
+    cs = sum(float(f.double().abs().sum()) for f in feats.values() if f is not None)
+    if abs(cs - float(z[name + "/checksum"])) > 1e-6 * abs(cs):
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    leaves = {m: (f.cuda().requires_grad_(True) if f is not None else None) for m, f in feats.items()}
+    loss = sdm_alignment_loss(leaves, {m: v.cuda() for m, v in masks.items()}, labels.cuda(), tau=tau)
+    want = float(z[name + "/loss"])
+    assert abs(float(loss.detach()) - want) <= 1e-5 * max(1.0, abs(want))                # north star: 1e-5 relative (fp32)
+    if loss.requires_grad:
+        loss.backward()
+    for m, t in leaves.items():
+        key = name + "/grad_" + m
+        if key in z.files:
+            r = z[key]
+            assert t.grad is not None, m
+            assert np.abs(t.grad.cpu().numpy() - r).max() <= 1e-5 * max(float(np.abs(r).max()), 1e-12), m
+        elif t is not None and t.grad is not None:
+            assert float(t.grad.abs().sum()) == 0.0, m                                  # no gradient in the reference
