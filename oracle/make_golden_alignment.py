@@ -50,8 +50,8 @@ def make_inputs(seed, B, d, n_ids, kind):
 CASES = {  # name: (seed, B, d, n_ids, kind, tau)
     "full": (1, 12, 512, 4, "full", 0.2),
     "ragged": (2, 12, 512, 4, "ragged", 0.2),
-    "no_vis": (3, 8, 64, 3, "no_vis", 0.2),
-    "no_pairs": (4, 8, 64, 3, "no_pairs", 0.2),
+    "no_vis": (3, 8, 128, 3, "no_vis", 0.2),
+    "no_pairs": (4, 8, 128, 3, "no_pairs", 0.2),
     "missing": (5, 10, 128, 3, "missing", 0.1),
 }
 
