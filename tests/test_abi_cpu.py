@@ -179,3 +179,13 @@ def test_entry_points_reject_invalid_arguments_before_touching_the_device():
     bad["sdm_fwd empty pair"] = L.reid_sdm_fwd(pairs, 1, 0, 512, 0.2, 1e-8, N)
     wrong = {k: v for k, v in bad.items() if v != -1}
     assert not wrong, wrong
+
+
+def test_missing_library_raises_instead_of_falling_back(monkeypatch, tmp_path):
+    """No silent fallback: without the built shared library every kernel entry raises ReidError."""
+    from prcv2025reid_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "libreid_b200.so"))
+    with pytest.raises(_cabi.ReidError, match="no CPU or PyTorch fallback"):
+        _cabi.lib()
+    assert issubclass(_cabi.ReidError, RuntimeError)
