@@ -404,11 +404,12 @@ def main():
                     "replayed as one CUDA graph (device time)")
             us, ab, npairs, gu = time_sdm(torch, synth, sdm_loss_pairs, 4, 2, 4, torch.float32)
             sdm["c2_p4k2_fp32_4pairs"] = {"us_per_step_eager": us, "us_per_step_graph": gu, "algorithmic_bytes": ab,
-                                          "hbm_gbs_graph": ab / (gu * 1e-6) / 1e9, "kernels": "graph: sdm_small_step (forward + backward in ONE launch, fp32 SIMT, 1 CTA per pair); eager: sdm_small_fwd + sdm_small_bwd",
+                                          "hbm_gbs_graph": ab / (gu * 1e-6) / 1e9, "frac_of_hbm_peak_graph": ab / (gu * 1e-6) / 1e9 / hbm_peak,
+                                          "kernels": "graph: sdm_small_step (forward + backward in ONE launch, fp32 SIMT, 1 CTA per pair); eager: sdm_small_fwd + sdm_small_bwd",
                                           "note": note}
             us, ab, npairs, gu = time_sdm(torch, synth, sdm_loss_pairs, 64, 8, 10, torch.bfloat16)
             sdm["c5_p64k8_bf16_10pairs"] = {"us_per_step_eager": us, "us_per_step_graph": gu, "algorithmic_bytes": ab,
-                                            "hbm_gbs_graph": ab / (gu * 1e-6) / 1e9,
+                                            "hbm_gbs_graph": ab / (gu * 1e-6) / 1e9, "frac_of_hbm_peak_graph": ab / (gu * 1e-6) / 1e9 / hbm_peak,
                                             "tensor_tflops_graph": 10 * 3 * 2.0 * 512 * 512 * 512 / (gu * 1e-6) / 1e12,
                                             "kernels": "tc_prep + tc_fwd + tc_bwd (tcgen05, bf16)"}
             line["sdm"] = sdm
