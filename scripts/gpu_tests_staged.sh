@@ -8,3 +8,6 @@ run sdm    tests/test_gpu_kernels.py -k "sdm"
 run exact  tests/test_gpu_kernels.py -k "exact or pid_index"
 run gemm   tests/test_gpu_kernels.py -k "sim_gemm"
 run fused  tests/test_gpu_kernels.py -k "fused"
+run rest   tests/test_gpu_kernels.py -k "not (l2norm or fuse or sdm or exact or pid_index or sim_gemm or fused)"
+run proto  tests/test_zz_protocol_gpu.py
+run native tests/test_zz_native_host_gpu.py
