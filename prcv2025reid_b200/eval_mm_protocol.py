@@ -160,7 +160,7 @@ def _fuse_batch(queries: List[dict], extractor, weight_cfg: Dict[str, float]) ->
     w = torch.tensor([float(weight_cfg.get(m, 1.0)) for m in names], dtype=torch.float32, device=dev)   # :362
     for k, idxs in weighted.items():
         it = torch.tensor(idxs, device=dev)
-        rows = torch.stack([flat[offs[qi] + j] for qi in idxs for j in range(k)]).view(len(idxs), k, D)
+        rows = flat[torch.tensor([offs[qi] + j for qi in idxs for j in range(k)], device=dev)].view(len(idxs), k, D)   # one gather
         mid = torch.tensor([[ids[m] for m in mods[qi]] for qi in idxs], dtype=torch.int32, device=dev)
         if k == 1:      # weighted path with one feature: l2n(w * f) -- keep the weight (no hook result)
             rows = torch.cat([rows, torch.zeros_like(rows)], dim=1)
