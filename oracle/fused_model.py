@@ -19,8 +19,14 @@ built.  It follows the kernel, not the reference:
                      are skipped; rows >= G_local are no rows
   pos_above[j]       prefix sum of the bucket histogram                               hist_to_above_kernel
 
-Not modelled: the candidate / re-scoring side (top-k and CMC are exact by construction there, and positives inside
-the re-scored top list get their exact rank from it, which only removes error).
+  re-scoring         the RTOP best local rows by fp16 score are re-scored in fp32; cut = KLIST-th best     rescore_topk_kernel, rank.cu
+                     fp16 score, bound = cut + eps; a positive with t_j > bound gets its EXACT local
+                     count from the re-scored rows, the others keep max(fused count, that lower bound);
+                     flags: top-k undecidable (k-th exact score < bound), CMC@10 undecidable
+                     (best positive not above the bound and fewer than 10 re-scored rows above it)
+
+Not modelled: the running candidate thresholds (the model takes the candidate set as complete down to the KLIST-th best
+score, which is what the kernel guarantees) and the exact re-run of flagged queries (engine.retrieve).
 """
 from typing import Dict, Optional
 
@@ -30,6 +36,9 @@ import torch
 SAMPLE_W = 32        # REID_SAMPLE_W
 CALIB_ROWS = 2048    # REID_CALIB_ROWS
 SAMPLE_PHASE = 5     # rows with (row % SAMPLE_W) == 5
+KLIST = 32           # REID_KLIST
+RTOP = 32            # REID_RTOP
+EPS_FP16 = 2.0 ** -10 + 2.0 ** -13    # engine.EPS_FP16
 
 
 def positive_thresholds(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, g_pid: torch.Tensor,
@@ -117,6 +126,52 @@ def fused_counts(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, 
                     lo_mask &= ~(s > t[ne - 1])
                 pos_above[q, j] = top + sample_w * int(lo_mask.sum())
     return {"pos_above": pos_above, "n_pos": n_pos, "n_exact": n_exact, "thr": thr}
+
+
+def rescore_stage(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, g_pid: torch.Tensor, counts: Dict[str, np.ndarray],
+                  excl: Optional[torch.Tensor] = None, g_offset: int = 0, topk: int = 10, eps: float = EPS_FP16):
+    """One rank's reid_rescore_topk applied to the modelled counts of fused_counts (same shard).
+    -> {"pos_above" (corrected copy), "flag" [Q] (bit1 top-k undecidable, bit2 CMC@10 undecidable),
+        "top_idx" [Q, RTOP] global gallery rows by exact score (-1 pad), "top_score" [Q, RTOP]}."""
+    Q, G = q_f32.shape[0], g_f32.shape[0]
+    S16 = (q_f32.half().float() @ g_f32.half().float().T).numpy()
+    S32 = (q_f32 @ g_f32.T).numpy()
+    gp, qp = g_pid.numpy(), q_pid.numpy()
+    pos_above = counts["pos_above"].copy()
+    thr, n_pos = counts["thr"], counts["n_pos"]
+    flag = np.zeros(Q, dtype=np.int32)
+    top_idx = np.full((Q, RTOP), -1, dtype=np.int64)
+    top_score = np.full((Q, RTOP), -np.inf, dtype=np.float32)
+    for q in range(Q):
+        s16 = S16[q].copy()
+        if excl is not None:
+            e = excl.numpy()[q].astype(np.int64)
+            e = e[e >= 0] - g_offset
+            s16[e[(e >= 0) & (e < G)]] = -np.inf                      # masked rows are never candidates
+        order = np.argsort(-s16, kind="stable")
+        total = int(np.isfinite(s16).sum())
+        R = min(total, RTOP)
+        cand = order[:R]
+        cut = s16[order[KLIST - 1]] if total >= KLIST else -np.inf
+        bound = cut + np.float32(eps)
+        ex = S32[q, cand]
+        o2 = np.lexsort((cand, -ex))                                   # score desc, index asc
+        cand, ex = cand[o2], ex[o2]
+        top_idx[q, :R] = cand + g_offset
+        top_score[q, :R] = ex
+        neg = gp[cand] != qp[q]
+        for j in range(int(n_pos[q])):
+            t = thr[q, j]
+            lb = int((neg & (ex > t)).sum())
+            if t > bound or cut == -np.inf:
+                pos_above[q, j] = lb                                   # exact local count
+            else:
+                pos_above[q, j] = max(pos_above[q, j], lb)
+                if j == 0 and lb < 10:
+                    flag[q] |= 4
+        if cut > -np.inf and R >= topk and ex[topk - 1] < bound:
+            flag[q] |= 2
+    return {"pos_above": pos_above, "flag": flag, "top_idx": top_idx, "top_score": top_score}
 
 
 def metrics_from_counts(pos_above: np.ndarray, n_pos: np.ndarray) -> Dict[str, object]:

@@ -68,3 +68,31 @@ def test_counts_are_exact_on_exact_scores():
     assert [m["R@1"], m["R@5"], m["R@10"]] == [loop["R@1"], loop["R@5"], loop["R@10"]]
     v = loop["_valid"]
     assert np.abs(m["_ap"][v] - loop["_ap"][v]).max() <= 1e-12
+
+
+def test_rescoring_stage_makes_the_head_exact():
+    """rescore_topk restated (oracle/fused_model.rescore_stage): the RTOP best rows by fp16 score, re-scored in fp32, give
+    the exact top-10 of every unflagged query, exact counts for the positives above the completeness bound, and only
+    shrink the error of the modelled AP."""
+    case, q, g, exact = _case(1000, 96)
+    c = fm.fused_counts(q, g, case.q_pid, case.g_pid, case.excl, n_chunks=4)
+    r = fm.rescore_stage(q, g, case.q_pid, case.g_pid, c, case.excl)
+    ok = r["flag"] == 0
+    assert ok.mean() >= 0.9                                            # flagged queries are re-run exactly by engine.retrieve
+    assert np.array_equal(r["top_idx"][ok][:, :10], exact["_top_idx"][ok])
+    before = fm.metrics_from_counts(c["pos_above"], c["n_pos"])
+    after = fm.metrics_from_counts(r["pos_above"], c["n_pos"])
+    v = exact["_valid"] & ok
+    e0 = np.abs(before["_ap"][v] - exact["_ap"][v]).max()
+    e1 = np.abs(after["_ap"][v] - exact["_ap"][v]).max()
+    assert e1 <= e0 and abs(after["mAP"] - exact["mAP"]) <= 1e-4
+    assert [after["R@1"], after["R@5"], after["R@10"]] == [exact["R@1"], exact["R@5"], exact["R@10"]]
+    # every positive above the bound has its exact rank
+    S = (q @ g.T).numpy()
+    for qi in np.nonzero(v)[0][:16]:
+        t0 = c["thr"][qi, 0]
+        if r["top_score"][qi, fm.KLIST - 1] + 2 * fm.EPS_FP16 < t0:      # clearly above the completeness bound
+            use = np.ones(g.shape[0], dtype=bool)
+            e = case.excl[qi].numpy(); use[e[e >= 0]] = False
+            use &= (case.g_pid.numpy() != int(case.q_pid[qi]))
+            assert r["pos_above"][qi, 0] == int((use & (S[qi] > t0)).sum())
