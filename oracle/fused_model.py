@@ -129,7 +129,8 @@ def fused_counts(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, 
 
 
 def rescore_stage(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, g_pid: torch.Tensor, counts: Dict[str, np.ndarray],
-                  excl: Optional[torch.Tensor] = None, g_offset: int = 0, topk: int = 10, eps: float = EPS_FP16):
+                  excl: Optional[torch.Tensor] = None, g_offset: int = 0, topk: int = 10, eps: float = EPS_FP16,
+                  klist: int = KLIST, rtop: int = RTOP):
     """One rank's reid_rescore_topk applied to the modelled counts of fused_counts (same shard).
     -> {"pos_above" (corrected copy), "flag" [Q] (bit1 top-k undecidable, bit2 CMC@10 undecidable),
         "top_idx" [Q, RTOP] global gallery rows by exact score (-1 pad), "top_score" [Q, RTOP]}."""
@@ -140,8 +141,8 @@ def rescore_stage(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor,
     pos_above = counts["pos_above"].copy()
     thr, n_pos = counts["thr"], counts["n_pos"]
     flag = np.zeros(Q, dtype=np.int32)
-    top_idx = np.full((Q, RTOP), -1, dtype=np.int64)
-    top_score = np.full((Q, RTOP), -np.inf, dtype=np.float32)
+    top_idx = np.full((Q, rtop), -1, dtype=np.int64)
+    top_score = np.full((Q, rtop), -np.inf, dtype=np.float32)
     for q in range(Q):
         s16 = S16[q].copy()
         if excl is not None:
@@ -150,9 +151,9 @@ def rescore_stage(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor,
             s16[e[(e >= 0) & (e < G)]] = -np.inf                      # masked rows are never candidates
         order = np.argsort(-s16, kind="stable")
         total = int(np.isfinite(s16).sum())
-        R = min(total, RTOP)
+        R = min(total, rtop)
         cand = order[:R]
-        cut = s16[order[KLIST - 1]] if total >= KLIST else -np.inf
+        cut = s16[order[klist - 1]] if total >= klist else -np.inf
         bound = cut + np.float32(eps)
         ex = S32[q, cand]
         o2 = np.lexsort((cand, -ex))                                   # score desc, index asc
