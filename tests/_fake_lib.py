@@ -1,0 +1,233 @@
+"""A CPU stand-in for libreid_b200.so, for testing the HOST logic of prcv2025reid_b200.engine without a GPU.  TEST ONLY.
+
+Every method implements the CONTRACT of the entry point of the same name as written in include/reid_b200.h, with
+torch CPU arithmetic and tensors instead of device pointers (`install()` swaps `engine.ptr` for the identity and
+`engine.stream_ptr` for a no-op, so `engine` hands the tensors / views themselves to these methods and in-place
+results land where the real kernels would write them).  The "fused" pass scores with the fp16 operand copies like the
+tensor cores do, so the engine's flag -> exact re-run path is exercised for real.  Nothing here is product code, and the
+product never loads it: `prcv2025reid_b200._cabi.lib()` raises when the real library is missing.
+"""
+import torch
+import torch.nn.functional as F
+
+KLIST = 32
+RTOP = 32
+NEG_INF = float("-inf")
+
+
+class FakeLib:
+    def __init__(self, sm_count=148, force_flag_every=0):
+        self.sm_count = sm_count
+        self.calls = []
+        # > 0: the re-scorer of the FUSED pass declares every n-th query of a block undecidable and leaves garbage in its
+        # outputs, as a kernel that gave up on the query might -- the host must repair it through the exact pass
+        self.force_flag_every = force_flag_every
+
+    # ------------------------------------------------------------------ utilities
+    def _log(self, name):
+        self.calls.append(name)
+        return 0
+
+    def reid_device_sm_count(self):
+        return self.sm_count
+
+    def reid_workspace_bytes(self, which, Q, G, d):
+        return 64
+
+    def reid_strerror(self, rc):
+        return b"fake"
+
+    # ------------------------------------------------------------------ K1 / K2
+    def reid_l2norm_rows(self, x, out32, out16, rows, d, eps, st):
+        y = F.normalize(x.float(), dim=-1, eps=eps)
+        if out32 is not None:
+            out32.copy_(y)
+        if out16 is not None:
+            out16.copy_(y.half())
+        return self._log("reid_l2norm_rows")
+
+    def reid_mm_fuse_normalize(self, feats, mod_id, w, n_mod, out32, out16, Q, k, d, st):
+        f = F.normalize(feats.float(), dim=-1)
+        if k == 1:
+            acc = f[:, 0]
+        else:
+            acc = None
+            for j in range(k):
+                use = mod_id[:, j] >= 0
+                wj = torch.where(use, w[mod_id[:, j].clamp(min=0).long()], torch.zeros(Q))
+                term = f[:, j] * wj[:, None]
+                acc = term if acc is None else acc + term
+        y = F.normalize(acc, dim=-1)
+        out32.copy_(y)
+        if out16 is not None:
+            out16.copy_(y.half())
+        return self._log("reid_mm_fuse_normalize")
+
+    # ------------------------------------------------------------------ identity index
+    def reid_pid_index_build(self, g_pid, G, sorted_pid, order, max_run, ws, ws_bytes, st):
+        s, o = torch.sort(g_pid, stable=True)
+        sorted_pid.copy_(s); order.copy_(o.to(torch.int32))
+        _, counts = torch.unique_consecutive(s, return_counts=True)
+        max_run.fill_(int(counts.max()))
+        return self._log("reid_pid_index_build")
+
+    def reid_pid_lookup(self, sorted_pid, G, pids, n, code, count, st):
+        lo = torch.searchsorted(sorted_pid, pids, right=False)
+        hi = torch.searchsorted(sorted_pid, pids, right=True)
+        found = hi > lo
+        code.copy_(torch.where(found, lo, torch.full_like(lo, -1)).to(torch.int32))
+        if count is not None:
+            count.copy_((hi - lo).to(torch.int32))
+        return self._log("reid_pid_lookup")
+
+    # ------------------------------------------------------------------ positives
+    @staticmethod
+    def _masked(excl, E, nb, G_local, g_offset):
+        m = torch.zeros(nb, G_local, dtype=torch.bool)
+        if excl is not None and E > 0:
+            loc = excl.long() - g_offset
+            ok = (excl >= 0) & (loc >= 0) & (loc < G_local)
+            rows = torch.arange(nb)[:, None].expand_as(loc)
+            m[rows[ok], loc[ok]] = True
+        return m
+
+    def reid_pos_scores(self, q32, g32, order, q_code, q_count, excl, E, Q, G_local, g_offset, d, Pmax, pos_score, st):
+        pos_score.fill_(NEG_INF)
+        masked = self._masked(excl, E, Q, G_local, g_offset)
+        for q in range(Q):
+            c, n = int(q_code[q]), int(q_count[q])
+            for j in range(min(n, Pmax) if c >= 0 else 0):
+                row = int(order[c + j]) - g_offset
+                if 0 <= row < G_local and not masked[q, row]:
+                    pos_score[q, j] = torch.dot(q32[q], g32[row])
+        return self._log("reid_pos_scores")
+
+    def reid_pos_sort(self, pos_score, n_pos, Q, Pmax, st):
+        s, _ = torch.sort(pos_score, dim=1, descending=True)
+        pos_score.copy_(s)
+        n_pos.copy_(torch.isfinite(s).sum(1).to(torch.int32))
+        return self._log("reid_pos_sort")
+
+    # ------------------------------------------------------------------ the ranking step
+    def _rank_pass(self, S, sel, q_code, g_code, masked, pos_thr, n_pos, Pmax, n_chunks, cap, rows_per_chunk, pos_above,
+                   cand_score, cand_idx, cand_count, cand_thr):
+        G = S.shape[1]
+        for q in sel:
+            s = S[q].clone()
+            ok = ~masked[q]
+            nonpos = ok & (g_code != q_code[q])
+            for j in range(min(int(n_pos[q]), Pmax)):
+                pos_above[q, j] += int((nonpos & (s > pos_thr[q, j])).sum())
+            s_ok = torch.where(ok, s, torch.full_like(s, NEG_INF))
+            n_ok = int(ok.sum())
+            thr = torch.topk(s_ok, KLIST).values[-1] if n_ok >= KLIST else torch.tensor(NEG_INF)
+            if cand_thr is not None:
+                cand_thr[q] = thr
+            keep = torch.nonzero(ok & (s_ok >= thr)).flatten()         # complete down to the KLIST-th best row
+            for c in range(n_chunks):
+                mine = keep[(keep // rows_per_chunk) == c]
+                cand_count[q, c] = mine.numel()
+                m = min(mine.numel(), cap)
+                cand_score[q, c, :m] = s[mine[:m]]
+                cand_idx[q, c, :m] = mine[:m].to(torch.int32)
+
+    def reid_retrieve_fused(self, q16, g16, q_code, g_code, excl, E, pos_thr, n_pos, Q, G_local, g_offset, d, Pmax, n_chunks,
+                            total_chunks, cap, pos_above, cand_score, cand_idx, cand_count, cand_thr, ws, ws_bytes, st):
+        S = q16.float() @ g16.float().T                                # fp16 operands, fp32 accumulation
+        rpc = -(-G_local // n_chunks)
+        rpc = -(-rpc // 256) * 256
+        self._rank_pass(S, range(Q), q_code, g_code, self._masked(excl, E, Q, G_local, g_offset), pos_thr, n_pos, Pmax, n_chunks, cap,
+                        rpc, pos_above, cand_score, cand_idx, cand_count, cand_thr)
+        return self._log("reid_retrieve_fused")
+
+    def reid_retrieve_exact(self, q32, g32, q_code, g_code, excl, E, pos_thr, n_pos, q_sel, n_sel, Q, G_local, g_offset, d, Pmax,
+                            n_chunks, cap, pos_above, cand_score, cand_idx, cand_count, st):
+        sel = range(Q) if q_sel is None else [int(v) for v in q_sel[:n_sel]]
+        S = q32 @ g32.T
+        rpc = -(-G_local // n_chunks)
+        self._rank_pass(S, sel, q_code, g_code, self._masked(excl, E, Q, G_local, g_offset), pos_thr, n_pos, Pmax, n_chunks, cap,
+                        rpc, pos_above, cand_score, cand_idx, cand_count, None)
+        return self._log("reid_retrieve_exact" if q_sel is None else "reid_retrieve_exact(sel)")
+
+    def reid_rescore_topk(self, q32, g32, q_code, g_code, pos_thr, n_pos, cand_score, cand_idx, cand_count, cand_thr, q_sel, n_sel,
+                          Q, G_local, g_offset, d, Pmax, n_chunks, cap, topk, eps, pos_above, top_score, top_idx, flag, st):
+        sel = range(Q) if q_sel is None else [int(v) for v in q_sel[:n_sel]]
+        for q in sel:
+            keep = float(cand_thr[q]) if cand_thr is not None else NEG_INF
+            sc, ix, overflow = [], [], False
+            for c in range(n_chunks):
+                n = int(cand_count[q, c])
+                if n > cap:
+                    n, overflow = cap, True
+                sc.append(cand_score[q, c, :n]); ix.append(cand_idx[q, c, :n])
+            sc, ix = torch.cat(sc), torch.cat(ix).long()
+            m = sc >= keep
+            sc, ix = sc[m], ix[m]
+            o = torch.argsort(sc, descending=True, stable=True)
+            sc, ix = sc[o], ix[o]
+            total = sc.numel()
+            R = min(total, RTOP)
+            cut = float(sc[KLIST - 1]) if total >= KLIST else NEG_INF
+            ex = (g32[ix[:R]] @ q32[q]) if R else torch.empty(0)
+            gi = ix[:R]
+            o2 = sorted(range(R), key=lambda r: (-float(ex[r]), int(gi[r])))
+            ex, gi = ex[o2], gi[o2]
+            top_score[q].fill_(NEG_INF); top_idx[q].fill_(-1)
+            top_score[q, :R] = ex
+            top_idx[q, :R] = (gi + g_offset).to(torch.int32)
+            bound = cut + eps
+            neg = g_code[gi] != q_code[q] if R else torch.zeros(0, dtype=torch.bool)
+            f = 1 if overflow else 0
+            for j in range(min(int(n_pos[q]), Pmax)):
+                t = float(pos_thr[q, j])
+                lb = int((neg & (ex > t)).sum())
+                if t > bound or cut == NEG_INF:
+                    pos_above[q, j] = lb
+                else:
+                    pos_above[q, j] = max(int(pos_above[q, j]), lb)
+                    if j == 0 and lb < 10:
+                        f |= 4
+            if cut > NEG_INF and R >= topk and float(ex[topk - 1]) < bound:
+                f |= 2
+            if self.force_flag_every and q_sel is None and eps > 0 and q % self.force_flag_every == 3:
+                f |= 2
+                pos_above[q].fill_(12345); top_idx[q].fill_(-7); top_score[q].fill_(9.0)
+            flag[q] = f
+        return self._log("reid_rescore_topk" if q_sel is None else "reid_rescore_topk(sel)")
+
+    def reid_merge_topk(self, scores, idx, n_lists, Q, list_len, topk, out_s, out_i, st):
+        s = scores.view(n_lists, Q, list_len).permute(1, 0, 2).reshape(Q, -1)
+        i = idx.view(n_lists, Q, list_len).permute(1, 0, 2).reshape(Q, -1)
+        for q in range(Q):
+            ent = sorted(((-float(a), int(b)) for a, b in zip(s[q], i[q]) if int(b) >= 0))[:topk]
+            out_s[q].fill_(NEG_INF); out_i[q].fill_(-1)
+            for r, (a, b) in enumerate(ent):
+                out_s[q, r] = -a; out_i[q, r] = b
+        return self._log("reid_merge_topk")
+
+    def reid_metrics_reduce(self, pos_above, n_pos, Q, Pmax, out, ap, st):
+        acc = torch.zeros(5, dtype=torch.float64)
+        for q in range(Q):
+            n = min(int(n_pos[q]), Pmax)
+            if ap is not None:
+                ap[q] = -1.0
+            if n == 0:
+                continue
+            a = sum((j + 1) / (int(pos_above[q, j]) + j + 1) for j in range(n)) / n
+            first = int(pos_above[q, 0]) + 1
+            acc += torch.tensor([a, first <= 1, first <= 5, first <= 10, 1.0], dtype=torch.float64)
+            if ap is not None:
+                ap[q] = a
+        out.copy_(torch.cat([acc[:4] / acc[4] if acc[4] > 0 else torch.zeros(4, dtype=torch.float64), acc[4:]]))
+        return self._log("reid_metrics_reduce")
+
+
+def install(monkeypatch, fake=None, **kw):
+    """Route prcv2025reid_b200.engine to a FakeLib (tensors instead of device pointers).  -> the FakeLib."""
+    from prcv2025reid_b200 import _cabi, engine
+    fake = fake or FakeLib(**kw)
+    monkeypatch.setattr(_cabi, "lib", lambda: fake)
+    monkeypatch.setattr(engine, "ptr", lambda t: t)
+    monkeypatch.setattr(engine, "stream_ptr", lambda: None)
+    monkeypatch.setattr(engine, "check", lambda rc, what="": None if rc == 0 else (_ for _ in ()).throw(RuntimeError(what)))
+    return fake
