@@ -222,6 +222,20 @@ class FakeLib:
         return self._log("reid_metrics_reduce")
 
 
+    def reid_topk_label_metrics(self, top_idx, q_label, g_label, Q, list_len, k, ap, hit, st):
+        for q in range(Q):                                             # train.py:116-124 / :133-136 (fp32 like the reference)
+            row = top_idx[q, :k].long()
+            m = (row >= 0) & (g_label[row.clamp(min=0)] == q_label[q])
+            n = int(m.sum())
+            hit[q] = 1 if n else 0
+            if n:
+                prec = torch.cumsum(m.float(), 0) / torch.arange(1, k + 1, dtype=torch.float32)
+                ap[q] = (prec * m.float()).sum() / n
+            else:
+                ap[q] = -1.0
+        return self._log("reid_topk_label_metrics")
+
+
 def install(monkeypatch, fake=None, **kw):
     """Route prcv2025reid_b200.engine to a FakeLib (tensors instead of device pointers).  -> the FakeLib."""
     from prcv2025reid_b200 import _cabi, engine
@@ -229,5 +243,11 @@ def install(monkeypatch, fake=None, **kw):
     monkeypatch.setattr(_cabi, "lib", lambda: fake)
     monkeypatch.setattr(engine, "ptr", lambda t: t)
     monkeypatch.setattr(engine, "stream_ptr", lambda: None)
-    monkeypatch.setattr(engine, "check", lambda rc, what="": None if rc == 0 else (_ for _ in ()).throw(RuntimeError(what)))
+    chk = lambda rc, what="": None if rc == 0 else (_ for _ in ()).throw(RuntimeError(what))   # noqa: E731
+    monkeypatch.setattr(engine, "check", chk)
+    from prcv2025reid_b200 import train_eval
+    monkeypatch.setattr(train_eval, "ptr", lambda t: t)
+    monkeypatch.setattr(train_eval, "stream_ptr", lambda: None)
+    monkeypatch.setattr(train_eval, "check", chk)
+    monkeypatch.setattr(train_eval, "_dev", lambda t: t)
     return fake

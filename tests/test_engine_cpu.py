@@ -122,3 +122,61 @@ def test_sharded_retrieve_host_logic_matches_oracle(tmp_path, world):
         assert abs(r["metrics"]["mAP"] - ref["mAP"]) <= 1e-4
         assert [r["metrics"][k] for k in ("R@1", "R@5", "R@10")] == [ref[k] for k in ("R@1", "R@5", "R@10")]
         assert np.array_equal(r["top_idx"].numpy().astype(np.int64), ref["_top_idx"])
+
+
+def test_topk_ranking_passes_concatenate_to_the_full_argsort(monkeypatch):
+    """topk.topk_ranking (ranking core of export_submission_csv, eval_mm_protocol.py:617-625): ranks beyond the exact
+    top-32 of a pass come from further passes that exclude the rows already ranked; the concatenation is the argsort."""
+    from prcv2025reid_b200 import topk
+    fake = _fake_lib.install(monkeypatch)
+    g = torch.Generator().manual_seed(5)
+    gal = torch.randn(150, 64, generator=g)
+    q = torch.nn.functional.normalize(torch.randn(9, 64, generator=g), dim=1)
+    want = torch.argsort(q @ torch.nn.functional.normalize(gal, dim=1).T, dim=1, descending=True)
+    got = topk.topk_ranking(q, gal, top_k=100, mode="fused")
+    assert got.shape == (9, 100) and torch.equal(got.long(), want[:, :100])
+    assert fake.calls.count("reid_retrieve_fused") == 4                       # 32 + 32 + 32 + 4
+    short = topk.topk_ranking(q, gal[:20], top_k=50, mode="exact")            # fewer rows than top_k: -1 padded
+    want20 = torch.argsort(q @ torch.nn.functional.normalize(gal[:20], dim=1).T, dim=1, descending=True)
+    assert torch.equal(short[:, :20].long(), want20) and bool((short[:, 20:] == -1).all())
+
+
+def test_export_submission_csv_host_logic(monkeypatch, tmp_path):
+    import csv
+    from prcv2025reid_b200 import eval_mm_protocol as emp
+    _fake_lib.install(monkeypatch)
+    monkeypatch.setattr(emp, "_dev", lambda: torch.device("cpu"))
+    case = synth.make_retrieval_case(61, 12, 4, 2, 3, excl_frac=0.0)
+    queries, gmeta, ext = synth.case_to_reference_inputs(case)
+    path = str(tmp_path / "sub.csv")
+    emp.export_submission_csv(queries, orc.l2n(case.gallery_raw), gmeta, ext, dict(synth.DEFAULT_WEIGHTS), path, top_k=20)
+    qf = orc.fuse_queries(case.query_raw, case.mod_id, synth.weights_tensor())
+    want = orc.submission_ranking(qf, orc.l2n(case.gallery_raw), top_k=20)
+    rows = list(csv.DictReader(open(path, newline="", encoding="utf-8")))
+    assert len(rows) == case.Q and list(rows[0]) == ["query_key", "ranked_gallery_ids"]        # :634-643
+    for qi, row in enumerate(rows):
+        assert [int(t[1:]) for t in row["ranked_gallery_ids"].split()] == want[qi].tolist()
+        pid, mods, _ = row["query_key"].split("|")
+        assert int(pid) == int(case.q_pid[qi]) and mods == "+".join(sorted(queries[qi]["modalities"]))
+
+
+def test_train_eval_dropins_host_logic(monkeypatch):
+    """compute_map / compute_cmc / reid_map (train.py:101-138, :451-479) through the engine with the stand-in library,
+    against the oracle ports that are pinned to the unmodified train.py functions."""
+    from prcv2025reid_b200 import train_eval as te
+    _fake_lib.install(monkeypatch)
+    g = torch.Generator().manual_seed(3)
+    centres = torch.randn(20, 32, generator=g)
+    gl = torch.arange(120) // 6
+    ql = torch.randint(0, 20, (40,), generator=g); ql[:3] = 999
+    gf = centres[gl] + 2.0 * torch.randn(120, 32, generator=g)
+    qf = centres[ql.clamp(max=19)] + 2.0 * torch.randn(40, 32, generator=g)
+    for k in (1, 5, 100):
+        assert te.compute_map(qf, gf, ql, gl, k=k) == pytest.approx(orc.compute_map_oracle(qf, gf, ql, gl, k=k), abs=1e-6)
+    for k in (1, 10):
+        assert te.compute_cmc(qf, gf, ql, gl, k=k) == pytest.approx(orc.compute_cmc_oracle(qf, gf, ql, gl, k=k), abs=1e-12)
+    qn, gn = torch.nn.functional.normalize(qf, dim=1), torch.nn.functional.normalize(gf, dim=1)
+    m, t1 = te.reid_map(qn, gn, ql, gl)
+    wm, wt1 = orc.reid_map_oracle(qn @ gn.T, ql, gl)
+    assert m == pytest.approx(wm, abs=1e-4) and t1 == pytest.approx(wt1, abs=1e-12)
+    assert te.compute_map(qf[:0], gf, ql[:0], gl) == 0.0 and te.reid_map(qn[:0], gn, ql[:0], gl) == (0.0, 0.0)
