@@ -236,6 +236,73 @@ class FakeLib:
         return self._log("reid_topk_label_metrics")
 
 
+    # ------------------------------------------------------------------ SDM (pairs arrive as the packed reid_sdm_pair array)
+    @staticmethod
+    def _tensor(addr, shape, dtype):
+        """A torch view of host memory at `addr` (the stand-in of a device pointer)."""
+        import ctypes
+        import numpy as np
+        n = 1
+        for v in shape:
+            n *= int(v)
+        if dtype == torch.bfloat16:
+            arr = np.ctypeslib.as_array((ctypes.c_uint16 * n).from_address(addr))
+            return torch.from_numpy(arr).view(torch.bfloat16).view(*shape)
+        ct = {torch.float32: ctypes.c_float, torch.int32: ctypes.c_int32}[dtype]
+        return torch.from_numpy(np.ctypeslib.as_array((ct * n).from_address(addr))).view(*shape)
+
+    def _pairs(self, arr, n, code, d):
+        dt = torch.float32 if code == 0 else torch.bfloat16
+        out = []
+        for p in range(n):
+            w = [int(arr[10 * p + i]) for i in range(10)]
+            N, M = w[3] & 0xFFFFFFFF, w[3] >> 32
+            out.append(dict(q=self._tensor(w[0], (N, d), dt), g=self._tensor(w[1], (M, d), dt), y=self._tensor(w[2], (N, M), torch.float32),
+                            loss=self._tensor(w[4], (1,), torch.float32), status=self._tensor(w[5], (1,), torch.int32),
+                            grad=self._tensor(w[7], (1,), torch.float32) if w[7] else None,
+                            dq=self._tensor(w[8], (N, d), dt) if w[8] else None, dg=self._tensor(w[9], (M, d), dt) if w[9] else None))
+        return out
+
+    def reid_sdm_saved_floats(self, N, M, d):
+        return 64
+
+    def reid_sdm_uses_tensor_cores(self, arr, n, code, d):
+        return 0
+
+    def reid_sdm_step_launches(self, arr, n, code, d):
+        return 1
+
+    def _sdm(self, arr, n, code, d, tau, eps, fwd, bwd):
+        from oracle import sdm as osdm
+        for P in self._pairs(arr, n, code, d):
+            with torch.enable_grad():                                  # (autograd is off inside Function.backward)
+                q = P["q"].clone().requires_grad_(True); g = P["g"].clone().requires_grad_(True)
+                L = osdm.sdm_loss_oracle(q, g, P["y"], tau=tau, eps=eps)
+            if fwd:
+                P["loss"][0] = float(L.detach())
+                P["status"][0] = 0 if L.requires_grad else 1           # bit0: the reference's non-differentiable zero
+            if bwd:
+                if L.requires_grad:
+                    with torch.enable_grad():
+                        L.backward()
+                    P["dq"].copy_(q.grad * P["grad"][0]); P["dg"].copy_(g.grad * P["grad"][0])
+                else:
+                    P["dq"].zero_(); P["dg"].zero_()                   # guard path: exact-zero gradients
+        return 0
+
+    def reid_sdm_fwd(self, arr, n, code, d, tau, eps, st):
+        self._log("reid_sdm_fwd")
+        return self._sdm(arr, n, code, d, tau, eps, True, False)
+
+    def reid_sdm_bwd(self, arr, n, code, d, tau, eps, st):
+        self._log("reid_sdm_bwd")
+        return self._sdm(arr, n, code, d, tau, eps, False, True)
+
+    def reid_sdm_step(self, arr, n, code, d, tau, eps, st):
+        self._log("reid_sdm_step")
+        return self._sdm(arr, n, code, d, tau, eps, True, True)
+
+
 def install(monkeypatch, fake=None, **kw):
     """Route prcv2025reid_b200.engine to a FakeLib (tensors instead of device pointers).  -> the FakeLib."""
     from prcv2025reid_b200 import _cabi, engine
@@ -250,4 +317,8 @@ def install(monkeypatch, fake=None, **kw):
     monkeypatch.setattr(train_eval, "stream_ptr", lambda: None)
     monkeypatch.setattr(train_eval, "check", chk)
     monkeypatch.setattr(train_eval, "_dev", lambda t: t)
+    from prcv2025reid_b200 import sdm_loss
+    monkeypatch.setattr(sdm_loss, "check", chk)
+    monkeypatch.setattr(sdm_loss, "_raw_stream", lambda dev: None)
+    monkeypatch.setattr(sdm_loss, "_SAVED_FLOATS", {})
     return fake
