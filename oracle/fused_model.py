@@ -90,6 +90,7 @@ def fused_counts(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, 
     tc_all = max(total_chunks, n_chunks)
     pos_above = np.zeros((Q, Pmax), dtype=np.int64)
     n_exact = np.zeros(Q, dtype=np.int64)
+    hits = np.zeros((Q, 2), dtype=np.int64)                                 # epilogue hit volume: [ordinary rows, sampled rows]
     countable = ~masked & (gp[None, :] != qp[:, None])                      # neither masked nor a positive of the query
     if sample_deep:
         stride = G // calib_rows
@@ -115,6 +116,10 @@ def fused_counts(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, 
         # (the chunk structure does not change the counts: every chunk of a rank uses the same n_exact and the same
         #  row sample, and counts are additive over chunks)
         top = int((use & (s > t[ne - 1])).sum()) if ne > 0 else 0
+        # rows the epilogue has to classify (counting side only): above the lowest exactly counted threshold, plus the
+        # sampled rows above the lowest threshold of all
+        hits[q, 0] = int((s > t[ne - 1]).sum()) if ne > 0 else 0
+        hits[q, 1] = int((sampled & (s > t[npq - 1])).sum()) if ne < npq else 0
         for j in range(npq):
             if j < ne:
                 pos_above[q, j] = int((use & (s > t[j])).sum())            # exact on every row
@@ -125,7 +130,7 @@ def fused_counts(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, 
                 if ne > 0:
                     lo_mask &= ~(s > t[ne - 1])
                 pos_above[q, j] = top + sample_w * int(lo_mask.sum())
-    return {"pos_above": pos_above, "n_pos": n_pos, "n_exact": n_exact, "thr": thr}
+    return {"pos_above": pos_above, "n_pos": n_pos, "n_exact": n_exact, "thr": thr, "hits": hits}
 
 
 def rescore_stage(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, g_pid: torch.Tensor, counts: Dict[str, np.ndarray],
