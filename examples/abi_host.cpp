@@ -27,6 +27,7 @@
 namespace {
 
 int g_fail = 0;
+int g_checks = 0;
 #define CK(call)                                                                                    \
   do {                                                                                              \
     const int rc_ = (call);                                                                         \
@@ -41,6 +42,7 @@ int g_fail = 0;
 void expect(bool ok, const char* what, double got, double bound) {
   std::printf("%s %-58s %.3e (bound %.1e)\n", ok ? "ok  " : "FAIL", what, got, bound);
   std::fflush(stdout);
+  ++g_checks;
   if (!ok) ++g_fail;
 }
 
@@ -353,6 +355,7 @@ int main() {
 
   CU(cudaStreamDestroy(st));
   if (g_fail) { std::printf("%d CHECK(S) FAILED\n", g_fail); return 1; }
+  std::printf("CHECKS %d\n", g_checks);
   std::printf("ALL OK\n");
   return 0;
 }
