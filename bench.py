@@ -45,6 +45,18 @@ def workload_name(w):
         k, n_ids * qpi, n_ids * gpi, seed)
 
 
+EXCL_FRAC, N_EXCL, TOPK = 0.01, 2, 10
+
+
+def bench_config(w):
+    """The workload description BOTH arms print (identical dicts: the driver compares them)."""
+    seed, n_ids, gpi, k, qpi = WORKLOADS[w]
+    G, Q = n_ids * gpi, n_ids * qpi
+    return {"workload": workload_name(w), "k": k, "topk": TOPK, "excl_frac": EXCL_FRAC, "n_excl": N_EXCL,
+            "l2": "inputs larger than L2, no flush needed (query features %d MB fp32, gallery %d MB fp16 / %d MB fp32 per "
+                  "step; L2 = 126 MB)" % ((Q * k * FEAT_DIM * 4) >> 20, (G * FEAT_DIM * 2) >> 20, (G * FEAT_DIM * 4) >> 20)}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -118,7 +130,7 @@ def run_reference(args):
     sample = args.ref_queries
     n_need = sample * (args.steps + args.warmup)
     # the first queries of the workload, generated with the full workload's identity centres
-    small = synth.make_retrieval_case(seed, n_ids, gpi, k, qpi, excl_frac=0.0, gallery_rows=(0, 0),
+    small = synth.make_retrieval_case(seed, n_ids, gpi, k, qpi, excl_frac=EXCL_FRAC, n_excl=N_EXCL, gallery_rows=(0, 0),
                                       max_queries=n_need)
     w = synth.weights_tensor()
     times = []
@@ -126,7 +138,7 @@ def run_reference(args):
         sl = slice(it * sample, (it + 1) * sample)
         t0 = time.perf_counter()
         q = orc.fuse_queries(small.query_raw[sl], small.mod_id[sl], w)
-        orc.rank_and_metrics_loop(q, g, small.q_pid[sl], g_pid, None)
+        orc.rank_and_metrics_loop(q, g, small.q_pid[sl], g_pid, small.excl[sl])
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
@@ -136,10 +148,10 @@ def run_reference(args):
         "impl": "reference", "metric": "queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload), "k": k, "topk": 10},
+        "config": bench_config(args.workload),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                         "sample": "%d queries per step against the full %d-row gallery, per-query loop of "
-                                   "eval_mm_protocol.py:396-455 (torch CPU GEMV + argsort + AP walk)" % (sample, G)},
+                         "sample": "%d queries per step (same-image exclusion list included) against the full %d-row gallery, "
+                                   "per-query loop of eval_mm_protocol.py:396-455 (torch CPU GEMV + argsort + AP walk)" % (sample, G)},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -223,6 +235,110 @@ def torch_gpu_baseline(torch, engine, shard, case, weights, nq, iters=3):
             "sample": "first %d queries of the workload against the full gallery shard" % nq, "mAP_on_sample": m[0], "R@1_on_sample": m[1]}
 
 
+def parity_check(torch, engine, synth, shard, case, weights, args, group, rank, world, dev):
+    """Oracle check inside the run: the first `parity_queries` queries through engine.retrieve (every rank takes part),
+    rank 0 compares with oracle.rank_and_metrics_counting on the unsharded gallery.  CMC must be identical, the top-10
+    lists identical modulo 2e-6 ties of the reference's own fp32 scores, mAP within 1e-4."""
+    import numpy as np
+    nq = min(args.parity_queries, case.Q)
+    seed, n_ids, gpi, k, qpi = WORKLOADS[args.workload]
+    q32, q16 = engine.fuse_queries(case.query_raw[:nq], case.mod_id[:nq], weights)
+    r = engine.retrieve(shard, q32, q16, case.q_pid[:nq], case.excl[:nq], topk=TOPK, mode=args.mode, group=group, want_ap=True)
+    if rank != 0:
+        return None
+    from oracle import retrieval as orc
+    centres, bias = synth.make_centres(seed, n_ids, device=dev)
+    G = n_ids * gpi
+    g = orc.l2n(synth.make_gallery_rows(seed, centres, bias, gpi, 0, G).cpu())
+    q = orc.fuse_queries(case.query_raw[:nq].cpu(), case.mod_id[:nq].cpu(), weights.cpu())
+    t0 = time.perf_counter()
+    o = orc.rank_and_metrics_counting(q, g, case.q_pid[:nq].cpu(), case.g_pid.cpu(), case.excl[:nq].cpu(), return_per_query=True)
+    oracle_s = time.perf_counter() - t0
+    v = o["_valid"]
+    ap = r.ap.cpu().numpy()
+    first = r.pos_above[:, 0].cpu().numpy() + 1
+    ti = r.top_idx.cpu().numpy().astype(np.int64)
+    beyond = 0
+    for qi in np.nonzero((ti[:, :TOPK] != o["_top_idx"][:, :TOPK]).any(axis=1))[0]:
+        sc = (q[qi:qi + 1] @ g.T).squeeze(0).numpy()
+        if any(ti[qi, j] != o["_top_idx"][qi, j] and abs(float(sc[ti[qi, j]]) - float(sc[o["_top_idx"][qi, j]])) > 2e-6 for j in range(TOPK)):
+            beyond += 1
+    d_ap = np.abs(ap[v] - o["_ap"][v])
+    out = {"queries": nq, "oracle": "oracle.retrieval.rank_and_metrics_counting (CPU fp32, full ranking of the unsharded gallery)",
+           "mAP": r.metrics["mAP"], "mAP_oracle": o["mAP"], "d_mAP": r.metrics["mAP"] - o["mAP"],
+           "cmc": [r.metrics["R@1"], r.metrics["R@5"], r.metrics["R@10"]], "cmc_oracle": [o["R@1"], o["R@5"], o["R@10"]],
+           "cmc_rank_mismatches": int((np.minimum(first[v], 11) != np.minimum(o["_first"][v], 11)).sum()), "top10_lists_differing_beyond_2e-6_ties": beyond,
+           "per_query_dAP_max": float(d_ap.max()), "per_query_dAP_mean": float(d_ap.mean()), "oracle_seconds": round(oracle_s, 2)}
+    out["ok"] = bool(abs(out["d_mAP"]) <= 1e-4 and out["cmc"] == out["cmc_oracle"] and beyond == 0)
+    return out
+
+
+def secondary_workloads(torch, engine, synth, _cabi, weights, dev, steps=5):
+    """The other BASELINE retrieval configs on one GPU (C3a, C3b: 20k x 100k; C1: 3k x 10k), same step as the headline,
+    plus the dict-level drop-in `rank_and_metrics(queries, ...)` on C1 (the call a user of the reference makes)."""
+    out = {}
+    for w in ("c3a", "c3b", "c1"):
+        seed, n_ids, gpi, k, qpi = WORKLOADS[w]
+        G, Q = n_ids * gpi, n_ids * qpi
+        case = synth.make_retrieval_case(seed, n_ids, gpi, k, qpi, excl_frac=EXCL_FRAC, n_excl=N_EXCL, device=dev)
+        shard = engine.prepare_gallery(case.gallery_raw, case.g_pid)
+
+        def step():
+            q32, q16 = engine.fuse_queries(case.query_raw, case.mod_id, weights)
+            return engine.retrieve(shard, q32, q16, case.q_pid, case.excl, topk=TOPK)
+        for _ in range(3):
+            res = step()
+        torch.cuda.synchronize()
+        _cabi.PROFILE = []
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            res = step()
+        e.record()
+        torch.cuda.synchronize()
+        prof, _cabi.PROFILE = _cabi.PROFILE, None
+        ms = s.elapsed_time(e) / steps
+        fused_ms = sum(a.elapsed_time(b) for n, a, b in prof if n == "reid_retrieve_fused") / steps
+        tf = 2.0 * Q * G * FEAT_DIM / (fused_ms * 1e-3) / 1e12 if fused_ms > 0 else None
+        out[w] = {"workload": workload_name(w), "queries_per_sec": Q / (ms * 1e-3), "ms_per_step": ms,
+                  "fused_kernel_ms": fused_ms, "fused_tflops": tf, "metrics": res.metrics, "path": res.path,
+                  "flagged_queries": res.n_flagged}
+        if w == "c1":
+            out["c1_dropin"] = dropin_c1(torch, synth, case)
+        del case, shard
+        torch.cuda.empty_cache()
+    return out
+
+
+def dropin_c1(torch, synth, case):
+    """rank_and_metrics(queries, gallery_feats, gallery_meta, extractor, weight_cfg) -- the reference's own signature
+    (tools/eval_mm_protocol.py:369) with its list-of-dicts inputs on the HOST -- timed end to end beside the oracle port
+    of the reference's per-query CPU loop on the same inputs."""
+    from oracle import retrieval as orc
+    from prcv2025reid_b200 import eval_mm_protocol as emp
+    cpu = synth.RetrievalCase(case.gallery_raw.cpu(), case.g_pid.cpu(), case.query_raw.cpu(), case.mod_id.cpu(),
+                              case.q_pid.cpu(), case.excl.cpu(), case.k)
+    queries, gmeta, ext = synth.case_to_reference_inputs(cpu)
+    g = emp.l2n(cpu.gallery_raw)
+    wcfg = dict(synth.DEFAULT_WEIGHTS)
+    emp.rank_and_metrics(queries, g, gmeta, ext, wcfg, ignore_same_img=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 3
+    for _ in range(n):
+        m = emp.rank_and_metrics(queries, g, gmeta, ext, wcfg, ignore_same_img=True)
+    torch.cuda.synchronize()
+    ours = (time.perf_counter() - t0) / n
+    nq = 300
+    t0 = time.perf_counter()
+    q = orc.fuse_queries(cpu.query_raw[:nq], cpu.mod_id[:nq], synth.weights_tensor())
+    orc.rank_and_metrics_loop(q, orc.l2n(cpu.gallery_raw), cpu.q_pid[:nq], cpu.g_pid, cpu.excl[:nq])
+    ref = (time.perf_counter() - t0) / nq
+    return {"call": "rank_and_metrics(queries, gallery_feats, gallery_meta, extractor, weight_cfg, ignore_same_img=True)",
+            "queries_per_sec": len(queries) / ours, "seconds_per_call": ours, "metrics": m,
+            "cpu_port_queries_per_sec": 1.0 / ref, "cpu_port_sample": "first %d queries, per-query loop" % nq}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -230,8 +346,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-queries", type=int, default=8, help="queries per step of the CPU reference arm")
-    ap.add_argument("--cpu-baseline-queries", type=int, default=24)
+    ap.add_argument("--ref-queries", type=int, default=24, help="queries per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-queries", type=int, default=128)
+    ap.add_argument("--parity-queries", type=int, default=256, help="queries of the in-run oracle check (0 = skip)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C1 / C3 secondary workloads")
     ap.add_argument("--no-sdm", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fused", choices=["fused", "exact"])
@@ -259,7 +377,7 @@ def main():
     seed, n_ids, gpi, k, qpi = WORKLOADS[args.workload]
     G, Q = n_ids * gpi, n_ids * qpi
     r0, r1 = sharding.shard_range(G, rank, world)
-    case = synth.make_retrieval_case(seed, n_ids, gpi, k, qpi, excl_frac=0.01, n_excl=2, device=dev,
+    case = synth.make_retrieval_case(seed, n_ids, gpi, k, qpi, excl_frac=EXCL_FRAC, n_excl=N_EXCL, device=dev,
                                      gallery_rows=(r0, r1))
     weights = synth.weights_tensor(device=dev)
     torch.cuda.synchronize()
@@ -351,10 +469,13 @@ def main():
         except Exception:
             peak, which = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
         traffic, traffic_src = None, None
-        try:      # DRAM bytes per launch from the committed ncu --set full capture of this exact configuration
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01e_traffic.json")))[dom]
-            if tr["workload"] == args.workload and tr["n_gpus"] == world:
-                traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+        try:      # DRAM bytes per launch from the newest committed ncu --set full capture of this exact configuration
+            import glob
+            for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+                tr = json.load(open(path)).get(dom)
+                if tr and tr["workload"] == args.workload and tr["n_gpus"] == world:
+                    traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"] + " [" + os.path.basename(path) + "]"
+                    break
         except Exception:
             pass
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -380,21 +501,32 @@ def main():
                                                  "frac_of_hbm_peak": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak,
                                                  "note": "k x 2 KB read + 3 KB (fp32 + fp16) written per query"}
 
+    # ---- in-run parity: the first queries of the workload through the same engine call (same shards, same exchange)
+    #      against the oracle's full ranking walk on the CPU (tools/eval_mm_protocol.py:396-455); outside the timed region
+    parity = None
+    if args.parity_queries > 0:
+        parity = parity_check(torch, engine, synth, shard, case, weights, args, group, rank, world, dev)
+
     line = {
         "metric": "queries_per_sec", "value": Q / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+        "metrics": res.metrics, "parity": parity,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate / f32 re-score",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.workload), "k": k, "topk": 10, "mode": args.mode,
-                   "gallery_rows_per_gpu": r1 - r0, "l2": "inputs larger than L2 (query batch %d MB, gallery shard %d MB fp16)"
-                   % (h2d_bytes >> 20, ((r1 - r0) * FEAT_DIM * 2) >> 20),
-                   "gallery_prepare_ms": round(gallery_prepare_ms, 2), "flagged_queries": res.n_flagged},
-        "metrics": res.metrics,
+        "config": bench_config(args.workload),
+        "run_info": {"mode": args.mode, "path": res.path, "gallery_rows_per_gpu": r1 - r0,
+                     "gallery_prepare_ms": round(gallery_prepare_ms, 2), "flagged_queries": res.n_flagged,
+                     "query_block": engine.default_query_block(_cabi.lib().reid_device_sm_count())},
         "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 40, "ms_per_step": ms_e2e},
+                "d2h_bytes_per_step": 48, "ms_per_step": ms_e2e, "metrics_equal_resident": all(abs(res2.metrics[m_] - res.metrics[m_]) <= 1e-12 for m_ in res.metrics)},
         "gpu_launches": launches, "kernel_ms_per_step": kernel_ms, "roofline": roofline,
         "hbm_kernels": hbm_kernels, "clocks": clocks,
     }
+
+    if rank == 0 and world == 1 and not args.no_secondary and args.workload == "c4":
+        del h_query, res, res2
+        torch.cuda.empty_cache()
+        line["secondary"] = secondary_workloads(torch, engine, synth, _cabi, weights, dev)
 
     if rank == 0 and world == 1:
         if not args.no_sdm:

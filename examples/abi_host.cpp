@@ -262,8 +262,8 @@ int main() {
     if (fused) {
       const size_t wsb = reid_workspace_bytes(1, Q, G, D);
       Dev<uint8_t> ws(wsb);
-      CK(reid_retrieve_fused(d_q16.p, d_g16.p, d_qcode.p, d_gcode.p, nullptr, 0, d_thr.p, d_npos.p, Q, G, 0, D, Pmax, n_chunks,
-                             n_chunks, cap, d_above.p, d_cs.p, d_cidx.p, d_ccnt.p, d_cthr.p, ws.p, wsb, st));
+      CK(reid_retrieve_fused(d_q16.p, d_g16.p, d_qcode.p, d_gcode.p, nullptr, 0, d_thr.p, d_npos.p, Q, G, 0, D, Pmax, Pmax, n_chunks,
+                             1, cap, 0, d_above.p, d_cs.p, d_cidx.p, d_ccnt.p, d_cthr.p, ws.p, wsb, st));
       CK(reid_rescore_topk(d_q32.p, d_g32.p, d_qcode.p, d_gcode.p, d_thr.p, d_npos.p, d_cs.p, d_cidx.p, d_ccnt.p, d_cthr.p, nullptr, Q,
                            Q, G, 0, D, Pmax, n_chunks, cap, topk, eps16, d_above.p, d_tops.p, d_topi.p, d_flag.p, st));
       CU(cudaStreamSynchronize(st));                                  // (ws must outlive the kernels)

@@ -79,19 +79,29 @@ int reid_pos_sort(float* pos_score, int32_t* n_pos, int64_t Q, int Pmax, void* s
  *       that are neither positives of q nor masked and score above it  -> pos_above[q,j] (+=)
  *   (b) appends every row that beats the running REID_KLIST-th best of its (query, chunk) to
  *       cand_score/cand_idx[q, chunk, :cand_cap] (local row index), count in cand_count[q,chunk].
- * g_code / q_code: pid codes from reid_pid_lookup.  n_chunks = gallery chunks per query block
- * (work decomposition; buffers are sized with it).  pos_above and cand_count must be zeroed.
+ * g_code / q_code: pid codes from reid_pid_lookup.  n_chunks = candidate slots per query (buffers are sized with it):
+ * work items are (block of 256 queries, gallery rows); the query blocks that fill whole waves of the persistent CTA
+ * pairs run against the whole shard (slot 0 only), the blocks of the last, partial wave are cut into n_chunks gallery
+ * chunks so that this wave is full too.  pos_above and cand_count must be zeroed.
+ * Pmax <= 64 thresholds per query and call; pos_stride = row stride (elements) of pos_thr and pos_above (0 = Pmax),
+ * so that a query with more positives is processed in windows of 64 thresholds (pointers advanced by the caller).
  * cand_thr [Q] (optional): per-query score with >= REID_KLIST candidates at or above it (-inf if fewer);
  * every candidate the re-scorer can need lies at or above it.
- * total_chunks = chunks the WHOLE gallery of a query is cut into over all ranks (n_chunks x world size;
- * 0 = n_chunks): thresholds deeper than max(1024 / total_chunks, 8 calibration hits) rows of a chunk are
- * counted on the 1/32 row sample, so a deep rank rests on >= 32 sampled rows gallery-wide. */
+ * n_shards = ranks the WHOLE gallery of a query is partitioned over (0 / 1 = this shard is the whole gallery).
+ * Counting classes (shards of >= 32768 rows; a calibration pre-pass over a strided 1/16 of the shard, 2048 .. 8192
+ * rows, estimates every threshold's rank inside the shard): thresholds ranked above max(1024 / n_shards, 8 calibration hits) rows are
+ * counted on a 1/32 row sample, those above 32768 / n_shards rows on a 1/1024 row sample, so that a sampled count
+ * rests on >= 32 sampled rows gallery-wide; all shallower thresholds on every row.
+ * flags: REID_FUSED_EXACT_COUNTS = count every threshold on every row (no sampling; slow for deep positives);
+ *        REID_FUSED_NO_CANDIDATES = counting only (cand_* may be NULL). */
+#define REID_FUSED_EXACT_COUNTS 1
+#define REID_FUSED_NO_CANDIDATES 2
 int reid_retrieve_fused(const void* q_f16, const void* g_f16, const int32_t* q_code,
                         const int32_t* g_code, const int32_t* excl, int E, const float* pos_thr,
                         const int32_t* n_pos, int64_t Q, int64_t G_local, int64_t g_offset, int d,
-                        int Pmax, int n_chunks, int total_chunks, int cand_cap, int32_t* pos_above,
-                        float* cand_score, int32_t* cand_idx, int32_t* cand_count, float* cand_thr,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        int Pmax, int pos_stride, int n_chunks, int n_shards, int cand_cap, int flags,
+                        int32_t* pos_above, float* cand_score, int32_t* cand_idx, int32_t* cand_count,
+                        float* cand_thr, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- exact fp32 SIMT form of the same step (all scores in fp32, CUDA cores).  Used for the
  * queries the fused path flags, for tiny problems, and as the in-library cross-check.

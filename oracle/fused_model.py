@@ -9,15 +9,18 @@ built.  It follows the kernel, not the reference:
 
   scores             fp32 accumulation of fp16-rounded operands                       retrieve_fused.cu kernel comment (kind::f16 MMA)
   thresholds t_j     the positives' EXACT fp32 scores, sorted descending              reid_pos_scores / reid_pos_sort
-  calibration        strided sample of CALIB_ROWS rows, every threshold exact         reid_retrieve_fused host code (`sample_deep`)
-  exact / deep split calib_split_kernel: threshold j is exact while the estimated     retrieve_fused.cu:237-255
-                     in-chunk rank of thresholds 0..j stays <= limit,
-                     limit = max(32 * SAMPLE_W / total_chunks, 8 * scale)
-  main pass          ordinary rows see thresholds [0, n_exact); rows with             epi_drain32, retrieve_fused.cu:159-176
-                     local_row % SAMPLE_W == 5 see all of them and weigh SAMPLE_W
-                     in the deep buckets; positives of the query and masked rows
-                     are skipped; rows >= G_local are no rows
-  pos_above[j]       prefix sum of the bucket histogram                               hist_to_above_kernel
+  calibration        strided sample of G_local/16 rows (2048 .. 8192), every threshold exact         reid_retrieve_fused host code (`sample_deep`)
+  counting classes   calib_split_kernel: threshold j is counted on every row while    retrieve_fused.cu calib_split_kernel
+                     the estimated rank INSIDE THE SHARD of thresholds 0..j stays
+                     <= limit1 = max(32 * W1 / n_shards, 8 * scale), on the level-1
+                     row sample while it stays <= limit2 = max(32 * W2 / n_shards,
+                     limit1), else on the level-2 sample; scale = G_local / CALIB_ROWS
+  main pass          ordinary rows see thresholds [0, n_exact); rows with             epi_drain32
+                     local_row % W1 == 5 see [0, n_l1) and weigh W1 in buckets
+                     [n_exact, n_l1); rows with local_row % W2 == 5 see all of them and
+                     weigh W2 in buckets [n_l1, n_pos); positives of the query and
+                     masked rows are skipped; rows >= G_local are no rows
+  pos_above[j]       weighted prefix sum of the bucket histogram                      hist_to_above_kernel
 
   re-scoring         the RTOP best local rows by fp16 score are re-scored in fp32; cut = KLIST-th best     rescore_topk_kernel, rank.cu
                      fp16 score, bound = cut + eps; a positive with t_j > bound gets its EXACT local
@@ -33,9 +36,11 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-SAMPLE_W = 32        # REID_SAMPLE_W
-CALIB_ROWS = 2048    # REID_CALIB_ROWS
-SAMPLE_PHASE = 5     # rows with (row % SAMPLE_W) == 5
+SAMPLE_W = 32        # W1: level-1 row sample
+SAMPLE_W2 = 1024     # W2: level-2 row sample
+CALIB_ROWS = 8192    # REID_CALIB_ROWS (upper bound of the calibration sample)
+CALIB_MIN = 2048     # lower bound; shards below 16 * CALIB_MIN rows are never sampled
+SAMPLE_PHASE = 5     # rows with (row % W) == 5
 KLIST = 32           # REID_KLIST
 RTOP = 32            # REID_RTOP
 EPS_FP16 = 2.0 ** -10 + 2.0 ** -13    # engine.EPS_FP16
@@ -61,16 +66,18 @@ def positive_thresholds(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.T
 
 
 def fused_counts(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, g_pid: torch.Tensor,
-                 excl: Optional[torch.Tensor] = None, n_chunks: int = 1, total_chunks: int = 0, exact_all: bool = False,
-                 sample_w: int = SAMPLE_W, calib_rows: int = CALIB_ROWS, thr: Optional[np.ndarray] = None,
-                 n_pos: Optional[np.ndarray] = None, g_offset: int = 0) -> Dict[str, np.ndarray]:
+                 excl: Optional[torch.Tensor] = None, n_shards: int = 1, exact_all: bool = False,
+                 sample_w: int = SAMPLE_W, sample_w2: int = SAMPLE_W2, calib_rows: int = CALIB_ROWS,
+                 thr: Optional[np.ndarray] = None, n_pos: Optional[np.ndarray] = None, g_offset: int = 0) -> Dict[str, np.ndarray]:
     """One rank's reid_retrieve_fused -> {"pos_above" [Q, Pmax] int64 (modelled LOCAL counts, additive over ranks),
-    "n_pos" [Q], "n_exact" [Q], "thr" [Q, Pmax]}.
+    "n_pos" [Q], "n_exact" [Q], "n_l1" [Q], "thr" [Q, Pmax], "hits" [Q, 3] (epilogue hit volume by row class)}.
 
     q_f32 [Q, D] fused + normalised queries; g_f32 [G_local, D] / g_pid [G_local] this rank's normalised gallery rows,
     which are rows [g_offset, g_offset + G_local) of the whole gallery; excl [Q, E] GLOBAL gallery rows masked per query
     (-1 pad); thr / n_pos: the gallery-wide positive thresholds (positive_thresholds; default: computed from this shard,
-    i.e. a one-rank job).  exact_all = the kernel with REID_FUSED_DEBUG=64 (no deep sampling)."""
+    i.e. a one-rank job).  exact_all = REID_FUSED_EXACT_COUNTS (no sampling).  sample_w2 = 0: one sampling level only
+    (the round-1 rule).  The work decomposition (query blocks, gallery chunks) does not change the counts: a threshold's
+    class is the same in every chunk of a shard, chunk starts are multiples of W2 and counts are additive."""
     Q, G = q_f32.shape[0], g_f32.shape[0]
     S16 = (q_f32.half().float() @ g_f32.half().float().T).numpy()          # what the tensor cores score with
     gp, qp = g_pid.numpy(), q_pid.numpy()
@@ -84,53 +91,51 @@ def fused_counts(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, 
         thr, n_pos = positive_thresholds(q_f32, g_f32, q_pid, g_pid,
                                          None if excl is None else torch.from_numpy(np.where(excl.numpy() >= 0, excl.numpy() - g_offset, -1)))
     Pmax = thr.shape[1]
-    rows_per_chunk = -(-G // n_chunks)
-    rows_per_chunk = -(-rows_per_chunk // 256) * 256                       # tiles of 256 rows (pair layout)
-    sample_deep = (G >= 16 * calib_rows) and not exact_all
-    tc_all = max(total_chunks, n_chunks)
+    sample_deep = (G >= 16 * CALIB_MIN) and not exact_all
+    calib_rows = max(CALIB_MIN, min(calib_rows, G // 16 // 256 * 256))    # 1/16 of the shard in whole tiles
     pos_above = np.zeros((Q, Pmax), dtype=np.int64)
     n_exact = np.zeros(Q, dtype=np.int64)
-    hits = np.zeros((Q, 2), dtype=np.int64)                                 # epilogue hit volume: [ordinary rows, sampled rows]
+    n_l1 = np.zeros(Q, dtype=np.int64)
+    hits = np.zeros((Q, 3), dtype=np.int64)                                 # epilogue hit volume: [ordinary, level-1, level-2 rows]
     countable = ~masked & (gp[None, :] != qp[:, None])                      # neither masked nor a positive of the query
     if sample_deep:
         stride = G // calib_rows
         cal_rows = np.arange(calib_rows) * stride
-        scale = rows_per_chunk / calib_rows
-        limit = max(32.0 * sample_w / tc_all, 8.0 * scale)
+        scale = np.float32(G) / np.float32(calib_rows)
+        limit1 = max(32.0 * sample_w / max(1, n_shards), 8.0 * float(scale))
+        limit2 = max(32.0 * sample_w2 / max(1, n_shards), limit1) if sample_w2 else np.inf
     rows = np.arange(G)
-    sampled = (rows % sample_w) == SAMPLE_PHASE                            # chunk starts are multiples of 256: local row % W
+    s1 = (rows % sample_w) == SAMPLE_PHASE
+    s2 = ((rows % sample_w2) == SAMPLE_PHASE) if sample_w2 else np.zeros(G, dtype=bool)
     for q in range(Q):
         npq = int(n_pos[q])
         if npq == 0:
             continue
         t = thr[q, :npq]
-        ne = npq
+        ne = n1 = npq
         if sample_deep:
             # calibration pass: bucket histogram of the strided sample, every threshold exact
             cs = S16[q, cal_rows][countable[q, cal_rows]]
             acc = np.array([(cs > tj).sum() for tj in t])                  # prefix sums over buckets <= j
-            ok = acc.astype(np.float32) * np.float32(scale) <= np.float32(limit)
-            ne = npq if ok.all() else int(np.argmin(ok))                  # the first threshold over the limit closes the prefix
-        n_exact[q] = ne
+            est = acc.astype(np.float32) * np.float32(scale)
+            ok1, ok2 = est <= np.float32(limit1), est <= np.float32(limit2)
+            ne = npq if ok1.all() else int(np.argmin(ok1))                # the first threshold over the limit closes the prefix
+            n1 = max(ne, npq if ok2.all() else int(np.argmin(ok2)))
+        n_exact[q], n_l1[q] = ne, n1
         s, use = S16[q], countable[q]
-        # (the chunk structure does not change the counts: every chunk of a rank uses the same n_exact and the same
-        #  row sample, and counts are additive over chunks)
-        top = int((use & (s > t[ne - 1])).sum()) if ne > 0 else 0
-        # rows the epilogue has to classify (counting side only): above the lowest exactly counted threshold, plus the
-        # sampled rows above the lowest threshold of all
+        # rows the epilogue has to classify (counting side only)
         hits[q, 0] = int((s > t[ne - 1]).sum()) if ne > 0 else 0
-        hits[q, 1] = int((sampled & (s > t[npq - 1])).sum()) if ne < npq else 0
-        for j in range(npq):
-            if j < ne:
-                pos_above[q, j] = int((use & (s > t[j])).sum())            # exact on every row
-            else:
-                # rows above the lowest exact threshold are counted exactly (buckets < n_exact), the rest of the way
-                # down to t_j on the row sample with weight sample_w
-                lo_mask = use & sampled & (s > t[j])
-                if ne > 0:
-                    lo_mask &= ~(s > t[ne - 1])
-                pos_above[q, j] = top + sample_w * int(lo_mask.sum())
-    return {"pos_above": pos_above, "n_pos": n_pos, "n_exact": n_exact, "thr": thr, "hits": hits}
+        hits[q, 1] = int((s1 & (s > t[n1 - 1])).sum()) if n1 > ne else 0
+        hits[q, 2] = int((s2 & (s > t[npq - 1])).sum()) if npq > n1 else 0
+        # bucket b of a row = #{j : t_j >= s}: the row lies above thresholds j >= b
+        bucket = np.searchsorted(-t, -s, side="right")                     # t descending; t_j >= s  <=>  -t_j <= -s
+        hist = np.zeros(npq + 1, dtype=np.int64)
+        cls_w = np.where(np.arange(npq + 1) < ne, 1, np.where(np.arange(npq + 1) < n1, sample_w, sample_w2 or sample_w))
+        sees = np.where(s2, npq, np.where(s1, n1, ne))                     # thresholds [0, sees) are visible to the row
+        counted = use & (bucket < sees)
+        np.add.at(hist, bucket[counted], 1)
+        pos_above[q, :npq] = np.cumsum(hist[:npq] * cls_w[:npq])
+    return {"pos_above": pos_above, "n_pos": n_pos, "n_exact": n_exact, "n_l1": n_l1, "thr": thr, "hits": hits}
 
 
 def rescore_stage(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, g_pid: torch.Tensor, counts: Dict[str, np.ndarray],

@@ -11,6 +11,8 @@ KLIST = 32
 RTOP = 32
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 SDM_MAX_PAIRS = 16
+FUSED_EXACT_COUNTS, FUSED_NO_CANDIDATES = 1, 2
+FUSED_PMAX = 64           # thresholds per query and reid_retrieve_fused call
 
 
 class ReidError(RuntimeError):
@@ -37,8 +39,8 @@ _SIGS = {
                                 c_int64, c_int, c_int, c_void_p, c_void_p]),
     "reid_pos_sort": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "reid_retrieve_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                    c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                    c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "reid_retrieve_exact": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

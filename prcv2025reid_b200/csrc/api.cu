@@ -15,7 +15,7 @@ extern "C" const char* reid_strerror(int code) {
   }
 }
 
-extern "C" int reid_abi_version(void) { return 1; }
+extern "C" int reid_abi_version(void) { return 2; }
 
 extern "C" size_t reid_workspace_bytes(int which, int64_t Q, int64_t G, int d) {
   if (which == 0) return reid_pid_index_workspace_bytes(G);

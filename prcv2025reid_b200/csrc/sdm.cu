@@ -30,6 +30,7 @@ using SdmBatch = sdm::Batch;
 using sdm::ld_elem;
 using sdm::norm_elem;
 using sdm::st_out;
+using sdm::round_dt;
 
 struct Saved {
   float *den_q, *den_g, *lse_r, *lse_c, *cnt_r, *cnt_c, *ce_r, *ce_c, *hdr, *S, *dqn, *dgn, *qn, *gn;
@@ -96,7 +97,7 @@ __device__ __forceinline__ void tile_gemm(int K, LA la, LB lb, float (&acc)[4][4
 }
 
 // row denominators max(||x||, eps) in the reference's dtype path + non-finite detection
-template <bool BF16>
+template <int BF16>
 __device__ void phase_norms(const void* x, int rows, int d, float eps, float* den, float* xn, int* flags, int cta, int nctas) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = cta * (TB / 32) + warp; r < rows; r += nctas * (TB / 32)) {
@@ -104,7 +105,7 @@ __device__ void phase_norms(const void* x, int rows, int d, float eps, float* de
     for (int c = lane; c < d; c += 32) { const float v = ld_elem<BF16>(x, (size_t)r * d + c); ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
     float nrm = sqrtf(ss), e = eps;
-    if (BF16) { nrm = __bfloat162float(__float2bfloat16_rn(nrm)); e = __bfloat162float(__float2bfloat16_rn(eps)); }
+    if (BF16) { nrm = round_dt<BF16>(nrm); e = round_dt<BF16>(eps); }
     const float dn = fmaxf(nrm, e);
     bool bad = false;
     for (int c = lane; c < d; c += 32) {
@@ -117,7 +118,7 @@ __device__ void phase_norms(const void* x, int rows, int d, float eps, float* de
   }
 }
 
-template <bool BF16>
+template <int BF16>
 __global__ void __launch_bounds__(TB)
 sdm_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   __shared__ __align__(16) float As[KC][TM + 4];
@@ -235,7 +236,7 @@ sdm_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   }
 }
 
-template <bool BF16>
+template <int BF16>
 __global__ void __launch_bounds__(TB)
 sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   __shared__ __align__(16) float As[KC][TM + 4];
@@ -303,7 +304,7 @@ sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
     const float den = isq ? sv.den_q[row] : sv.den_g[row];
     const float* dxn = (isq ? sv.dqn : sv.dgn) + (size_t)row * d;
     float e = eps;
-    if (BF16) e = __bfloat162float(__float2bfloat16_rn(eps));
+    if (BF16) e = round_dt<BF16>(eps);
     const bool clamped = !(den > e);   // norm <= eps: denominator is the constant eps
     if (dead) {
       for (int c = lane; c < d; c += 32) st_out<BF16>(out, (size_t)row * d + c, 0.f);
@@ -328,17 +329,22 @@ sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
 constexpr int SMALL_MAX = 32;
 
 // one row (d <= 512, d % 128 == 0) into registers: lane owns elements k*128 + lane*4 .. +3; all loads issued up front
-template <bool BF16>
+template <int BF16>
 __device__ __forceinline__ void small_load_row(const void* x, size_t row, int d, int lane, float (&v)[16]) {
   const int nchunk = d >> 7;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (k < nchunk) {
       const size_t o = row * d + k * 128 + lane * 4;
-      if (BF16) {
+      if (BF16 == REID_DTYPE_BF16) {
         const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + o);
         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
         const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+        v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = b.x; v[4 * k + 3] = b.y;
+      } else if (BF16 == REID_DTYPE_F16) {
+        const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(x) + o);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
         v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = b.x; v[4 * k + 3] = b.y;
       } else {
         const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + o);
@@ -350,7 +356,7 @@ __device__ __forceinline__ void small_load_row(const void* x, size_t row, int d,
   }
 }
 // normalised row into shared memory (reference dtype path); returns whether every element is finite
-template <bool BF16>
+template <int BF16>
 __device__ __forceinline__ bool small_store_norm(const float (&v)[16], float dn, float* dst, int d, int lane) {
   const int nchunk = d >> 7;
   bool fin = true;
@@ -361,7 +367,7 @@ __device__ __forceinline__ bool small_store_norm(const float (&v)[16], float dn,
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         o[e] = __fdiv_rn(v[4 * k + e], dn);
-        if (BF16) o[e] = __bfloat162float(__float2bfloat16_rn(o[e]));
+        o[e] = round_dt<BF16>(o[e]);
         fin = fin && isfinite(o[e]);
       }
       *reinterpret_cast<float4*>(dst + k * 128 + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
@@ -369,7 +375,7 @@ __device__ __forceinline__ bool small_store_norm(const float (&v)[16], float dn,
   return fin;
 }
 
-template <bool BF16>
+template <int BF16>
 __global__ void __launch_bounds__(TB)
 sdm_small_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   extern __shared__ __align__(16) float small_smem[];
@@ -395,7 +401,7 @@ sdm_small_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
     for (int c = 0; c < 16; ++c) ss = fmaf(v[c], v[c], ss);
     ss = warp_sum(ss);
     float nrm = sqrtf(ss), e = eps;
-    if (BF16) { nrm = __bfloat162float(__float2bfloat16_rn(nrm)); e = __bfloat162float(__float2bfloat16_rn(eps)); }
+    if (BF16) { nrm = round_dt<BF16>(nrm); e = round_dt<BF16>(eps); }
     const float dn = fmaxf(nrm, e);
     const bool bad = !small_store_norm<BF16>(v, dn, xs + (size_t)r * d, d, lane);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_flags, 2);
@@ -461,7 +467,7 @@ sdm_small_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   }
 }
 
-template <bool BF16>
+template <int BF16>
 __global__ void __launch_bounds__(TB)
 sdm_small_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   extern __shared__ __align__(16) float small_smem[];
@@ -507,7 +513,7 @@ sdm_small_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   // one warp per output row: dx^ = sum_k dS * (other side's x^), then the normalisation Jacobian
   const int nchunk = d >> 7;                           // 128 columns per chunk, 4 per lane (d <= 512)
   float e = eps;
-  if (BF16) e = __bfloat162float(__float2bfloat16_rn(eps));
+  if (BF16) e = round_dt<BF16>(eps);
   for (int r = warp; r < N + M; r += TB / 32) {
     const bool isq = r < N;
     const int row = isq ? r : r - N, len = isq ? M : N;
@@ -563,7 +569,7 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-template <bool BF16, bool D512>                        // D512: the reference's feature width as a compile-time constant
+template <int BF16, bool D512>                        // D512: the reference's feature width as a compile-time constant
 __global__ void __launch_bounds__(STB, 1)
 sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
   extern __shared__ __align__(16) float small_smem[];
@@ -596,7 +602,7 @@ sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
     for (int c = 0; c < 16; ++c) ss = fmaf(v[c], v[c], ss);
     ss = warp_sum(ss);
     float nrm = sqrtf(ss), e = eps;
-    if (BF16) { nrm = __bfloat162float(__float2bfloat16_rn(nrm)); e = __bfloat162float(__float2bfloat16_rn(eps)); }
+    if (BF16) { nrm = round_dt<BF16>(nrm); e = round_dt<BF16>(eps); }
     const float dn = fmaxf(nrm, e);
     const bool bad = !small_store_norm<BF16>(v, dn, xs + (size_t)r * d, d, lane);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_flags, 2);
@@ -701,7 +707,7 @@ sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
   __syncthreads();
   const int nchunk = d >> 7;
   float e = eps;
-  if (BF16) e = __bfloat162float(__float2bfloat16_rn(eps));
+  if (BF16) e = round_dt<BF16>(eps);
   for (int r = warp; r < N + M; r += NW) {
     const bool isq = r < N;
     const int row = isq ? r : r - N, len = isq ? M : N;
@@ -826,24 +832,30 @@ extern "C" int reid_sdm_uses_tensor_cores(const reid_sdm_pair* pairs, int n_pair
 }
 
 extern "C" int reid_sdm_fwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
   if (small_eligible(pairs, n_pairs, d)) {
-    if (dtype == REID_DTYPE_F32) return launch_small(sdm_small_fwd_kernel<false>, pairs, n_pairs, d, tau, eps, false, (cudaStream_t)stream);
-    if (dtype == REID_DTYPE_BF16) return launch_small(sdm_small_fwd_kernel<true>, pairs, n_pairs, d, tau, eps, false, (cudaStream_t)stream);
+    if (dtype == REID_DTYPE_F32) return launch_small(sdm_small_fwd_kernel<REID_DTYPE_F32>, pairs, n_pairs, d, tau, eps, false, st);
+    if (dtype == REID_DTYPE_BF16) return launch_small(sdm_small_fwd_kernel<REID_DTYPE_BF16>, pairs, n_pairs, d, tau, eps, false, st);
+    if (dtype == REID_DTYPE_F16) return launch_small(sdm_small_fwd_kernel<REID_DTYPE_F16>, pairs, n_pairs, d, tau, eps, false, st);
   }
-  if (dtype == REID_DTYPE_F32) return launch_sdm(sdm_fwd_kernel<false>, pairs, n_pairs, d, tau, eps, false, (cudaStream_t)stream);
-  if (sdm::tc_eligible(pairs, n_pairs, dtype, d)) return sdm::tc_forward(pairs, n_pairs, d, tau, eps, (cudaStream_t)stream);
-  if (dtype == REID_DTYPE_BF16) return launch_sdm(sdm_fwd_kernel<true>, pairs, n_pairs, d, tau, eps, false, (cudaStream_t)stream);
+  if (dtype == REID_DTYPE_F32) return launch_sdm(sdm_fwd_kernel<REID_DTYPE_F32>, pairs, n_pairs, d, tau, eps, false, st);
+  if (sdm::tc_eligible(pairs, n_pairs, dtype, d)) return sdm::tc_forward(pairs, n_pairs, d, tau, eps, st);
+  if (dtype == REID_DTYPE_BF16) return launch_sdm(sdm_fwd_kernel<REID_DTYPE_BF16>, pairs, n_pairs, d, tau, eps, false, st);
+  if (dtype == REID_DTYPE_F16) return launch_sdm(sdm_fwd_kernel<REID_DTYPE_F16>, pairs, n_pairs, d, tau, eps, false, st);
   return REID_E_UNSUPPORTED;
 }
 
 extern "C" int reid_sdm_bwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
   if (small_eligible(pairs, n_pairs, d)) {
-    if (dtype == REID_DTYPE_F32) return launch_small(sdm_small_bwd_kernel<false>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
-    if (dtype == REID_DTYPE_BF16) return launch_small(sdm_small_bwd_kernel<true>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
+    if (dtype == REID_DTYPE_F32) return launch_small(sdm_small_bwd_kernel<REID_DTYPE_F32>, pairs, n_pairs, d, tau, eps, true, st);
+    if (dtype == REID_DTYPE_BF16) return launch_small(sdm_small_bwd_kernel<REID_DTYPE_BF16>, pairs, n_pairs, d, tau, eps, true, st);
+    if (dtype == REID_DTYPE_F16) return launch_small(sdm_small_bwd_kernel<REID_DTYPE_F16>, pairs, n_pairs, d, tau, eps, true, st);
   }
-  if (dtype == REID_DTYPE_F32) return launch_sdm(sdm_bwd_kernel<false>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
-  if (sdm::tc_eligible(pairs, n_pairs, dtype, d)) return sdm::tc_backward(pairs, n_pairs, d, tau, eps, (cudaStream_t)stream);
-  if (dtype == REID_DTYPE_BF16) return launch_sdm(sdm_bwd_kernel<true>, pairs, n_pairs, d, tau, eps, true, (cudaStream_t)stream);
+  if (dtype == REID_DTYPE_F32) return launch_sdm(sdm_bwd_kernel<REID_DTYPE_F32>, pairs, n_pairs, d, tau, eps, true, st);
+  if (sdm::tc_eligible(pairs, n_pairs, dtype, d)) return sdm::tc_backward(pairs, n_pairs, d, tau, eps, st);
+  if (dtype == REID_DTYPE_BF16) return launch_sdm(sdm_bwd_kernel<REID_DTYPE_BF16>, pairs, n_pairs, d, tau, eps, true, st);
+  if (dtype == REID_DTYPE_F16) return launch_sdm(sdm_bwd_kernel<REID_DTYPE_F16>, pairs, n_pairs, d, tau, eps, true, st);
   return REID_E_UNSUPPORTED;
 }
 
@@ -853,11 +865,14 @@ extern "C" int reid_sdm_step(const reid_sdm_pair* pairs, int n_pairs, int dtype,
   if (small_eligible(pairs, n_pairs, d)) {
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == REID_DTYPE_F32)
-      return d == 512 ? launch_small(sdm_small_step_kernel<false, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
-                      : launch_small(sdm_small_step_kernel<false, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
+      return d == 512 ? launch_small(sdm_small_step_kernel<REID_DTYPE_F32, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
+                      : launch_small(sdm_small_step_kernel<REID_DTYPE_F32, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
     if (dtype == REID_DTYPE_BF16)
-      return d == 512 ? launch_small(sdm_small_step_kernel<true, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
-                      : launch_small(sdm_small_step_kernel<true, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
+      return d == 512 ? launch_small(sdm_small_step_kernel<REID_DTYPE_BF16, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
+                      : launch_small(sdm_small_step_kernel<REID_DTYPE_BF16, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
+    if (dtype == REID_DTYPE_F16)
+      return d == 512 ? launch_small(sdm_small_step_kernel<REID_DTYPE_F16, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
+                      : launch_small(sdm_small_step_kernel<REID_DTYPE_F16, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
   }
   const int rc = reid_sdm_fwd(pairs, n_pairs, dtype, d, tau, eps, stream);
   return rc != REID_OK ? rc : reid_sdm_bwd(pairs, n_pairs, dtype, d, tau, eps, stream);
@@ -865,6 +880,6 @@ extern "C" int reid_sdm_step(const reid_sdm_pair* pairs, int n_pairs, int dtype,
 
 // kernel launches reid_sdm_step issues for this batch (1 small / 3 tcgen05: pack + forward + backward / 2 general)
 extern "C" int reid_sdm_step_launches(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d) {
-  if (small_eligible(pairs, n_pairs, d) && (dtype == REID_DTYPE_F32 || dtype == REID_DTYPE_BF16)) return 1;
+  if (small_eligible(pairs, n_pairs, d) && (dtype == REID_DTYPE_F32 || dtype == REID_DTYPE_BF16 || dtype == REID_DTYPE_F16)) return 1;
   return (dtype == REID_DTYPE_BF16 && sdm::tc_eligible(pairs, n_pairs, dtype, d)) ? 3 : 2;
 }

@@ -15,21 +15,29 @@ struct Batch {
 // status bits (include/reid_b200.h): 1 = the reference returned its non-differentiable zero,
 // 2 = non-finite feature (:79-81), 4 = non-finite S (:89-91), 8 = no positives (:105-106), 16 = bad result (:145-147)
 
-template <bool BF16>
-__device__ __forceinline__ float ld_elem(const void* base, size_t i) {
-  if (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
-  return reinterpret_cast<const float*>(base)[i];
-}
-// normalised element exactly as the reference forms it: fp32: x / den ; bf16: round_bf16(x / den)
-template <bool BF16>
-__device__ __forceinline__ float norm_elem(const void* base, size_t i, float den) {
-  const float v = __fdiv_rn(ld_elem<BF16>(base, i), den);
-  if (BF16) return __bfloat162float(__float2bfloat16_rn(v));
+// element type of the features: DT = REID_DTYPE_F32 (0), REID_DTYPE_BF16 (1) or REID_DTYPE_F16 (2).  The template
+// parameter keeps its historic name BF16: non-zero = a 16-bit type whose rounding the reference's normalisation sees.
+template <int BF16>
+__device__ __forceinline__ float round_dt(float v) {
+  if (BF16 == REID_DTYPE_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  if (BF16 == REID_DTYPE_F16) return __half2float(__float2half_rn(v));
   return v;
 }
-template <bool BF16>
+template <int BF16>
+__device__ __forceinline__ float ld_elem(const void* base, size_t i) {
+  if (BF16 == REID_DTYPE_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
+  if (BF16 == REID_DTYPE_F16) return __half2float(reinterpret_cast<const __half*>(base)[i]);
+  return reinterpret_cast<const float*>(base)[i];
+}
+// normalised element exactly as the reference forms it: fp32: x / den ; bf16 / fp16: round(x / den)
+template <int BF16>
+__device__ __forceinline__ float norm_elem(const void* base, size_t i, float den) {
+  return round_dt<BF16>(__fdiv_rn(ld_elem<BF16>(base, i), den));
+}
+template <int BF16>
 __device__ __forceinline__ void st_out(void* base, size_t i, float v) {
-  if (BF16) reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
+  if (BF16 == REID_DTYPE_BF16) reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
+  else if (BF16 == REID_DTYPE_F16) reinterpret_cast<__half*>(base)[i] = __float2half_rn(v);
   else reinterpret_cast<float*>(base)[i] = v;
 }
 

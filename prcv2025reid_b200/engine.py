@@ -18,10 +18,14 @@ from ._cabi import check, ptr, stream_ptr
 
 # bound on |fp16 tensor-core score - fp32 score| for unit-norm rows: both operands are rounded to
 # fp16 (relative 2^-11 each), so |err| <= (2*2^-11 + 2^-22) * sum|q_i g_i| <= 2^-10 (Cauchy-Schwarz),
-# plus fp32 accumulation slack.  Queries whose top-k / CMC cannot be decided within this bound are
-# re-run through the all-fp32 kernel, so the bound only affects speed, never results.
+# plus fp32 accumulation slack.  Top-k lists and CMC never depend on it: queries whose top-k / CMC cannot be
+# decided within this bound are re-run through the all-fp32 kernel.  AP does: ranks beyond the re-scored head are
+# counted on fp16 scores (a row within ~1e-5 of a positive's score may fall on either side of it) and, for deep
+# positives of large shards, on row samples (include/reid_b200.h, reid_retrieve_fused) -- per-query AP moves by
+# <= ~2e-3 in the worst case and mAP by ~1e-5 (asserted against the oracle in tests/test_fused_oracle_gpu.py);
+# `exact_ap=True` switches the sampling off.
 EPS_FP16 = 2.0 ** -10 + 2.0 ** -13
-PAIR_MODE = bool(int(os.environ.get("REID_FUSED_PAIR", "1")))   # cta_group::2 variant of the fused kernel
+WAVE_QUERIES = 256           # queries per work item of the fused kernel (one CTA pair)
 _DEBUG_KEEP = None   # set to a dict to keep the flags / candidate counts of the last block (debug scripts)
 
 
@@ -40,6 +44,7 @@ class GalleryShard:
     g_offset: int
     G_total: int
     _bufs: dict = None         # work buffers reused across query blocks / calls (no allocator churn)
+    img_index: dict = None     # img_id -> gallery rows (set by eval_mm_protocol.install_gallery: the same-image rule)
 
     def buf(self, name, shape, dtype, zero=False):
         """A cached scratch tensor; contents are undefined unless zero=True.  Stream-ordered reuse only."""
@@ -123,21 +128,19 @@ def prepare_gallery(gallery: torch.Tensor, g_pid_all: torch.Tensor, g_offset: in
     return GalleryShard(g32, g16, g_code, sorted_pid, order, max(1, pmax), int(g_offset), int(G_total))
 
 
-def _pick_chunks(n_qblocks: int, G_local: int, sms: int) -> int:
-    """Gallery chunks per query block: the smallest split whose last wave is >= 95% full."""
-    if os.environ.get("REID_CHUNKS"):                      # tuning experiments
-        return max(1, int(os.environ["REID_CHUNKS"]))
-    best, best_eff = 1, 0.0
-    max_chunks = max(1, min(8, G_local // (128 * 32)))
-    for c in range(1, max_chunks + 1):
-        items = n_qblocks * c
-        waves = -(-items // sms)
-        eff = items / (waves * sms)
-        if eff > best_eff + 1e-9:
-            best, best_eff = c, eff
-        if eff >= 0.95:
-            return c
-    return best
+def fused_slots(n_queries: int, G_local: int, sms: int) -> int:
+    """Candidate slots per query (= gallery chunks of the query blocks in the last, partial wave of the persistent
+    CTA pairs; reid_retrieve_fused runs all whole waves against the whole shard)."""
+    units = max(1, sms // 2)
+    left = (-(-n_queries // WAVE_QUERIES)) % units
+    if left == 0:
+        return 1
+    return max(1, min(8, units // left, G_local // 4096))
+
+
+def default_query_block(sms: int) -> int:
+    """Two whole waves of the fused kernel's work items."""
+    return 2 * max(1, sms // 2) * WAVE_QUERIES
 
 
 @dataclass
@@ -146,25 +149,102 @@ class RetrievalResult:
     top_idx: torch.Tensor            # [Q, topk] int32 global gallery index (-1 pad)
     top_score: torch.Tensor          # [Q, topk] fp32 exact scores
     ap: Optional[torch.Tensor]       # [Q] float64, -1 for skipped queries
-    n_flagged: int                   # queries re-run through the exact kernel (this rank)
-    pos_above: torch.Tensor          # [Q, Pmax] int32
+    n_flagged: int                   # queries re-run through the exact kernel
+    pos_above: torch.Tensor          # [Q, Pmax] int32 (gallery-wide)
     n_pos: torch.Tensor              # [Q] int32
+    path: str = ""                   # "fused" (tcgen05) or "exact" (fp32 SIMT): which kernel ranked the queries
+
+
+def _rank_block(shard, q32_b, q16_b, pid_b, ex_b, E, pos_above_b, n_pos_b, top_score_b, top_idx_b, flag_b, *, fused,
+                topk, eps, cand_cap, group, world, exact_ap, n_slots=None):
+    """Enqueue the ranking kernels of one query block on the current stream (no host synchronisation unless an
+    identity has more than 64 gallery rows).  Local counts -> pos_above_b, exact local top list -> top_*_b."""
+    L = _cabi.lib()
+    st = stream_ptr()
+    d, Pmax = shard.d, shard.pmax
+    nb = pid_b.shape[0]
+    sms = L.reid_device_sm_count()
+    q_code = shard.buf("q_code", (nb,), torch.int32)
+    q_count = shard.buf("q_count", (nb,), torch.int32)
+    check(L.reid_pid_lookup(ptr(shard.sorted_pid), shard.G_total, ptr(pid_b), nb, ptr(q_code), ptr(q_count), st),
+          "reid_pid_lookup")
+    pos_thr = shard.buf("pos_thr", (nb, Pmax), torch.float32)
+    check(L.reid_pos_scores(ptr(q32_b), ptr(shard.g_f32), ptr(shard.order), ptr(q_code), ptr(q_count), ptr(ex_b), E,
+                            nb, shard.G_local, shard.g_offset, d, Pmax, ptr(pos_thr), st), "reid_pos_scores")
+    if world > 1:
+        sharding.exchange_pos_scores(pos_thr, group)                # owner rank holds the score, others -inf
+    check(L.reid_pos_sort(ptr(pos_thr), ptr(n_pos_b), nb, Pmax, st), "reid_pos_sort")
+
+    if fused:
+        n_chunks = int(n_slots) if n_slots else fused_slots(nb, shard.G_local, sms)
+    else:
+        n_chunks = max(1, min(16, (2 * sms) // max(1, -(-nb // 8)), shard.G_local // 1024 or 1))
+    cap = max(int(cand_cap), 64) // 4 * 4
+    cand_score = shard.buf("cand_score", (nb, n_chunks, cap), torch.float32)
+    cand_idx = shard.buf("cand_idx", (nb, n_chunks, cap), torch.int32)
+    cand_count = shard.buf("cand_count", (nb, n_chunks), torch.int32, zero=True)
+    cand_thr = shard.buf("cand_thr", (nb,), torch.float32) if fused else None
+    if fused:
+        ws_bytes = L.reid_workspace_bytes(1, nb, shard.G_local, d)
+        ws = shard.buf("fused_ws", (ws_bytes,), torch.uint8)
+        flags = _cabi.FUSED_EXACT_COUNTS if exact_ap else 0
+        PW = _cabi.FUSED_PMAX
+        check(L.reid_retrieve_fused(ptr(q16_b), ptr(shard.g_f16), ptr(q_code), ptr(shard.g_code), ptr(ex_b), E,
+                                    ptr(pos_thr), ptr(n_pos_b), nb, shard.G_local, shard.g_offset, d, min(Pmax, PW), Pmax,
+                                    n_chunks, world, cap, flags, ptr(pos_above_b), ptr(cand_score), ptr(cand_idx),
+                                    ptr(cand_count), ptr(cand_thr), ptr(ws), ws_bytes, st), "reid_retrieve_fused")
+        for w0 in range(PW, Pmax, PW):
+            # identities with more than 64 gallery rows: thresholds [w0, w0 + 64) of the queries that have them, in a
+            # counting-only pass over a compact copy of those queries (one host read: how many there are)
+            sel = torch.nonzero(n_pos_b > w0).flatten()
+            ns = int(sel.numel())
+            if ns == 0:
+                break
+            pw = min(PW, Pmax - w0)
+            thr_w = pos_thr[sel, w0:w0 + pw].contiguous()
+            np_w = (n_pos_b[sel] - w0).clamp_(max=pw).to(torch.int32)
+            above_w = torch.zeros(ns, pw, dtype=torch.int32, device=sel.device)
+            q16_w = q16_b[sel].contiguous()
+            code_w = q_code[sel].contiguous()
+            ex_w = ex_b[sel].contiguous() if ex_b is not None else None
+            ws_w = torch.empty(L.reid_workspace_bytes(1, ns, shard.G_local, d), dtype=torch.uint8, device=sel.device)
+            check(L.reid_retrieve_fused(ptr(q16_w), ptr(shard.g_f16), ptr(code_w), ptr(shard.g_code), ptr(ex_w), E,
+                                        ptr(thr_w), ptr(np_w), ns, shard.G_local, shard.g_offset, d, pw, pw,
+                                        fused_slots(ns, shard.G_local, sms), world, cap,
+                                        flags | _cabi.FUSED_NO_CANDIDATES, ptr(above_w), None, None, None, None,
+                                        ptr(ws_w), ws_w.numel(), st), "reid_retrieve_fused(window)")
+            pos_above_b[sel, w0:w0 + pw] += above_w
+    else:
+        check(L.reid_retrieve_exact(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code), ptr(ex_b), E,
+                                    ptr(pos_thr), ptr(n_pos_b), None, nb, nb, shard.G_local, shard.g_offset, d, Pmax,
+                                    n_chunks, cap, ptr(pos_above_b), ptr(cand_score), ptr(cand_idx), ptr(cand_count), st),
+              "reid_retrieve_exact")
+    check(L.reid_rescore_topk(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code), ptr(pos_thr),
+                              ptr(n_pos_b), ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), None, nb, nb,
+                              shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap, topk,
+                              float(eps if fused else 0.0), ptr(pos_above_b), ptr(top_score_b),
+                              ptr(top_idx_b), ptr(flag_b), st), "reid_rescore_topk")
+    if _DEBUG_KEEP is not None:
+        _DEBUG_KEEP.update(flag=flag_b.clone(), cand_count=cand_count.clone(), n_chunks=n_chunks)
 
 
 def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional[torch.Tensor], q_pid: torch.Tensor,
              excl: Optional[torch.Tensor] = None, topk: int = 10, mode: str = "fused", eps: float = EPS_FP16,
-             cand_cap: int = 2048, query_block: int = 32768, group=None, want_ap: bool = False,
-             host_queries=None) -> RetrievalResult:
+             cand_cap: int = 2048, query_block: Optional[int] = None, group=None, want_ap: bool = False,
+             host_queries=None, exact_ap: bool = False, n_slots: Optional[int] = None) -> RetrievalResult:
     """Ranking statistics of a batch of queries against the gallery shard(s).
 
     mode "fused": tcgen05 GEMM with the counting / candidate epilogue, exact fp32 re-score of the
     candidates, exact fp32 re-run of the (rare) queries whose top-k / CMC is not decidable within eps.
     mode "exact": everything through the fp32 SIMT kernel.
+    exact_ap: count every positive's rank on every gallery row (no row sampling for deep positives; slower).
     group: a torch.distributed process group whose ranks hold disjoint contiguous gallery shards.
     host_queries: (query_raw [Q,k,D], mod_id [Q,k], weights) in pinned HOST memory instead of q_f32/q_f16;
     q_pid / excl may then be host tensors too.  Query blocks are copied on a side stream while the previous
     block computes (H2D overlapped with the kernels); with a process group every rank uploads and fuses only its
     1/world slice of a block and the fused block is all-gathered over NVLink (sharding.gather_query_block).
+    The host is synchronised ONCE, by the read of the metrics (plus once per query block when an identity has more than
+    64 gallery rows, and once more in the rare case that queries were flagged for the exact re-run).
     """
     assert mode in ("fused", "exact")
     assert 1 <= topk <= _cabi.RTOP
@@ -173,59 +253,64 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
     d = shard.d
     Pmax = shard.pmax
     Q = q_pid.shape[0]
-    world = 1
+    world, rank = 1, 0
     if group is not None:
         import torch.distributed as dist_mod
         world = dist_mod.get_world_size(group)
+        rank = dist_mod.get_rank(group)
     st = stream_ptr()
     sms = L.reid_device_sm_count()
     E = 0 if excl is None or excl.numel() == 0 else excl.shape[1]
     if E == 0:
         excl = None
+    if query_block is None:
+        query_block = default_query_block(sms)
 
     pos_above = torch.zeros(Q, Pmax, dtype=torch.int32, device=dev)
     n_pos = torch.empty(Q, dtype=torch.int32, device=dev)
     top_score = torch.empty(Q, _cabi.RTOP, dtype=torch.float32, device=dev)
     top_idx = torch.empty(Q, _cabi.RTOP, dtype=torch.int32, device=dev)
     flag = torch.zeros(Q, dtype=torch.int32, device=dev)
-    n_flagged = 0
-    use_fused = mode == "fused" and Pmax <= 64 and d % 64 == 0 and d <= 512 and shard.G_local <= (1 << 22)
+    use_fused = (mode == "fused" and Pmax <= 2048 and d % 64 == 0 and d <= 512 and shard.G_local <= (1 << 22)
+                 and (host_queries is not None or q_f16 is not None))
 
     blocks = [(b0, min(Q, b0 + query_block)) for b0 in range(0, Q, query_block)]
     staged = {}
-    copy_stream = None
+    kept = []                                 # (q32, pid, excl) of every block: the exact re-run of flagged queries reads them
     if host_queries is not None:
         h_raw, h_mod, weights = host_queries
         weights = weights.to(dev)
+        # staging sets (two, alternating) are allocated on the compute stream, once, at the size of the largest block
+        mmax = max(sharding.block_slice(b1 - b0, 0, world)[2] for b0, b1 in blocks)
+        nmax = max(b1 - b0 for b0, b1 in blocks)
+        sets = []
+        for tag in ("stage0_", "stage1_"):
+            sets.append((shard.buf(tag + "raw", (mmax,) + tuple(h_raw.shape[1:]), h_raw.dtype),
+                         shard.buf(tag + "mod", (mmax,) + tuple(h_mod.shape[1:]), h_mod.dtype),
+                         shard.buf(tag + "pid", (nmax,), q_pid.dtype),
+                         shard.buf(tag + "excl", (nmax,) + tuple(excl.shape[1:]), excl.dtype) if excl is not None else None))
         copy_stream = torch.cuda.Stream(device=dev)
-
+        copy_stream.wait_stream(torch.cuda.current_stream())      # (the buffers may have just been allocated)
         done_ev = {}                                          # compute-stream event after block bi has consumed its staging set
-
-        rank = 0
-        if world > 1:
-            rank = dist_mod.get_rank(group)
 
         def stage(bi):
             # upload this rank's slice of block bi (the features: 8 KB per query at k = 4) and the whole block's ids
             b0, b1 = blocks[bi]
             n = b1 - b0
             s0, s1, m = sharding.block_slice(n, rank, world)
-            tag = "stage%d_" % (bi & 1)                        # two alternating staging sets (cached, no allocator churn)
+            raw, mod, pid, ex = sets[bi & 1]
+            raw, mod, pid = raw[:m], mod[:m], pid[:n]
+            ex = ex[:n] if ex is not None else None
             with torch.cuda.stream(copy_stream):
                 if bi - 2 in done_ev:
                     copy_stream.wait_event(done_ev.pop(bi - 2))   # the set is free once block bi-2 has finished
-                raw = shard.buf(tag + "raw", (m,) + tuple(h_raw.shape[1:]), h_raw.dtype)
-                mod = shard.buf(tag + "mod", (m,) + tuple(h_mod.shape[1:]), h_mod.dtype)
-                pid = shard.buf(tag + "pid", (n,), q_pid.dtype)
                 if s1 > s0:
                     raw[:s1 - s0].copy_(h_raw[b0 + s0:b0 + s1], non_blocking=True)
                     mod[:s1 - s0].copy_(h_mod[b0 + s0:b0 + s1], non_blocking=True)
                 if s1 - s0 < m:
                     mod[s1 - s0:].fill_(-1)                      # unused slot rows: empty queries (dropped after the gather)
                 pid.copy_(q_pid[b0:b1], non_blocking=True)
-                ex = None
-                if excl is not None:
-                    ex = shard.buf(tag + "excl", (n,) + tuple(excl.shape[1:]), excl.dtype)
+                if ex is not None:
                     ex.copy_(excl[b0:b1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
@@ -253,86 +338,54 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
         else:
             q32_b, q16_b = q_f32[sl], (q_f16[sl] if q_f16 is not None else None)
             pid_b, ex_b = q_pid[sl], (excl[sl] if excl is not None else None)
-        fused_b = use_fused and q16_b is not None
-
-        q_code = shard.buf("q_code", (nb,), torch.int32)
-        q_count = shard.buf("q_count", (nb,), torch.int32)
-        check(L.reid_pid_lookup(ptr(shard.sorted_pid), shard.G_total, ptr(pid_b), nb, ptr(q_code), ptr(q_count), st),
-              "reid_pid_lookup")
-        pos_thr = shard.buf("pos_thr", (nb, Pmax), torch.float32)
-        check(L.reid_pos_scores(ptr(q32_b), ptr(shard.g_f32), ptr(shard.order), ptr(q_code), ptr(q_count), ptr(ex_b), E,
-                                nb, shard.G_local, shard.g_offset, d, Pmax, ptr(pos_thr), st), "reid_pos_scores")
-        if world > 1:
-            sharding.exchange_pos_scores(pos_thr, group)                # owner rank holds the score, others -inf
-        check(L.reid_pos_sort(ptr(pos_thr), ptr(n_pos[sl]), nb, Pmax, st), "reid_pos_sort")
-
-        if fused_b and PAIR_MODE:
-            # cta_group::2 pairs: sms/2 scheduling units, blocks of 256 queries
-            n_chunks = _pick_chunks(-(-nb // 256), shard.G_local, sms // 2)
-        elif fused_b:
-            n_chunks = _pick_chunks(-(-nb // 128), shard.G_local, sms)
-        else:
-            n_chunks = max(1, min(16, (2 * sms) // max(1, -(-nb // 8)), shard.G_local // 1024 or 1))
-        cap = max(int(os.environ.get("REID_CAND_CAP") or cand_cap), 64) // 4 * 4      # (env: tuning experiments)
-        cand_score = shard.buf("cand_score", (nb, n_chunks, cap), torch.float32)
-        cand_idx = shard.buf("cand_idx", (nb, n_chunks, cap), torch.int32)
-        cand_count = shard.buf("cand_count", (nb, n_chunks), torch.int32, zero=True)
-        common_tail = (nb, shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap)
-        cand_thr = shard.buf("cand_thr", (nb,), torch.float32) if fused_b else None
-        if fused_b:
-            ws_bytes = L.reid_workspace_bytes(1, nb, shard.G_local, d)
-            ws = shard.buf("fused_ws", (ws_bytes,), torch.uint8)
-            check(L.reid_retrieve_fused(ptr(q16_b), ptr(shard.g_f16), ptr(q_code), ptr(shard.g_code), ptr(ex_b), E,
-                                        ptr(pos_thr), ptr(n_pos[sl]), nb, shard.G_local, shard.g_offset, d, Pmax, n_chunks,
-                                        n_chunks * world, cap, ptr(pos_above[sl]),
-                                        ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), ptr(ws), ws_bytes, st),
-                  "reid_retrieve_fused")
-        else:
-            check(L.reid_retrieve_exact(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code), ptr(ex_b), E,
-                                        ptr(pos_thr), ptr(n_pos[sl]), None, nb, *common_tail, ptr(pos_above[sl]),
-                                        ptr(cand_score), ptr(cand_idx), ptr(cand_count), st), "reid_retrieve_exact")
-        check(L.reid_rescore_topk(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code), ptr(pos_thr),
-                                  ptr(n_pos[sl]), ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), None, nb, nb,
-                                  shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap, topk,
-                                  float(eps if fused_b else 0.0), ptr(pos_above[sl]), ptr(top_score[sl]),
-                                  ptr(top_idx[sl]), ptr(flag[sl]), st), "reid_rescore_topk")
-        if _DEBUG_KEEP is not None:
-            _DEBUG_KEEP.update(flag=flag[sl].clone(), cand_count=cand_count.clone())
-        if host_queries is not None and not fused_b:
+        _rank_block(shard, q32_b, q16_b, pid_b, ex_b, E, pos_above[sl], n_pos[sl], top_score[sl], top_idx[sl], flag[sl],
+                    fused=use_fused, topk=topk, eps=eps, cand_cap=cand_cap, group=group, world=world,
+                    exact_ap=exact_ap, n_slots=n_slots)
+        if use_fused:
+            if host_queries is not None:                         # (the staging set is overwritten two blocks later)
+                pid_b, ex_b = pid_b.clone(), (ex_b.clone() if ex_b is not None else None)
+            kept.append((q32_b, pid_b, ex_b))
+        if host_queries is not None:
             done_ev[bi] = torch.cuda.Event(); done_ev[bi].record()
-        if fused_b:
-            sel = torch.nonzero(flag[sl]).flatten().to(torch.int32)      # host sync: how many to re-run
-            ns = int(sel.numel())
-            if ns:
-                n_flagged += ns
-                pa = pos_above[sl]
-                pa[sel.long()] = 0
-                cand_count[sel.long()] = 0
-                check(L.reid_retrieve_exact(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code),
-                                            ptr(ex_b), E, ptr(pos_thr), ptr(n_pos[sl]), ptr(sel), ns,
-                                            *common_tail, ptr(pa), ptr(cand_score), ptr(cand_idx), ptr(cand_count), st),
-                      "reid_retrieve_exact(fallback)")
-                check(L.reid_rescore_topk(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code),
-                                          ptr(pos_thr), ptr(n_pos[sl]), ptr(cand_score), ptr(cand_idx),
-                                          ptr(cand_count), None, ptr(sel), ns, nb, shard.G_local, shard.g_offset, d, Pmax,
-                                          n_chunks, cap, topk, 0.0, ptr(pa), ptr(top_score[sl]), ptr(top_idx[sl]),
-                                          ptr(flag[sl]), st), "reid_rescore_topk(fallback)")
-            if host_queries is not None:
-                done_ev[bi] = torch.cuda.Event(); done_ev[bi].record()
 
-    if world > 1:
-        sharding.exchange_counts(pos_above, group)                      # counts are additive over shards
-        # the global top-k is contained in the union of the shards' (exactly ordered) top-k lists
-        all_s, all_i = sharding.gather_top_lists(top_score[:, :topk].contiguous(), top_idx[:, :topk].contiguous(), group)
-        out_s = torch.empty(Q, topk, dtype=torch.float32, device=dev)
-        out_i = torch.empty(Q, topk, dtype=torch.int32, device=dev)
-        check(L.reid_merge_topk(ptr(all_s), ptr(all_i), world, Q, topk, topk, ptr(out_s), ptr(out_i), st), "reid_merge_topk")
-    else:
-        out_s, out_i = top_score[:, :topk].contiguous(), top_idx[:, :topk].contiguous()   # one shard: already ordered
+    def finish():
+        """Exchange over the shards, metrics; -> (pos_above gallery-wide, top lists, metrics tensor incl. the flag count)."""
+        pa = pos_above
+        if world > 1:
+            pa = sharding.exchange_counts(pos_above.clone(), group)         # counts are additive over shards
+            # the global top-k is contained in the union of the shards' (exactly ordered) top-k lists
+            all_s, all_i = sharding.gather_top_lists(top_score[:, :topk].contiguous(), top_idx[:, :topk].contiguous(), group)
+            out_s = torch.empty(Q, topk, dtype=torch.float32, device=dev)
+            out_i = torch.empty(Q, topk, dtype=torch.int32, device=dev)
+            check(L.reid_merge_topk(ptr(all_s), ptr(all_i), world, Q, topk, topk, ptr(out_s), ptr(out_i), st), "reid_merge_topk")
+            sharding.exchange_flags(flag, group)                             # a query flagged on one shard is re-run on all
+        else:
+            out_s, out_i = top_score[:, :topk].contiguous(), top_idx[:, :topk].contiguous()   # one shard: already ordered
+        out = torch.empty(6, dtype=torch.float64, device=dev)
+        ap = torch.empty(Q, dtype=torch.float64, device=dev) if want_ap else None
+        check(L.reid_metrics_reduce(ptr(pa), ptr(n_pos), Q, Pmax, ptr(out), ptr(ap), st), "reid_metrics_reduce")
+        out[5] = torch.count_nonzero(flag)
+        return pa, out_s, out_i, ap, out.cpu().tolist()                     # the step's result: D2H read
 
-    out = torch.empty(5, dtype=torch.float64, device=dev)
-    ap = torch.empty(Q, dtype=torch.float64, device=dev) if want_ap else None
-    check(L.reid_metrics_reduce(ptr(pos_above), ptr(n_pos), Q, Pmax, ptr(out), ptr(ap), st), "reid_metrics_reduce")
-    m = out.cpu().tolist()                                               # the step's result: D2H read
+    pa, out_s, out_i, ap, m = finish()
+    n_flagged = int(round(m[5]))
+    if n_flagged and use_fused:
+        # rare: top-k / CMC of these queries is not decidable from fp16 scores within eps (or a candidate buffer
+        # overflowed): all-fp32 re-run on a compact copy, results written back, exchange + metrics redone
+        sel = torch.nonzero(flag).flatten()
+        q32_s = torch.cat([k[0] for k in kept])[sel].contiguous()
+        pid_s = torch.cat([k[1] for k in kept])[sel].contiguous()
+        ex_s = torch.cat([k[2] for k in kept])[sel].contiguous() if E else None
+        ns = int(sel.numel())
+        pa_s = torch.zeros(ns, Pmax, dtype=torch.int32, device=dev)
+        np_s = torch.empty(ns, dtype=torch.int32, device=dev)
+        ts_s = torch.empty(ns, _cabi.RTOP, dtype=torch.float32, device=dev)
+        ti_s = torch.empty(ns, _cabi.RTOP, dtype=torch.int32, device=dev)
+        fl_s = torch.zeros(ns, dtype=torch.int32, device=dev)
+        _rank_block(shard, q32_s, None, pid_s, ex_s, E, pa_s, np_s, ts_s, ti_s, fl_s, fused=False, topk=topk, eps=0.0,
+                    cand_cap=cand_cap, group=group, world=world, exact_ap=True)
+        pos_above[sel] = pa_s; n_pos[sel] = np_s; top_score[sel] = ts_s; top_idx[sel] = ti_s
+        flag.zero_()
+        pa, out_s, out_i, ap, m = finish()
     metrics = {"mAP": m[0], "R@1": m[1], "R@5": m[2], "R@10": m[3], "num_queries": int(round(m[4]))}
-    return RetrievalResult(metrics, out_i, out_s, ap, n_flagged, pos_above, n_pos)
+    return RetrievalResult(metrics, out_i, out_s, ap, n_flagged, pa, n_pos, "fused" if use_fused else "exact")

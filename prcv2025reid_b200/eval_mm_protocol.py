@@ -121,53 +121,68 @@ def _encode(extractor, m: str, sample: dict) -> torch.Tensor:
     raise ValueError(f"未知模态: {m}")
 
 
-def _fuse_batch(queries: List[dict], extractor, weight_cfg: Dict[str, float]) -> torch.Tensor:
-    """Batched extract_query_feat (eval_mm_protocol.py:328-365) -> [Q, D] fp32 on the CUDA device."""
+def _fuse_batch(queries: List[dict], extractor, weight_cfg: Dict[str, float], want_f16: bool = False):
+    """Batched extract_query_feat (eval_mm_protocol.py:328-365) -> [Q, D] fp32 on the CUDA device (and, with want_f16,
+    the fp16 tensor-core operand copy the kernels write in the same pass).
+
+    The extractor is duck-typed like the reference's (one `encode_*` call per sample, one `fuse_features_if_any` call per
+    query, :341-357): those calls are the only per-query Python left; features travel to the device in ONE copy, the
+    per-modality l2n (:353), the weighted sum (:362-364) and the final l2n (:365) are one kernel per distinct k."""
+    import numpy as np
     dev = _dev()
-    raw, mods = [], []
-    for q in queries:
-        fs, ms = [], []
-        for m, sample in q["samples"].items():
-            fs.append(_encode(extractor, m, sample).float().view(-1))
-            ms.append(m)
-        raw.append(fs); mods.append(ms)
     Q = len(queries)
+    feats, mods, counts = [], [], []
+    for q in queries:
+        ms = []
+        for m, sample in q["samples"].items():
+            feats.append(_encode(extractor, m, sample).float().view(-1))
+            ms.append(m)
+        mods.append(ms); counts.append(len(ms))
     if Q == 0:
-        return torch.empty(0, 0, device=dev)
-    D = raw[0][0].numel()
+        e = torch.empty(0, 0, device=dev)
+        return (e, e.to(torch.float16)) if want_f16 else e
+    D = feats[0].numel()
     out = torch.empty(Q, D, dtype=torch.float32, device=dev)
-    # per-modality l2n (:353) in one pass, needed as the argument of the extractor's fusion hook
-    flat = torch.stack([f for fs in raw for f in fs]).to(dev)
-    flat_n, _ = engine.l2norm_rows(flat)
-    offs, o = [], 0
-    for fs in raw:
-        offs.append(o); o += len(fs)
-    weighted: Dict[int, List[int]] = {}
-    hooked_rows, hooked_idx = [], []
+    out16 = torch.empty(Q, D, dtype=torch.float16, device=dev) if want_f16 else None
+    flat = torch.stack(feats).to(dev)                                    # one host -> device copy
+    flat_n, _ = engine.l2norm_rows(flat)                                 # per-modality l2n (:353): the fusion hook's argument
+    rows_n = flat_n.unbind(0)
+    counts = np.asarray(counts, dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    hooked_rows, hooked_idx, weighted = [], [], []
     for qi in range(Q):
-        k = len(raw[qi])
-        feats_n = [flat_n[offs[qi] + j] for j in range(k)]
-        fused = extractor.fuse_features_if_any(feats_n, mods[qi])       # :357
+        o, k = int(offs[qi]), int(counts[qi])
+        fused = extractor.fuse_features_if_any(list(rows_n[o:o + k]), mods[qi])       # :357
         if fused is not None:
-            hooked_rows.append(fused.float().view(-1).to(dev)); hooked_idx.append(qi)   # -> l2n(fused) (:359)
+            hooked_rows.append(fused.float().view(-1)); hooked_idx.append(qi)         # -> l2n(fused) (:359)
         else:
-            weighted.setdefault(k, []).append(qi)
+            weighted.append(qi)
     if hooked_idx:
-        hn, _ = engine.l2norm_rows(torch.stack(hooked_rows))
-        out[torch.tensor(hooked_idx, device=dev)] = hn
-    names = list(MODALITIES) + sorted(set(m for ms in mods for m in ms) - set(MODALITIES))
-    ids = {m: i for i, m in enumerate(names)}
-    w = torch.tensor([float(weight_cfg.get(m, 1.0)) for m in names], dtype=torch.float32, device=dev)   # :362
-    for k, idxs in weighted.items():
-        it = torch.tensor(idxs, device=dev)
-        rows = flat[torch.tensor([offs[qi] + j for qi in idxs for j in range(k)], device=dev)].view(len(idxs), k, D)   # one gather
-        mid = torch.tensor([[ids[m] for m in mods[qi]] for qi in idxs], dtype=torch.int32, device=dev)
-        if k == 1:      # weighted path with one feature: l2n(w * f) -- keep the weight (no hook result)
-            rows = torch.cat([rows, torch.zeros_like(rows)], dim=1)
-            mid = torch.cat([mid, torch.full_like(mid, -1)], dim=1)
-        q32, _ = engine.fuse_queries(rows, mid, w)
-        out[it] = q32
-    return out
+        hn, hn16 = engine.l2norm_rows(torch.stack(hooked_rows).to(dev), want_f16=want_f16)
+        it = torch.as_tensor(hooked_idx, device=dev)
+        out[it] = hn
+        if want_f16:
+            out16[it] = hn16
+    if weighted:
+        names = list(MODALITIES) + sorted(set(m for ms in mods for m in ms) - set(MODALITIES))
+        ids = {m: i for i, m in enumerate(names)}
+        w = torch.tensor([float(weight_cfg.get(m, 1.0)) for m in names], dtype=torch.float32, device=dev)   # :362
+        flat_mid = np.fromiter((ids[m] for ms in mods for m in ms), dtype=np.int32, count=int(counts.sum()))
+        weighted = np.asarray(weighted, dtype=np.int64)
+        for k in np.unique(counts[weighted]).tolist():
+            idxs = weighted[counts[weighted] == k]
+            rix = offs[idxs][:, None] + np.arange(k)[None, :]                                  # [n, k] rows of `flat`
+            rows = flat[torch.from_numpy(rix.reshape(-1)).to(dev)].view(len(idxs), k, D)       # one gather
+            mid = torch.from_numpy(flat_mid[rix]).to(dev)
+            if k == 1:      # weighted path with one feature: l2n(w * f) -- keep the weight (no hook result)
+                rows = torch.cat([rows, torch.zeros_like(rows)], dim=1)
+                mid = torch.cat([mid, torch.full_like(mid, -1)], dim=1)
+            q32, q16 = engine.fuse_queries(rows, mid, w)
+            it = torch.from_numpy(idxs).to(dev)
+            out[it] = q32
+            if want_f16:
+                out16[it] = q16
+    return (out, out16) if want_f16 else out
 
 
 def extract_query_feat(q: dict, extractor, weight_cfg: Dict[str, float]) -> torch.Tensor:
@@ -178,30 +193,42 @@ def extract_query_feat(q: dict, extractor, weight_cfg: Dict[str, float]) -> torc
     return f.to(src)
 
 
-def _exclusions(queries, g_imgid, ignore_same_img: bool, dev) -> Optional[torch.Tensor]:
-    # eval_mm_protocol.py:408-418: gallery rows whose img_id is one of the query samples' img_ids
-    if not ignore_same_img:
-        return None
+def _image_index(g_imgid) -> Dict[object, List[int]]:
     by_id: Dict[object, List[int]] = {}
     for i, gid in enumerate(g_imgid):
         if gid is not None:
             by_id.setdefault(gid, []).append(i)
+    return by_id
+
+
+def _exclusions(queries, g_imgid, ignore_same_img: bool, dev, by_id=None) -> Optional[torch.Tensor]:
+    # eval_mm_protocol.py:408-418: gallery rows whose img_id is one of the query samples' img_ids.
+    # One pass over the gallery ids (cached on the installed gallery), one dictionary probe per query sample.
+    if not ignore_same_img:
+        return None
+    import numpy as np
+    if by_id is None:
+        by_id = _image_index(g_imgid)
     rows, width = [], 0
     for q in queries:
         hit = []
         for s in q["samples"].values():
             iid = s.get("img_id") if "img_id" in s else None
-            if iid is not None and iid in by_id:
-                hit.extend(by_id[iid])
-        hit = sorted(set(hit))
-        rows.append(hit); width = max(width, len(hit))
+            if iid is not None:
+                h = by_id.get(iid)
+                if h:
+                    hit.extend(h)
+        if len(hit) > 1:
+            hit = sorted(set(hit))
+        rows.append(hit)
+        width = max(width, len(hit))
     if width == 0:
         return None
-    ex = torch.full((len(queries), width), -1, dtype=torch.int32)
+    ex = np.full((len(queries), width), -1, dtype=np.int32)
     for i, h in enumerate(rows):
         if h:
-            ex[i, :len(h)] = torch.tensor(h, dtype=torch.int32)
-    return ex.to(dev)
+            ex[i, :len(h)] = h
+    return torch.from_numpy(ex).to(dev)
 
 
 def install_gallery(gallery_feats: torch.Tensor, gallery_meta: List[dict]) -> engine.GalleryShard:
@@ -210,7 +237,9 @@ def install_gallery(gallery_feats: torch.Tensor, gallery_meta: List[dict]) -> en
     `shard=` to rank_and_metrics when several query sets run against the same gallery (run_eval's MM-1..4 loop)."""
     dev = _dev()
     g_pids = torch.tensor([m["pid"] for m in gallery_meta], dtype=torch.long)                 # :390
-    return engine.prepare_gallery(gallery_feats.to(dev), g_pids.to(dev))
+    shard = engine.prepare_gallery(gallery_feats.to(dev), g_pids.to(dev))
+    shard.img_index = _image_index([m.get("img_id", None) for m in gallery_meta])             # :391, for the same-image rule
+    return shard
 
 
 def rank_and_metrics(queries: List[dict], gallery_feats: torch.Tensor, gallery_meta: List[dict], extractor,
@@ -224,15 +253,15 @@ def rank_and_metrics(queries: List[dict], gallery_feats: torch.Tensor, gallery_m
     dev = _dev()
     if len(queries) == 0 or len(gallery_meta) == 0:
         return {"mAP": 0.0, "R@1": 0.0, "R@5": 0.0, "R@10": 0.0, "num_queries": 0}
-    g_imgid = [m.get("img_id", None) for m in gallery_meta]                                   # :391
     if shard is None:
         shard = install_gallery(gallery_feats, gallery_meta)
     elif shard.G_total != len(gallery_meta):
         raise ValueError("shard was installed for a gallery of %d rows, gallery_meta has %d" % (shard.G_total, len(gallery_meta)))
-    q32 = _fuse_batch(queries, extractor, weight_cfg)
-    q16 = q32.to(torch.float16)
+    q32, q16 = _fuse_batch(queries, extractor, weight_cfg, want_f16=True)
     q_pid = torch.tensor([int(q["pid"]) for q in queries], dtype=torch.long, device=dev)
-    excl = _exclusions(queries, g_imgid, ignore_same_img, dev)
+    by_id = getattr(shard, "img_index", None)
+    g_imgid = None if by_id is not None else [m.get("img_id", None) for m in gallery_meta]    # :391
+    excl = _exclusions(queries, g_imgid, ignore_same_img, dev, by_id)
     res = engine.retrieve(shard, q32, q16, q_pid, excl, topk=10, mode=mode)
     return res.metrics
 

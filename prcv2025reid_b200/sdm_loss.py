@@ -27,7 +27,9 @@ def _dtype_code(t: torch.Tensor) -> int:
         return _cabi.DTYPE_F32
     if t.dtype == torch.bfloat16:
         return _cabi.DTYPE_BF16
-    raise TypeError("sdm_loss: features must be float32 or bfloat16 (got %s)" % t.dtype)
+    if t.dtype == torch.float16:
+        return _cabi.DTYPE_F16
+    raise TypeError("sdm_loss: features must be float32, bfloat16 or float16 (got %s)" % t.dtype)
 
 
 _SAVED_FLOATS = {}
@@ -257,17 +259,28 @@ def sdm_alignment_loss(raw_modality_features, feature_masks, labels, tau=0.2, ep
     if vis_idx.numel() == 0:
         return zero                                                              # :572-574
     vis_idx = vis_idx.to(dev)
-    vfeat, vlab = vis.float()[vis_idx], labels[vis_idx]                            # compute_loss runs the SDM part in fp32 (:561)
-    qs, ys = [], []
+    # features keep the dtype the caller passes (bf16 / fp16 under the training autocast of train.py:852, fp32 otherwise):
+    # like the reference, the loss normalises in that dtype (sdm_loss.py:31-32) and only then computes in fp32 (:75)
+    vfeat, vlab = vis[vis_idx], labels[vis_idx]
+    groups = {}                                                                  # feature dtype -> (qs, ys)
+    order = []
     for k, m in enumerate(names):
         idx = torch.nonzero(host[k + 1]).flatten()
         if idx.numel() == 0:
             continue                                                             # :597-598
         idx = idx.to(dev)
-        qs.append(raw_modality_features[m].float()[idx])
-        ys.append((labels[idx].view(-1, 1) == vlab.view(1, -1)).float())          # :605
-    if not qs:
+        f = raw_modality_features[m][idx]
+        y = (labels[idx].view(-1, 1) == vlab.view(1, -1)).float()                 # :605
+        if f.dtype != vfeat.dtype:
+            raise TypeError("sdm_alignment_loss: %s features are %s but vis features are %s" % (m, f.dtype, vfeat.dtype))
+        qs, ys = groups.setdefault(f.dtype, ([], []))
+        qs.append(f); ys.append(y)
+        order.append(y)
+    if not order:
         return zero
-    losses = sdm_loss_pairs(qs, [vfeat] * len(qs), ys, tau, eps)
-    has_pos = torch.stack([y.any() for y in ys]) & torch.isfinite(losses)         # :608-618, on the device
-    return (losses * has_pos).sum() / has_pos.sum().clamp_min(1)                   # :621-625
+    parts = [sdm_loss_pairs(qs, [vfeat] * len(qs), ys, tau, eps) for qs, ys in groups.values()]
+    losses = parts[0] if len(parts) == 1 else torch.cat(parts)
+    all_ys = [y for _, ys in groups.values() for y in ys]
+    has_pos = torch.stack([y.any() for y in all_ys]) & torch.isfinite(losses)     # :608-618, on the device
+    kept = torch.where(has_pos, losses, torch.zeros_like(losses))                 # (a skipped loss must not leak a NaN)
+    return kept.sum() / has_pos.sum().clamp_min(1)                                # :621-625

@@ -4,7 +4,8 @@ The reference has no distributed code; this is the B200 de
 queries replicated, gallery rows partitioned contiguously, three small collectives per batch:
   1. all_reduce(MAX) of the positives' exact scores   (owner rank holds the score, others -inf)
   2. all_reduce(SUM) of the per-positive "rows ranked above" counts (additive over shards)
-  3. all_gather of the per-shard exact top lists, merged per query.
+  3. all_gather of the per-shard exact top lists, merged per query;
+  4. all_reduce(MAX) of the per-query "undecidable from fp16 scores" flags (normally all zero).
 With HOST-resident query features a fourth step precedes them: every rank uploads and fuses only its
 1/world slice of a query block and `gather_query_block` assembles the fused block on every rank over
 NVLink (all_gather), so the PCIe upload of a block is paid once per box instead of once per GPU.
@@ -34,6 +35,14 @@ def exchange_counts(pos_above: torch.Tensor, group=None) -> torch.Tensor:
     if group is not None or dist.is_initialized():
         dist.all_reduce(pos_above, op=dist.ReduceOp.SUM, group=group)
     return pos_above
+
+
+def exchange_flags(flag: torch.Tensor, group=None) -> torch.Tensor:
+    """A query whose top-k / CMC one shard could not decide is re-run exactly on EVERY shard: MAX over the ranks."""
+    import torch.distributed as dist
+    if group is not None or dist.is_initialized():
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    return flag
 
 
 def gather_top_lists(top_score: torch.Tensor, top_idx: torch.Tensor, group=None):

@@ -128,6 +128,60 @@ def make_retrieval_case(seed: int, n_ids: int, gal_per_id: int, k: int, queries_
     return RetrievalCase(gallery, g_pid, query, mod_id, q_pid, excl, k)
 
 
+def make_ragged_case(seed: int, n_ids: int, min_rows: int = 1, max_rows: int = 120, k: int = 2, queries_per_id: int = 2,
+                     dup_frac: float = 0.0, excl_frac: float = 0.02, n_excl: int = 2, device="cpu",
+                     dim: int = FEAT_DIM, heavy_tail: bool = True) -> RetrievalCase:
+    """A gallery shaped like a real ReID one (ORBench: 45 113 RGB images of 1 000 identities, a long tail of image
+    counts per identity): identity i owns between min_rows and max_rows gallery rows (heavy_tail: most identities are
+    small, a few are large), rows are stored in SHUFFLED order (no periodic structure), person ids are non-contiguous,
+    and a fraction dup_frac of the rows are bit-identical copies of another row filed under a DIFFERENT identity
+    (exact score ties between a positive and a non-positive, between top-list neighbours)."""
+    dev = torch.device(device)
+    gen = _chunk_gen(dev, seed, 5, 0)
+    centres = torch.randn(n_ids, dim, generator=gen, device=dev)
+    bias = {m: BIAS_SCALE * torch.randn(dim, generator=gen, device=dev) for m in ("rgb",) + MODALITIES}
+    u = torch.rand(n_ids, generator=gen, device=dev)
+    if heavy_tail:
+        u = u ** 2.5
+    rows_of = (min_rows + torch.floor(u * (max_rows - min_rows + 1)).long()).clamp(min_rows, max_rows)
+    rows_of[0] = max_rows                                     # the extremes are always present
+    rows_of[1 % n_ids] = min_rows
+    pid_of_id = 1000 + 7 * torch.arange(n_ids, device=dev, dtype=torch.int64)
+    owner = torch.repeat_interleave(torch.arange(n_ids, device=dev), rows_of)
+    G = int(owner.numel())
+    perm = torch.randperm(G, generator=gen, device=dev)
+    owner = owner[perm]
+    gallery = centres[owner] + bias["rgb"] + SIGMA_RGB * torch.randn(G, dim, generator=gen, device=dev)
+    g_pid = pid_of_id[owner]
+    n_dup = int(dup_frac * G)
+    if n_dup > 0:
+        dst = torch.randperm(G, generator=gen, device=dev)[:n_dup]
+        src = torch.randint(0, G, (n_dup,), generator=gen, device=dev)
+        keep = ~torch.isin(src, dst)                          # a copy of a row that is itself overwritten would not be a copy
+        gallery[dst[keep]] = gallery[src[keep]]               # features copied, identity of the destination row kept
+    combos = mm_combos(k)
+    Q = n_ids * queries_per_id
+    q_id = torch.arange(Q, device=dev) // queries_per_id
+    combo_tab = torch.tensor([[MOD_ID[m] for m in c] for c in combos], device=dev, dtype=torch.int32)
+    mod_id = combo_tab[(torch.arange(Q, device=dev) % queries_per_id) % len(combos)]
+    sig_tab = torch.tensor([SIGMA[m] for m in MODALITIES], device=dev)
+    bias_tab = torch.stack([bias[m] for m in MODALITIES])
+    mid = mod_id.long()
+    query = centres[q_id][:, None, :] + bias_tab[mid] + sig_tab[mid][..., None] * torch.randn(Q, k, dim, generator=gen, device=dev)
+    q_pid = pid_of_id[q_id]
+    n_excl = max(1, n_excl)
+    excl = torch.full((Q, n_excl), -1, device=dev, dtype=torch.int32)
+    if excl_frac > 0:
+        # same-image rule: a seeded fraction of the queries masks gallery rows of its own identity
+        order = torch.argsort(owner, stable=True)              # rows grouped by identity
+        start = torch.cumsum(rows_of, 0) - rows_of
+        pick = torch.rand(Q, generator=gen, device=dev) < excl_frac
+        off = (torch.rand(Q, n_excl, generator=gen, device=dev) * rows_of[q_id][:, None]).long()
+        rows = order[(start[q_id][:, None] + off)].to(torch.int32)
+        excl = torch.where(pick[:, None], rows, excl)
+    return RetrievalCase(gallery, g_pid, query, mod_id, q_pid, excl, k)
+
+
 def weights_tensor(weight_cfg: Optional[Dict[str, float]] = None, device="cpu") -> torch.Tensor:
     cfg = DEFAULT_WEIGHTS if weight_cfg is None else weight_cfg
     return torch.tensor([float(cfg.get(m, 1.0)) for m in MODALITIES], dtype=torch.float32, device=device)

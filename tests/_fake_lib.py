@@ -131,14 +131,21 @@ class FakeLib:
                 cand_score[q, c, :m] = s[mine[:m]]
                 cand_idx[q, c, :m] = mine[:m].to(torch.int32)
 
-    def reid_retrieve_fused(self, q16, g16, q_code, g_code, excl, E, pos_thr, n_pos, Q, G_local, g_offset, d, Pmax, n_chunks,
-                            total_chunks, cap, pos_above, cand_score, cand_idx, cand_count, cand_thr, ws, ws_bytes, st):
+    def reid_retrieve_fused(self, q16, g16, q_code, g_code, excl, E, pos_thr, n_pos, Q, G_local, g_offset, d, Pmax, pos_stride,
+                            n_chunks, n_shards, cap, flags, pos_above, cand_score, cand_idx, cand_count, cand_thr, ws, ws_bytes, st):
+        # (pos_thr / pos_above arrive as [Q, pos_stride] tensors; this call covers their first Pmax columns)
+        assert Pmax <= 64 and (pos_stride == 0 or pos_stride >= Pmax) and pos_thr.shape[1] == (pos_stride or Pmax)
         S = q16.float() @ g16.float().T                                # fp16 operands, fp32 accumulation
         rpc = -(-G_local // n_chunks)
-        rpc = -(-rpc // 256) * 256
+        rpc = -(-rpc // 1024) * 1024
+        if flags & 2:                                                  # REID_FUSED_NO_CANDIDATES: counting only
+            assert cand_score is None and cand_idx is None and cand_count is None
+            nb = Q
+            cand_score, cand_idx = torch.empty(nb, n_chunks, cap), torch.empty(nb, n_chunks, cap, dtype=torch.int32)
+            cand_count, cand_thr = torch.zeros(nb, n_chunks, dtype=torch.int32), None
         self._rank_pass(S, range(Q), q_code, g_code, self._masked(excl, E, Q, G_local, g_offset), pos_thr, n_pos, Pmax, n_chunks, cap,
                         rpc, pos_above, cand_score, cand_idx, cand_count, cand_thr)
-        return self._log("reid_retrieve_fused")
+        return self._log("reid_retrieve_fused" if not (flags & 2) else "reid_retrieve_fused(window)")
 
     def reid_retrieve_exact(self, q32, g32, q_code, g_code, excl, E, pos_thr, n_pos, q_sel, n_sel, Q, G_local, g_offset, d, Pmax,
                             n_chunks, cap, pos_above, cand_score, cand_idx, cand_count, st):
@@ -218,7 +225,7 @@ class FakeLib:
             acc += torch.tensor([a, first <= 1, first <= 5, first <= 10, 1.0], dtype=torch.float64)
             if ap is not None:
                 ap[q] = a
-        out.copy_(torch.cat([acc[:4] / acc[4] if acc[4] > 0 else torch.zeros(4, dtype=torch.float64), acc[4:]]))
+        out[:5].copy_(torch.cat([acc[:4] / acc[4] if acc[4] > 0 else torch.zeros(4, dtype=torch.float64), acc[4:]]))
         return self._log("reid_metrics_reduce")
 
 

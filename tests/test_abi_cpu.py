@@ -158,7 +158,7 @@ def test_entry_points_reject_invalid_arguments_before_touching_the_device():
         "pos_scores null": L.reid_pos_scores(N, N, N, N, N, N, 0, 1, 1, 0, 512, 4, N, N),
         "pos_scores excl missing": L.reid_pos_scores(one, one, one, one, one, N, 2, 1, 1, 0, 512, 4, one, N),
         "pos_sort null": L.reid_pos_sort(N, N, 1, 4, N),
-        "fused null": L.reid_retrieve_fused(N, N, N, N, N, 0, N, N, 1, 1, 0, 512, 4, 1, 1, 64, N, N, N, N, N, N, 0, N),
+        "fused null": L.reid_retrieve_fused(N, N, N, N, N, 0, N, N, 1, 1, 0, 512, 4, 4, 1, 1, 64, 0, N, N, N, N, N, N, 0, N),
         "exact null": L.reid_retrieve_exact(N, N, N, N, N, 0, N, N, N, 0, 1, 1, 0, 512, 4, 1, 64, N, N, N, N, N),
         "rescore null": L.reid_rescore_topk(N, N, N, N, N, N, N, N, N, N, N, 0, 1, 1, 0, 512, 4, 1, 64, 10, 0.0, N, N, N, N, N),
         "merge null": L.reid_merge_topk(N, N, 1, 1, 10, 10, N, N, N),

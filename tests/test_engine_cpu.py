@@ -52,14 +52,16 @@ def test_retrieve_host_logic_matches_oracle(monkeypatch, mode, query_block):
     res = engine.retrieve(shard, q32, q16, case.q_pid, case.excl, topk=10, mode=mode, query_block=query_block, want_ap=True)
     _check(res, _reference(case), case.Q, fused=mode == "fused")
     n_blocks = -(-case.Q // query_block)
-    assert fake.calls.count("reid_retrieve_fused" if mode == "fused" else "reid_retrieve_exact") == n_blocks
-    assert fake.calls.count("reid_metrics_reduce") == 1
-    if mode == "fused":                                     # flagged queries went through the exact pass, block by block
+    if mode == "fused":
+        # flagged queries (the forced ones among them) went through ONE all-fp32 pass over a compact copy at the end,
+        # then the exchange + metrics were redone
         forced = sum(1 for b0 in range(0, case.Q, query_block) for q in range(min(query_block, case.Q - b0)) if q % 7 == 3)
-        assert res.n_flagged >= forced > 0
-        assert fake.calls.count("reid_retrieve_exact(sel)") == fake.calls.count("reid_rescore_topk(sel)") == n_blocks
+        assert res.n_flagged >= forced > 0 and res.path == "fused"
+        assert fake.calls.count("reid_retrieve_fused") == n_blocks and fake.calls.count("reid_retrieve_exact") == 1
+        assert fake.calls.count("reid_metrics_reduce") == 2 and fake.calls.count("reid_rescore_topk") == n_blocks + 1
     else:
-        assert res.n_flagged == 0 and "reid_retrieve_exact(sel)" not in fake.calls
+        assert res.n_flagged == 0 and res.path == "exact"
+        assert fake.calls.count("reid_retrieve_exact") == n_blocks and fake.calls.count("reid_metrics_reduce") == 1
     # a second call on the same shard reuses its scratch buffers and gives the same answer
     res2 = engine.retrieve(shard, q32, q16, case.q_pid, None, topk=10, mode=mode, query_block=query_block, want_ap=True)
     case.excl = None
@@ -77,13 +79,30 @@ def test_prepare_gallery_codes_and_lookup(monkeypatch):
     assert torch.allclose(shard.g_f32.norm(dim=1), torch.ones(3), atol=1e-6) and shard.g_f16.dtype == torch.float16
 
 
-def test_pick_chunks_fills_the_last_wave():
+def test_fused_slots_fill_the_last_wave():
     from prcv2025reid_b200 import engine
-    assert engine._pick_chunks(128, 1_000_000, 74) == 4          # C4 on one GPU: 512 items over 74 pairs = 6.9 waves
-    assert engine._pick_chunks(1, 192, 74) == 1                  # tiny gallery: never split below 4096 rows per chunk
-    for nq, G, units in ((79, 100_000, 74), (13, 125_000, 74), (391, 1_000_000, 148)):
-        c = engine._pick_chunks(nq, G, units)
-        assert 1 <= c <= 8 and G // c >= 4096
+    # whole waves of 74 CTA pairs need no split; the blocks of a partial wave are cut so that it is full too
+    assert engine.fused_slots(74 * 256, 1_000_000, 148) == 1 and engine.fused_slots(2 * 74 * 256, 125_000, 148) == 1
+    assert engine.fused_slots(24224, 1_000_000, 148) == 3          # 95 blocks = 74 + 21 left -> 3 chunks each
+    assert engine.fused_slots(20_000, 100_000, 148) == 8           # C3: 79 blocks = 74 + 5 left (capped at 8)
+    assert engine.fused_slots(1, 192, 148) == 1                    # tiny gallery: never split below 4096 rows per chunk
+    assert engine.fused_slots(2048, 100_000, 148) == 8
+    assert engine.default_query_block(148) == 37888
+
+
+def test_identities_with_more_than_64_gallery_rows_use_threshold_windows(monkeypatch):
+    """Pmax > 64: the fused pass handles 64 thresholds per query and call; deeper positives of the large identities are
+    counted by further counting-only passes over those queries (engine._rank_block), results equal to the oracle."""
+    from prcv2025reid_b200 import engine
+    fake = _fake_lib.install(monkeypatch)
+    case = synth.make_ragged_case(71, 12, 1, 150, 2, 2, excl_frac=0.3)
+    shard = engine.prepare_gallery(case.gallery_raw, case.g_pid)
+    assert shard.pmax == 150
+    q32, q16 = engine.fuse_queries(case.query_raw, case.mod_id, synth.weights_tensor())
+    res = engine.retrieve(shard, q32, q16, case.q_pid, case.excl, topk=10, mode="fused", want_ap=True)
+    assert res.path == "fused" and fake.calls.count("reid_retrieve_fused") == 1
+    assert 1 <= fake.calls.count("reid_retrieve_fused(window)") <= 2
+    _check(res, _reference(case), case.Q, fused=True)
 
 
 def _worker(rank, world, port, out):

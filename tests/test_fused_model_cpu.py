@@ -1,4 +1,4 @@
-"""The counting rule of the fused kernel (deep-rank sampling) restated in numpy
+"""The counting rule of the fused kernel (two-level deep-rank sampling) restated in numpy
 (oracle/fused_model.py) and measured against the exact oracle WITHOUT a GPU: the approximation must keep mAP inside the
 north star's 1e-4 and leave CMC / the number of valid queries untouched, also when the gallery is split over ranks and
 chunks.  (The GPU tests compare the kernel itself with the exact path at 100k and 1M rows.)"""
@@ -19,23 +19,23 @@ def _case(n_ids, nq):
     return case, q, g, exact
 
 
-def _model(case, q, g, world, n_chunks, **kw):
+def _model(case, q, g, world, **kw):
     thr, n_pos = fm.positive_thresholds(q, g, case.q_pid, case.g_pid, case.excl)
     total = np.zeros_like(thr, dtype=np.int64)
     n_exact = []
     for r in range(world):
         r0, r1 = sharding.shard_range(g.shape[0], r, world)
-        c = fm.fused_counts(q, g[r0:r1], case.q_pid, case.g_pid[r0:r1], case.excl, n_chunks=n_chunks,
-                            total_chunks=n_chunks * world, thr=thr, n_pos=n_pos, g_offset=r0, **kw)
+        c = fm.fused_counts(q, g[r0:r1], case.q_pid, case.g_pid[r0:r1], case.excl, n_shards=world, thr=thr, n_pos=n_pos,
+                            g_offset=r0, **kw)
         total += c["pos_above"]                                   # sharding.exchange_counts: counts are additive
         n_exact.append(c["n_exact"])
     return fm.metrics_from_counts(total, n_pos), n_pos, np.stack(n_exact)
 
 
-@pytest.mark.parametrize("n_ids,world,n_chunks", [(1000, 1, 4), (2000, 2, 2)])
-def test_deep_rank_sampling_keeps_map_within_the_bar(n_ids, world, n_chunks):
+@pytest.mark.parametrize("n_ids,world", [(1000, 1), (2000, 2)])
+def test_deep_rank_sampling_keeps_map_within_the_bar(n_ids, world):
     case, q, g, exact = _case(n_ids, 128)
-    m, n_pos, n_exact = _model(case, q, g, world, n_chunks)
+    m, n_pos, n_exact = _model(case, q, g, world)
     assert (n_exact < n_pos[None, :]).any()                       # the sampled path is exercised
     assert m["num_queries"] == exact["num_queries"]
     assert abs(m["mAP"] - exact["mAP"]) <= 1e-4                   # north star: mAP within 1e-4
@@ -46,7 +46,7 @@ def test_deep_rank_sampling_keeps_map_within_the_bar(n_ids, world, n_chunks):
 
 def test_without_sampling_only_fp16_rounding_remains():
     case, q, g, exact = _case(1000, 96)
-    m, n_pos, n_exact = _model(case, q, g, 1, 4, exact_all=True)   # REID_FUSED_DEBUG=64
+    m, n_pos, n_exact = _model(case, q, g, 1, exact_all=True)      # REID_FUSED_EXACT_COUNTS
     assert np.array_equal(n_exact[0], n_pos)
     assert abs(m["mAP"] - exact["mAP"]) <= 5e-5
     # a shard below 16 x CALIB_ROWS rows is never sampled (reid_retrieve_fused `sample_deep`)
@@ -75,7 +75,7 @@ def test_rescoring_stage_makes_the_head_exact():
     the exact top-10 of every unflagged query, exact counts for the positives above the completeness bound, and only
     shrink the error of the modelled AP."""
     case, q, g, exact = _case(1000, 96)
-    c = fm.fused_counts(q, g, case.q_pid, case.g_pid, case.excl, n_chunks=4)
+    c = fm.fused_counts(q, g, case.q_pid, case.g_pid, case.excl)
     r = fm.rescore_stage(q, g, case.q_pid, case.g_pid, c, case.excl)
     ok = r["flag"] == 0
     assert ok.mean() >= 0.9                                            # flagged queries are re-run exactly by engine.retrieve

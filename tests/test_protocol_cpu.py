@@ -87,7 +87,8 @@ class _OracleEngine:
         self.installs = 0
 
     def l2norm_rows(self, x, want_f16=False, eps=1e-12):
-        return orc.l2n(x.float()), None
+        y = orc.l2n(x.float())
+        return y, (y.half() if want_f16 else None)
 
     def fuse_queries(self, rows, mid, w):
         Q, k, D = rows.shape
@@ -97,7 +98,8 @@ class _OracleEngine:
             use = (mid[:, j] >= 0)
             wj = torch.where(use, w[mid[:, j].clamp(min=0).long()], torch.zeros(Q))
             acc = acc + f[:, j] * wj[:, None] if j else f[:, j] * wj[:, None]
-        return orc.l2n(acc), None
+        y = orc.l2n(acc)
+        return y, y.half()
 
     def prepare_gallery(self, gallery, g_pid_all, g_offset=0):
         self.installs += 1
