@@ -259,19 +259,27 @@ int main() {
     const int n_chunks = fused ? 1 : 4;
     Dev<int32_t> d_above((size_t)Q * Pmax), d_cidx((size_t)Q * n_chunks * cap), d_ccnt((size_t)Q * n_chunks), d_topi((size_t)Q * REID_RTOP), d_flag(Q);
     Dev<float> d_cs((size_t)Q * n_chunks * cap), d_cthr(Q), d_tops((size_t)Q * REID_RTOP);
+    // candidate selection -> re-scoring -> decidability check (one shard: the completeness bound is the shard's own cut-off)
+    Dev<float> d_sels((size_t)Q * REID_RTOP), d_bound(Q);
+    Dev<int32_t> d_seli((size_t)Q * REID_RTOP), d_seln(Q), d_lb0(Q);
+    auto head = [&](const float* cand_thr, float eps) {
+      CK(reid_cand_select(d_cs.p, d_cidx.p, d_ccnt.p, cand_thr, Q, n_chunks, cap, REID_KLIST, d_sels.p, d_seli.p, d_seln.p,
+                          d_bound.p, d_flag.p, st));
+      CK(reid_rescore_topk(d_q32.p, d_g32.p, d_qcode.p, d_gcode.p, d_thr.p, d_npos.p, d_sels.p, d_seli.p, d_seln.p, d_bound.p, Q,
+                           G, 0, D, Pmax, eps, d_above.p, d_tops.p, d_topi.p, d_lb0.p, st));
+      CK(reid_topk_check(d_tops.p, REID_RTOP, topk, d_bound.p, eps, d_thr.p, d_npos.p, Pmax, d_lb0.p, Q, d_flag.p, st));
+    };
     if (fused) {
       const size_t wsb = reid_workspace_bytes(1, Q, G, D);
       Dev<uint8_t> ws(wsb);
       CK(reid_retrieve_fused(d_q16.p, d_g16.p, d_qcode.p, d_gcode.p, nullptr, 0, d_thr.p, d_npos.p, Q, G, 0, D, Pmax, Pmax, n_chunks,
                              1, cap, 0, d_above.p, d_cs.p, d_cidx.p, d_ccnt.p, d_cthr.p, ws.p, wsb, st));
-      CK(reid_rescore_topk(d_q32.p, d_g32.p, d_qcode.p, d_gcode.p, d_thr.p, d_npos.p, d_cs.p, d_cidx.p, d_ccnt.p, d_cthr.p, nullptr, Q,
-                           Q, G, 0, D, Pmax, n_chunks, cap, topk, eps16, d_above.p, d_tops.p, d_topi.p, d_flag.p, st));
+      head(d_cthr.p, eps16);
       CU(cudaStreamSynchronize(st));                                  // (ws must outlive the kernels)
     } else {
       CK(reid_retrieve_exact(d_q32.p, d_g32.p, d_qcode.p, d_gcode.p, nullptr, 0, d_thr.p, d_npos.p, nullptr, Q, Q, G, 0, D, Pmax,
                              n_chunks, cap, d_above.p, d_cs.p, d_cidx.p, d_ccnt.p, st));
-      CK(reid_rescore_topk(d_q32.p, d_g32.p, d_qcode.p, d_gcode.p, d_thr.p, d_npos.p, d_cs.p, d_cidx.p, d_ccnt.p, nullptr, nullptr, Q,
-                           Q, G, 0, D, Pmax, n_chunks, cap, topk, 0.0f, d_above.p, d_tops.p, d_topi.p, d_flag.p, st));
+      head(nullptr, 0.0f);
     }
     Dev<double> d_out(5);
     CK(reid_metrics_reduce(d_above.p, d_npos.p, Q, Pmax, d_out.p, nullptr, st));

@@ -88,7 +88,7 @@ int reid_pos_sort(float* pos_score, int32_t* n_pos, int64_t Q, int Pmax, void* s
  * cand_thr [Q] (optional): per-query score with >= REID_KLIST candidates at or above it (-inf if fewer);
  * every candidate the re-scorer can need lies at or above it.
  * n_shards = ranks the WHOLE gallery of a query is partitioned over (0 / 1 = this shard is the whole gallery).
- * Counting classes (shards of >= 32768 rows; a calibration pre-pass over a strided 1/16 of the shard, 2048 .. 8192
+ * Counting classes (shards of >= 32768 rows; a calibration pre-pass over a strided 1/32 of the shard, 2048 .. 8192
  * rows, estimates every threshold's rank inside the shard): thresholds ranked above max(1024 / n_shards, 8 calibration hits) rows are
  * counted on a 1/32 row sample, those above 32768 / n_shards rows on a 1/1024 row sample, so that a sampled count
  * rests on >= 32 sampled rows gallery-wide; all shallower thresholds on every row.
@@ -113,21 +113,33 @@ int reid_retrieve_exact(const float* q_f32, const float* g_f32, const int32_t* q
                         int cand_cap, int32_t* pos_above, float* cand_score, int32_t* cand_idx,
                         int32_t* cand_count, void* stream);
 
-/* ---- candidate re-scoring: gathers a query's candidates, keeps the REID_RTOP best by
- * approximate score, re-scores them in fp32 (same dot routine as reid_pos_scores), sorts
- * them (score desc, index asc) -> top_score/top_idx[q, REID_RTOP] (global gallery index, -1 pad).
- * Positives whose threshold lies above the completeness cut-off (+eps) get their exact
- * local count written to pos_above.  flag[q] != 0 when exactness of top-`topk` / CMC cannot be
- * guaranteed within eps (or a candidate buffer overflowed): re-run those through
- * reid_retrieve_exact.  eps = bound on |approx - exact| score error (0 for the exact path). */
-int reid_rescore_topk(const float* q_f32, const float* g_f32, const int32_t* q_code,
-                      const int32_t* g_code, const float* pos_thr, const int32_t* n_pos,
-                      const float* cand_score, const int32_t* cand_idx, const int32_t* cand_count,
-                      const float* cand_thr /* optional, from reid_retrieve_fused */,
-                      const int32_t* q_sel, int64_t n_sel, int64_t Q, int64_t G_local,
-                      int64_t g_offset, int d, int Pmax, int n_chunks, int cand_cap, int topk,
-                      float eps, int32_t* pos_above, float* top_score, int32_t* top_idx,
-                      int32_t* flag, void* stream);
+/* ---- candidate selection, re-scoring and the decidability check (replace `argsort` :423 for the head of the ranking).
+ * reid_cand_select: gathers a query's candidate slots (those at or above cand_thr when given), sorts them by approximate
+ *   score and keeps the REID_RTOP best -> sel_score / sel_idx [Q, REID_RTOP] (descending; local row index, -1 pad),
+ *   sel_n [Q]; sel_cut [Q] = the kx-th best approximate score (kx <= REID_KLIST; -inf when the shard offers fewer than
+ *   kx candidates); sel_flag [Q] = 1 when a candidate buffer overflowed.
+ * With several gallery shards the host all-reduces sel_cut with MAX (`bound`: the best shard's kx-th best score), so
+ *   that every shard re-scores only the few rows that can still reach the gallery-wide head; one shard: bound = sel_cut.
+ * reid_rescore_topk: re-scores the selected rows at or above `bound` in fp32 (same dot routine as reid_pos_scores),
+ *   sorts them (score desc, index asc) -> top_score / top_idx [Q, REID_RTOP] (global gallery index, -1 pad).  A local
+ *   row that is not re-scored has an exact score <= bound + eps (eps = bound on |approx - exact|, 0 for the exact
+ *   path): positives whose threshold lies above bound + eps get their exact local count written to pos_above, the
+ *   others keep max(count so far, re-scored rows above them).  lb0 [Q] = re-scored non-positive rows above the best positive.
+ * reid_topk_check (after the exchange; top_score = the merged list [Q, list_len], lb0 summed over the shards): flag |= 2
+ *   when the k-th best exact score is not above bound + eps, |= 4 when CMC@10 is undecidable (best positive not above
+ *   bound + eps and fewer than 10 re-scored rows above it); flag != 0 -> re-run the query through reid_retrieve_exact. */
+int reid_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* cand_count,
+                     const float* cand_thr /* optional, from reid_retrieve_fused */, int64_t Q, int n_chunks,
+                     int cand_cap, int kx, float* sel_score, int32_t* sel_idx, int32_t* sel_n, float* sel_cut,
+                     int32_t* sel_flag, void* stream);
+int reid_rescore_topk(const float* q_f32, const float* g_f32, const int32_t* q_code, const int32_t* g_code,
+                      const float* pos_thr, const int32_t* n_pos, const float* sel_score, const int32_t* sel_idx,
+                      const int32_t* sel_n, const float* bound, int64_t Q, int64_t G_local, int64_t g_offset, int d,
+                      int Pmax, float eps, int32_t* pos_above, float* top_score, int32_t* top_idx, int32_t* lb0,
+                      void* stream);
+int reid_topk_check(const float* top_score, int list_len, int topk, const float* bound, float eps,
+                    const float* pos_thr, const int32_t* n_pos, int Pmax, const int32_t* lb0, int64_t Q,
+                    int32_t* flag, void* stream);
 
 /* merge n_lists per-shard top lists [n_lists, Q, list_len] (each sorted; the global top-k is contained in the union of
  * the shards' top-k, so list_len = topk suffices) into out[Q, topk] (score desc, idx asc) */

@@ -9,7 +9,7 @@ built.  It follows the kernel, not the reference:
 
   scores             fp32 accumulation of fp16-rounded operands                       retrieve_fused.cu kernel comment (kind::f16 MMA)
   thresholds t_j     the positives' EXACT fp32 scores, sorted descending              reid_pos_scores / reid_pos_sort
-  calibration        strided sample of G_local/16 rows (2048 .. 8192), every threshold exact         reid_retrieve_fused host code (`sample_deep`)
+  calibration        strided sample of G_local/32 rows (2048 .. 8192), every threshold exact         reid_retrieve_fused host code (`sample_deep`)
   counting classes   calib_split_kernel: threshold j is counted on every row while    retrieve_fused.cu calib_split_kernel
                      the estimated rank INSIDE THE SHARD of thresholds 0..j stays
                      <= limit1 = max(32 * W1 / n_shards, 8 * scale), on the level-1
@@ -92,7 +92,7 @@ def fused_counts(q_f32: torch.Tensor, g_f32: torch.Tensor, q_pid: torch.Tensor, 
                                          None if excl is None else torch.from_numpy(np.where(excl.numpy() >= 0, excl.numpy() - g_offset, -1)))
     Pmax = thr.shape[1]
     sample_deep = (G >= 16 * CALIB_MIN) and not exact_all
-    calib_rows = max(CALIB_MIN, min(calib_rows, G // 16 // 256 * 256))    # 1/16 of the shard in whole tiles
+    calib_rows = max(CALIB_MIN, min(calib_rows, G // 32 // 256 * 256))    # 1/32 of the shard in whole tiles
     pos_above = np.zeros((Q, Pmax), dtype=np.int64)
     n_exact = np.zeros(Q, dtype=np.int64)
     n_l1 = np.zeros(Q, dtype=np.int64)

@@ -24,10 +24,14 @@ def make_self(tau=0.2, epoch=5, warmup=0, weight=0.3, training=True):
                                  contrastive_weight=weight, sdm_temperature=tau, training=training)
 
 
-def make_inputs(seed, B, d, n_ids, kind):
+DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def make_inputs(seed, B, d, n_ids, kind, dtype="fp32"):
+    """dtype: what the training autocast (train.py:852) hands to compute_loss as `raw_modality_features`."""
     g = torch.Generator().manual_seed(seed)
     labels = torch.randint(0, n_ids, (B,), generator=g)
-    feats = {m: torch.randn(B, d, generator=g) for m in MODS}
+    feats = {m: torch.randn(B, d, generator=g).to(DTYPES[dtype]) for m in MODS}
     masks = {m: (torch.rand(B, 1, generator=g) > 0.3).float() for m in MODS}
     if kind == "ragged":
         masks["cp"] = torch.zeros(B, 1)                          # a modality without valid rows (:597)
@@ -47,12 +51,17 @@ def make_inputs(seed, B, d, n_ids, kind):
     return feats, masks, labels
 
 
-CASES = {  # name: (seed, B, d, n_ids, kind, tau)
+CASES = {  # name: (seed, B, d, n_ids, kind, tau[, dtype])
     "full": (1, 12, 512, 4, "full", 0.2),
     "ragged": (2, 12, 512, 4, "ragged", 0.2),
     "no_vis": (3, 8, 128, 3, "no_vis", 0.2),
     "no_pairs": (4, 8, 128, 3, "no_pairs", 0.2),
     "missing": (5, 10, 128, 3, "missing", 0.1),
+    # features in the autocast dtype: the loss normalises in that dtype (sdm_loss.py:31-32)
+    "full_bf16": (6, 16, 512, 5, "full", 0.2, "bf16"),
+    "ragged_bf16": (7, 12, 512, 4, "ragged", 0.2, "bf16"),
+    "full_fp16": (8, 16, 512, 5, "full", 0.2, "fp16"),
+    "large_bf16": (9, 96, 512, 12, "full", 0.2, "bf16"),       # valid rows >= 64: the tcgen05 path
 }
 
 
@@ -72,8 +81,9 @@ def run_reference(feats, masks, labels, tau):
 
 def main():
     payload = {}
-    for name, (seed, B, d, n_ids, kind, tau) in CASES.items():
-        feats, masks, labels = make_inputs(seed, B, d, n_ids, kind)
+    for name, spec in CASES.items():
+        seed, B, d, n_ids, kind, tau = spec[:6]
+        feats, masks, labels = make_inputs(seed, B, d, n_ids, kind, *spec[6:])
         loss, grads, out = run_reference(feats, masks, labels, tau)
         payload[name + "/loss"] = np.float32(float(loss))
         payload[name + "/args"] = np.array([seed, B, d, n_ids], dtype=np.int64)
@@ -81,7 +91,7 @@ def main():
         payload[name + "/checksum"] = np.float64(sum(float(f.double().abs().sum()) for f in feats.values() if f is not None))
         payload[name + "/total"] = np.float32(float(out["total_loss"].detach()))
         for m, gr in grads.items():
-            payload[name + "/grad_" + m] = gr.numpy()
+            payload[name + "/grad_" + m] = gr.float().numpy()
         print(name, float(loss), sorted(grads))
     np.savez_compressed(os.path.join(GOLDEN, "sdm_alignment.npz"), **payload)
 

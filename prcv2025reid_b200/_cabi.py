@@ -44,9 +44,13 @@ _SIGS = {
     "reid_retrieve_exact": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "reid_cand_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "reid_rescore_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
-                                  c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "reid_topk_check": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int64,
+                                c_void_p, c_void_p]),
     "reid_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "reid_metrics_reduce": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "reid_topk_label_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -65,7 +69,7 @@ _lib = None
 _LAUNCHES_PER_CALL = {
     "reid_l2norm_rows": 1, "reid_mm_fuse_normalize": 1, "reid_sim_gemm": 1, "reid_pid_index_build": 2,
     "reid_pid_lookup": 1, "reid_pos_scores": 1, "reid_pos_sort": 1, "reid_retrieve_fused": 4,
-    "reid_retrieve_exact": 1, "reid_rescore_topk": 1, "reid_merge_topk": 1, "reid_metrics_reduce": 2,
+    "reid_retrieve_exact": 1, "reid_cand_select": 1, "reid_rescore_topk": 1, "reid_topk_check": 1, "reid_merge_topk": 1, "reid_metrics_reduce": 2,
     "reid_topk_label_metrics": 1, "reid_sdm_fwd": 1, "reid_sdm_bwd": 1,   # (tcgen05 path: fwd = 2 launches, counted in sdm_loss.py)
     "reid_sdm_step": 0,                                                   # (counted in sdm_loss.py: reid_sdm_step_launches)
 }

@@ -160,7 +160,15 @@ retrieve_exact_kernel(const float* __restrict__ q_f32, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// re-scoring: one CTA (4 warps) per query
+// candidate selection + re-scoring
+//   cand_select:  one CTA (4 warps) per query: gather the query's candidate slots, sort by approximate score, keep the
+//                 REID_RTOP best -> sel_score / sel_idx (sorted descending) and sel_cut = the kx-th best approximate score.
+//   (multi-shard: the host all-reduces sel_cut with MAX -> bound: the best shard's kx-th best score)
+//   rescore_topk: one CTA per query: the selected rows at or above `bound` are re-scored in fp32, sorted, written as the
+//                 shard's exact top list; exact local counts for the positives above bound + eps.
+//   topk_check:   after the exchange: is the merged top-k / CMC decidable within eps?
+// Completeness: a local row that is NOT re-scored has an approximate score <= bound (below it inside the selected list, or
+// <= the REID_KLIST-th best <= sel_cut <= bound outside it), hence an exact score <= bound + eps.
 // ------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 128;
 
@@ -184,25 +192,16 @@ __device__ void block_bitonic_desc(float* key, int32_t* val, int n2) {
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
-rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g_f32,
-                    const int32_t* __restrict__ q_code, const int32_t* __restrict__ g_code,
-                    const float* __restrict__ pos_thr, const int32_t* __restrict__ n_pos,
-                    const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
-                    const int32_t* __restrict__ cand_count, const float* __restrict__ cand_thr,
-                    const int32_t* __restrict__ q_sel,
-                    int64_t G_local, int64_t g_offset, int d, int Pmax, int n_chunks, int cand_cap, int topk,
-                    float eps, int n2, int32_t* __restrict__ pos_above, float* __restrict__ top_score,
-                    int32_t* __restrict__ top_idx, int32_t* __restrict__ flag) {
+cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                   const int32_t* __restrict__ cand_count, const float* __restrict__ cand_thr, int n_chunks, int cand_cap,
+                   int kx, int n2, float* __restrict__ sel_score, int32_t* __restrict__ sel_idx, int32_t* __restrict__ sel_n,
+                   float* __restrict__ sel_cut, int32_t* __restrict__ sel_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* key = reinterpret_cast<float*>(smem_raw);        // [n2]
   int32_t* val = reinterpret_cast<int32_t*>(key + n2);    // [n2]
-  __shared__ float ex_s[REID_RTOP];
-  __shared__ int32_t ex_i[REID_RTOP];
-  __shared__ int s_total, s_overflow, s_flag;
-
-  const int qi = q_sel ? q_sel[blockIdx.x] : (int)blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { s_total = 0; s_overflow = 0; s_flag = 0; }
+  __shared__ int s_total, s_overflow;
+  const int qi = blockIdx.x;
+  if (threadIdx.x == 0) { s_total = 0; s_overflow = 0; }
   __syncthreads();
   // gather the chunk buffers (compact, order irrelevant: sorted next).  When the producer supplied a
   // per-query threshold with >= KLIST candidates at or above it, only those can reach the top list.
@@ -266,16 +265,46 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
   __syncthreads();
   block_bitonic_desc(key, val, ns);
   const int R = min(total, REID_RTOP);
-  // completeness cut-off: every local row whose approximate score exceeds `cut` is a candidate
-  const float cut = (total >= REID_KLIST) ? key[REID_KLIST - 1] : REID_NEG_INF;
-  // exact fp32 re-score of the R best candidates (same dot routine as reid_pos_scores)
+  if (threadIdx.x < REID_RTOP) {
+    sel_score[(int64_t)qi * REID_RTOP + threadIdx.x] = threadIdx.x < R ? key[threadIdx.x] : REID_NEG_INF;
+    sel_idx[(int64_t)qi * REID_RTOP + threadIdx.x] = threadIdx.x < R ? val[threadIdx.x] : -1;
+  }
+  if (threadIdx.x == 0) {
+    sel_n[qi] = R;
+    // completeness cut-off: every local row whose approximate score exceeds it is among the selected rows
+    // (fewer than kx candidates: the shard has no other rows to offer, -inf)
+    sel_cut[qi] = (total >= kx) ? key[kx - 1] : REID_NEG_INF;
+    __syncwarp();
+    sel_flag[qi] = s_overflow ? 1 : 0;                        // bit0: a candidate buffer overflowed
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g_f32,
+                    const int32_t* __restrict__ q_code, const int32_t* __restrict__ g_code,
+                    const float* __restrict__ pos_thr, const int32_t* __restrict__ n_pos,
+                    const float* __restrict__ sel_score, const int32_t* __restrict__ sel_idx,
+                    const int32_t* __restrict__ sel_n, const float* __restrict__ bound_in,
+                    int64_t g_offset, int d, int Pmax, float eps, int32_t* __restrict__ pos_above,
+                    float* __restrict__ top_score, int32_t* __restrict__ top_idx, int32_t* __restrict__ lb0) {
+  __shared__ float ex_s[REID_RTOP];
+  __shared__ int32_t ex_i[REID_RTOP];
+  __shared__ int s_neg[REID_RTOP];                             // re-scored row r is NOT a positive of the query
+  const int qi = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float b = bound_in[qi];
+  // rows to re-score: the prefix of the (descending) selected list at or above the bound
+  const int n_sel = sel_n[qi];
+  const float my = lane < n_sel ? sel_score[(int64_t)qi * REID_RTOP + lane] : REID_NEG_INF;
+  const int R = __popc(__ballot_sync(0xffffffffu, lane < n_sel && my >= b));
+  // exact fp32 re-score (same dot routine as reid_pos_scores)
   constexpr int RW = RS_THREADS / 32;
+  const float* qrow = q_f32 + (int64_t)qi * d;
   for (int r = warp; r < REID_RTOP; r += 2 * RW) {               // two rows per warp at a time: both gathers in flight
     const int r2 = r + RW;
     float s0 = REID_NEG_INF, s1 = REID_NEG_INF; int g0 = 0x7fffffff, g1 = 0x7fffffff;
-    if (r < R) g0 = val[r];
-    if (r2 < R) g1 = val[r2];
-    const float* qrow = q_f32 + (int64_t)qi * d;
+    if (r < R) g0 = sel_idx[(int64_t)qi * REID_RTOP + r];
+    if (r2 < R) g1 = sel_idx[(int64_t)qi * REID_RTOP + r2];
     if (d == 512 && r2 < R) {
       warp_dot2_512(qrow, g_f32 + (int64_t)g0 * d, g_f32 + (int64_t)g1 * d, lane, s0, s1);
     } else {
@@ -307,11 +336,10 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
     top_idx[(int64_t)qi * REID_RTOP + lane] = (lane < R) ? (int32_t)(g_offset + gi) : -1;
   }
   __syncthreads();
-  // exact counts for positives above the cut-off; exactness flags
+  // exact counts for the positives above the completeness bound
   const int np = min(n_pos[qi], Pmax);
   const int qcode = q_code[qi];
-  const float bound = cut + eps;   // no local non-candidate row can score above this
-  __shared__ int s_neg[REID_RTOP];                             // re-scored row r is NOT a positive of the query
+  const float bound = b + eps;     // no local row that was not re-scored can score above this
   if (threadIdx.x < REID_RTOP) s_neg[threadIdx.x] = (threadIdx.x < R && g_code[ex_i[threadIdx.x]] != qcode) ? 1 : 0;
   __syncthreads();
   for (int j = threadIdx.x; j < np; j += blockDim.x) {
@@ -319,17 +347,30 @@ rescore_topk_kernel(const float* __restrict__ q_f32, const float* __restrict__ g
     int lb = 0;
     for (int r = 0; r < R; ++r) lb += (s_neg[r] && ex_s[r] > t) ? 1 : 0;
     int32_t* dst = pos_above + (int64_t)qi * Pmax + j;
-    if (t > bound || cut == REID_NEG_INF) *dst = lb;       // exact local count
-    else {
-      if (*dst < lb) *dst = lb;                            // lb is a rigorous lower bound
-      if (j == 0 && lb < 10) atomicOr(&s_flag, 4);          // CMC@10 undecidable within eps
+    if (t > bound || b == REID_NEG_INF) *dst = lb;         // exact local count
+    else if (*dst < lb) *dst = lb;                         // lb is a rigorous lower bound
+    if (j == 0) lb0[qi] = lb;
+  }
+  if (np == 0 && threadIdx.x == 0) lb0[qi] = 0;
+}
+
+// After the exchange (or directly, one shard): can the top-k list and CMC@10 be decided within eps?
+//   top: the merged exact top list [Q, list_len]; bound: the (gallery-wide) completeness cut-off; lb0: re-scored rows above
+//   the best positive, summed over the shards; flag |= 2 (top-k) / 4 (CMC); flag bit0 (overflow) is kept.
+__global__ void __launch_bounds__(256)
+topk_check_kernel(const float* __restrict__ top, int list_len, int topk, const float* __restrict__ bound_in, float eps,
+                  const float* __restrict__ pos_thr, const int32_t* __restrict__ n_pos, int Pmax,
+                  const int32_t* __restrict__ lb0, int64_t Q, int32_t* __restrict__ flag) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
+    const float b = bound_in[q];
+    int f = flag[q] ? 1 : 0;
+    if (b > REID_NEG_INF) {
+      const float bound = b + eps;
+      if (!(top[q * list_len + topk - 1] >= bound)) f |= 2;                       // k-th best not above the bound (or missing)
+      if (n_pos[q] > 0 && !(pos_thr[q * Pmax] > bound) && lb0[q] < 10) f |= 4;    // CMC@10 undecidable within eps
     }
+    flag[q] = f;
   }
-  if (threadIdx.x == 0) {
-    if (cut > REID_NEG_INF && R >= topk && ex_s[topk - 1] < bound) atomicOr(&s_flag, 2);   // top-k undecidable
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) flag[qi] = s_flag | (s_overflow ? 1 : 0);   // bit0 overflow, bit1 top-k, bit2 CMC
 }
 
 // merge per-shard top lists: one warp-multiple CTA per query, bitonic over n_lists*RTOP entries
@@ -438,28 +479,49 @@ extern "C" int reid_retrieve_exact(const float* q_f32, const float* g_f32, const
   return REID_OK;
 }
 
-extern "C" int reid_rescore_topk(const float* q_f32, const float* g_f32, const int32_t* q_code,
-                                 const int32_t* g_code, const float* pos_thr, const int32_t* n_pos,
-                                 const float* cand_score, const int32_t* cand_idx, const int32_t* cand_count,
-                                 const float* cand_thr, const int32_t* q_sel, int64_t n_sel, int64_t Q, int64_t G_local,
-                                 int64_t g_offset,
-                                 int d, int Pmax, int n_chunks, int cand_cap, int topk, float eps,
-                                 int32_t* pos_above, float* top_score, int32_t* top_idx, int32_t* flag,
-                                 void* stream) {
-  if (!q_f32 || !g_f32 || !q_code || !g_code || !pos_thr || !n_pos || !cand_score || !cand_idx || !cand_count ||
-      !pos_above || !top_score || !top_idx || !flag || d <= 0 || d % 4 != 0 || topk <= 0 || topk > REID_RTOP)
+extern "C" int reid_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* cand_count,
+                                const float* cand_thr, int64_t Q, int n_chunks, int cand_cap, int kx, float* sel_score,
+                                int32_t* sel_idx, int32_t* sel_n, float* sel_cut, int32_t* sel_flag, void* stream) {
+  if (!cand_score || !cand_idx || !cand_count || !sel_score || !sel_idx || !sel_n || !sel_cut || !sel_flag || n_chunks <= 0 ||
+      cand_cap <= 0 || kx <= 0 || kx > REID_KLIST)
     return REID_E_INVALID;
-  if (!q_sel) n_sel = Q;
-  if (n_sel <= 0) return REID_OK;
+  if (Q <= 0) return REID_OK;
   int n2 = 32;                                   // staging entries: enough for every candidate, at most 4096
   while (n2 < n_chunks * cand_cap && n2 < 4096) n2 <<= 1;
   const size_t smem = (size_t)n2 * 8;
   if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(rescore_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return REID_E_CUDA;
-  rescore_topk_kernel<<<(unsigned)n_sel, RS_THREADS, smem, (cudaStream_t)stream>>>(
-      q_f32, g_f32, q_code, g_code, pos_thr, n_pos, cand_score, cand_idx, cand_count, cand_thr, q_sel, G_local, g_offset, d,
-      Pmax, n_chunks, cand_cap, topk, eps, n2, pos_above, top_score, top_idx, flag);
+  cand_select_kernel<<<(unsigned)Q, RS_THREADS, smem, (cudaStream_t)stream>>>(cand_score, cand_idx, cand_count, cand_thr, n_chunks,
+                                                                            cand_cap, kx, n2, sel_score, sel_idx, sel_n, sel_cut,
+                                                                            sel_flag);
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}
+
+extern "C" int reid_rescore_topk(const float* q_f32, const float* g_f32, const int32_t* q_code, const int32_t* g_code,
+                                 const float* pos_thr, const int32_t* n_pos, const float* sel_score, const int32_t* sel_idx,
+                                 const int32_t* sel_n, const float* bound, int64_t Q, int64_t G_local, int64_t g_offset,
+                                 int d, int Pmax, float eps, int32_t* pos_above, float* top_score, int32_t* top_idx,
+                                 int32_t* lb0, void* stream) {
+  if (!q_f32 || !g_f32 || !q_code || !g_code || !pos_thr || !n_pos || !sel_score || !sel_idx || !sel_n || !bound ||
+      !pos_above || !top_score || !top_idx || !lb0 || d <= 0 || d % 4 != 0 || Pmax <= 0 || G_local <= 0)
+    return REID_E_INVALID;
+  if (Q <= 0) return REID_OK;
+  rescore_topk_kernel<<<(unsigned)Q, RS_THREADS, 0, (cudaStream_t)stream>>>(q_f32, g_f32, q_code, g_code, pos_thr, n_pos, sel_score,
+                                                                          sel_idx, sel_n, bound, g_offset, d, Pmax, eps, pos_above,
+                                                                          top_score, top_idx, lb0);
+  REID_CHECK_LAUNCH();
+  return REID_OK;
+}
+
+extern "C" int reid_topk_check(const float* top_score, int list_len, int topk, const float* bound, float eps,
+                               const float* pos_thr, const int32_t* n_pos, int Pmax, const int32_t* lb0, int64_t Q,
+                               int32_t* flag, void* stream) {
+  if (!top_score || !bound || !pos_thr || !n_pos || !lb0 || !flag || topk <= 0 || topk > list_len || Pmax <= 0) return REID_E_INVALID;
+  if (Q <= 0) return REID_OK;
+  topk_check_kernel<<<(int)reid_min64((Q + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(top_score, list_len, topk, bound, eps,
+                                                                                               pos_thr, n_pos, Pmax, lb0, Q, flag);
   REID_CHECK_LAUNCH();
   return REID_OK;
 }

@@ -121,6 +121,7 @@ struct Params {
   int32_t* n_exact;      // [Q] thresholds [0, n_exact) are counted on every row
   int32_t* n_l1;         // [Q] thresholds [n_exact, n_l1) on the level-1 row sample, [n_l1, n_pos) on the level-2 sample
   int calib;             // 1 = calibration pre-pass: all thresholds exact, no candidates
+  int calib_cap;         // calibration: a threshold with this many sample rows above it is retired (its class is known)
   int64_t row_stride;    // gallery row stride of this pass (1, or the sample stride of the pre-pass)
   float* cand_score; int32_t* cand_idx; int32_t* cand_count;
 };
@@ -592,7 +593,38 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
           // ballot + prefix popc to compact the round into the dense warp queue.  Rounds per step = max flagged
           // columns per lane (usually 1), not the number of hit columns.
           if (FDBG(4096)) colmask = 0;
-#if REID_SLOW_X1
+#if REID_SLOW_X1 == 2
+          // slow path, column by column (warp-uniform loop over the flagged columns, usually one or two per step): the
+          // column index is uniform, so the lane's score comes out of the 16 registers through a jump table (one MOV)
+          // instead of a per-lane select tree; exact fp32 test, one ballot + prefix popc into the dense warp queue.
+          while (colmask) {
+            const int bp = __ffs(colmask) - 1;
+            colmask &= colmask - 1;
+            const int i = ((bp & 15) << 1) | (bp >> 4);
+            uint32_t rv;
+            switch (i) {
+              case 0: rv = r[0]; break;   case 1: rv = r[1]; break;   case 2: rv = r[2]; break;   case 3: rv = r[3]; break;
+              case 4: rv = r[4]; break;   case 5: rv = r[5]; break;   case 6: rv = r[6]; break;   case 7: rv = r[7]; break;
+              case 8: rv = r[8]; break;   case 9: rv = r[9]; break;   case 10: rv = r[10]; break; case 11: rv = r[11]; break;
+              case 12: rv = r[12]; break; case 13: rv = r[13]; break; case 14: rv = r[14]; break; default: rv = r[15]; break;
+            }
+            const float sc = __uint_as_float(rv);
+            const bool smp_col = i == 5 && step_s1;
+            const bool hit = sc > (smp_col ? minS : minA);             // exact test
+            const unsigned c = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+              const int pos = qn + __popc(c & lt_mask);
+              my_qs[pos] = sc;
+              my_qm[pos] = (uint32_t)myq | (smp_col ? (step_s2 ? (M_S1 | M_S2) : M_S1) : 0u) |
+                           ((uint32_t)(tile_row0 + c0 + i) << M_ROW_SHIFT);
+            }
+            qn += __popc(c);
+            if (qn > QCAP - 32) {                        // queue nearly full: drain the newest 32 now (order is irrelevant)
+              qn -= 32;
+              epi_drain32(A, &p, ew, qn, 32, lane, q0, chunk);
+            }
+          }
+#elif REID_SLOW_X1
           // slow path, column by column (warp-uniform loop over the flagged columns, usually one or two per step): the
           // column is read again from TMEM (one 32x32b.x1 load: every lane gets ITS score of that column -- no register
           // select tree), tested exactly in fp32, and the hits of the 32 lanes are compacted into the dense warp queue with
@@ -698,6 +730,25 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
 #endif
           }
         }
+        if (p.calib && lane < UPD_PER_WARP) {
+          // calibration: thresholds whose count has reached calib_cap are already known to be level-2; retiring them stops
+          // the rows between them from being hits at all (most sample rows score above a query's DEEPEST positives)
+          const int uq = ew * UPD_PER_WARP + lane;
+          const uint32_t cn = es->s_cnts[uq];
+          const int np = cn & 255;
+          int acc = 0, na = np;
+#pragma unroll 1
+          for (int j = 0; j < np; ++j) {
+            const uint32_t w = s_hist32[(uq * p.pcap + j) >> 1];
+            acc += (j & 1) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
+            if (acc >= p.calib_cap) { na = j; break; }
+          }
+          if (na < np) {
+            es->s_cnts[uq] = (cn & 0xFF000000u) | (uint32_t)na | ((uint32_t)na << 8) | ((uint32_t)na << 16);
+            const float tl = na > 0 ? s_thr[uq * p.pcap + na - 1] : INFINITY;
+            es->s_min[uq] = tl; es->s_minS1[uq] = tl; es->s_minS2[uq] = tl;
+          }
+        }
         if (((t + 1) % FLUSH_TILES) == 0) epi_flush_hist(A, &p, et, q0);
 #if REID_DEBUG & 8192
         if (FDBG(8192) && lane == 0) {
@@ -773,7 +824,7 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
   p.rows_per_chunk = (rpc + W2 - 1) / W2 * W2;         // chunk starts are multiples of W2: (local row % W) is a tile column
   p.hist = (int32_t*)workspace; p.thr_share = (uint32_t*)workspace + (size_t)Q * Pmax;
   p.n_exact = (int32_t*)workspace + (size_t)Q * (Pmax + 1); p.n_l1 = (int32_t*)workspace + (size_t)Q * (Pmax + 2);
-  p.calib = 0; p.row_stride = 1; p.no_cand = no_cand ? 1 : 0;
+  p.calib = 0; p.calib_cap = 0; p.row_stride = 1; p.no_cand = no_cand ? 1 : 0;
   p.cand_score = cand_score; p.cand_idx = cand_idx; p.cand_count = cand_count;
   p.debug = REID_DEBUG;
   int stages = REID_MAX_STAGES < MAX_STAGES ? REID_MAX_STAGES : MAX_STAGES;
@@ -804,8 +855,8 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
   if (cudaMemsetAsync(workspace, 0, (size_t)Q * (Pmax + 3) * sizeof(int32_t), st) != cudaSuccess) return REID_E_CUDA;
   const int aux_grid = (int)reid_min64((Q + 255) / 256, 148 * 8);
   bool sample_deep = (G_local >= 16 * CALIB_MIN) && !(flags & REID_FUSED_EXACT_COUNTS);
-  // calibration sample: 1/16 of the shard in whole tiles, CALIB_MIN .. CALIB_ROWS rows
-  int64_t calib_rows = G_local / 16 / TROWS * TROWS;
+  // calibration sample: 1/32 of the shard in whole tiles, CALIB_MIN .. CALIB_ROWS rows
+  int64_t calib_rows = G_local / 32 / TROWS * TROWS;
   if (calib_rows > CALIB_ROWS) calib_rows = CALIB_ROWS;
   if (calib_rows < CALIB_MIN) calib_rows = CALIB_MIN;
   if (FDBG(64)) sample_deep = false;
@@ -832,7 +883,6 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return REID_E_CUDA;
     }
-    if (!launch(tmS, c)) return REID_E_CUDA;
     // a sampled count must rest on >= 32 sampled rows above the threshold OVER ALL SHARDS (17.7 % standard error at
     // the boundary): the budgets are gallery-wide, a threshold's class is the same in every chunk of a shard;
     // never classify on fewer than 8 calibration hits.  scale: calibration hits -> estimated rank inside the shard
@@ -840,6 +890,8 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
     const int shards = n_shards > 1 ? n_shards : 1;
     const float limit1 = fmaxf(32.f * (float)W1 / (float)shards, 8.f * scale);
     const float limit2 = fmaxf(32.f * (float)W2 / (float)shards, limit1);
+    c.calib_cap = (int)(limit2 / scale) + 8;
+    if (!launch(tmS, c)) return REID_E_CUDA;
     calib_split_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, scale, limit1, limit2, p.n_exact, p.n_l1);
   } else {
     fill_n_exact_kernel<<<aux_grid, 256, 0, st>>>(n_pos, Q, Pmax, p.n_exact, p.n_l1);

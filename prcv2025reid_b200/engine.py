@@ -155,10 +155,16 @@ class RetrievalResult:
     path: str = ""                   # "fused" (tcgen05) or "exact" (fp32 SIMT): which kernel ranked the queries
 
 
-def _rank_block(shard, q32_b, q16_b, pid_b, ex_b, E, pos_above_b, n_pos_b, top_score_b, top_idx_b, flag_b, *, fused,
-                topk, eps, cand_cap, group, world, exact_ap, n_slots=None):
+RESCORE_KX_ONE_SHARD = 32     # completeness cut-off of the re-scorer: the kx-th best approximate score of a shard ...
+RESCORE_KX_SHARDED = 16       # ... with several shards the MAX over the shards' cut-offs is used and 16 suffice for top-10
+
+
+def _rank_block(shard, q32_b, q16_b, pid_b, ex_b, E, pos_above_b, n_pos_b, top_score_b, top_idx_b, flag_b, bound_b, lb0_b, t0_b,
+                *, fused, eps, cand_cap, group, world, exact_ap, n_slots=None):
     """Enqueue the ranking kernels of one query block on the current stream (no host synchronisation unless an
-    identity has more than 64 gallery rows).  Local counts -> pos_above_b, exact local top list -> top_*_b."""
+    identity has more than 64 gallery rows).  Local counts -> pos_above_b, exact local top list -> top_*_b, the
+    completeness cut-off (MAX over the shards) -> bound_b, re-scored rows above the best positive -> lb0_b, the best
+    positive's score -> t0_b, candidate-buffer overflow -> flag_b."""
     L = _cabi.lib()
     st = stream_ptr()
     d, Pmax = shard.d, shard.pmax
@@ -219,13 +225,21 @@ def _rank_block(shard, q32_b, q16_b, pid_b, ex_b, E, pos_above_b, n_pos_b, top_s
                                     ptr(pos_thr), ptr(n_pos_b), None, nb, nb, shard.G_local, shard.g_offset, d, Pmax,
                                     n_chunks, cap, ptr(pos_above_b), ptr(cand_score), ptr(cand_idx), ptr(cand_count), st),
               "reid_retrieve_exact")
-    check(L.reid_rescore_topk(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code), ptr(pos_thr),
-                              ptr(n_pos_b), ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), None, nb, nb,
-                              shard.G_local, shard.g_offset, d, Pmax, n_chunks, cap, topk,
-                              float(eps if fused else 0.0), ptr(pos_above_b), ptr(top_score_b),
-                              ptr(top_idx_b), ptr(flag_b), st), "reid_rescore_topk")
+    t0_b.copy_(pos_thr[:, 0])
+    sel_score = shard.buf("sel_score", (nb, _cabi.RTOP), torch.float32)
+    sel_idx = shard.buf("sel_idx", (nb, _cabi.RTOP), torch.int32)
+    sel_n = shard.buf("sel_n", (nb,), torch.int32)
+    kx = RESCORE_KX_ONE_SHARD if world == 1 else RESCORE_KX_SHARDED
+    check(L.reid_cand_select(ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), nb, n_chunks, cap, kx,
+                             ptr(sel_score), ptr(sel_idx), ptr(sel_n), ptr(bound_b), ptr(flag_b), st), "reid_cand_select")
+    if world > 1:
+        sharding.exchange_bound(bound_b, group)                     # the best shard's kx-th best approximate score
+    check(L.reid_rescore_topk(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code), ptr(pos_thr), ptr(n_pos_b),
+                              ptr(sel_score), ptr(sel_idx), ptr(sel_n), ptr(bound_b), nb, shard.G_local, shard.g_offset, d,
+                              Pmax, float(eps if fused else 0.0), ptr(pos_above_b), ptr(top_score_b), ptr(top_idx_b),
+                              ptr(lb0_b), st), "reid_rescore_topk")
     if _DEBUG_KEEP is not None:
-        _DEBUG_KEEP.update(flag=flag_b.clone(), cand_count=cand_count.clone(), n_chunks=n_chunks)
+        _DEBUG_KEEP.update(cand_count=cand_count.clone(), n_chunks=n_chunks, sel_n=sel_n.clone())
 
 
 def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional[torch.Tensor], q_pid: torch.Tensor,
@@ -271,6 +285,9 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
     top_score = torch.empty(Q, _cabi.RTOP, dtype=torch.float32, device=dev)
     top_idx = torch.empty(Q, _cabi.RTOP, dtype=torch.int32, device=dev)
     flag = torch.zeros(Q, dtype=torch.int32, device=dev)
+    bound = torch.empty(Q, dtype=torch.float32, device=dev)     # completeness cut-off of the re-scored head (gallery-wide)
+    lb0 = torch.zeros(Q, dtype=torch.int32, device=dev)         # re-scored rows above the best positive (this shard)
+    t0 = torch.empty(Q, dtype=torch.float32, device=dev)        # best positive's exact score
     use_fused = (mode == "fused" and Pmax <= 2048 and d % 64 == 0 and d <= 512 and shard.G_local <= (1 << 22)
                  and (host_queries is not None or q_f16 is not None))
 
@@ -339,7 +356,7 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
             q32_b, q16_b = q_f32[sl], (q_f16[sl] if q_f16 is not None else None)
             pid_b, ex_b = q_pid[sl], (excl[sl] if excl is not None else None)
         _rank_block(shard, q32_b, q16_b, pid_b, ex_b, E, pos_above[sl], n_pos[sl], top_score[sl], top_idx[sl], flag[sl],
-                    fused=use_fused, topk=topk, eps=eps, cand_cap=cand_cap, group=group, world=world,
+                    bound[sl], lb0[sl], t0[sl], fused=use_fused, eps=eps, cand_cap=cand_cap, group=group, world=world,
                     exact_ap=exact_ap, n_slots=n_slots)
         if use_fused:
             if host_queries is not None:                         # (the staging set is overwritten two blocks later)
@@ -348,31 +365,37 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
         if host_queries is not None:
             done_ev[bi] = torch.cuda.Event(); done_ev[bi].record()
 
+    eps_check = float(eps) if use_fused else 0.0
+
     def finish():
-        """Exchange over the shards, metrics; -> (pos_above gallery-wide, top lists, metrics tensor incl. the flag count)."""
-        pa = pos_above
+        """Exchange over the shards, decidability check, metrics; -> (pos_above gallery-wide, top lists, metrics incl. flag count)."""
+        pa, aux = pos_above, torch.stack([lb0, flag], dim=1)
         if world > 1:
             pa = sharding.exchange_counts(pos_above.clone(), group)         # counts are additive over shards
+            sharding.exchange_counts(aux, group)                            # re-scored rows above the best positive; overflows
             # the global top-k is contained in the union of the shards' (exactly ordered) top-k lists
             all_s, all_i = sharding.gather_top_lists(top_score[:, :topk].contiguous(), top_idx[:, :topk].contiguous(), group)
             out_s = torch.empty(Q, topk, dtype=torch.float32, device=dev)
             out_i = torch.empty(Q, topk, dtype=torch.int32, device=dev)
             check(L.reid_merge_topk(ptr(all_s), ptr(all_i), world, Q, topk, topk, ptr(out_s), ptr(out_i), st), "reid_merge_topk")
-            sharding.exchange_flags(flag, group)                             # a query flagged on one shard is re-run on all
         else:
             out_s, out_i = top_score[:, :topk].contiguous(), top_idx[:, :topk].contiguous()   # one shard: already ordered
+        lb0_g, fl_g = aux[:, 0].contiguous(), aux[:, 1].contiguous()
+        # every rank holds the same gallery-wide data here, so every rank derives the same flags
+        check(L.reid_topk_check(ptr(out_s), topk, topk, ptr(bound), eps_check, ptr(t0), ptr(n_pos), 1, ptr(lb0_g), Q,
+                                ptr(fl_g), st), "reid_topk_check")
         out = torch.empty(6, dtype=torch.float64, device=dev)
         ap = torch.empty(Q, dtype=torch.float64, device=dev) if want_ap else None
         check(L.reid_metrics_reduce(ptr(pa), ptr(n_pos), Q, Pmax, ptr(out), ptr(ap), st), "reid_metrics_reduce")
-        out[5] = torch.count_nonzero(flag)
-        return pa, out_s, out_i, ap, out.cpu().tolist()                     # the step's result: D2H read
+        out[5] = torch.count_nonzero(fl_g)
+        return pa, out_s, out_i, ap, fl_g, out.cpu().tolist()               # the step's result: D2H read
 
-    pa, out_s, out_i, ap, m = finish()
+    pa, out_s, out_i, ap, fl_g, m = finish()
     n_flagged = int(round(m[5]))
     if n_flagged and use_fused:
         # rare: top-k / CMC of these queries is not decidable from fp16 scores within eps (or a candidate buffer
         # overflowed): all-fp32 re-run on a compact copy, results written back, exchange + metrics redone
-        sel = torch.nonzero(flag).flatten()
+        sel = torch.nonzero(fl_g).flatten()
         q32_s = torch.cat([k[0] for k in kept])[sel].contiguous()
         pid_s = torch.cat([k[1] for k in kept])[sel].contiguous()
         ex_s = torch.cat([k[2] for k in kept])[sel].contiguous() if E else None
@@ -382,10 +405,15 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
         ts_s = torch.empty(ns, _cabi.RTOP, dtype=torch.float32, device=dev)
         ti_s = torch.empty(ns, _cabi.RTOP, dtype=torch.int32, device=dev)
         fl_s = torch.zeros(ns, dtype=torch.int32, device=dev)
-        _rank_block(shard, q32_s, None, pid_s, ex_s, E, pa_s, np_s, ts_s, ti_s, fl_s, fused=False, topk=topk, eps=0.0,
+        bd_s = torch.empty(ns, dtype=torch.float32, device=dev)
+        lb_s = torch.zeros(ns, dtype=torch.int32, device=dev)
+        t0_s = torch.empty(ns, dtype=torch.float32, device=dev)
+        _rank_block(shard, q32_s, None, pid_s, ex_s, E, pa_s, np_s, ts_s, ti_s, fl_s, bd_s, lb_s, t0_s, fused=False, eps=0.0,
                     cand_cap=cand_cap, group=group, world=world, exact_ap=True)
         pos_above[sel] = pa_s; n_pos[sel] = np_s; top_score[sel] = ts_s; top_idx[sel] = ti_s
+        lb0[sel] = lb_s; t0[sel] = t0_s
+        bound[sel] = float("-inf")                 # ranked in fp32: exact by construction, nothing left to decide
         flag.zero_()
-        pa, out_s, out_i, ap, m = finish()
+        pa, out_s, out_i, ap, fl_g, m = finish()
     metrics = {"mAP": m[0], "R@1": m[1], "R@5": m[2], "R@10": m[3], "num_queries": int(round(m[4]))}
     return RetrievalResult(metrics, out_i, out_s, ap, n_flagged, pa, n_pos, "fused" if use_fused else "exact")

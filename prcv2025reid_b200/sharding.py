@@ -5,7 +5,9 @@ queries replicated, gallery rows partitioned contiguously, three small collectiv
   1. all_reduce(MAX) of the positives' exact scores   (owner rank holds the score, others -inf)
   2. all_reduce(SUM) of the per-positive "rows ranked above" counts (additive over shards)
   3. all_gather of the per-shard exact top lists, merged per query;
-  4. all_reduce(MAX) of the per-query "undecidable from fp16 scores" flags (normally all zero).
+  4. all_reduce(MAX) of the per-shard completeness cut-off of the re-scored head (before re-scoring: every shard then
+     re-scores only the rows that can still reach the gallery-wide head) and all_reduce(SUM) of two small per-query
+     counters (re-scored rows above the best positive, candidate-buffer overflows) for the decidability check.
 With HOST-resident query features a fourth step precedes them: every rank uploads and fuses only its
 1/world slice of a query block and `gather_query_block` assembles the fused block on every rank over
 NVLink (all_gather), so the PCIe upload of a block is paid once per box instead of once per GPU.
@@ -37,12 +39,13 @@ def exchange_counts(pos_above: torch.Tensor, group=None) -> torch.Tensor:
     return pos_above
 
 
-def exchange_flags(flag: torch.Tensor, group=None) -> torch.Tensor:
-    """A query whose top-k / CMC one shard could not decide is re-run exactly on EVERY shard: MAX over the ranks."""
+def exchange_bound(cut: torch.Tensor, group=None) -> torch.Tensor:
+    """Completeness cut-off of the re-scored head: MAX over the shards of each shard's kx-th best approximate score --
+    at least kx gallery rows score at or above it, so rows below it cannot belong to the gallery-wide head."""
     import torch.distributed as dist
     if group is not None or dist.is_initialized():
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-    return flag
+        dist.all_reduce(cut, op=dist.ReduceOp.MAX, group=group)
+    return cut
 
 
 def gather_top_lists(top_score: torch.Tensor, top_idx: torch.Tensor, group=None):

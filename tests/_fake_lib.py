@@ -22,6 +22,7 @@ class FakeLib:
         # > 0: the re-scorer of the FUSED pass declares every n-th query of a block undecidable and leaves garbage in its
         # outputs, as a kernel that gave up on the query might -- the host must repair it through the exact pass
         self.force_flag_every = force_flag_every
+        self._last_fused = False
 
     # ------------------------------------------------------------------ utilities
     def _log(self, name):
@@ -135,6 +136,7 @@ class FakeLib:
                             n_chunks, n_shards, cap, flags, pos_above, cand_score, cand_idx, cand_count, cand_thr, ws, ws_bytes, st):
         # (pos_thr / pos_above arrive as [Q, pos_stride] tensors; this call covers their first Pmax columns)
         assert Pmax <= 64 and (pos_stride == 0 or pos_stride >= Pmax) and pos_thr.shape[1] == (pos_stride or Pmax)
+        self._last_fused = True
         S = q16.float() @ g16.float().T                                # fp16 operands, fp32 accumulation
         rpc = -(-G_local // n_chunks)
         rpc = -(-rpc // 1024) * 1024
@@ -149,6 +151,7 @@ class FakeLib:
 
     def reid_retrieve_exact(self, q32, g32, q_code, g_code, excl, E, pos_thr, n_pos, q_sel, n_sel, Q, G_local, g_offset, d, Pmax,
                             n_chunks, cap, pos_above, cand_score, cand_idx, cand_count, st):
+        self._last_fused = False
         sel = range(Q) if q_sel is None else [int(v) for v in q_sel[:n_sel]]
         S = q32 @ g32.T
         rpc = -(-G_local // n_chunks)
@@ -156,10 +159,9 @@ class FakeLib:
                         rpc, pos_above, cand_score, cand_idx, cand_count, None)
         return self._log("reid_retrieve_exact" if q_sel is None else "reid_retrieve_exact(sel)")
 
-    def reid_rescore_topk(self, q32, g32, q_code, g_code, pos_thr, n_pos, cand_score, cand_idx, cand_count, cand_thr, q_sel, n_sel,
-                          Q, G_local, g_offset, d, Pmax, n_chunks, cap, topk, eps, pos_above, top_score, top_idx, flag, st):
-        sel = range(Q) if q_sel is None else [int(v) for v in q_sel[:n_sel]]
-        for q in sel:
+    def reid_cand_select(self, cand_score, cand_idx, cand_count, cand_thr, Q, n_chunks, cap, kx, sel_score, sel_idx, sel_n,
+                         sel_cut, sel_flag, st):
+        for q in range(Q):
             keep = float(cand_thr[q]) if cand_thr is not None else NEG_INF
             sc, ix, overflow = [], [], False
             for c in range(n_chunks):
@@ -167,40 +169,65 @@ class FakeLib:
                 if n > cap:
                     n, overflow = cap, True
                 sc.append(cand_score[q, c, :n]); ix.append(cand_idx[q, c, :n])
-            sc, ix = torch.cat(sc), torch.cat(ix).long()
+            sc, ix = torch.cat(sc), torch.cat(ix)
             m = sc >= keep
             sc, ix = sc[m], ix[m]
             o = torch.argsort(sc, descending=True, stable=True)
             sc, ix = sc[o], ix[o]
             total = sc.numel()
             R = min(total, RTOP)
-            cut = float(sc[KLIST - 1]) if total >= KLIST else NEG_INF
-            ex = (g32[ix[:R]] @ q32[q]) if R else torch.empty(0)
-            gi = ix[:R]
+            sel_score[q].fill_(NEG_INF); sel_idx[q].fill_(-1)
+            sel_score[q, :R] = sc[:R]; sel_idx[q, :R] = ix[:R].to(torch.int32)
+            sel_n[q] = R
+            sel_cut[q] = float(sc[kx - 1]) if total >= kx else NEG_INF
+            sel_flag[q] = 1 if overflow else 0
+            if self.force_flag_every and self._last_fused and q % self.force_flag_every == 3:
+                sel_flag[q] = 1                                        # "this query's candidate buffer overflowed"
+        return self._log("reid_cand_select")
+
+    def reid_rescore_topk(self, q32, g32, q_code, g_code, pos_thr, n_pos, sel_score, sel_idx, sel_n, bound, Q, G_local, g_offset,
+                          d, Pmax, eps, pos_above, top_score, top_idx, lb0, st):
+        for q in range(Q):
+            b = float(bound[q])
+            n = int(sel_n[q])
+            R = int((sel_score[q, :n] >= b).sum())                     # the prefix of the descending list at or above the bound
+            gi = sel_idx[q, :R].long()
+            ex = (g32[gi] @ q32[q]) if R else torch.empty(0)
             o2 = sorted(range(R), key=lambda r: (-float(ex[r]), int(gi[r])))
             ex, gi = ex[o2], gi[o2]
             top_score[q].fill_(NEG_INF); top_idx[q].fill_(-1)
             top_score[q, :R] = ex
             top_idx[q, :R] = (gi + g_offset).to(torch.int32)
-            bound = cut + eps
+            lim = b + eps
             neg = g_code[gi] != q_code[q] if R else torch.zeros(0, dtype=torch.bool)
-            f = 1 if overflow else 0
+            lb0[q] = 0
             for j in range(min(int(n_pos[q]), Pmax)):
                 t = float(pos_thr[q, j])
                 lb = int((neg & (ex > t)).sum())
-                if t > bound or cut == NEG_INF:
+                if t > lim or b == NEG_INF:
                     pos_above[q, j] = lb
                 else:
                     pos_above[q, j] = max(int(pos_above[q, j]), lb)
-                    if j == 0 and lb < 10:
-                        f |= 4
-            if cut > NEG_INF and R >= topk and float(ex[topk - 1]) < bound:
-                f |= 2
-            if self.force_flag_every and q_sel is None and eps > 0 and q % self.force_flag_every == 3:
-                f |= 2
+                if j == 0:
+                    lb0[q] = lb
+            if self.force_flag_every and eps > 0 and q % self.force_flag_every == 3:
+                # a kernel that gave up on the query leaves garbage: the host must repair it through the exact pass
                 pos_above[q].fill_(12345); top_idx[q].fill_(-7); top_score[q].fill_(9.0)
+        return self._log("reid_rescore_topk")
+
+    def reid_topk_check(self, top, list_len, topk, bound, eps, pos_thr, n_pos, Pmax, lb0, Q, flag, st):
+        for q in range(Q):
+            b = float(bound[q])
+            f = 1 if int(flag[q]) else 0
+            if b > NEG_INF:
+                lim = b + eps
+                if not float(top[q, topk - 1]) >= lim:
+                    f |= 2
+                t0 = float(pos_thr[q]) if pos_thr.dim() == 1 else float(pos_thr[q, 0])
+                if int(n_pos[q]) > 0 and not t0 > lim and int(lb0[q]) < 10:
+                    f |= 4
             flag[q] = f
-        return self._log("reid_rescore_topk" if q_sel is None else "reid_rescore_topk(sel)")
+        return self._log("reid_topk_check")
 
     def reid_merge_topk(self, scores, idx, n_lists, Q, list_len, topk, out_s, out_i, st):
         s = scores.view(n_lists, Q, list_len).permute(1, 0, 2).reshape(Q, -1)

@@ -160,7 +160,11 @@ def test_entry_points_reject_invalid_arguments_before_touching_the_device():
         "pos_sort null": L.reid_pos_sort(N, N, 1, 4, N),
         "fused null": L.reid_retrieve_fused(N, N, N, N, N, 0, N, N, 1, 1, 0, 512, 4, 4, 1, 1, 64, 0, N, N, N, N, N, N, 0, N),
         "exact null": L.reid_retrieve_exact(N, N, N, N, N, 0, N, N, N, 0, 1, 1, 0, 512, 4, 1, 64, N, N, N, N, N),
-        "rescore null": L.reid_rescore_topk(N, N, N, N, N, N, N, N, N, N, N, 0, 1, 1, 0, 512, 4, 1, 64, 10, 0.0, N, N, N, N, N),
+        "select null": L.reid_cand_select(N, N, N, N, 1, 1, 64, 32, N, N, N, N, N, N),
+        "select kx > KLIST": L.reid_cand_select(one, one, one, N, 1, 1, 64, 33, one, one, one, one, one, N),
+        "rescore null": L.reid_rescore_topk(N, N, N, N, N, N, N, N, N, N, 1, 1, 0, 512, 4, 0.0, N, N, N, N, N),
+        "check null": L.reid_topk_check(N, 32, 10, N, 0.0, N, N, 4, N, 1, N, N),
+        "check topk > list": L.reid_topk_check(one, 8, 10, one, 0.0, one, one, 4, one, 1, one, N),
         "merge null": L.reid_merge_topk(N, N, 1, 1, 10, 10, N, N, N),
         "metrics null": L.reid_metrics_reduce(N, N, 1, 4, N, N, N),
         "label_metrics null": L.reid_topk_label_metrics(N, N, N, 1, 10, 10, N, N, N),

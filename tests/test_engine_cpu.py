@@ -59,6 +59,7 @@ def test_retrieve_host_logic_matches_oracle(monkeypatch, mode, query_block):
         assert res.n_flagged >= forced > 0 and res.path == "fused"
         assert fake.calls.count("reid_retrieve_fused") == n_blocks and fake.calls.count("reid_retrieve_exact") == 1
         assert fake.calls.count("reid_metrics_reduce") == 2 and fake.calls.count("reid_rescore_topk") == n_blocks + 1
+        assert fake.calls.count("reid_cand_select") == n_blocks + 1 and fake.calls.count("reid_topk_check") == 2
     else:
         assert res.n_flagged == 0 and res.path == "exact"
         assert fake.calls.count("reid_retrieve_exact") == n_blocks and fake.calls.count("reid_metrics_reduce") == 1
