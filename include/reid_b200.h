@@ -159,8 +159,8 @@ int reid_topk_label_metrics(const int32_t* top_idx, const int64_t* q_label, cons
                             int64_t Q, int list_len, int k, float* ap, int32_t* hit, void* stream);
 
 /* ---- SDM loss: models/sdm_loss.py:13-149 `sdm_loss_stable`, batched over modality pairs.
- * One launch computes every pair; pair p uses qry[p] [N_p, d], gal[p] [M_p, d] (dtype F32 or
- * BF16), y[p] [N_p, M_p] float {0,1}.  loss[p] (fp32), status[p] (bit0: returned the reference's
+ * One launch computes every pair; pair p uses qry[p] [N_p, d], gal[p] [M_p, d] (dtype F32, BF16 or
+ * F16), y[p] [N_p, M_p] float {0,1}.  loss[p] (fp32), status[p] (bit0: returned the reference's
  * non-differentiable zero; bit1: non-finite feature; bit2: non-finite S; bit3: no positives).
  * saved[p]: scratch of reid_sdm_saved_floats(N,M,d) floats kept for the backward (S, row / column
  * statistics and the normalised operands). */
@@ -170,6 +170,14 @@ typedef struct {
   float* loss; int32_t* status; float* saved;
   const float* grad_out;   /* backward only: upstream scalar gradient */
   void* dqry; void* dgal;  /* backward only: gradients in the input dtype */
+  /* LABEL FORM (y == NULL), the SDM section of compute_loss, models/model.py:586-622, without materialising y:
+   *   y[i][j] = row_valid[i] && col_valid[j] && row_label[i] == col_label[j]   (:605)
+   * and rows of qry / gal whose valid byte is 0 (the feature masks, :570-602) are left out of the loss altogether --
+   * out of the softmax denominators, the means and the guards -- and receive exact-zero gradients.  row_valid /
+   * col_valid may be NULL (all valid).  Served by the tcgen05 path only (reid_sdm_uses_tensor_cores); other shapes
+   * return REID_E_UNSUPPORTED and the caller builds y. */
+  const int64_t* row_label; const int64_t* col_label;
+  const uint8_t* row_valid; const uint8_t* col_valid;
 } reid_sdm_pair;
 #define REID_SDM_MAX_PAIRS 16
 size_t reid_sdm_saved_floats(int N, int M, int d);

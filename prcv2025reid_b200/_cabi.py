@@ -22,7 +22,8 @@ class ReidError(RuntimeError):
 class SdmPair(Structure):
     _fields_ = [("qry", c_void_p), ("gal", c_void_p), ("y", c_void_p), ("N", c_int32), ("M", c_int32),
                 ("loss", c_void_p), ("status", c_void_p), ("saved", c_void_p), ("grad_out", c_void_p),
-                ("dqry", c_void_p), ("dgal", c_void_p)]
+                ("dqry", c_void_p), ("dgal", c_void_p), ("row_label", c_void_p), ("col_label", c_void_p),
+                ("row_valid", c_void_p), ("col_valid", c_void_p)]
 
 
 _SIGS = {

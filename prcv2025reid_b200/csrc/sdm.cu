@@ -767,6 +767,7 @@ int launch_small(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float
   size_t smem = 0;
   for (int i = 0; i < n_pairs; ++i) {
     const reid_sdm_pair& p = pairs[i];
+    if (!p.y && p.row_label && p.col_label) return REID_E_UNSUPPORTED;         // label form: tcgen05 path only
     if (!p.qry || !p.gal || !p.y || !p.loss || !p.status || !p.saved) return REID_E_INVALID;
     if (bwd && (!p.grad_out || !p.dqry || !p.dgal)) return REID_E_INVALID;
     b.p[i] = p;
@@ -789,6 +790,7 @@ int launch_sdm(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float t
   int max_tiles = 1;
   for (int i = 0; i < n_pairs; ++i) {
     const reid_sdm_pair& p = pairs[i];
+    if (!p.y && p.row_label && p.col_label) return REID_E_UNSUPPORTED;         // label form: tcgen05 path only
     if (!p.qry || !p.gal || !p.y || !p.loss || !p.status || !p.saved || p.N <= 0 || p.M <= 0) return REID_E_INVALID;
     if (bwd && (!p.grad_out || !p.dqry || !p.dgal)) return REID_E_INVALID;
     b.p[i] = p;

@@ -51,6 +51,7 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 // hdr: [0] nR  [1] nC  [2] status bits (int)  [3] loss  [4] CTA completion counter (int)
 //      [8 .. 8+64)  non-finite-feature flag per 16-row slab of qry / gal (int, 32 each)
 //      [72 .. 80)   non-finite-S flag per forward CTA (int)
+//      [128 .. 160) validity bits of the qry / gal rows (16 words each)
 struct TcLayout {
   int N, M, d, Np, Mp;
   size_t den_q, den_g, lse_r, lse_c, cnt_r, cnt_c, ce_r, ce_c, hdr, S, St;
@@ -58,7 +59,9 @@ struct TcLayout {
   size_t qn, gn, qnt, gnt;         // byte offsets of the images
   size_t total_bytes;
 };
-constexpr int TC_HDR_FLOATS = 128;    // (words 80..111: optional phase time stamps of REID_SDM_TIMING builds)
+constexpr int TC_HDR_FLOATS = 192;    // (words 80..111: optional phase time stamps of REID_SDM_TIMING builds)
+constexpr int TC_HDR_VALID_Q = 128;   // 16 words: validity bits of the qry rows (label form; all ones otherwise)
+constexpr int TC_HDR_VALID_G = 144;   // 16 words: validity bits of the gal rows
 __host__ __device__ inline TcLayout tc_layout(int N, int M, int d) {
   TcLayout L;
   L.N = N; L.M = M; L.d = d; L.Np = round_up(N, 128); L.Mp = round_up(M, 128);

@@ -27,7 +27,12 @@
 // (+ the lo pass of the backward).  See DESIGN.md section 6.
 #include "sdm_common.cuh"
 #include "tc_common.cuh"
-#include <stdlib.h>
+
+// -DREID_SDM_PAIR=1 builds the cta_group::2 pair variant of the forward / backward kernels (an experiment that is kept
+// parity-tested but is slower on C5: see tc_forward).  Nothing in this file reads the environment.
+#ifndef REID_SDM_PAIR
+#define REID_SDM_PAIR 0
+#endif
 
 namespace sdm {
 namespace {
@@ -95,6 +100,17 @@ tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
   if (threadIdx.x == 0) s_bad = 0;
   if (blockIdx.x == 0 && which == 0 && threadIdx.x == 0) hdr_i[4] = 0;     // forward completion counter
   __syncthreads();
+  // label form: rows whose valid byte is 0 take no part (models/model.py:570-602): their normalised image is zero, their
+  // denominator 1, they raise no non-finite flag; validity bit rows for the forward / backward go to the header
+  const uint8_t* valid = P.y ? nullptr : (which ? P.col_valid : P.row_valid);
+  if (blockIdx.x == 0 && threadIdx.x < 16) {
+    uint32_t w = 0;
+    for (int e = 0; e < 32; ++e) {
+      const int r = threadIdx.x * 32 + e;
+      if (r < R && (!valid || valid[r])) w |= 1u << e;
+    }
+    hdr_i[(which ? TC_HDR_VALID_G : TC_HDR_VALID_Q) + threadIdx.x] = (int)w;
+  }
   const float e_b = bf16r(eps);
   const int nchunk = d >> 3;                         // 16-byte chunks per row (<= 64)
   bool bad = false;
@@ -114,7 +130,7 @@ tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
   for (int a = 0; a < RPW; ++a) {
     const int rr = warp + a * (PREP_THREADS / 32);
     const int r = r0 + rr;
-    const bool live = r < R;
+    const bool live = r < R && (!valid || valid[r]);
     float ss = 0.f;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -124,8 +140,8 @@ tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
       for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
     }
     ss = warp_sum(ss);
-    const float dn = fmaxf(bf16r(sqrtf(ss)), e_b);   // F.normalize in bf16: max(||x||, eps), :31-32
-    if (lane == 0 && live) den[r] = dn;
+    const float dn = live ? fmaxf(bf16r(sqrtf(ss)), e_b) : 1.f;   // F.normalize in bf16: max(||x||, eps), :31-32
+    if (lane == 0 && r < R) den[r] = dn;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int c = lane + 32 * u;
@@ -218,6 +234,7 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
   __shared__ int s_bad, s_last, s_st;
   __shared__ float s_part[FWD_EPI_WARPS / 4 - 1][3][128];
   __shared__ double s_red[FWD_EPI_WARPS][5];
+  __shared__ int64_t s_collab[512];                          // label form: the labels of this side's columns
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = d >> 6;
   if (threadIdx.x == 0) {
@@ -303,19 +320,34 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
     const int et = threadIdx.x - 64;                       // 0..FWD_EPI_THREADS-1
     const int row = quad * 32 + lane;
     const int i = rb * 128 + row;
-    const bool live = i < R;
+    const int* vrow = hdr_i + (side ? TC_HDR_VALID_G : TC_HDR_VALID_Q);      // validity bits of this side's rows / columns
+    const int* vcol = hdr_i + (side ? TC_HDR_VALID_Q : TC_HDR_VALID_G);
+    const bool live = i < R && ((__ldcg(vrow + (i >> 5)) >> (i & 31)) & 1);
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int cstep = round_up((C + PARTS - 1) / PARTS, 32);
     const int c_begin = part * cstep < C ? part * cstep : C, c_end = (part + 1) * cstep < C ? (part + 1) * cstep : C;
+    if (!P.y) {                                            // label form: the column labels of this side, once per CTA
+      const int64_t* cl = side ? P.row_label : P.col_label;
+      for (int c = et; c < C; c += FWD_EPI_THREADS) s_collab[c] = cl[c];
+      named_bar(1, FWD_EPI_THREADS);
+    }
     // positive mask of this thread's columns (<= 128 = 4 words), formed from y WHILE the MMAs run and kept in
     // registers; also stored as bit rows (ybits [N][16] / ybitsT [M][16]) for the backward
-    uint32_t mb[4] = {0u, 0u, 0u, 0u};
+    uint32_t mb[4] = {0u, 0u, 0u, 0u}, vb[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+      if (c_begin + 32 * w < c_end) vb[w] = (uint32_t)__ldcg(vcol + ((c_begin + 32 * w) >> 5));
     if (live) {
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const int cw = c_begin + 32 * w;
         if (cw < c_end) {
-          if (side == 0) {
+          if (!P.y) {
+            // y[i][j] = (label_i == label_j) (models/model.py:605), restricted to valid columns below
+            const int64_t rl = (side ? P.col_label : P.row_label)[i];
+#pragma unroll 8
+            for (int e = 0; e < 32; ++e) mb[w] |= (cw + e < c_end && s_collab[cw + e] == rl ? 1u : 0u) << e;
+          } else if (side == 0) {
             const float* yp = P.y + (size_t)i * M + cw;
             float4 t[8];
 #pragma unroll
@@ -330,9 +362,15 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
 #pragma unroll
             for (int e = 0; e < 32; ++e) mb[w] |= (t[e] > 0.f ? 1u : 0u) << e;
           }
+          mb[w] &= vb[w];
           reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(bytes) + (side ? L.ybitsT : L.ybits))[(size_t)i * 16 + (cw >> 5)] = mb[w];
         }
       }
+    } else if (i < R) {                                    // a row that takes no part: no positives anywhere
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (c_begin + 32 * w < c_end)
+          reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(bytes) + (side ? L.ybitsT : L.ybits))[(size_t)i * 16 + ((c_begin + 32 * w) >> 5)] = 0u;
     }
     const float inv_tau = 1.f / tau_eff;
     float se = 0.f, ps = 0.f, pc = 0.f;
@@ -356,6 +394,7 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
         __syncwarp();                                          // tcgen05.ld is .sync.aligned: reconverge first
         const int wsel = (c0 - c_begin) >> 5;
         const uint32_t bw = (wsel == 0 ? mb[0] : wsel == 1 ? mb[1] : wsel == 2 ? mb[2] : mb[3]) >> ((c0 - c_begin) & 31);
+        const uint32_t vw = (wsel == 0 ? vb[0] : wsel == 1 ? vb[1] : wsel == 2 ? vb[2] : vb[3]) >> ((c0 - c_begin) & 31);
         tc::tmem_ld_x16(taddr + c0, r);
         tc::tmem_wait_ld();
         const int nv = c_end - c0 < 16 ? c_end - c0 : 16;       // 16, or 8 in the ragged tail (C is a multiple of 8)
@@ -364,7 +403,7 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           float s = __uint_as_float(r[e]) * inv_tau;            // :86 (x 1/tau: <= 1 ulp from the reference's division)
-          const bool in = live && e < nv;
+          const bool in = live && e < nv && ((vw >> e) & 1u);    // (columns that take no part are not in the softmax)
           bad |= in && !(fabsf(s) <= 3.0e38f);                  // :89-91 (NaN or Inf)
           s = fminf(fmaxf(s, -20.f), 20.f);                     // :94 (and :46)
           sv[e] = s;
@@ -395,10 +434,10 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
     if (part > 0) { s_part[part - 1][0][row] = se; s_part[part - 1][1][row] = ps; s_part[part - 1][2][row] = pc; }
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_bad, 1);
     named_bar(1, FWD_EPI_THREADS);
-    if (part == 0 && live) {
+    if (part == 0 && i < R) {
 #pragma unroll
       for (int q = 0; q < PARTS - 1; ++q) { se += s_part[q][0][row]; ps += s_part[q][1][row]; pc += s_part[q][2][row]; }
-      const float lse = logf(se);
+      const float lse = se > 0.f ? logf(se) : 0.f;            // (se == 0: a row that takes no part, or no valid column)
       float* lse_a = base + (side ? L.lse_c : L.lse_r);
       float* cnt_a = base + (side ? L.cnt_c : L.cnt_r);
       float* ce_a = base + (side ? L.ce_c : L.ce_r);
@@ -473,8 +512,8 @@ constexpr int BWD_STAGES = 2;
 constexpr int BWDP_STAGE = 2 * A_TILE + 2 * A_TILE;  // pair mode: dS hi, dS lo, this CTA's half of the two 256-row chunks
 constexpr int BWDP_STAGES = 3;
 constexpr int BWD_KMAX = 512;
-constexpr size_t BWD_SMEM = (size_t)BWD_STAGES * BWD_STAGE + (3 * BWD_KMAX + 3 * 128) * sizeof(float) + 1024;
-constexpr size_t BWDP_SMEM = (size_t)BWDP_STAGES * BWDP_STAGE + (3 * BWD_KMAX + 3 * 128) * sizeof(float) + 1024;
+constexpr size_t BWD_SMEM = (size_t)BWD_STAGES * BWD_STAGE + (4 * BWD_KMAX + 4 * 128) * sizeof(float) + 1024;
+constexpr size_t BWDP_SMEM = (size_t)BWDP_STAGES * BWDP_STAGE + (4 * BWD_KMAX + 4 * 128) * sizeof(float) + 1024;
 
 // PAIR = true: row blocks 2p / 2p+1 of one (pair, side) as a cta_group::2 pair (see tc_fwd_kernel): every CTA forms
 // its own dS tiles, loads half of the transposed operand chunk, the leader issues M = 256 MMAs; ring depth 3.
@@ -509,12 +548,14 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
   }
   extern __shared__ uint8_t bwd_smem_raw[];
   uint8_t* smem = bwd_smem_raw + ((1024u - (tc::smem_u32(bwd_smem_raw) & 1023u)) & 1023u);
-  float* KL = reinterpret_cast<float*>(smem + STAGES * STAGE);           // per K index: lse, weight, 1/count
+  float* KL = reinterpret_cast<float*>(smem + STAGES * STAGE);           // per K index: lse, weight, 1/count, takes part (1 / 0)
   float* KW = KL + BWD_KMAX;
   float* KIC = KW + BWD_KMAX;
-  float* RL = KIC + BWD_KMAX;                                            // per tile row
+  float* KV = KIC + BWD_KMAX;
+  float* RL = KV + BWD_KMAX;                                             // per tile row
   float* RW = RL + 128;
   float* RIC = RW + 128;
+  float* RV = RIC + 128;
   __shared__ __align__(8) uint64_t bfull[STAGES], afull[STAGES], empty[STAGES], accfull, xfull;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -607,6 +648,8 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       const float* cnt_k = base + (side ? L.cnt_r : L.cnt_c);
       const float* ce_k = base + (side ? L.ce_r : L.ce_c);
       const float wk = side ? wr : wc;
+      const int* vk = hdr_i + (side ? TC_HDR_VALID_Q : TC_HDR_VALID_G);       // rows of the OTHER operand index K
+      const int* vr = hdr_i + (side ? TC_HDR_VALID_G : TC_HDR_VALID_Q);
       for (int k = t; k < KB * 64; k += BWD_PROD_THREADS) {
         const bool in = k < K;
         const float c = in ? cnt_k[k] : 0.f;
@@ -614,6 +657,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
         KL[k] = in ? lse_k[k] : 0.f;
         KW[k] = valid ? wk : 0.f;
         KIC[k] = c > 0.f ? 1.f / c : 0.f;
+        KV[k] = (in && ((vk[k >> 5] >> (k & 31)) & 1)) ? 1.f : 0.f;
       }
       const float* lse_r = base + (side ? L.lse_c : L.lse_r);
       const float* cnt_r = base + (side ? L.cnt_c : L.cnt_r);
@@ -627,6 +671,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
         RL[t] = in ? lse_r[gi] : 0.f;
         RW[t] = valid ? wrow : 0.f;
         RIC[t] = c > 0.f ? 1.f / c : 0.f;
+        RV[t] = (in && ((vr[gi >> 5] >> (gi & 31)) & 1)) ? 1.f : 0.f;
       }
     }
     named_bar(1, BWD_PROD_THREADS);
@@ -661,15 +706,16 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       uint32_t nw[4];
       if (kb + 1 < KB) load_block(kb + 1, na, nb, nw);       // next block's loads fly while this one is formed
       float kl[8], kw[8], kic[8];
+      uint32_t kvm = 0;                                        // K indices of this thread that take part
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { kl[e] = KL[k0 + e]; kw[e] = KW[k0 + e]; kic[e] = KIC[k0 + e]; }
+      for (int e = 0; e < 8; ++e) { kl[e] = KL[k0 + e]; kw[e] = KW[k0 + e]; kic[e] = KIC[k0 + e]; kvm |= (KV[k0 + e] != 0.f ? 1u : 0u) << e; }
       tc::mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
       uint8_t* Ahi = smem + s * STAGE;
       uint8_t* Alo = Ahi + A_TILE;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int row = (t >> 3) + 32 * u;
-        const bool in = row0 + row < R && k0 < K;
+        const bool in = row0 + row < R && k0 < K && RV[row] != 0.f;   // (rows that take no part: dS = 0)
         const float rl = RL[row], rw = RW[row], ric = RIC[row];
         const float sv[8] = {sa[u].x, sa[u].y, sa[u].z, sa[u].w, sb[u].x, sb[u].y, sb[u].z, sb[u].w};
         float hi[8], lo[8];
@@ -678,7 +724,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
           // dL/dS (chain through the clamp: zero where saturated); row statistics r*, K-index statistics k*
           const float pos = ((bw[u] >> e) & 1u) ? 1.f : 0.f;
           float g = rw * (fast_exp(sv[e] - rl) - pos * ric) + kw[e] * (fast_exp(sv[e] - kl[e]) - pos * kic[e]);
-          if (!in || sv[e] >= 20.f || sv[e] <= -20.f) g = 0.f;
+          if (!in || !((kvm >> e) & 1u) || sv[e] >= 20.f || sv[e] <= -20.f) g = 0.f;
           hi[e] = bf16r(g);
           lo[e] = g - hi[e];
         }
@@ -814,7 +860,8 @@ int fill_batch(Batch& b, const reid_sdm_pair* pairs, int n_pairs, bool bwd, int*
   int mb = 1;
   for (int i = 0; i < n_pairs; ++i) {
     const reid_sdm_pair& p = pairs[i];
-    if (!p.qry || !p.gal || !p.y || !p.loss || !p.status || !p.saved) return REID_E_INVALID;
+    if (!p.qry || !p.gal || !p.loss || !p.status || !p.saved) return REID_E_INVALID;
+    if (!p.y && (!p.row_label || !p.col_label)) return REID_E_INVALID;         // dense y, or the label form
     if (bwd && (!p.grad_out || !p.dqry || !p.dgal || !aligned16(p.dqry) || !aligned16(p.dgal))) return REID_E_INVALID;
     b.p[i] = p;
     const int blocks = ((p.N > p.M ? p.N : p.M) + 127) / 128;
@@ -833,7 +880,8 @@ bool tc_eligible(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d) {
   for (int i = 0; i < n_pairs; ++i) {
     const reid_sdm_pair& p = pairs[i];
     if (p.N < 64 || p.M < 64 || p.N > 512 || p.M > 512 || (p.N & 7) || (p.M & 7)) return false;
-    if (!aligned16(p.qry) || !aligned16(p.gal) || !aligned16(p.y)) return false;
+    if (!aligned16(p.qry) || !aligned16(p.gal) || (p.y && !aligned16(p.y))) return false;
+    if (!p.y && (!p.row_label || !p.col_label)) return false;
   }
   return true;
 }
@@ -853,11 +901,10 @@ int tc_forward(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float 
   const size_t prep_smem = (size_t)PREP_ROWS * (d + 8) * 2;
   tc_prep_kernel<<<dim3(mb * 128 / PREP_ROWS, 2, n_pairs), PREP_THREADS, prep_smem, st>>>(b, d, eps);
   REID_CHECK_LAUNCH();
-  // REID_SDM_PAIR=1 selects the cta_group::2 pair kernels.  They are parity-tested but NOT the default: measured on
+  // -DREID_SDM_PAIR=1 selects the cta_group::2 pair kernels.  They are parity-tested but NOT the default: measured on
   // C5 (10 pairs) the step takes 90 us against 78 us with the single-CTA kernels -- the six to eight 4-8 KB tensor-map
   // loads per stage and the cluster launch cost more than the halved operand stream and the deeper ring save.
-  const char* pe = getenv("REID_SDM_PAIR");
-  const bool pair = pe ? atoi(pe) != 0 : false;
+  const bool pair = REID_SDM_PAIR != 0;
   PairMaps maps;                                             // (only the entries of this launch are read by the kernel)
   if (pair) {
     if (!fill_maps(maps, pairs, n_pairs, d, false)) return REID_E_CUDA;
@@ -887,8 +934,7 @@ int tc_backward(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float
     if (cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWDP_SMEM) != cudaSuccess) return REID_E_CUDA;
     attr_done = true;
   }
-  const char* pe = getenv("REID_SDM_PAIR");
-  const bool pair = pe ? atoi(pe) != 0 : false;             // (see tc_forward)
+  const bool pair = REID_SDM_PAIR != 0;                     // (see tc_forward)
   PairMaps maps;
   if (pair) {
     if (!fill_maps(maps, pairs, n_pairs, d, true)) return REID_E_CUDA;

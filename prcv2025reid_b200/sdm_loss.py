@@ -47,25 +47,32 @@ def _raw_stream(dev):
     return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device()))
 
 
-def _pair_words(qs, gs, ys, losses, status, saved):
-    """The `reid_sdm_pair` array (include/reid_b200.h) as 10 64-bit words per pair (N and M share one);
-    the three backward-only slots stay zero."""
+PAIR_WORDS = 14      # sizeof(reid_sdm_pair) / 8
+
+
+def _pair_words(qs, gs, ys, losses, status, saved, labels=None):
+    """The `reid_sdm_pair` array (include/reid_b200.h) as PAIR_WORDS 64-bit words per pair (N and M share one);
+    the three backward-only slots stay zero.  ys[i] is None in the label form: labels[i] = (row_label, col_label,
+    row_valid or None, col_valid or None)."""
     words = []
     lp, sp = losses.data_ptr(), status.data_ptr()
     for i, (q, g, y) in enumerate(zip(qs, gs, ys)):
-        words += [q.data_ptr(), g.data_ptr(), y.data_ptr(), q.shape[0] | (g.shape[0] << 32), lp + 4 * i, sp + 4 * i,
-                  saved[i].data_ptr(), 0, 0, 0]
+        lab = [0, 0, 0, 0]
+        if y is None:
+            lab = [t.data_ptr() if t is not None else 0 for t in labels[i]]
+        words += [q.data_ptr(), g.data_ptr(), y.data_ptr() if y is not None else 0, q.shape[0] | (g.shape[0] << 32),
+                  lp + 4 * i, sp + 4 * i, saved[i].data_ptr(), 0, 0, 0] + lab
     return words
 
 
-def _pair_table(qs, gs, ys, losses, status, saved, grad=None, dq=None, dg=None):
-    words = _pair_words(qs, gs, ys, losses, status, saved)
+def _pair_table(qs, gs, ys, losses, status, saved, grad=None, dq=None, dg=None, labels=None):
+    words = _pair_words(qs, gs, ys, losses, status, saved, labels)
     if grad is not None:
         gp = grad.data_ptr()
         for i in range(len(qs)):
-            words[10 * i + 7] = gp + 4 * i
-            words[10 * i + 8] = dq[i].data_ptr()
-            words[10 * i + 9] = dg[i].data_ptr()
+            words[PAIR_WORDS * i + 7] = gp + 4 * i
+            words[PAIR_WORDS * i + 8] = dq[i].data_ptr()
+            words[PAIR_WORDS * i + 9] = dg[i].data_ptr()
     return (ctypes.c_uint64 * len(words))(*words)
 
 
@@ -73,6 +80,7 @@ class _SdmPairsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tau, eps, n, *tensors):
         qrys, gals, ys = tensors[:n], tensors[n:2 * n], tensors[2 * n:3 * n]
+        labels = tensors[3 * n] if len(tensors) > 3 * n else None      # label form: list of (row_label, col_label, row_valid, col_valid)
         L = _cabi.lib()
         dev = qrys[0].device
         d = qrys[0].shape[1]
@@ -80,17 +88,18 @@ class _SdmPairsFn(torch.autograd.Function):
         code = _dtype_code(qrys[0])
         qs = [q if q.is_contiguous() else q.contiguous() for q in qrys]
         gs = [g if g.is_contiguous() else g.contiguous() for g in gals]
-        yy = [y if (y.dtype == torch.float32 and y.is_contiguous()) else y.to(torch.float32).contiguous() for y in ys]
+        yy = [None if y is None else (y if (y.dtype == torch.float32 and y.is_contiguous()) else y.to(torch.float32).contiguous())
+              for y in ys]
         for q, g, y in zip(qs, gs, yy):
             if q.dtype != dt or g.dtype != dt or q.shape[1] != d or g.shape[1] != d:
                 raise TypeError("sdm_loss: all features of a batch must share dtype and width")
-            if y.shape[0] != q.shape[0] or y.shape[1] != g.shape[0]:
+            if y is not None and (y.shape[0] != q.shape[0] or y.shape[1] != g.shape[0]):
                 raise ValueError("sdm_loss: y must be [N, M]")
         losses = torch.empty(n, dtype=torch.float32, device=dev)
         status = torch.empty(n, dtype=torch.int32, device=dev)
         sizes = [_saved_floats(L, q.shape[0], g.shape[0], d) for q, g in zip(qs, gs)]
         saved = torch.empty(sum(sizes), dtype=torch.float32, device=dev).split(sizes)
-        words = _pair_words(qs, gs, yy, losses, status, saved)
+        words = _pair_words(qs, gs, yy, losses, status, saved, labels)
         arr = (ctypes.c_uint64 * len(words))(*words)
         if L.reid_sdm_uses_tensor_cores(arr, n, code, d):
             _cabi.LAUNCH_COUNT["n"] += 1                              # normalise/pack + forward = 2 launches
@@ -99,13 +108,15 @@ class _SdmPairsFn(torch.autograd.Function):
         # NOTE: the output must not be reachable from ctx (output -> grad_fn -> ctx -> output would keep every
         # step's buffers alive until the cyclic GC runs); the backward only needs the device-side status bits
         for i in range(n):
-            words[10 * i + 4] = words[10 * i + 5]                     # (the loss slot is not written again)
-        ctx.keep = (qs, gs, yy, status, saved, words)
-        return losses
+            words[PAIR_WORDS * i + 4] = words[PAIR_WORDS * i + 5]     # (the loss slot is not written again)
+        ctx.keep = (qs, gs, yy, status, saved, words, labels)
+        ctx.n_in = len(tensors)
+        ctx.mark_non_differentiable(status)
+        return losses, status
 
     @staticmethod
-    def backward(ctx, grad_losses):
-        qs, gs, yy, status, saved, words = ctx.keep
+    def backward(ctx, grad_losses, _grad_status=None):
+        qs, gs, yy, status, saved, words, labels = ctx.keep
         L = _cabi.lib()
         n = ctx.n
         grad = grad_losses
@@ -124,12 +135,12 @@ class _SdmPairsFn(torch.autograd.Function):
         gp = grad.data_ptr()
         w = list(words)
         for i in range(n):
-            w[10 * i + 7] = gp + 4 * i
-            w[10 * i + 8] = dq[i].data_ptr()
-            w[10 * i + 9] = dg[i].data_ptr()
+            w[PAIR_WORDS * i + 7] = gp + 4 * i
+            w[PAIR_WORDS * i + 8] = dq[i].data_ptr()
+            w[PAIR_WORDS * i + 9] = dg[i].data_ptr()
         arr = (ctypes.c_uint64 * len(w))(*w)
         check(L.reid_sdm_bwd(arr, n, ctx.code, ctx.d, ctx.tau, ctx.eps, _raw_stream(q0.device)), "reid_sdm_bwd")
-        return (None, None, None) + tuple(dq) + tuple(dg) + (None,) * n
+        return (None, None, None) + tuple(dq) + tuple(dg) + (None,) * (ctx.n_in - 2 * n)
 
 
 class SdmStep:
@@ -222,8 +233,33 @@ def sdm_loss_pairs(qrys: Sequence[torch.Tensor], gals: Sequence[torch.Tensor], y
     out: List[torch.Tensor] = []
     for s in range(0, n, _cabi.SDM_MAX_PAIRS):
         e = min(n, s + _cabi.SDM_MAX_PAIRS)
-        out.append(_SdmPairsFn.apply(tau, eps, e - s, *qrys[s:e], *gals[s:e], *ys[s:e]))
+        out.append(_SdmPairsFn.apply(tau, eps, e - s, *qrys[s:e], *gals[s:e], *ys[s:e])[0])
     return out[0] if len(out) == 1 else torch.cat(out)
+
+
+def label_form_supported(n_rows: int, d: int, dtype) -> bool:
+    """Shapes the label form of the C entry points serves (the tcgen05 path: include/reid_b200.h, reid_sdm_pair)."""
+    return dtype == torch.bfloat16 and 64 <= n_rows <= 512 and n_rows % 8 == 0 and d % 64 == 0 and 64 <= d <= 512
+
+
+def sdm_loss_pairs_labels(qrys: Sequence[torch.Tensor], gals: Sequence[torch.Tensor], row_labels, col_labels,
+                          row_valid=None, col_valid=None, tau: float = 0.2, eps: float = 1e-8):
+    """The pairs of a step in the LABEL FORM: y is never materialised, y[i][j] = valid_i & valid_j & (label_i == label_j),
+    rows whose valid byte is 0 are left out of the loss altogether (the feature masks of models/model.py:570-602).
+    -> (losses [n] fp32 differentiable, status [n] int32: bit 3 = the pair has no positive, include/reid_b200.h)."""
+    n = len(qrys)
+    if n == 0 or n > _cabi.SDM_MAX_PAIRS or not (n == len(gals) == len(row_labels) == len(col_labels)):
+        raise ValueError("sdm_loss_pairs_labels: need equally long lists of 1..%d pairs" % _cabi.SDM_MAX_PAIRS)
+    labs = []
+    for i in range(n):
+        rl = row_labels[i].to(torch.int64).contiguous()
+        cl = col_labels[i].to(torch.int64).contiguous()
+        rv = None if row_valid is None or row_valid[i] is None else row_valid[i].to(torch.uint8).contiguous()
+        cv = None if col_valid is None or col_valid[i] is None else col_valid[i].to(torch.uint8).contiguous()
+        if rl.numel() != qrys[i].shape[0] or cl.numel() != gals[i].shape[0]:
+            raise ValueError("sdm_loss_pairs_labels: one label per feature row")
+        labs.append((rl, cl, rv, cv))
+    return _SdmPairsFn.apply(tau, eps, n, *qrys, *gals, *([None] * n), labs)
 
 
 def sdm_loss_stable(qry, gal, y, tau=0.2, eps=1e-8):
@@ -254,6 +290,24 @@ def sdm_alignment_loss(raw_modality_features, feature_masks, labels, tau=0.2, ep
     names = [m for m, f in raw_modality_features.items()
              if m != "vis" and f is not None and feature_masks.get(m) is not None]                # :586-592
     flat = [(feature_masks[m] > 0).reshape(labels.shape[0], -1)[:, 0] for m in ["vis"] + names]
+    B = labels.shape[0]
+    if names and vis.dim() == 2 and label_form_supported(B, vis.shape[1], vis.dtype) and \
+            all(raw_modality_features[m].dtype == vis.dtype and raw_modality_features[m].shape == vis.shape for m in names):
+        # large bf16 batches: the label form of the kernels -- labels [B], masks [5, B], features [5, B, d] in, no y, NO
+        # host synchronisation; masked rows are left out inside the kernels, "no positive" / finiteness (:608-618) come
+        # back as device-side status bits
+        out = []
+        for s0 in range(0, len(names), _cabi.SDM_MAX_PAIRS):
+            ms = names[s0:s0 + _cabi.SDM_MAX_PAIRS]
+            k = len(ms)
+            losses, status = sdm_loss_pairs_labels([raw_modality_features[m] for m in ms], [vis] * k, [labels] * k, [labels] * k,
+                                                   [flat[1 + names.index(m)] for m in ms], [flat[0]] * k, tau, eps)
+            out.append((losses, status))
+        losses = torch.cat([o[0] for o in out]) if len(out) > 1 else out[0][0]
+        status = torch.cat([o[1] for o in out]) if len(out) > 1 else out[0][1]
+        has_pos = ((status & 8) == 0) & torch.isfinite(losses)                   # :608-618
+        kept = torch.where(has_pos, losses, torch.zeros_like(losses))
+        return kept.sum() / has_pos.sum().clamp_min(1)                           # :621-625
     host = torch.stack(flat).cpu()                                               # the one host read
     vis_idx = torch.nonzero(host[0]).flatten()
     if vis_idx.numel() == 0:

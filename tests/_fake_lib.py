@@ -282,26 +282,39 @@ class FakeLib:
         if dtype == torch.bfloat16:
             arr = np.ctypeslib.as_array((ctypes.c_uint16 * n).from_address(addr))
             return torch.from_numpy(arr).view(torch.bfloat16).view(*shape)
-        ct = {torch.float32: ctypes.c_float, torch.int32: ctypes.c_int32}[dtype]
+        if dtype == torch.float16:
+            arr = np.ctypeslib.as_array((ctypes.c_uint16 * n).from_address(addr))
+            return torch.from_numpy(arr).view(torch.float16).view(*shape)
+        ct = {torch.float32: ctypes.c_float, torch.int32: ctypes.c_int32, torch.int64: ctypes.c_int64, torch.uint8: ctypes.c_uint8}[dtype]
         return torch.from_numpy(np.ctypeslib.as_array((ct * n).from_address(addr))).view(*shape)
 
     def _pairs(self, arr, n, code, d):
-        dt = torch.float32 if code == 0 else torch.bfloat16
+        dt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}[code]
+        W = 14                                                          # sizeof(reid_sdm_pair) / 8
         out = []
         for p in range(n):
-            w = [int(arr[10 * p + i]) for i in range(10)]
+            w = [int(arr[W * p + i]) for i in range(W)]
             N, M = w[3] & 0xFFFFFFFF, w[3] >> 32
-            out.append(dict(q=self._tensor(w[0], (N, d), dt), g=self._tensor(w[1], (M, d), dt), y=self._tensor(w[2], (N, M), torch.float32),
-                            loss=self._tensor(w[4], (1,), torch.float32), status=self._tensor(w[5], (1,), torch.int32),
-                            grad=self._tensor(w[7], (1,), torch.float32) if w[7] else None,
-                            dq=self._tensor(w[8], (N, d), dt) if w[8] else None, dg=self._tensor(w[9], (M, d), dt) if w[9] else None))
+            P = dict(q=self._tensor(w[0], (N, d), dt), g=self._tensor(w[1], (M, d), dt),
+                     y=self._tensor(w[2], (N, M), torch.float32) if w[2] else None,
+                     loss=self._tensor(w[4], (1,), torch.float32), status=self._tensor(w[5], (1,), torch.int32),
+                     grad=self._tensor(w[7], (1,), torch.float32) if w[7] else None,
+                     dq=self._tensor(w[8], (N, d), dt) if w[8] else None, dg=self._tensor(w[9], (M, d), dt) if w[9] else None,
+                     rows=None, cols=None)
+            if P["y"] is None:                                          # label form: rows that take part, y from the labels
+                rl, cl = self._tensor(w[10], (N,), torch.int64), self._tensor(w[11], (M,), torch.int64)
+                rv = self._tensor(w[12], (N,), torch.uint8).bool() if w[12] else torch.ones(N, dtype=torch.bool)
+                cv = self._tensor(w[13], (M,), torch.uint8).bool() if w[13] else torch.ones(M, dtype=torch.bool)
+                P["rows"], P["cols"] = torch.nonzero(rv).flatten(), torch.nonzero(cv).flatten()
+                P["y"] = (rl[P["rows"]][:, None] == cl[P["cols"]][None, :]).float()
+            out.append(P)
         return out
 
     def reid_sdm_saved_floats(self, N, M, d):
         return 64
 
     def reid_sdm_uses_tensor_cores(self, arr, n, code, d):
-        return 0
+        return 1 if any(int(arr[14 * p + 2]) == 0 for p in range(n)) else 0   # (the label form is a tcgen05-path feature)
 
     def reid_sdm_step_launches(self, arr, n, code, d):
         return 1
@@ -311,10 +324,16 @@ class FakeLib:
         for P in self._pairs(arr, n, code, d):
             with torch.enable_grad():                                  # (autograd is off inside Function.backward)
                 q = P["q"].clone().requires_grad_(True); g = P["g"].clone().requires_grad_(True)
-                L = osdm.sdm_loss_oracle(q, g, P["y"], tau=tau, eps=eps)
+                if P["rows"] is not None:                              # label form: the reference filters the rows first
+                    if P["rows"].numel() == 0 or P["cols"].numel() == 0 or not bool(P["y"].any()):
+                        L = torch.zeros([])
+                    else:
+                        L = osdm.sdm_loss_oracle(q[P["rows"]], g[P["cols"]], P["y"], tau=tau, eps=eps)
+                else:
+                    L = osdm.sdm_loss_oracle(q, g, P["y"], tau=tau, eps=eps)
             if fwd:
                 P["loss"][0] = float(L.detach())
-                P["status"][0] = 0 if L.requires_grad else 1           # bit0: the reference's non-differentiable zero
+                P["status"][0] = 0 if L.requires_grad else (9 if not bool(P["y"].any()) else 1)   # bit0: the reference's zero; bit3: no positive
             if bwd:
                 if L.requires_grad:
                     with torch.enable_grad():

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_binding_table_covers_the_header():
     from prcv2025reid_b200 import _cabi
     assert set(_declared()) <= set(_cabi.EXPORTED_SYMBOLS) | {"reid_sdm_pair"}
-    assert ctypes.sizeof(_cabi.SdmPair) == 80      # struct reid_sdm_pair: 10 x 8 bytes (N and M share a word)
+    assert ctypes.sizeof(_cabi.SdmPair) == 112      # struct reid_sdm_pair: 14 x 8 bytes (N and M share a word), sdm_loss.PAIR_WORDS
 
 
 def test_host_only_entry_points(lib):

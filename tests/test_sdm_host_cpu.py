@@ -84,14 +84,14 @@ def test_step_object_matches_autograd(monkeypatch):
         SdmStep(qs * 5, vs * 5, ys * 5)                                 # more than REID_SDM_MAX_PAIRS
 
 
-@pytest.mark.parametrize("name", ["full", "ragged", "no_vis", "no_pairs", "missing", "full_bf16"])
+@pytest.mark.parametrize("name", ["full", "ragged", "no_vis", "no_pairs", "missing", "full_bf16", "large_bf16"])
 def test_alignment_loss_host_logic_matches_compute_loss_golden(monkeypatch, name):
     """sdm_alignment_loss (mask filtering with one host read, y from labels, pairs without a positive dropped, mean)
     against the fixture produced by the UNMODIFIED compute_loss (models/model.py:512-659)."""
     import os
     from oracle.make_golden_alignment import CASES, make_inputs
     from prcv2025reid_b200.sdm_loss import sdm_alignment_loss
-    _fake_lib.install(monkeypatch)
+    fake = _fake_lib.install(monkeypatch)
     z = np.load(os.path.join(_golden.GOLDEN, "sdm_alignment.npz"))
     spec = CASES[name]
     seed, B, d, n_ids, kind, tau = spec[:6]
@@ -100,7 +100,14 @@ def test_alignment_loss_host_logic_matches_compute_loss_golden(monkeypatch, name
     if abs(cs - float(z[name + "/checksum"])) > 1e-6 * abs(cs):
         pytest.skip("torch RNG stream differs from the one the fixture was generated with")
     leaves = {m: (f.clone().requires_grad_(True) if f is not None else None) for m, f in feats.items()}
+    if name == "large_bf16":
+        # 96 bf16 rows: the LABEL FORM of the C entry points -- no y, no host read of the masks
+        real_cpu = torch.Tensor.cpu
+        monkeypatch.setattr(torch.Tensor, "cpu", lambda self, *a, **k: (_ for _ in ()).throw(AssertionError("host read")))
     loss = sdm_alignment_loss(leaves, masks, labels, tau=tau)
+    if name == "large_bf16":
+        monkeypatch.setattr(torch.Tensor, "cpu", real_cpu)
+        assert fake.calls.count("reid_sdm_fwd") == 1
     want = float(z[name + "/loss"])
     assert float(loss.detach()) == pytest.approx(want, rel=1e-6, abs=1e-7)
     if loss.requires_grad:

@@ -145,7 +145,7 @@ def test_sdm_alignment_loss_matches_compute_loss_golden(name):
                 e_ref = np.linalg.norm(r - g64) / np.linalg.norm(g64)
                 print("%s grad_%s: |got - exact| %.2e, reference autograd vs exact %.2e, got vs reference %.2e"
                       % (name, m, e_got, e_ref, np.linalg.norm(got - r) / np.linalg.norm(r)))
-                assert e_got <= 3e-3 and e_got <= e_ref + 1e-4, m
+                assert e_got <= (5e-3 if spec[6] == "bf16" else 1.5e-3) and e_got <= e_ref + 1e-4, m
             else:
                 assert np.abs(t.grad.cpu().numpy() - r).max() <= 1e-5 * max(float(np.abs(r).max()), 1e-12), m
         elif t is not None and t.grad is not None:
