@@ -93,9 +93,12 @@ int reid_pos_sort(float* pos_score, int32_t* n_pos, int64_t Q, int Pmax, void* s
  * counted on a 1/32 row sample, those above 32768 / n_shards rows on a 1/1024 row sample, so that a sampled count
  * rests on >= 32 sampled rows gallery-wide; all shallower thresholds on every row.
  * flags: REID_FUSED_EXACT_COUNTS = count every threshold on every row (no sampling; slow for deep positives);
- *        REID_FUSED_NO_CANDIDATES = counting only (cand_* may be NULL). */
+ *        REID_FUSED_NO_CANDIDATES = counting only (cand_* may be NULL);
+ *        REID_FUSED_KLIST16 = candidates complete down to the 16th (not the REID_KLIST-th) best score of a slot: what the
+ *        re-scorer needs when the completeness bound is exchanged over several shards (reid_cand_select kx = 16). */
 #define REID_FUSED_EXACT_COUNTS 1
 #define REID_FUSED_NO_CANDIDATES 2
+#define REID_FUSED_KLIST16 4
 int reid_retrieve_fused(const void* q_f16, const void* g_f16, const int32_t* q_code,
                         const int32_t* g_code, const int32_t* excl, int E, const float* pos_thr,
                         const int32_t* n_pos, int64_t Q, int64_t G_local, int64_t g_offset, int d,

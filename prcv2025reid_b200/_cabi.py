@@ -11,7 +11,7 @@ KLIST = 32
 RTOP = 32
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 SDM_MAX_PAIRS = 16
-FUSED_EXACT_COUNTS, FUSED_NO_CANDIDATES = 1, 2
+FUSED_EXACT_COUNTS, FUSED_NO_CANDIDATES, FUSED_KLIST16 = 1, 2, 4
 FUSED_PMAX = 64           # thresholds per query and reid_retrieve_fused call
 
 

@@ -401,6 +401,49 @@ merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
   }
 }
 
+// small unions (n_lists * list_len <= 96: eight shards x top-10): one WARP per query, three entries per lane, topk rounds of a
+// warp-wide arg-best (score desc, index asc); eight queries per CTA.  Same result as merge_topk_kernel.
+__global__ void __launch_bounds__(256)
+merge_topk_warp_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, int n_lists, int64_t Q,
+                       int list_len, int topk, float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const int n = n_lists * list_len;
+  float v[3]; int g[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int i = lane + 32 * u;
+    v[u] = REID_NEG_INF; g[u] = 0x7fffffff;
+    if (i < n) {
+      const int l = i / list_len, r = i % list_len;
+      const int64_t o = ((int64_t)l * Q + q) * list_len + r;
+      const int gi = idx[o];
+      if (gi >= 0) { g[u] = gi; v[u] = scores[o]; }
+    }
+  }
+  float os = REID_NEG_INF; int oi = -1;
+  for (int round = 0; round < topk; ++round) {
+    float bv = REID_NEG_INF; int bi = 0x7fffffff;
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (g[u] != 0x7fffffff && ranks_before(v[u], g[u], bv, bi)) { bv = v[u]; bi = g[u]; }
+    float wv = bv; int wi = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int oi2 = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (ranks_before(ov, oi2, wv, wi)) { wv = ov; wi = oi2; }
+    }
+    if (wi == 0x7fffffff) break;                       // the union is exhausted
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (g[u] == wi && v[u] == wv) g[u] = 0x7fffffff;  // (a gallery row appears in exactly one shard's list)
+    if (lane == round) { os = wv; oi = wi; }
+  }
+  if (lane < topk) { out_score[q * topk + lane] = os; out_idx[q * topk + lane] = oi; }
+}
+
 // ------------------------------------------------------------------------------------------
 // metrics
 // ------------------------------------------------------------------------------------------
@@ -531,6 +574,12 @@ extern "C" int reid_merge_topk(const float* scores, const int32_t* idx, int n_li
   if (!scores || !idx || !out_score || !out_idx || n_lists <= 0 || topk <= 0 || list_len <= 0 || n_lists * list_len > 8192)
     return REID_E_INVALID;
   if (Q <= 0) return REID_OK;
+  if (n_lists * list_len <= 96 && topk <= 32) {
+    merge_topk_warp_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, (cudaStream_t)stream>>>(scores, idx, n_lists, Q, list_len, topk,
+                                                                                    out_score, out_idx);
+    REID_CHECK_LAUNCH();
+    return REID_OK;
+  }
   int n2 = 32;
   while (n2 < n_lists * list_len) n2 <<= 1;
   merge_topk_kernel<<<(unsigned)Q, 128, (size_t)n2 * 8, (cudaStream_t)stream>>>(scores, idx, n_lists, Q, list_len, topk, n2,

@@ -115,6 +115,7 @@ struct Params {
   int Pmax, pos_stride, pcap, kchunks, stages, n_chunks, n_qblocks, n_full, cand_cap;
   int debug;             // FDBG bits (always 0 unless built with -DREID_DEBUG)
   int no_cand;           // REID_FUSED_NO_CANDIDATES: counting only
+  int klist;             // candidates are complete down to the klist-th best score of a slot: 32, or 16 (REID_FUSED_KLIST16)
   int64_t rows_per_chunk;
   int32_t* hist;         // [Q, Pmax] global bucket histogram (workspace), raw hit counts
   uint32_t* thr_share;   // [Q] best known candidate threshold per query (ordered key), shared by all chunks
@@ -257,11 +258,13 @@ __device__ __noinline__ void epi_drain32(EpiAddr A, const Params* pp, int ew, in
   __syncwarp();
 }
 
-// Candidate-threshold refresh for query qq (whole warp): 32nd largest of the last 64 appended scores.
+// Candidate-threshold refresh for query qq (whole warp): the klist-th largest of the last 2 * klist appended scores
+// (klist = 32: a 64-entry window, two values per lane; klist = 16: one value per lane).
 __device__ __noinline__ void epi_refresh_thr(EpiAddr A, const Params* pp, int qq, int cnt, int lane, int64_t q0, int chunk) {
   const Params& p = *pp;
-  const float* win = p.cand_score + ((q0 + qq) * p.n_chunks + chunk) * (int64_t)p.cand_cap + (cnt - 64);
-  const float a0 = __ldcg(win + lane), a1 = __ldcg(win + 32 + lane);
+  const int kl = p.klist;
+  const float* win = p.cand_score + ((q0 + qq) * p.n_chunks + chunk) * (int64_t)p.cand_cap + (cnt - 2 * kl);
+  const float a0 = __ldcg(win + lane), a1 = kl == 32 ? __ldcg(win + 32 + lane) : -INFINITY;
   int r0 = 0, r1 = 0;                                          // number of window values greater than a0 / a1
 #pragma unroll 4
   for (int k = 0; k < 32; ++k) {
@@ -269,12 +272,12 @@ __device__ __noinline__ void epi_refresh_thr(EpiAddr A, const Params* pp, int qq
     r0 += (b0 > a0) + (b1 > a0);
     r1 += (b0 > a1) + (b1 > a1);
   }
-  // the values with fewer than 32 greater ones are >= 32 scores; their minimum bounds the 32nd largest
-  const float cand = fminf(r0 < 32 ? a0 : INFINITY, r1 < 32 ? a1 : INFINITY);
+  // the values with fewer than klist greater ones are >= klist scores; their minimum bounds the klist-th largest
+  const float cand = fminf(r0 < kl ? a0 : INFINITY, (kl == 32 && r1 < kl) ? a1 : INFINITY);
   const float nthr = unkey32(__reduce_min_sync(0xffffffffu, key32(cand)));
   if (lane == 0) {
     const uint32_t q4 = (uint32_t)qq * 4u;
-    sts_s32(A.es + ES_OFF(s_nextupd) + q4, cnt + 16);
+    sts_s32(A.es + ES_OFF(s_nextupd) + q4, cnt + kl / 2);
     if (nthr > lds_f32(A.es + ES_OFF(s_thrtop) + q4)) {
       sts_f32(A.es + ES_OFF(s_thrtop) + q4, nthr);
       sts_f32(A.es + ES_OFF(s_min) + q4, fminf(nthr, lds_f32(A.es + ES_OFF(s_threx) + q4)));
@@ -516,7 +519,7 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         es->s_minS1[et] = fminf(tt, t1);
         es->s_minS2[et] = fminf(tt, tl);
         es->s_candcnt[et] = 0;
-        es->s_nextupd[et] = 64;
+        es->s_nextupd[et] = 2 * p.klist;
         uint32_t he = 0;
         if (live) {
 #pragma unroll 1
@@ -720,7 +723,7 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         if (appends) {
           const int uq = ew * UPD_PER_WARP + (lane & (UPD_PER_WARP - 1));
           const int cnt = min(*(volatile int*)&es->s_candcnt[uq], p.cand_cap);
-          unsigned um = __ballot_sync(0xffffffffu, lane < UPD_PER_WARP && cnt >= 64 && cnt >= es->s_nextupd[uq]);
+          unsigned um = __ballot_sync(0xffffffffu, lane < UPD_PER_WARP && cnt >= 2 * p.klist && cnt >= es->s_nextupd[uq]);
           while (um) {
             const int src = __ffs(um) - 1;
             um &= um - 1;
@@ -802,7 +805,8 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
                                    size_t workspace_bytes, void* stream) {
   const bool no_cand = (flags & REID_FUSED_NO_CANDIDATES) != 0;
   if (!q_f16 || !g_f16 || !q_code || !g_code || !pos_thr || !n_pos || !pos_above || Q <= 0 || G_local <= 0 ||
-      n_chunks <= 0 || (E > 0 && !excl) || E < 0 || (flags & ~(REID_FUSED_EXACT_COUNTS | REID_FUSED_NO_CANDIDATES)))
+      n_chunks <= 0 || (E > 0 && !excl) || E < 0 ||
+      (flags & ~(REID_FUSED_EXACT_COUNTS | REID_FUSED_NO_CANDIDATES | REID_FUSED_KLIST16)))
     return REID_E_INVALID;
   if (!no_cand && (!cand_score || !cand_idx || !cand_count || cand_cap < 64 || cand_cap % 4 != 0)) return REID_E_INVALID;
   if (pos_stride == 0) pos_stride = Pmax;
@@ -825,6 +829,7 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
   p.hist = (int32_t*)workspace; p.thr_share = (uint32_t*)workspace + (size_t)Q * Pmax;
   p.n_exact = (int32_t*)workspace + (size_t)Q * (Pmax + 1); p.n_l1 = (int32_t*)workspace + (size_t)Q * (Pmax + 2);
   p.calib = 0; p.calib_cap = 0; p.row_stride = 1; p.no_cand = no_cand ? 1 : 0;
+  p.klist = (flags & REID_FUSED_KLIST16) ? 16 : KL;
   p.cand_score = cand_score; p.cand_idx = cand_idx; p.cand_count = cand_count;
   p.debug = REID_DEBUG;
   int stages = REID_MAX_STAGES < MAX_STAGES ? REID_MAX_STAGES : MAX_STAGES;

@@ -9,7 +9,10 @@
 // the same operand roles; this kernel materialises S and is the drop-in for `cosine_sim` and
 // the debug / verification mode of the fused path.
 // Roofline: tensor (2*Q*G*d flop) but the fp32 S store makes it HBM-bound for d = 512
-// (256 flop per output byte vs a ridge of ~212 flop/B): it is NOT the benchmarked path.
+// (256 flop per output byte vs a ridge of ~212 flop/B): algorithmic bytes = 4*Q*G written (+ operands).  It is NOT the
+// benchmarked path -- the ranking step never materialises S (retrieve_fused.cu) -- but the drop-in for `cosine_sim`
+// and the verification kernel of the fused path.  One tile per CTA, 2 ring stages (65 KB) so that THREE CTAs share an SM
+// (3 x 128 TMEM columns): the store epilogue of one tile overlaps the loads / MMAs of the next ones.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -18,11 +21,11 @@ namespace {
 constexpr int BM = 128;      // gallery rows per CTA tile (MMA M)
 constexpr int BN = 128;      // queries per CTA tile (MMA N)
 constexpr int BK = 64;       // one 128-byte swizzle atom of fp16
-constexpr int STAGES = 4;
+constexpr int STAGES = 2;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 3)
 sim_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmQ,
                 float* __restrict__ S, int64_t Q, int64_t G, int64_t ldS, int kchunks) {
   extern __shared__ uint8_t smem_raw[];

@@ -107,9 +107,16 @@ def prepare_gallery(gallery: torch.Tensor, g_pid_all: torch.Tensor, g_offset: in
 
     gallery [G_local, D] (cuda, any float dtype), g_pid_all [G_total] int64 (replicated on every rank).
     """
-    L = _cabi.lib()
-    dev = gallery.device
     g32, g16 = l2norm_rows(gallery, want_f16=True)
+    return install_normalised(g32, g16, g_pid_all, g_offset)
+
+
+def install_normalised(g_f32: torch.Tensor, g_f16: torch.Tensor, g_pid_all: torch.Tensor, g_offset: int = 0) -> GalleryShard:
+    """A shard whose rows are ALREADY normalised (K1 output kept on disk: gallery_store's pre-normalised store): only the
+    identity index is built.  g_f32 [G_local, D] fp32, g_f16 its fp16 copy, g_pid_all [G_total] int64."""
+    L = _cabi.lib()
+    dev = g_f32.device
+    assert g_f32.dtype == torch.float32 and g_f16.dtype == torch.float16 and g_f32.shape == g_f16.shape
     g_pid_all = g_pid_all.to(device=dev, dtype=torch.int64).contiguous()
     G_total = g_pid_all.numel()
     sorted_pid = torch.empty_like(g_pid_all)
@@ -119,13 +126,13 @@ def prepare_gallery(gallery: torch.Tensor, g_pid_all: torch.Tensor, g_offset: in
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(L.reid_pid_index_build(ptr(g_pid_all), G_total, ptr(sorted_pid), ptr(order), ptr(max_run), ptr(ws),
                                  ws_bytes, stream_ptr()), "reid_pid_index_build")
-    G_local = g32.shape[0]
+    G_local = g_f32.shape[0]
     g_code = torch.empty(G_local, dtype=torch.int32, device=dev)
     local_pid = g_pid_all[g_offset:g_offset + G_local].contiguous()
     check(L.reid_pid_lookup(ptr(sorted_pid), G_total, ptr(local_pid), G_local, ptr(g_code), None, stream_ptr()),
           "reid_pid_lookup")
     pmax = int(max_run.item())          # one-time host read when a gallery is installed
-    return GalleryShard(g32, g16, g_code, sorted_pid, order, max(1, pmax), int(g_offset), int(G_total))
+    return GalleryShard(g_f32.contiguous(), g_f16.contiguous(), g_code, sorted_pid, order, max(1, pmax), int(g_offset), int(G_total))
 
 
 def fused_slots(n_queries: int, G_local: int, sms: int) -> int:
@@ -193,7 +200,7 @@ def _rank_block(shard, q32_b, q16_b, pid_b, ex_b, E, pos_above_b, n_pos_b, top_s
     if fused:
         ws_bytes = L.reid_workspace_bytes(1, nb, shard.G_local, d)
         ws = shard.buf("fused_ws", (ws_bytes,), torch.uint8)
-        flags = _cabi.FUSED_EXACT_COUNTS if exact_ap else 0
+        flags = (_cabi.FUSED_EXACT_COUNTS if exact_ap else 0) | (_cabi.FUSED_KLIST16 if world > 1 else 0)
         PW = _cabi.FUSED_PMAX
         check(L.reid_retrieve_fused(ptr(q16_b), ptr(shard.g_f16), ptr(q_code), ptr(shard.g_code), ptr(ex_b), E,
                                     ptr(pos_thr), ptr(n_pos_b), nb, shard.G_local, shard.g_offset, d, min(Pmax, PW), Pmax,

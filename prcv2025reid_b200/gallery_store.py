@@ -7,6 +7,12 @@ and installs them as gallery shards: every rank memory-maps the .npy, copies ONL
 (`sharding.shard_range`) through a pinned staging buffer to the device in slabs, and runs the one-time
 normalise + identity-index pass (`engine.prepare_gallery`).  The 2 GB fp32 file of a 1M-row gallery is therefore
 never resident in host memory as a whole, and at N ranks each reads 1/N of it.
+
+PRE-NORMALISED STORE (`write_store` / `load_store_shard`): the output of that one-time pass kept on disk -- per row range
+one raw fp32 file (normalised rows, what the re-scorer reads) and one raw fp16 file (the tensor-core operand copy), the
+person ids once, a small JSON index.  Loading a shard is then two memory-mapped files -> pinned slabs -> HBM plus the
+identity index: no normalisation kernel, no fp32 -> fp16 pass, no host-side dtype conversion, and 6 B instead of 4 B + a
+kernel per element; any rank count can read a store written for another one (row ranges are looked up in the index).
 """
 import json
 import os
@@ -85,3 +91,76 @@ def load_pickle_cache(path: str):
     g_feat = g_feat.detach().cpu().numpy() if isinstance(g_feat, torch.Tensor) else np.asarray(g_feat)
     g_id = g_id.detach().cpu().numpy() if isinstance(g_id, torch.Tensor) else np.asarray(g_id)
     return g_feat.astype(np.float32, copy=False), g_id.astype(np.int64, copy=False)
+
+
+# ---------------------------------------------------------------------------------------------
+# pre-normalised sharded store
+# ---------------------------------------------------------------------------------------------
+STORE_INDEX = "store.json"
+
+
+def write_store(feats, pids, store_dir: str, n_parts: int = 8, device=None, slab_rows: int = 65536) -> dict:
+    """Normalise `feats` ([G, D] numpy array / memmap / tensor, un-normalised like the reference's cache) ONCE on the
+    device (K1, reid_l2norm_rows) and write the store: part p holds rows shard_range(G, p, n_parts)."""
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("prcv2025reid_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        device = torch.device("cuda", torch.cuda.current_device())
+    os.makedirs(store_dir, exist_ok=True)
+    G, D = feats.shape
+    parts = []
+    for p in range(n_parts):
+        r0, r1 = sharding.shard_range(G, p, n_parts)
+        f32 = np.lib.format.open_memmap(os.path.join(store_dir, "part_%03d.f32.npy" % p), mode="w+", dtype=np.float32, shape=(r1 - r0, D))
+        f16 = np.lib.format.open_memmap(os.path.join(store_dir, "part_%03d.f16.npy" % p), mode="w+", dtype=np.float16, shape=(r1 - r0, D))
+        for s0 in range(r0, r1, slab_rows):
+            s1 = min(r1, s0 + slab_rows)
+            x = feats[s0:s1]
+            x = x.detach() if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            n32, n16 = engine.l2norm_rows(x.to(device=device, dtype=torch.float32), want_f16=True)
+            f32[s0 - r0:s1 - r0] = n32.cpu().numpy()
+            f16[s0 - r0:s1 - r0] = n16.cpu().numpy()
+        f32.flush(); f16.flush()
+        parts.append([int(r0), int(r1)])
+    np.save(os.path.join(store_dir, "pids.npy"), np.asarray(pids, dtype=np.int64))
+    index = {"format": "prcv2025reid_b200 pre-normalised gallery store v1", "rows": int(G), "dim": int(D), "parts": parts,
+             "normalised": "F.normalize(x, dim=-1) (eval_mm_protocol.py:46-48, :546), fp32 + fp16 copy"}
+    with open(os.path.join(store_dir, STORE_INDEX), "w", encoding="utf-8") as f:
+        json.dump(index, f)
+    return index
+
+
+def load_store_shard(store_dir: str, rank: int = 0, world: int = 1, device=None, slab_rows: int = 65536):
+    """Rows shard_range(G, rank, world) of a pre-normalised store -> (GalleryShard, (row0, row1)).  No arithmetic on the
+    features: memory-mapped parts -> pinned slabs -> device, then the identity index (engine.install_normalised)."""
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("prcv2025reid_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        device = torch.device("cuda", torch.cuda.current_device())
+    with open(os.path.join(store_dir, STORE_INDEX), "r", encoding="utf-8") as f:
+        index = json.load(f)
+    G, D = index["rows"], index["dim"]
+    r0, r1 = sharding.shard_range(G, rank, world)
+    g32 = torch.empty(r1 - r0, D, dtype=torch.float32, device=device)
+    g16 = torch.empty(r1 - r0, D, dtype=torch.float16, device=device)
+    for kind, dst, dt in (("f32", g32, torch.float32), ("f16", g16, torch.float16)):
+        stage = [torch.empty(min(slab_rows, max(1, r1 - r0)), D, dtype=dt).pin_memory() for _ in range(2)]
+        done, i = [None, None], 0
+        for p, (p0, p1) in enumerate(index["parts"]):
+            a, b = max(r0, p0), min(r1, p1)
+            if a >= b:
+                continue
+            part = np.load(os.path.join(store_dir, "part_%03d.%s.npy" % (p, kind)), mmap_mode="r")
+            for s0 in range(a, b, slab_rows):
+                s1 = min(b, s0 + slab_rows)
+                k = i & 1
+                if done[k] is not None:
+                    done[k].synchronize()
+                host = stage[k][:s1 - s0]
+                host.numpy()[...] = part[s0 - p0:s1 - p0]
+                dst[s0 - r0:s1 - r0].copy_(host, non_blocking=True)
+                done[k] = torch.cuda.Event(); done[k].record()
+                i += 1
+        torch.cuda.current_stream().synchronize()
+    pids = torch.from_numpy(np.load(os.path.join(store_dir, "pids.npy")))
+    return engine.install_normalised(g32, g16, pids.to(device), g_offset=r0), (r0, r1)

@@ -7,17 +7,16 @@ rows = list(csv.reader(raw.splitlines()))
 hdr = rows[1]
 ia, isrc, isamp = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-body = []
-for r in rows[2:]:                      # several captured launches of the kernel: keep the first one
-    if len(r) != len(hdr):
+bodies, body = [], []
+for r in rows[2:]:                      # several captured launches of the kernel: keep the one with the most samples
+    if len(r) != len(hdr) or r[isamp] == "# Samples":
         if body:
-            break
-        continue
-    if r[isamp] == "# Samples":
-        if body:
-            break
+            bodies.append(body); body = []
         continue
     body.append(r)
+if body:
+    bodies.append(body)
+body = max(bodies, key=lambda b: sum(int(r[isamp]) for r in b))
 tot = sum(int(r[isamp]) for r in body)
 print("total samples", tot)
 order = sorted(range(len(body)), key=lambda k: -int(body[k][isamp]))[:n]

@@ -672,14 +672,45 @@ def test_gallery_store_shards_match_direct_install(eng, tmp_path):
     assert sum(rows) == case.G
     shard, meta2, _ = gallery_store.load_shard(str(tmp_path))
     assert meta2 == meta and torch.equal(shard.g_f16, ref.g_f16)
+    # the installed rows against the ORACLE's normalisation of the same file (eval_mm_protocol.py:546), not against ourselves
+    assert (shard.g_f32.cpu() - orc.l2n(torch.from_numpy(np.load(str(tmp_path / "rgb_feats.npy"))))).abs().max() <= 4e-7
 
 
-def test_merge_topk_of_shard_lists():
-    """The multi-GPU merge step on one GPU: per-shard sorted top-k lists [n_lists, Q, k] -> global top-k (score desc, idx asc)."""
+def test_prenormalised_store_installs_without_a_normalise_pass(eng, tmp_path):
+    """N3: the pre-normalised sharded store (fp32 + fp16 parts, written once): a store written in 3 parts is read by 1, 2 and
+    4 ranks; the shards hold exactly K1's output, no reid_l2norm_rows call happens at load time, and retrieval over the
+    installed shard equals the ORACLE on the raw features."""
+    from prcv2025reid_b200 import _cabi, gallery_store
+    case = synth.make_retrieval_case(43, 60, 6, 3, 2, excl_frac=0.1)
+    gallery_store.write_store(case.gallery_raw.numpy(), case.g_pid.numpy(), str(tmp_path), n_parts=3, slab_rows=50)
+    ref = eng.prepare_gallery(case.gallery_raw.cuda(), case.g_pid.cuda())
+    calls = []
+    real = eng.l2norm_rows
+    eng.l2norm_rows = lambda *a, **k: calls.append(1) or real(*a, **k)
+    try:
+        for world in (1, 2, 4):
+            for rank in range(world):
+                shard, (r0, r1) = gallery_store.load_store_shard(str(tmp_path), rank, world, slab_rows=70)
+                assert shard.g_offset == r0 and shard.G_total == case.G and shard.pmax == ref.pmax
+                assert torch.equal(shard.g_f32, ref.g_f32[r0:r1]) and torch.equal(shard.g_f16, ref.g_f16[r0:r1])
+                assert torch.equal(shard.g_code, ref.g_code[r0:r1])
+        shard, _ = gallery_store.load_store_shard(str(tmp_path))
+    finally:
+        eng.l2norm_rows = real
+    assert not calls                                            # no normalisation at load time
+    q32, q16 = eng.fuse_queries(case.query_raw.cuda(), case.mod_id.cuda(), synth.weights_tensor().cuda())
+    res = eng.retrieve(shard, q32, q16, case.q_pid.cuda(), case.excl.cuda(), mode="fused", want_ap=True)
+    _check_against_oracle(res, case, orc.fuse_queries(case.query_raw, case.mod_id, synth.weights_tensor()), orc.l2n(case.gallery_raw))
+
+
+@pytest.mark.parametrize("n_lists", [3, 8, 12])
+def test_merge_topk_of_shard_lists(n_lists):
+    """The multi-GPU merge step on one GPU: per-shard sorted top-k lists [n_lists, Q, k] -> global top-k (score desc, idx asc);
+    unions of up to 96 entries take the one-warp-per-query kernel, larger ones the block-wide sort."""
     from prcv2025reid_b200 import _cabi
     from prcv2025reid_b200._cabi import check, ptr, stream_ptr
     g = torch.Generator().manual_seed(4)
-    n_lists, Q, k = 3, 257, 10
+    Q, k = 257, 10
     sc = torch.randn(n_lists, Q, k, generator=g)
     sc[1, :, 5:] = float("-inf")                                  # a shard with fewer than k rows: -inf / -1 padding
     sc, _ = torch.sort(sc, dim=2, descending=True)
