@@ -122,7 +122,9 @@ struct Params {
   int32_t* n_exact;      // [Q] thresholds [0, n_exact) are counted on every row
   int32_t* n_l1;         // [Q] thresholds [n_exact, n_l1) on the level-1 row sample, [n_l1, n_pos) on the level-2 sample
   int calib;             // 1 = calibration pre-pass: all thresholds exact, no candidates
-  int calib_cap;         // calibration: a threshold with this many sample rows above it is retired (its class is known)
+  int calib_cap;         // calibration: sample rows above a threshold that put its estimated rank beyond the level-2 limit
+  int calib_floor;       // ... a threshold is never retired on fewer rows than this (>= klist)
+  float calib_rate;      // calib_cap / (rows of the sample)
   int64_t row_stride;    // gallery row stride of this pass (1, or the sample stride of the pre-pass)
   float* cand_score; int32_t* cand_idx; int32_t* cand_count;
 };
@@ -313,10 +315,11 @@ __device__ __noinline__ void epi_flush_hist(EpiAddr A, const Params* pp, int et,
 // level-1 sample while it stays <= limit2, else on the level-2 sample.
 __global__ void calib_split_kernel(int32_t* __restrict__ hist, const int32_t* __restrict__ n_pos, int64_t Q, int Pmax,
                                    float scale, float limit1, float limit2, int32_t* __restrict__ n_exact,
-                                   int32_t* __restrict__ n_l1) {
+                                   int32_t* __restrict__ n_l1, const float* __restrict__ pos_thr, int pos_stride, int klist,
+                                   uint32_t* __restrict__ thr_share) {
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
     const int np = min(n_pos[q], Pmax);
-    int acc = 0, ne = 0, n1 = 0;
+    int acc = 0, ne = 0, n1 = 0, seed = -1;
     bool open1 = true, open2 = true;
     for (int j = 0; j < Pmax; ++j) {
       acc += hist[q * Pmax + j];
@@ -325,10 +328,15 @@ __global__ void calib_split_kernel(int32_t* __restrict__ hist, const int32_t* __
         const float est = (float)acc * scale;
         if (open1) { if (est <= limit1) ne = j + 1; else open1 = false; }
         if (open2) { if (est <= limit2) n1 = j + 1; else open2 = false; }
+        if (seed < 0 && acc >= klist) seed = j;
       }
     }
     n_exact[q] = ne;
     n_l1[q] = max(n1, ne);
+    // seed of the candidate threshold: the sample rows are shard rows, so the shallowest positive threshold with >= klist
+    // sample rows (valid, non-positive) strictly above it has >= klist shard rows above it -- the main pass appends exactly
+    // the rows above it and skips the cold start (-inf: every row of the first tiles)
+    if (thr_share && seed >= 0) thr_share[q] = key32(pos_thr[q * (int64_t)pos_stride + seed]);
   }
 }
 __global__ void fill_n_exact_kernel(const int32_t* __restrict__ n_pos, int64_t Q, int Pmax, int32_t* __restrict__ n_exact,
@@ -734,22 +742,30 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
           }
         }
         if (p.calib && lane < UPD_PER_WARP) {
-          // calibration: thresholds whose count has reached calib_cap are already known to be level-2; retiring them stops
-          // the rows between them from being hits at all (most sample rows score above a query's DEEPEST positives)
+          // calibration: a threshold whose ESTIMATED in-shard rank (sample rows above it so far, scaled by the part of the
+          // sample seen) has passed the level-2 limit is retired on the spot -- never on fewer than calib_floor rows, so a
+          // retired threshold also has >= klist shard rows above it (the seed of the candidate threshold).  Retiring stops
+          // the rows between the deep thresholds from being hits at all (most sample rows score above a query's DEEPEST
+          // positives).  The bucket of the shallowest retired threshold receives calib_cap extra counts: calib_split then
+          // sees every retired threshold beyond the level-2 limit.
           const int uq = ew * UPD_PER_WARP + lane;
           const uint32_t cn = es->s_cnts[uq];
           const int np = cn & 255;
+          const int seen = min((t + 1) * TROWS, (int)p.G_local);            // (the sample has <= CALIB_ROWS rows)
+          const int cap = max(p.calib_floor, (int)(p.calib_rate * (float)seen));
           int acc = 0, na = np;
 #pragma unroll 1
           for (int j = 0; j < np; ++j) {
             const uint32_t w = s_hist32[(uq * p.pcap + j) >> 1];
             acc += (j & 1) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
-            if (acc >= p.calib_cap) { na = j; break; }
+            if (acc >= cap) { na = j; break; }
           }
           if (na < np) {
             es->s_cnts[uq] = (cn & 0xFF000000u) | (uint32_t)na | ((uint32_t)na << 8) | ((uint32_t)na << 16);
             const float tl = na > 0 ? s_thr[uq * p.pcap + na - 1] : INFINITY;
+            es->s_threx[uq] = tl; es->s_thrl1[uq] = tl; es->s_thrlow[uq] = tl;
             es->s_min[uq] = tl; es->s_minS1[uq] = tl; es->s_minS2[uq] = tl;
+            reds_add(A.hist + (uint32_t)((uq * p.pcap + na) >> 1) * 4u, (uint32_t)p.calib_cap << ((na & 1) * 16));
           }
         }
         if (((t + 1) % FLUSH_TILES) == 0) epi_flush_hist(A, &p, et, q0);
@@ -828,7 +844,7 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
   p.rows_per_chunk = (rpc + W2 - 1) / W2 * W2;         // chunk starts are multiples of W2: (local row % W) is a tile column
   p.hist = (int32_t*)workspace; p.thr_share = (uint32_t*)workspace + (size_t)Q * Pmax;
   p.n_exact = (int32_t*)workspace + (size_t)Q * (Pmax + 1); p.n_l1 = (int32_t*)workspace + (size_t)Q * (Pmax + 2);
-  p.calib = 0; p.calib_cap = 0; p.row_stride = 1; p.no_cand = no_cand ? 1 : 0;
+  p.calib = 0; p.calib_cap = 0; p.calib_floor = 0; p.calib_rate = 0.f; p.row_stride = 1; p.no_cand = no_cand ? 1 : 0;
   p.klist = (flags & REID_FUSED_KLIST16) ? 16 : KL;
   p.cand_score = cand_score; p.cand_idx = cand_idx; p.cand_count = cand_count;
   p.debug = REID_DEBUG;
@@ -896,8 +912,11 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
     const float limit1 = fmaxf(32.f * (float)W1 / (float)shards, 8.f * scale);
     const float limit2 = fmaxf(32.f * (float)W2 / (float)shards, limit1);
     c.calib_cap = (int)(limit2 / scale) + 8;
+    c.calib_floor = 32;
+    c.calib_rate = (float)c.calib_cap / (float)calib_rows;
     if (!launch(tmS, c)) return REID_E_CUDA;
-    calib_split_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, scale, limit1, limit2, p.n_exact, p.n_l1);
+    calib_split_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, scale, limit1, limit2, p.n_exact, p.n_l1, pos_thr,
+                                                 pos_stride, p.klist, no_cand ? nullptr : p.thr_share);
   } else {
     fill_n_exact_kernel<<<aux_grid, 256, 0, st>>>(n_pos, Q, Pmax, p.n_exact, p.n_l1);
   }

@@ -166,28 +166,55 @@ RESCORE_KX_ONE_SHARD = 32     # completeness cut-off of the re-scorer: the kx-th
 RESCORE_KX_SHARDED = 16       # ... with several shards the MAX over the shards' cut-offs is used and 16 suffice for top-10
 
 
-def _rank_block(shard, q32_b, q16_b, pid_b, ex_b, E, pos_above_b, n_pos_b, top_score_b, top_idx_b, flag_b, bound_b, lb0_b, t0_b,
-                *, fused, eps, cand_cap, group, world, exact_ap, n_slots=None):
-    """Enqueue the ranking kernels of one query block on the current stream (no host synchronisation unless an
-    identity has more than 64 gallery rows).  Local counts -> pos_above_b, exact local top list -> top_*_b, the
-    completeness cut-off (MAX over the shards) -> bound_b, re-scored rows above the best positive -> lb0_b, the best
-    positive's score -> t0_b, candidate-buffer overflow -> flag_b."""
+class _RankState:
+    """Per-call work arrays of `retrieve`, all sized for the WHOLE query batch so that the exchange steps over the shards
+    run once per call instead of once per query block: q_code [Q], pos_thr [Q, Pmax] (exact positive scores, sorted),
+    the selected candidates sel_* [Q, RTOP] and one flat int32 buffer [pos_above | lb0 | flag] (a single all-reduce)."""
+
+    def __init__(self, Q, Pmax, dev):
+        self.Q, self.Pmax = Q, Pmax
+        self.counts = torch.zeros(Q * (Pmax + 2), dtype=torch.int32, device=dev)
+        self.pos_above = self.counts[:Q * Pmax].view(Q, Pmax)            # rows ranked above each positive (this shard)
+        self.lb0 = self.counts[Q * Pmax:Q * (Pmax + 1)]                  # re-scored rows above the best positive (this shard)
+        self.flag = self.counts[Q * (Pmax + 1):]                         # candidate-buffer overflow
+        self.n_pos = torch.empty(Q, dtype=torch.int32, device=dev)
+        self.q_code = torch.empty(Q, dtype=torch.int32, device=dev)
+        self.pos_thr = torch.empty(Q, Pmax, dtype=torch.float32, device=dev)
+        self.top_score = torch.empty(Q, _cabi.RTOP, dtype=torch.float32, device=dev)
+        self.top_idx = torch.empty(Q, _cabi.RTOP, dtype=torch.int32, device=dev)
+        self.bound = torch.empty(Q, dtype=torch.float32, device=dev)     # completeness cut-off of the re-scored head (gallery-wide)
+        self.sel_score = torch.empty(Q, _cabi.RTOP, dtype=torch.float32, device=dev)
+        self.sel_idx = torch.empty(Q, _cabi.RTOP, dtype=torch.int32, device=dev)
+        self.sel_n = torch.empty(Q, dtype=torch.int32, device=dev)
+
+
+def _pos_stage(shard, S, sl, q32, pid, ex, E, *, group, world):
+    """Exact fp32 scores of the positives of queries `sl` (sorted descending -> S.pos_thr, S.n_pos); with several shards the
+    owner rank of a positive holds its score, the others -inf: all_reduce(MAX)."""
     L = _cabi.lib()
     st = stream_ptr()
-    d, Pmax = shard.d, shard.pmax
-    nb = pid_b.shape[0]
-    sms = L.reid_device_sm_count()
-    q_code = shard.buf("q_code", (nb,), torch.int32)
+    nb = pid.shape[0]
+    q_code, pos_thr, n_pos = S.q_code[sl], S.pos_thr[sl], S.n_pos[sl]
     q_count = shard.buf("q_count", (nb,), torch.int32)
-    check(L.reid_pid_lookup(ptr(shard.sorted_pid), shard.G_total, ptr(pid_b), nb, ptr(q_code), ptr(q_count), st),
+    check(L.reid_pid_lookup(ptr(shard.sorted_pid), shard.G_total, ptr(pid), nb, ptr(q_code), ptr(q_count), st),
           "reid_pid_lookup")
-    pos_thr = shard.buf("pos_thr", (nb, Pmax), torch.float32)
-    check(L.reid_pos_scores(ptr(q32_b), ptr(shard.g_f32), ptr(shard.order), ptr(q_code), ptr(q_count), ptr(ex_b), E,
-                            nb, shard.G_local, shard.g_offset, d, Pmax, ptr(pos_thr), st), "reid_pos_scores")
+    check(L.reid_pos_scores(ptr(q32), ptr(shard.g_f32), ptr(shard.order), ptr(q_code), ptr(q_count), ptr(ex), E,
+                            nb, shard.G_local, shard.g_offset, shard.d, S.Pmax, ptr(pos_thr), st), "reid_pos_scores")
     if world > 1:
-        sharding.exchange_pos_scores(pos_thr, group)                # owner rank holds the score, others -inf
-    check(L.reid_pos_sort(ptr(pos_thr), ptr(n_pos_b), nb, Pmax, st), "reid_pos_sort")
+        sharding.exchange_pos_scores(pos_thr, group)
+    check(L.reid_pos_sort(ptr(pos_thr), ptr(n_pos), nb, S.Pmax, st), "reid_pos_sort")
 
+
+def _scan_stage(shard, S, sl, q32_b, q16_b, ex_b, E, *, fused, cand_cap, world, exact_ap, n_slots=None):
+    """The gallery pass of one query block (<= two waves of work items) on the current stream: local counts ->
+    S.pos_above, candidates -> the best RTOP by approximate score (S.sel_*) and the shard's completeness cut-off (S.bound),
+    candidate-buffer overflow -> S.flag.  No host synchronisation unless an identity has more than 64 gallery rows."""
+    L = _cabi.lib()
+    st = stream_ptr()
+    d, Pmax = shard.d, S.Pmax
+    q_code, pos_thr, n_pos_b, pos_above_b = S.q_code[sl], S.pos_thr[sl], S.n_pos[sl], S.pos_above[sl]
+    nb = q_code.shape[0]
+    sms = L.reid_device_sm_count()
     if fused:
         n_chunks = int(n_slots) if n_slots else fused_slots(nb, shard.G_local, sms)
     else:
@@ -232,21 +259,24 @@ def _rank_block(shard, q32_b, q16_b, pid_b, ex_b, E, pos_above_b, n_pos_b, top_s
                                     ptr(pos_thr), ptr(n_pos_b), None, nb, nb, shard.G_local, shard.g_offset, d, Pmax,
                                     n_chunks, cap, ptr(pos_above_b), ptr(cand_score), ptr(cand_idx), ptr(cand_count), st),
               "reid_retrieve_exact")
-    t0_b.copy_(pos_thr[:, 0])
-    sel_score = shard.buf("sel_score", (nb, _cabi.RTOP), torch.float32)
-    sel_idx = shard.buf("sel_idx", (nb, _cabi.RTOP), torch.int32)
-    sel_n = shard.buf("sel_n", (nb,), torch.int32)
     kx = RESCORE_KX_ONE_SHARD if world == 1 else RESCORE_KX_SHARDED
     check(L.reid_cand_select(ptr(cand_score), ptr(cand_idx), ptr(cand_count), ptr(cand_thr), nb, n_chunks, cap, kx,
-                             ptr(sel_score), ptr(sel_idx), ptr(sel_n), ptr(bound_b), ptr(flag_b), st), "reid_cand_select")
-    if world > 1:
-        sharding.exchange_bound(bound_b, group)                     # the best shard's kx-th best approximate score
-    check(L.reid_rescore_topk(ptr(q32_b), ptr(shard.g_f32), ptr(q_code), ptr(shard.g_code), ptr(pos_thr), ptr(n_pos_b),
-                              ptr(sel_score), ptr(sel_idx), ptr(sel_n), ptr(bound_b), nb, shard.G_local, shard.g_offset, d,
-                              Pmax, float(eps if fused else 0.0), ptr(pos_above_b), ptr(top_score_b), ptr(top_idx_b),
-                              ptr(lb0_b), st), "reid_rescore_topk")
+                             ptr(S.sel_score[sl]), ptr(S.sel_idx[sl]), ptr(S.sel_n[sl]), ptr(S.bound[sl]), ptr(S.flag[sl]), st),
+          "reid_cand_select")
     if _DEBUG_KEEP is not None:
-        _DEBUG_KEEP.update(cand_count=cand_count.clone(), n_chunks=n_chunks, sel_n=sel_n.clone())
+        _DEBUG_KEEP.update(cand_count=cand_count.clone(), n_chunks=n_chunks, sel_n=S.sel_n[sl].clone())
+
+
+def _rescore_stage(shard, S, sl, q32, *, eps):
+    """Exact fp32 re-score of the selected rows of queries `sl` at or above S.bound (after the exchange of the cut-offs:
+    only the rows that can still reach the gallery-wide head) -> the shard's exact top list, exact local counts of the
+    positives above the bound, S.lb0."""
+    L = _cabi.lib()
+    nb = S.q_code[sl].shape[0]
+    check(L.reid_rescore_topk(ptr(q32), ptr(shard.g_f32), ptr(S.q_code[sl]), ptr(shard.g_code), ptr(S.pos_thr[sl]),
+                              ptr(S.n_pos[sl]), ptr(S.sel_score[sl]), ptr(S.sel_idx[sl]), ptr(S.sel_n[sl]), ptr(S.bound[sl]),
+                              nb, shard.G_local, shard.g_offset, shard.d, S.Pmax, float(eps), ptr(S.pos_above[sl]),
+                              ptr(S.top_score[sl]), ptr(S.top_idx[sl]), ptr(S.lb0[sl]), stream_ptr()), "reid_rescore_topk")
 
 
 def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional[torch.Tensor], q_pid: torch.Tensor,
@@ -259,11 +289,14 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
     candidates, exact fp32 re-run of the (rare) queries whose top-k / CMC is not decidable within eps.
     mode "exact": everything through the fp32 SIMT kernel.
     exact_ap: count every positive's rank on every gallery row (no row sampling for deep positives; slower).
-    group: a torch.distributed process group whose ranks hold disjoint contiguous gallery shards.
+    group: a torch.distributed process group whose ranks hold disjoint contiguous gallery shards.  The shards exchange
+    FOUR times per call (not per query block): the positives' scores before the gallery passes, the completeness
+    cut-offs after them, then the counts and the top lists (sharding.py).
     host_queries: (query_raw [Q,k,D], mod_id [Q,k], weights) in pinned HOST memory instead of q_f32/q_f16;
     q_pid / excl may then be host tensors too.  Query blocks are copied on a side stream while the previous
     block computes (H2D overlapped with the kernels); with a process group every rank uploads and fuses only its
-    1/world slice of a block and the fused block is all-gathered over NVLink (sharding.gather_query_block).
+    1/world slice of a block and the fused block is all-gathered over NVLink (sharding.gather_query_block) -- the
+    positives' scores are then exchanged per block.
     The host is synchronised ONCE, by the read of the metrics (plus once per query block when an identity has more than
     64 gallery rows, and once more in the rare case that queries were flagged for the exact re-run).
     """
@@ -287,20 +320,13 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
     if query_block is None:
         query_block = default_query_block(sms)
 
-    pos_above = torch.zeros(Q, Pmax, dtype=torch.int32, device=dev)
-    n_pos = torch.empty(Q, dtype=torch.int32, device=dev)
-    top_score = torch.empty(Q, _cabi.RTOP, dtype=torch.float32, device=dev)
-    top_idx = torch.empty(Q, _cabi.RTOP, dtype=torch.int32, device=dev)
-    flag = torch.zeros(Q, dtype=torch.int32, device=dev)
-    bound = torch.empty(Q, dtype=torch.float32, device=dev)     # completeness cut-off of the re-scored head (gallery-wide)
-    lb0 = torch.zeros(Q, dtype=torch.int32, device=dev)         # re-scored rows above the best positive (this shard)
-    t0 = torch.empty(Q, dtype=torch.float32, device=dev)        # best positive's exact score
+    S = _RankState(Q, Pmax, dev)
     use_fused = (mode == "fused" and Pmax <= 2048 and d % 64 == 0 and d <= 512 and shard.G_local <= (1 << 22)
                  and (host_queries is not None or q_f16 is not None))
 
     blocks = [(b0, min(Q, b0 + query_block)) for b0 in range(0, Q, query_block)]
     staged = {}
-    kept = []                                 # (q32, pid, excl) of every block: the exact re-run of flagged queries reads them
+    kept = []                                 # (q32, pid, excl) of every block: the re-scorer and the exact re-run read them
     if host_queries is not None:
         h_raw, h_mod, weights = host_queries
         weights = weights.to(dev)
@@ -344,6 +370,8 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
         q_pid = q_pid.to(device=dev, dtype=torch.int64).contiguous()
         if excl is not None:
             excl = excl.to(device=dev, dtype=torch.int32).contiguous()
+        # resident queries: the positives' scores of the WHOLE batch up front (one exchange over the shards)
+        _pos_stage(shard, S, slice(0, Q), q_f32, q_pid, excl, E, group=group, world=world)
 
     for bi, (b0, b1) in enumerate(blocks):
         nb = b1 - b0
@@ -354,46 +382,58 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
             (raw_b, mod_b, pid_b, ex_b), ev = staged.pop(bi)
             torch.cuda.current_stream().wait_event(ev)
             q32_b, q16_b = fuse_queries(raw_b, mod_b, weights)
-            if world > 1:                                        # every rank fused 1/world of the block: exchange over NVLink
+            if world > 1:
+                # every rank fused 1/world of the block: the fp32 rows travel over NVLink, the fp16 operand copy is
+                # re-derived from them (the same round-to-nearest conversion K2 applies)
                 q32_b = sharding.gather_query_block(q32_b, nb, group)
-                q16_b = sharding.gather_query_block(q16_b, nb, group)
+                q16_b = q32_b.to(torch.float16)
             pid_b = pid_b.to(torch.int64)
             ex_b = ex_b.to(torch.int32) if ex_b is not None else None
+            _pos_stage(shard, S, sl, q32_b, pid_b, ex_b, E, group=group, world=world)
         else:
             q32_b, q16_b = q_f32[sl], (q_f16[sl] if q_f16 is not None else None)
             pid_b, ex_b = q_pid[sl], (excl[sl] if excl is not None else None)
-        _rank_block(shard, q32_b, q16_b, pid_b, ex_b, E, pos_above[sl], n_pos[sl], top_score[sl], top_idx[sl], flag[sl],
-                    bound[sl], lb0[sl], t0[sl], fused=use_fused, eps=eps, cand_cap=cand_cap, group=group, world=world,
+        _scan_stage(shard, S, sl, q32_b, q16_b, ex_b, E, fused=use_fused, cand_cap=cand_cap, world=world,
                     exact_ap=exact_ap, n_slots=n_slots)
-        if use_fused:
-            if host_queries is not None:                         # (the staging set is overwritten two blocks later)
-                pid_b, ex_b = pid_b.clone(), (ex_b.clone() if ex_b is not None else None)
-            kept.append((q32_b, pid_b, ex_b))
         if host_queries is not None:
+            # (the staging set is overwritten two blocks later)
+            kept.append((q32_b, pid_b.clone(), ex_b.clone() if ex_b is not None else None))
             done_ev[bi] = torch.cuda.Event(); done_ev[bi].record()
+        else:
+            kept.append((q32_b, pid_b, ex_b))
 
-    eps_check = float(eps) if use_fused else 0.0
+    # the completeness cut-offs of all blocks are exchanged together, then every shard re-scores what can still reach the head
+    if world > 1:
+        sharding.exchange_bound(S.bound, group)                     # the best shard's kx-th best approximate score
+    eps_rs = float(eps) if use_fused else 0.0
+    for (b0, b1), k in zip(blocks, kept):
+        _rescore_stage(shard, S, slice(b0, b1), k[0], eps=eps_rs)
+    t0 = S.pos_thr[:, 0].contiguous()                               # best positive's exact score
+
+    eps_check = eps_rs
 
     def finish():
         """Exchange over the shards, decidability check, metrics; -> (pos_above gallery-wide, top lists, metrics incl. flag count)."""
-        pa, aux = pos_above, torch.stack([lb0, flag], dim=1)
+        cnt = S.counts
         if world > 1:
-            pa = sharding.exchange_counts(pos_above.clone(), group)         # counts are additive over shards
-            sharding.exchange_counts(aux, group)                            # re-scored rows above the best positive; overflows
+            cnt = sharding.exchange_counts(S.counts.clone(), group)         # counts are additive over shards (one all-reduce)
             # the global top-k is contained in the union of the shards' (exactly ordered) top-k lists
-            all_s, all_i = sharding.gather_top_lists(top_score[:, :topk].contiguous(), top_idx[:, :topk].contiguous(), group)
+            all_s, all_i = sharding.gather_top_lists(S.top_score[:, :topk], S.top_idx[:, :topk], group)
             out_s = torch.empty(Q, topk, dtype=torch.float32, device=dev)
             out_i = torch.empty(Q, topk, dtype=torch.int32, device=dev)
             check(L.reid_merge_topk(ptr(all_s), ptr(all_i), world, Q, topk, topk, ptr(out_s), ptr(out_i), st), "reid_merge_topk")
         else:
-            out_s, out_i = top_score[:, :topk].contiguous(), top_idx[:, :topk].contiguous()   # one shard: already ordered
-        lb0_g, fl_g = aux[:, 0].contiguous(), aux[:, 1].contiguous()
+            out_s, out_i = S.top_score[:, :topk].contiguous(), S.top_idx[:, :topk].contiguous()   # one shard: already ordered
+        pa = cnt[:Q * Pmax].view(Q, Pmax)
+        lb0_g, fl_g = cnt[Q * Pmax:Q * (Pmax + 1)], cnt[Q * (Pmax + 1):]
+        if world == 1:
+            fl_g = fl_g.clone()                                             # (topk_check adds its bits; S.flag keeps the overflow bit)
         # every rank holds the same gallery-wide data here, so every rank derives the same flags
-        check(L.reid_topk_check(ptr(out_s), topk, topk, ptr(bound), eps_check, ptr(t0), ptr(n_pos), 1, ptr(lb0_g), Q,
+        check(L.reid_topk_check(ptr(out_s), topk, topk, ptr(S.bound), eps_check, ptr(t0), ptr(S.n_pos), 1, ptr(lb0_g), Q,
                                 ptr(fl_g), st), "reid_topk_check")
         out = torch.empty(6, dtype=torch.float64, device=dev)
         ap = torch.empty(Q, dtype=torch.float64, device=dev) if want_ap else None
-        check(L.reid_metrics_reduce(ptr(pa), ptr(n_pos), Q, Pmax, ptr(out), ptr(ap), st), "reid_metrics_reduce")
+        check(L.reid_metrics_reduce(ptr(pa), ptr(S.n_pos), Q, Pmax, ptr(out), ptr(ap), st), "reid_metrics_reduce")
         out[5] = torch.count_nonzero(fl_g)
         return pa, out_s, out_i, ap, fl_g, out.cpu().tolist()               # the step's result: D2H read
 
@@ -407,20 +447,16 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
         pid_s = torch.cat([k[1] for k in kept])[sel].contiguous()
         ex_s = torch.cat([k[2] for k in kept])[sel].contiguous() if E else None
         ns = int(sel.numel())
-        pa_s = torch.zeros(ns, Pmax, dtype=torch.int32, device=dev)
-        np_s = torch.empty(ns, dtype=torch.int32, device=dev)
-        ts_s = torch.empty(ns, _cabi.RTOP, dtype=torch.float32, device=dev)
-        ti_s = torch.empty(ns, _cabi.RTOP, dtype=torch.int32, device=dev)
-        fl_s = torch.zeros(ns, dtype=torch.int32, device=dev)
-        bd_s = torch.empty(ns, dtype=torch.float32, device=dev)
-        lb_s = torch.zeros(ns, dtype=torch.int32, device=dev)
-        t0_s = torch.empty(ns, dtype=torch.float32, device=dev)
-        _rank_block(shard, q32_s, None, pid_s, ex_s, E, pa_s, np_s, ts_s, ti_s, fl_s, bd_s, lb_s, t0_s, fused=False, eps=0.0,
-                    cand_cap=cand_cap, group=group, world=world, exact_ap=True)
-        pos_above[sel] = pa_s; n_pos[sel] = np_s; top_score[sel] = ts_s; top_idx[sel] = ti_s
-        lb0[sel] = lb_s; t0[sel] = t0_s
-        bound[sel] = float("-inf")                 # ranked in fp32: exact by construction, nothing left to decide
-        flag.zero_()
+        X = _RankState(ns, Pmax, dev)
+        _pos_stage(shard, X, slice(0, ns), q32_s, pid_s, ex_s, E, group=group, world=world)
+        _scan_stage(shard, X, slice(0, ns), q32_s, None, ex_s, E, fused=False, cand_cap=cand_cap, world=world, exact_ap=True)
+        if world > 1:
+            sharding.exchange_bound(X.bound, group)
+        _rescore_stage(shard, X, slice(0, ns), q32_s, eps=0.0)
+        S.pos_above[sel] = X.pos_above; S.n_pos[sel] = X.n_pos; S.top_score[sel] = X.top_score; S.top_idx[sel] = X.top_idx
+        S.lb0[sel] = X.lb0; t0[sel] = X.pos_thr[:, 0]
+        S.bound[sel] = float("-inf")                 # ranked in fp32: exact by construction, nothing left to decide
+        S.flag.zero_()
         pa, out_s, out_i, ap, fl_g, m = finish()
     metrics = {"mAP": m[0], "R@1": m[1], "R@5": m[2], "R@10": m[3], "num_queries": int(round(m[4]))}
-    return RetrievalResult(metrics, out_i, out_s, ap, n_flagged, pa, n_pos, "fused" if use_fused else "exact")
+    return RetrievalResult(metrics, out_i, out_s, ap, n_flagged, pa, S.n_pos, "fused" if use_fused else "exact")

@@ -1,13 +1,14 @@
 """Gallery sharding across ranks (one process per GPU) and the exchange steps of the path.
 
 The reference has no distributed code; this is the B200 design of section 8e:
-queries replicated, gallery rows partitioned contiguously, three small collectives per batch:
+queries replicated, gallery rows partitioned contiguously, FOUR collectives per call of engine.retrieve (each over the
+whole query batch, not per query block):
   1. all_reduce(MAX) of the positives' exact scores   (owner rank holds the score, others -inf)
-  2. all_reduce(SUM) of the per-positive "rows ranked above" counts (additive over shards)
-  3. all_gather of the per-shard exact top lists, merged per query;
-  4. all_reduce(MAX) of the per-shard completeness cut-off of the re-scored head (before re-scoring: every shard then
-     re-scores only the rows that can still reach the gallery-wide head) and all_reduce(SUM) of two small per-query
-     counters (re-scored rows above the best positive, candidate-buffer overflows) for the decidability check.
+  2. all_reduce(MAX) of the per-shard completeness cut-off of the re-scored head (before re-scoring: every shard then
+     re-scores only the rows that can still reach the gallery-wide head)
+  3. all_reduce(SUM) of one flat counter buffer: the per-positive "rows ranked above" counts (additive over shards) and
+     two per-query counters (re-scored rows above the best positive, candidate-buffer overflows) for the decidability check
+  4. all_gather of the per-shard exact top lists (scores + indices in one buffer), merged per query.
 With HOST-resident query features a fourth step precedes them: every rank uploads and fuses only its
 1/world slice of a query block and `gather_query_block` assembles the fused block on every rank over
 NVLink (all_gather), so the PCIe upload of a block is paid once per box instead of once per GPU.
@@ -49,19 +50,21 @@ def exchange_bound(cut: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def gather_top_lists(top_score: torch.Tensor, top_idx: torch.Tensor, group=None):
-    """-> ([world, Q, R] scores, [world, Q, R] global indices)."""
+    """-> ([world, Q, R] scores, [world, Q, R] global indices).  ONE all_gather: scores (as their bit patterns) and indices
+    travel in the same [Q, 2, R] 32-bit buffer."""
     import torch.distributed as dist
     if not (group is not None or dist.is_initialized()):
-        return top_score[None], top_idx[None]
+        return top_score.contiguous()[None], top_idx.contiguous()[None]
     world = dist.get_world_size(group)
-    Q = top_score.shape[0]
-    rest = tuple(top_score.shape[1:])
-    # concatenated along dim 0 (the layout both NCCL and gloo accept), viewed as [world, Q, R]
-    all_s = torch.empty((world * Q,) + rest, dtype=top_score.dtype, device=top_score.device)
-    all_i = torch.empty((world * Q,) + rest, dtype=top_idx.dtype, device=top_idx.device)
-    dist.all_gather_into_tensor(all_s, top_score.contiguous(), group=group)
-    dist.all_gather_into_tensor(all_i, top_idx.contiguous(), group=group)
-    return all_s.view((world, Q) + rest), all_i.view((world, Q) + rest)
+    Q, R = top_score.shape
+    pack = torch.empty(Q, 2, R, dtype=torch.int32, device=top_score.device)
+    pack[:, 0].copy_(top_score.contiguous().view(torch.int32))
+    pack[:, 1].copy_(top_idx)
+    # concatenated along dim 0 (the layout both NCCL and gloo accept), viewed as [world, Q, 2, R]
+    both = torch.empty(world * Q, 2, R, dtype=torch.int32, device=top_score.device)
+    dist.all_gather_into_tensor(both, pack, group=group)
+    both = both.view(world, Q, 2, R)
+    return both[:, :, 0].contiguous().view(torch.float32), both[:, :, 1].contiguous()
 
 
 def block_slice(n: int, rank: int, world: int) -> Tuple[int, int, int]:
