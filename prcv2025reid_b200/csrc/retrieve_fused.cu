@@ -313,30 +313,45 @@ __device__ __noinline__ void epi_flush_hist(EpiAddr A, const Params* pp, int et,
 // calibration: hist holds bucket counts over the CALIB_ROWS calibration rows (zeroed here for the main pass).
 // Threshold j is counted exactly while the estimated in-chunk rank of thresholds 0..j stays <= limit1, on the
 // level-1 sample while it stays <= limit2, else on the level-2 sample.
-__global__ void calib_split_kernel(int32_t* __restrict__ hist, const int32_t* __restrict__ n_pos, int64_t Q, int Pmax,
-                                   float scale, float limit1, float limit2, int32_t* __restrict__ n_exact,
-                                   int32_t* __restrict__ n_l1, const float* __restrict__ pos_thr, int pos_stride, int klist,
-                                   uint32_t* __restrict__ thr_share) {
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
+// One warp per query (Pmax <= 64: two buckets per lane, warp-wide inclusive scan), coalesced over the histogram rows.
+__global__ void __launch_bounds__(256)
+calib_split_kernel(int32_t* __restrict__ hist, const int32_t* __restrict__ n_pos, int64_t Q, int Pmax,
+                   float scale, float limit1, float limit2, int32_t* __restrict__ n_exact,
+                   int32_t* __restrict__ n_l1, const float* __restrict__ pos_thr, int pos_stride, int klist,
+                   uint32_t* __restrict__ thr_share) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t q = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); q < Q; q += warps) {
     const int np = min(n_pos[q], Pmax);
-    int acc = 0, ne = 0, n1 = 0, seed = -1;
-    bool open1 = true, open2 = true;
-    for (int j = 0; j < Pmax; ++j) {
-      acc += hist[q * Pmax + j];
-      hist[q * Pmax + j] = 0;
-      if (j < np) {
-        const float est = (float)acc * scale;
-        if (open1) { if (est <= limit1) ne = j + 1; else open1 = false; }
-        if (open2) { if (est <= limit2) n1 = j + 1; else open2 = false; }
-        if (seed < 0 && acc >= klist) seed = j;
-      }
+    int32_t* h = hist + q * Pmax;
+    const int j0 = lane, j1 = lane + 32;
+    const int h0 = j0 < Pmax ? h[j0] : 0, h1 = j1 < Pmax ? h[j1] : 0;
+    if (j0 < Pmax) h[j0] = 0;
+    if (j1 < Pmax) h[j1] = 0;
+    int a0 = h0, a1 = h1;                                    // inclusive prefix sums over buckets 0..31 and 32..63
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u0 = __shfl_up_sync(0xffffffffu, a0, o), u1 = __shfl_up_sync(0xffffffffu, a1, o);
+      if (lane >= o) { a0 += u0; a1 += u1; }
     }
-    n_exact[q] = ne;
-    n_l1[q] = max(n1, ne);
-    // seed of the candidate threshold: the sample rows are shard rows, so the shallowest positive threshold with >= klist
-    // sample rows (valid, non-positive) strictly above it has >= klist shard rows above it -- the main pass appends exactly
-    // the rows above it and skips the cold start (-inf: every row of the first tiles)
-    if (thr_share && seed >= 0) thr_share[q] = key32(pos_thr[q * (int64_t)pos_stride + seed]);
+    a1 += __shfl_sync(0xffffffffu, a0, 31);
+    // first bucket (in order) whose estimate passes a limit / reaches klist rows: 64-bit ballots, lowest set bit
+    auto first = [&](bool c0, bool c1) -> int {
+      const unsigned b0 = __ballot_sync(0xffffffffu, c0 && j0 < np), b1 = __ballot_sync(0xffffffffu, c1 && j1 < np);
+      return b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : -1);
+    };
+    const int f1 = first((float)a0 * scale > limit1, (float)a1 * scale > limit1);
+    const int f2 = first((float)a0 * scale > limit2, (float)a1 * scale > limit2);
+    const int seed = first(a0 >= klist, a1 >= klist);
+    if (lane == 0) {
+      const int ne = f1 < 0 ? np : f1, n1 = f2 < 0 ? np : f2;
+      n_exact[q] = ne;
+      n_l1[q] = max(n1, ne);
+      // seed of the candidate threshold: the sample rows are shard rows, so the shallowest positive threshold with >= klist
+      // sample rows (valid, non-positive) strictly above it has >= klist shard rows above it -- the main pass appends exactly
+      // the rows above it and skips the cold start (-inf: every row of the first tiles)
+      if (thr_share && seed >= 0) thr_share[q] = key32(pos_thr[q * (int64_t)pos_stride + seed]);
+    }
   }
 }
 __global__ void fill_n_exact_kernel(const int32_t* __restrict__ n_pos, int64_t Q, int Pmax, int32_t* __restrict__ n_exact,
@@ -915,7 +930,7 @@ extern "C" int reid_retrieve_fused(const void* q_f16, const void* g_f16, const i
     c.calib_floor = 32;
     c.calib_rate = (float)c.calib_cap / (float)calib_rows;
     if (!launch(tmS, c)) return REID_E_CUDA;
-    calib_split_kernel<<<aux_grid, 256, 0, st>>>(p.hist, n_pos, Q, Pmax, scale, limit1, limit2, p.n_exact, p.n_l1, pos_thr,
+    calib_split_kernel<<<(int)reid_min64((Q + 7) / 8, 148 * 16), 256, 0, st>>>(p.hist, n_pos, Q, Pmax, scale, limit1, limit2, p.n_exact, p.n_l1, pos_thr,
                                                  pos_stride, p.klist, no_cand ? nullptr : p.thr_share);
   } else {
     fill_n_exact_kernel<<<aux_grid, 256, 0, st>>>(n_pos, Q, Pmax, p.n_exact, p.n_l1);

@@ -76,9 +76,60 @@ constexpr int PREP_ROWS = REID_PREP_ROWS;   // rows per CTA (8-row K chunks of t
 
 constexpr int PREP_THREADS = 256;
 
+// dense form: y [N][M] fp32 -> positive masks as bit rows, ybits [N][16 words] (bit c of row i: y[i][c] > 0) and
+// ybitsT [M][16 words] (bit r of row j: y[r][j] > 0), with coalesced 128-byte loads and one ballot / one bit per load.
+// Runs as the third y-slice of the prep grid, next to the normalisation CTAs (the forward used to form the masks
+// itself, one row per thread: 12 us on its critical path at N = M = 512).
+__device__ void prep_mask_bits(const reid_sdm_pair& P, int d) {
+  const int N = P.N, M = P.M;
+  const TcLayout L = tc_layout(N, M, d);
+  uint8_t* bytes = reinterpret_cast<uint8_t*>(tc_base(P.saved));
+  uint32_t* ybits = reinterpret_cast<uint32_t*>(bytes + L.ybits);
+  uint32_t* ybitsT = reinterpret_cast<uint32_t*>(bytes + L.ybitsT);
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (PREP_THREADS / 32) + (threadIdx.x >> 5);
+  const int nw = gridDim.x * (PREP_THREADS / 32);
+  const int wm = (M + 31) >> 5, wn = (N + 31) >> 5;                  // words per bit row (<= 16)
+  for (int r = wid; r < N; r += nw) {                                // ybits: one warp per row of y
+    const float* yr = P.y + (size_t)r * M;
+    float v[16];
+#pragma unroll
+    for (int w = 0; w < 16; ++w) v[w] = (w < wm && 32 * w + lane < M) ? yr[32 * w + lane] : 0.f;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      const uint32_t b = __ballot_sync(0xffffffffu, v[w] > 0.f);
+      if (lane == w) mine = b;
+    }
+    if (lane < 16) ybits[(size_t)r * 16 + lane] = mine;
+  }
+  for (int task = wid; task < wm * wn; task += nw) {                 // ybitsT: one warp per (32 columns, 32 rows) block
+    const int cg = task / wn, w = task % wn;
+    const int col = 32 * cg + lane;
+    uint32_t word = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                                     // 16 loads in flight at a time
+      float v[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int r = 32 * w + 16 * h + e;
+        v[e] = (r < N && col < M) ? P.y[(size_t)r * M + col] : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) word |= (v[e] > 0.f ? 1u : 0u) << (16 * h + e);
+    }
+    if (col < M) ybitsT[(size_t)col * 16 + w] = word;
+  }
+  // (words beyond wn / wm of a bit row are never read: the forward masks with the validity words, zero there)
+}
+
 __global__ void __launch_bounds__(PREP_THREADS, 5)
 tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
   const reid_sdm_pair& P = batch.p[blockIdx.z];
+  if (blockIdx.y == 2) {                             // mask slice of the grid (dense form only)
+    if (P.y) prep_mask_bits(P, d);
+    return;
+  }
   const int which = blockIdx.y;                      // 0 = qry, 1 = gal
   const int R = which ? P.M : P.N;
   const int Rp = round_up(R, 128);
@@ -347,20 +398,9 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
             const int64_t rl = (side ? P.col_label : P.row_label)[i];
 #pragma unroll 8
             for (int e = 0; e < 32; ++e) mb[w] |= (cw + e < c_end && s_collab[cw + e] == rl ? 1u : 0u) << e;
-          } else if (side == 0) {
-            const float* yp = P.y + (size_t)i * M + cw;
-            float4 t[8];
-#pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) t[e4] = (cw + 4 * e4 < c_end) ? *reinterpret_cast<const float4*>(yp + 4 * e4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4)
-              mb[w] |= ((t[e4].x > 0.f ? 1u : 0u) | (t[e4].y > 0.f ? 2u : 0u) | (t[e4].z > 0.f ? 4u : 0u) | (t[e4].w > 0.f ? 8u : 0u)) << (4 * e4);
           } else {
-            float t[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) t[e] = (cw + e < c_end) ? P.y[(size_t)(cw + e) * M + i] : 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mb[w] |= (t[e] > 0.f ? 1u : 0u) << e;
+            // dense form: the bit rows were formed by the prep launch (prep_mask_bits)
+            mb[w] = __ldcg(reinterpret_cast<const uint32_t*>(bytes + (side ? L.ybitsT : L.ybits)) + (size_t)i * 16 + (cw >> 5));
           }
           mb[w] &= vb[w];
           reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(bytes) + (side ? L.ybitsT : L.ybits))[(size_t)i * 16 + (cw >> 5)] = mb[w];
@@ -504,9 +544,12 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
 }
 
 // =============================================================================================== backward
-constexpr int BWD_PROD_WARPS = 8;
+constexpr int BWD_PROD_WARPS = 16;      // (8 left the dS loop latency-bound: two warps per scheduler)
 constexpr int BWD_PROD_THREADS = BWD_PROD_WARPS * 32;
-constexpr int BWD_THREADS = 64 + BWD_PROD_THREADS;   // warp 0: bulk-copy producer, warp 1: MMA + TMEM, warps 2-9: dS producers, then epilogue
+constexpr int BWD_THREADS = 64 + BWD_PROD_THREADS;   // warp 0: bulk-copy producer, warp 1: MMA + TMEM, warps 2-17: dS producers, then epilogue
+constexpr int BWD_ROWS_PASS = BWD_PROD_THREADS / 8;  // tile rows covered by one pass of the producers (8 threads per row)
+constexpr int BWD_U = 128 / BWD_ROWS_PASS;           // passes per 128-row tile
+constexpr int BWD_PARTS = BWD_PROD_WARPS / 4;        // epilogue: threads per output row (a 1/BWD_PARTS slice of the columns each)
 constexpr int BWD_STAGE = 2 * A_TILE + B_TILE_MAX;   // dS hi, dS lo, transposed operand chunk (d rows x 64)
 constexpr int BWD_STAGES = 2;
 constexpr int BWDP_STAGE = 2 * A_TILE + 2 * A_TILE;  // pair mode: dS hi, dS lo, this CTA's half of the two 256-row chunks
@@ -681,11 +724,11 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
     const uint32_t* bitsv = reinterpret_cast<const uint32_t*>(bytes + (side ? L.ybitsT : L.ybits));
     const int ch = t & 7;                                    // 8 lanes cover 64 consecutive K indices of one row
     // global loads of one K block: 4 rows x 32 bytes of S + 4 mask words per thread
-    auto load_block = [&](int kb, float4 (&sa)[4], float4 (&sb)[4], uint32_t (&bw)[4]) {
+    auto load_block = [&](int kb, float4 (&sa)[BWD_U], float4 (&sb)[BWD_U], uint32_t (&bw)[BWD_U]) {
       const int k0 = kb * 64 + ch * 8;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int gr = row0 + (t >> 3) + 32 * u;
+      for (int u = 0; u < BWD_U; ++u) {
+        const int gr = row0 + (t >> 3) + BWD_ROWS_PASS * u;
         sa[u] = sb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         bw[u] = 0;
         if (gr < R && k0 < K) {
@@ -695,15 +738,15 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
         }
       }
     };
-    float4 sa[4], sb[4];
-    uint32_t bw[4];
+    float4 sa[BWD_U], sb[BWD_U];
+    uint32_t bw[BWD_U];
     load_block(0, sa, sb, bw);
 #pragma unroll 1
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % STAGES;
       const int k0 = kb * 64 + ch * 8;
-      float4 na[4], nb[4];
-      uint32_t nw[4];
+      float4 na[BWD_U], nb[BWD_U];
+      uint32_t nw[BWD_U];
       if (kb + 1 < KB) load_block(kb + 1, na, nb, nw);       // next block's loads fly while this one is formed
       float kl[8], kw[8], kic[8];
       uint32_t kvm = 0;                                        // K indices of this thread that take part
@@ -713,8 +756,8 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       uint8_t* Ahi = smem + s * STAGE;
       uint8_t* Alo = Ahi + A_TILE;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int row = (t >> 3) + 32 * u;
+      for (int u = 0; u < BWD_U; ++u) {
+        const int row = (t >> 3) + BWD_ROWS_PASS * u;
         const bool in = row0 + row < R && k0 < K && RV[row] != 0.f;   // (rows that take no part: dS = 0)
         const float rl = RL[row], rw = RW[row], ric = RIC[row];
         const float sv[8] = {sa[u].x, sa[u].y, sa[u].z, sa[u].w, sb[u].x, sb[u].y, sb[u].z, sb[u].w};
@@ -736,12 +779,12 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       __syncwarp();
       if (lane == 0) { if (PAIR && !leader) tc::mbar_arrive_remote_release(&afull[s], 0); else tc::mbar_arrive(&afull[s]); }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { sa[u] = na[u]; sb[u] = nb[u]; bw[u] = nw[u]; }
+      for (int u = 0; u < BWD_U; ++u) { sa[u] = na[u]; sb[u] = nb[u]; bw[u] = nw[u]; }
     }
     BSTAMP(stamp && t == 0, 2);                           // all dS tiles formed
-    // ---------------------------------------------------------------- epilogue: two threads per output row (half the columns each)
+    // ---------------------------------------------------------------- epilogue: BWD_PARTS threads per output row (a slice of the columns each)
     if (active) {
-      const int quad = warp & 3, half = (warp - 2) >> 2;
+      const int quad = warp & 3, half = (warp - 2) >> 2;      // (half: index of this thread's column slice)
       const int row = quad * 32 + lane, gi = row0 + row;
       const bool live = gi < R;
       const int gl = live ? gi : row0;
@@ -749,9 +792,9 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       const float den = (base + (side ? L.den_g : L.den_q))[gl];
       const float rden = 1.f / den;
       const bool clamped = !(den > bf16r(eps));          // norm <= eps: the denominator is the constant eps
-      const int dh = d >> 1;
+      const int dh = d / BWD_PARTS;                      // (d % 64 == 0: a multiple of 16)
       const int c_begin = half * dh, c_end = c_begin + dh;
-      float* pdot = RL;                                  // the row statistics are dead now: reuse as [2][128] partial dots
+      float* pdot = RL;                                  // the row statistics RL / RW / RIC / RV are dead now: reuse as [BWD_PARTS][128] partial dots
       tc::mbar_wait(&accfull, 0);                        // every MMA has retired: the stage buffers are free
       tc::fence_after_sync();
       BSTAMP(stamp && t == 0, 3);                     // accumulator complete
@@ -789,7 +832,10 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       BSTAMP(stamp && t == 0, 5);                     // pass 1 (row dots) done
       pdot[half * 128 + row] = dot + dot2;
       named_bar(1, BWD_PROD_THREADS);
-      dot = clamped ? 0.f : (pdot[row] + pdot[128 + row]);
+      dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < BWD_PARTS; ++q) dot += pdot[q * 128 + row];
+      if (clamped) dot = 0.f;
       // the gradient rows leave through a per-warp staging tile (free ring space above the x^ tile): a thread owns a
       // row, so direct stores would write 32 bytes to each of 32 rows per step; staged, every store instruction writes
       // 128 contiguous bytes of four rows (d/2 is a multiple of 32: groups of 64 columns, the last may hold 32)
@@ -899,7 +945,7 @@ int tc_forward(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float 
     attr_done = true;
   }
   const size_t prep_smem = (size_t)PREP_ROWS * (d + 8) * 2;
-  tc_prep_kernel<<<dim3(mb * 128 / PREP_ROWS, 2, n_pairs), PREP_THREADS, prep_smem, st>>>(b, d, eps);
+  tc_prep_kernel<<<dim3(mb * 128 / PREP_ROWS, 3, n_pairs), PREP_THREADS, prep_smem, st>>>(b, d, eps);
   REID_CHECK_LAUNCH();
   // -DREID_SDM_PAIR=1 selects the cta_group::2 pair kernels.  They are parity-tested but NOT the default: measured on
   // C5 (10 pairs) the step takes 90 us against 78 us with the single-CTA kernels -- the six to eight 4-8 KB tensor-map
