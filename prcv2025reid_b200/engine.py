@@ -150,6 +150,28 @@ def default_query_block(sms: int) -> int:
     return 2 * max(1, sms // 2) * WAVE_QUERIES
 
 
+def host_query_blocks(Q: int, sms: int):
+    """Query blocks [(start, end)] for HOST-resident queries.  The upload of a block overlaps the kernels of the block
+    before it, but nothing hides the upload of the FIRST block: it is kept small (16 work items' worth of queries, run as
+    a chunked partial wave), the second block is one wave -- its upload (8 KB per query over PCIe) is shorter than the
+    first block's gallery pass --, the rest are the usual two waves; a short tail joins the last block."""
+    wave = max(1, sms // 2) * WAVE_QUERIES
+    big = 2 * wave
+    sizes, left = [], Q
+    for n in (16 * WAVE_QUERIES, wave):
+        if left > 0:
+            sizes.append(min(left, n)); left -= sizes[-1]
+    while left > 0:
+        n = min(left, big)
+        if 0 < left - n < big // 4:
+            n = left                                        # (a tail shorter than half a wave is not worth a block of its own)
+        sizes.append(n); left -= n
+    out, b0 = [], 0
+    for n in sizes:
+        out.append((b0, b0 + n)); b0 += n
+    return out
+
+
 @dataclass
 class RetrievalResult:
     metrics: Dict[str, float]
@@ -317,6 +339,7 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
     E = 0 if excl is None or excl.numel() == 0 else excl.shape[1]
     if E == 0:
         excl = None
+    ramp = query_block is None and host_queries is not None
     if query_block is None:
         query_block = default_query_block(sms)
 
@@ -324,7 +347,7 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
     use_fused = (mode == "fused" and Pmax <= 2048 and d % 64 == 0 and d <= 512 and shard.G_local <= (1 << 22)
                  and (host_queries is not None or q_f16 is not None))
 
-    blocks = [(b0, min(Q, b0 + query_block)) for b0 in range(0, Q, query_block)]
+    blocks = host_query_blocks(Q, sms) if ramp else [(b0, min(Q, b0 + query_block)) for b0 in range(0, Q, query_block)]
     staged = {}
     kept = []                                 # (q32, pid, excl) of every block: the re-scorer and the exact re-run read them
     if host_queries is not None:

@@ -200,3 +200,22 @@ def test_train_eval_dropins_host_logic(monkeypatch):
     wm, wt1 = orc.reid_map_oracle(qn @ gn.T, ql, gl)
     assert m == pytest.approx(wm, abs=1e-4) and t1 == pytest.approx(wt1, abs=1e-12)
     assert te.compute_map(qf[:0], gf, ql[:0], gl) == 0.0 and te.reid_map(qn[:0], gn, ql[:0], gl) == (0.0, 0.0)
+
+
+def test_host_query_blocks_partition():
+    """The ramped block schedule of host-resident queries: a partition of [0, Q) in order, a small first block, one wave,
+    then two-wave blocks, no short tail block."""
+    from prcv2025reid_b200 import engine
+    for sms in (148, 132, 2):
+        wave = max(1, sms // 2) * engine.WAVE_QUERIES
+        for Q in (1, 255, 4096, 4097, 20000, 37888, 100000, 250001):
+            bl = engine.host_query_blocks(Q, sms)
+            assert bl[0][0] == 0 and bl[-1][1] == Q and all(a[1] == b[0] for a, b in zip(bl, bl[1:]))
+            sizes = [b - a for a, b in bl]
+            assert all(n > 0 for n in sizes) and sizes[0] == min(Q, 16 * engine.WAVE_QUERIES)
+            if len(sizes) > 1:
+                assert sizes[1] == min(Q - sizes[0], wave)
+            assert all(n <= 2 * wave + 2 * wave // 4 for n in sizes[2:])
+            if len(sizes) > 3:
+                assert sizes[-1] >= 2 * wave // 4
+    assert engine.host_query_blocks(100000, 148) == [(0, 4096), (4096, 23040), (23040, 60928), (60928, 100000)]
