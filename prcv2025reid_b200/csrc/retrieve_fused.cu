@@ -756,32 +756,39 @@ retrieve_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
 #endif
           }
         }
-        if (p.calib && lane < UPD_PER_WARP) {
-          // calibration: a threshold whose ESTIMATED in-shard rank (sample rows above it so far, scaled by the part of the
-          // sample seen) has passed the level-2 limit is retired on the spot -- never on fewer than calib_floor rows, so a
-          // retired threshold also has >= klist shard rows above it (the seed of the candidate threshold).  Retiring stops
-          // the rows between the deep thresholds from being hits at all (most sample rows score above a query's DEEPEST
-          // positives).  The bucket of the shallowest retired threshold receives calib_cap extra counts: calib_split then
-          // sees every retired threshold beyond the level-2 limit.
-          const int uq = ew * UPD_PER_WARP + lane;
-          const uint32_t cn = es->s_cnts[uq];
-          const int np = cn & 255;
-          const int seen = min((t + 1) * TROWS, (int)p.G_local);            // (the sample has <= CALIB_ROWS rows)
-          const int cap = max(p.calib_floor, (int)(p.calib_rate * (float)seen));
-          int acc = 0, na = np;
+        if (p.calib) {
+          // (deterministic classes: every hit of this tile is counted, by all warps, before the owners look at the counts, and
+          //  every warp sees the retired state before it scans the next tile -- two barriers per tile, calibration only)
+          while (qn > 0) { const int n = qn < 32 ? qn : 32; qn -= n; epi_drain32(A, &p, ew, qn, n, lane, q0, chunk); }
+          epi_bar();
+          if (lane < UPD_PER_WARP) {
+            // calibration: a threshold whose ESTIMATED in-shard rank (sample rows above it so far, scaled by the part of the
+            // sample seen) has passed the level-2 limit is retired on the spot -- never on fewer than calib_floor rows, so a
+            // retired threshold also has >= klist shard rows above it (the seed of the candidate threshold).  Retiring stops
+            // the rows between the deep thresholds from being hits at all (most sample rows score above a query's DEEPEST
+            // positives).  The bucket of the shallowest retired threshold receives calib_cap extra counts: calib_split then
+            // sees every retired threshold beyond the level-2 limit.
+            const int uq = ew * UPD_PER_WARP + lane;
+            const uint32_t cn = es->s_cnts[uq];
+            const int np = cn & 255;
+            const int seen = min((t + 1) * TROWS, (int)p.G_local);            // (the sample has <= CALIB_ROWS rows)
+            const int cap = max(p.calib_floor, (int)(p.calib_rate * (float)seen));
+            int acc = 0, na = np;
 #pragma unroll 1
-          for (int j = 0; j < np; ++j) {
-            const uint32_t w = s_hist32[(uq * p.pcap + j) >> 1];
-            acc += (j & 1) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
-            if (acc >= cap) { na = j; break; }
+            for (int j = 0; j < np; ++j) {
+              const uint32_t w = s_hist32[(uq * p.pcap + j) >> 1];
+              acc += (j & 1) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
+              if (acc >= cap) { na = j; break; }
+            }
+            if (na < np) {
+              es->s_cnts[uq] = (cn & 0xFF000000u) | (uint32_t)na | ((uint32_t)na << 8) | ((uint32_t)na << 16);
+              const float tl = na > 0 ? s_thr[uq * p.pcap + na - 1] : INFINITY;
+              es->s_threx[uq] = tl; es->s_thrl1[uq] = tl; es->s_thrlow[uq] = tl;
+              es->s_min[uq] = tl; es->s_minS1[uq] = tl; es->s_minS2[uq] = tl;
+              reds_add(A.hist + (uint32_t)((uq * p.pcap + na) >> 1) * 4u, (uint32_t)p.calib_cap << ((na & 1) * 16));
+            }
           }
-          if (na < np) {
-            es->s_cnts[uq] = (cn & 0xFF000000u) | (uint32_t)na | ((uint32_t)na << 8) | ((uint32_t)na << 16);
-            const float tl = na > 0 ? s_thr[uq * p.pcap + na - 1] : INFINITY;
-            es->s_threx[uq] = tl; es->s_thrl1[uq] = tl; es->s_thrlow[uq] = tl;
-            es->s_min[uq] = tl; es->s_minS1[uq] = tl; es->s_minS2[uq] = tl;
-            reds_add(A.hist + (uint32_t)((uq * p.pcap + na) >> 1) * 4u, (uint32_t)p.calib_cap << ((na & 1) * 16));
-          }
+          epi_bar();
         }
         if (((t + 1) % FLUSH_TILES) == 0) epi_flush_hist(A, &p, et, q0);
 #if REID_DEBUG & 8192

@@ -34,6 +34,20 @@
 #define REID_SDM_PAIR 0
 #endif
 
+// -DREID_SDM_DS_F16=0 keeps dL/dS as two bf16 planes (hi + lo, 16 mantissa bits, two MMAs per K step) in the backward; the
+// default is ONE fp16 plane of dL/dS for grad_out = 1, scaled by 2^12 (|value| <= 8192; 11 mantissa bits, far inside the
+// bf16 rounding of the result).  kind::f16 wants A and B in the SAME 16-bit type (a mixed fp16 x bf16 descriptor is an
+// illegal instruction on sm_100a), so the prep kernel writes the TRANSPOSED operand images -- read by the backward only --
+// in fp16: the normalised bf16 values (8 mantissa bits, |x| <= 1) are exact in fp16 down to 2^-14 and lose at most 2^-25
+// absolutely below that.
+#ifndef REID_SDM_DS_F16
+#define REID_SDM_DS_F16 1
+#endif
+// -DREID_SDM_PDL=0 launches the three kernels of a step without programmatic dependent launch.
+#ifndef REID_SDM_PDL
+#define REID_SDM_PDL 1
+#endif
+
 namespace sdm {
 namespace {
 
@@ -125,6 +139,7 @@ __device__ void prep_mask_bits(const reid_sdm_pair& P, int d) {
 
 __global__ void __launch_bounds__(PREP_THREADS, 5)
 tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
+  tc::grid_launch_dependents();                      // the forward's CTAs may take their SMs as soon as every prep CTA runs
   const reid_sdm_pair& P = batch.p[blockIdx.z];
   if (blockIdx.y == 2) {                             // mask slice of the grid (dense form only)
     if (P.y) prep_mask_bits(P, d);
@@ -221,7 +236,10 @@ tc_prep_kernel(const __grid_constant__ Batch batch, int d, float eps) {
       uint4 o;
       bf16* ob = reinterpret_cast<bf16*>(&o);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) ob[e] = tile[(q * 8 + e) * ld + c];
+      for (int e = 0; e < 8; ++e) {
+        if (REID_SDM_DS_F16) reinterpret_cast<__half*>(ob)[e] = __float2half_rn(__bfloat162float(tile[(q * 8 + e) * ld + c]));
+        else ob[e] = tile[(q * 8 + e) * ld + c];
+      }
       const int k0 = r0 + q * 8;
       const int kb = k0 >> 6, ch = (k0 & 63) >> 3;
       *reinterpret_cast<uint4*>(imgT + (size_t)kb * ((size_t)d * 128) + (size_t)(c >> 3) * 1024 + (c & 7) * 128 +
@@ -303,6 +321,10 @@ tc_fwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
   const uint32_t tmem_base = tmem_base_s;
   const bool stamp = rb == 0 && side == 0;
   (void)stamp;
+  // programmatic dependent launch: everything above ran while the prep kernel was still finishing; the backward's CTAs
+  // may start their own prologue on the SMs this grid leaves free
+  tc::grid_launch_dependents();
+  tc::grid_dependency_wait();
   SDM_STAMP(stamp && threadIdx.x == 0, 0);                   // prologue done
 
   if (warp == 0 && lane == 0) {
@@ -581,14 +603,8 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
   const uint8_t* imgB = bytes + (side ? L.qnt : L.gnt);      // [d rows][K] transposed operand image
   const int* hdr_i = reinterpret_cast<const int*>(base + L.hdr);
   const float* hdr = base + L.hdr;
-  const int st = hdr_i[2];
   bf16* out = reinterpret_cast<bf16*>(side ? P.dgal : P.dqry);
   const int rows_here = !active ? 0 : (R - row0 < 128 ? R - row0 : 128);
-  if (st & 1) {      // the reference returned its non-differentiable zero: gradients are exact zeros
-    uint4* o = reinterpret_cast<uint4*>(out + (size_t)row0 * d);
-    for (int a = threadIdx.x; a < rows_here * d / 8; a += BWD_THREADS) o[a] = make_uint4(0, 0, 0, 0);
-    return;                                                  // (uniform over the pair: same status word)
-  }
   extern __shared__ uint8_t bwd_smem_raw[];
   uint8_t* smem = bwd_smem_raw + ((1024u - (tc::smem_u32(bwd_smem_raw) & 1023u)) & 1023u);
   float* KL = reinterpret_cast<float*>(smem + STAGES * STAGE);           // per K index: lse, weight, 1/count, takes part (1 / 0)
@@ -622,9 +638,16 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
 #else
 #define BSTAMP(cond, slot) do { } while (0)
 #endif
+  // programmatic dependent launch: the prologue above overlapped the forward's tail; nothing the forward writes (the
+  // status word included) is read before this point
+  tc::grid_dependency_wait();
+  const int st = __ldcg(&hdr_i[2]);
   BSTAMP(stamp && threadIdx.x == 64, 0);                     // prologue done
 
-  if (warp == 0 && lane == 0) {
+  if (st & 1) {      // the reference returned its non-differentiable zero: gradients are exact zeros (uniform over the pair)
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)row0 * d);
+    for (int a = threadIdx.x; a < rows_here * d / 8; a += BWD_THREADS) o[a] = make_uint4(0, 0, 0, 0);
+  } else if (warp == 0 && lane == 0) {
     if (PAIR) {
       const CUtensorMap* mapB = side ? &maps.qt[blockIdx.z] : &maps.gt[blockIdx.z];
       uint32_t tx = 0;                                        // bytes of BOTH CTAs per stage
@@ -666,14 +689,14 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
           const int n = d - n0 < 256 ? d - n0 : 256;
           if (PAIR) {
             const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * STAGE + 2 * A_TILE + c * A_TILE));
-            const uint32_t idesc = tc::make_idesc_f16(256, n, 1);
+            const uint32_t idesc = tc::make_idesc_f16(256, n, REID_SDM_DS_F16 ? 0 : 1);
             tc::mma_f16_ss_pair(tmem_base + n0, tc::advance_desc_k(ah, k), tc::advance_desc_k(bd, k), idesc, (kb | k) != 0);
-            tc::mma_f16_ss_pair(tmem_base + n0, tc::advance_desc_k(al, k), tc::advance_desc_k(bd, k), idesc, 1);
+            if (!REID_SDM_DS_F16) tc::mma_f16_ss_pair(tmem_base + n0, tc::advance_desc_k(al, k), tc::advance_desc_k(bd, k), idesc, 1);
           } else {
             const uint64_t bd = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * STAGE + 2 * A_TILE + n0 * 128));
-            const uint32_t idesc = tc::make_idesc_f16(128, n, 1);
+            const uint32_t idesc = tc::make_idesc_f16(128, n, REID_SDM_DS_F16 ? 0 : 1);
             tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(ah, k), tc::advance_desc_k(bd, k), idesc, (kb | k) != 0);
-            tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(al, k), tc::advance_desc_k(bd, k), idesc, 1);
+            if (!REID_SDM_DS_F16) tc::mma_f16_ss(tmem_base + n0, tc::advance_desc_k(al, k), tc::advance_desc_k(bd, k), idesc, 1);
           }
         }
       }
@@ -685,7 +708,11 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
     const int t = threadIdx.x - 64;                          // 0..255
     const float nR = hdr[0], nC = hdr[1];
     const float gscale = (*P.grad_out) * 0.5f / tau_eff;
-    const float wr = nR > 0.f ? gscale / nR : 0.f, wc = nC > 0.f ? gscale / nC : 0.f;
+    // fp16 plane: dL/dS is formed for grad_out = 1 and scaled by 2^12 (the operand then never leaves the fp16 range whatever
+    // the upstream gradient is); the epilogue multiplies the rows by gscale / 2^12
+    const float wscale = REID_SDM_DS_F16 ? 4096.f : gscale;
+    const float out_scale = REID_SDM_DS_F16 ? gscale * (1.f / 4096.f) : 1.f;
+    const float wr = nR > 0.f ? wscale / nR : 0.f, wc = nC > 0.f ? wscale / nC : 0.f;
     {
       const float* lse_k = base + (side ? L.lse_r : L.lse_c);
       const float* cnt_k = base + (side ? L.cnt_r : L.cnt_c);
@@ -768,12 +795,20 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
           const float pos = ((bw[u] >> e) & 1u) ? 1.f : 0.f;
           float g = rw * (fast_exp(sv[e] - rl) - pos * ric) + kw[e] * (fast_exp(sv[e] - kl[e]) - pos * kic[e]);
           if (!in || !((kvm >> e) & 1u) || sv[e] >= 20.f || sv[e] <= -20.f) g = 0.f;
-          hi[e] = bf16r(g);
+          hi[e] = REID_SDM_DS_F16 ? g : bf16r(g);
           lo[e] = g - hi[e];
         }
         const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(Ahi + off) = pack8(hi);
-        *reinterpret_cast<uint4*>(Alo + off) = pack8(lo);
+        if (REID_SDM_DS_F16) {
+          uint4 o;
+          __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) oh[e2] = __floats2half2_rn(hi[2 * e2], hi[2 * e2 + 1]);
+          *reinterpret_cast<uint4*>(Ahi + off) = o;
+        } else {
+          *reinterpret_cast<uint4*>(Ahi + off) = pack8(hi);
+          *reinterpret_cast<uint4*>(Alo + off) = pack8(lo);
+        }
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
@@ -790,7 +825,7 @@ tc_bwd_kernel(const __grid_constant__ Batch batch, const __grid_constant__ PairM
       const int gl = live ? gi : row0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
       const float den = (base + (side ? L.den_g : L.den_q))[gl];
-      const float rden = 1.f / den;
+      const float rden = out_scale / den;
       const bool clamped = !(den > bf16r(eps));          // norm <= eps: the denominator is the constant eps
       const int dh = d / BWD_PARTS;                      // (d % 64 == 0: a multiple of 16)
       const int c_begin = half * dh, c_end = c_begin + dh;
@@ -956,13 +991,22 @@ int tc_forward(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float 
     if (!fill_maps(maps, pairs, n_pairs, d, false)) return REID_E_CUDA;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((mb + 1) / 2 * 2, 2, n_pairs); cfg.blockDim = dim3(FWD_THREADS); cfg.dynamicSmemBytes = FWDP_SMEM; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = REID_SDM_PDL ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, tc_fwd_kernel<true>, b, maps, d, tau_eff) != cudaSuccess) return REID_E_CUDA;
   } else {
-    tc_fwd_kernel<false><<<dim3(mb, 2, n_pairs), FWD_THREADS, FWD_SMEM, st>>>(b, maps, d, tau_eff);
+    // programmatic dependent launch: the forward's CTAs start (barriers, TMEM) while the prep kernel drains
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(mb, 2, n_pairs); cfg.blockDim = dim3(FWD_THREADS); cfg.dynamicSmemBytes = FWD_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = REID_SDM_PDL ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, tc_fwd_kernel<false>, b, maps, d, tau_eff) != cudaSuccess) return REID_E_CUDA;
   }
   REID_CHECK_LAUNCH();
   return REID_OK;
@@ -986,13 +1030,23 @@ int tc_backward(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float
     if (!fill_maps(maps, pairs, n_pairs, d, true)) return REID_E_CUDA;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((mb + 1) / 2 * 2, 2, n_pairs); cfg.blockDim = dim3(BWD_THREADS); cfg.dynamicSmemBytes = BWDP_SMEM; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = REID_SDM_PDL ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, tc_bwd_kernel<true>, b, maps, d, tau_eff, eps) != cudaSuccess) return REID_E_CUDA;
   } else {
-    tc_bwd_kernel<false><<<dim3(mb, 2, n_pairs), BWD_THREADS, BWD_SMEM, st>>>(b, maps, d, tau_eff, eps);
+    // programmatic dependent launch: whatever kernel precedes this one on the stream (the forward, in a fused step),
+    // the prologue overlaps its tail; the kernel waits (griddepcontrol.wait) before it reads any input
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(mb, 2, n_pairs); cfg.blockDim = dim3(BWD_THREADS); cfg.dynamicSmemBytes = BWD_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = REID_SDM_PDL ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, tc_bwd_kernel<false>, b, maps, d, tau_eff, eps) != cudaSuccess) return REID_E_CUDA;
   }
   REID_CHECK_LAUNCH();
   return REID_OK;

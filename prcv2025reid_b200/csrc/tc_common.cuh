@@ -33,6 +33,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while the kernel before it on the
+// stream is still running (once every CTA of that kernel has called grid_launch_dependents or exited); it must call
+// grid_dependency_wait before it touches anything the earlier kernel writes (the wait returns when that kernel has
+// completed and its writes are visible; without a programmatic dependency it returns at once).
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -186,6 +194,8 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int ab_forma
   return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+
+// (A and B must share the element type: a descriptor with a_format != b_format raises an illegal-instruction error on sm_100a)
 
 }  // namespace tc
 
