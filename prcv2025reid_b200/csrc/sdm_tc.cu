@@ -43,9 +43,12 @@
 #ifndef REID_SDM_DS_F16
 #define REID_SDM_DS_F16 1
 #endif
-// -DREID_SDM_PDL=0 launches the three kernels of a step without programmatic dependent launch.
+// -DREID_SDM_PDL=1 launches the forward / backward with programmatic dependent launch (their prologues then overlap the
+// tail of the kernel before them).  Parity-tested, but OFF by default: measured on C5 as a CUDA graph the step takes 69.3-69.8 us
+// with it against 68.2 us without (profiles/r02t_sdm_ab.txt) -- the early CTAs compete with the running kernel for issue slots
+// and the launch gaps inside a graph are already short.
 #ifndef REID_SDM_PDL
-#define REID_SDM_PDL 1
+#define REID_SDM_PDL 0
 #endif
 
 namespace sdm {
