@@ -477,12 +477,17 @@ metrics_kernel(const int32_t* __restrict__ pos_above, const int32_t* __restrict_
   if (threadIdx.x < 5) {
     double s = 0.0;
     for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
-    atomicAdd(&acc[threadIdx.x], s);
+    // The order in which the blocks arrive is not fixed.  The hit counts are integers (exact in a double whatever the order);
+    // the AP sum of a block is added as a 64-bit FIXED-POINT number (2^-40 units: integer addition is associative), so the
+    // result is bit-identical from run to run and from rank to rank (every rank of a sharded run reduces the same counts).
+    if (threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&acc[0]), (unsigned long long)__double2ll_rn(s * 1099511627776.0));
+    else atomicAdd(&acc[threadIdx.x], s);
   }
 }
 
 __global__ void metrics_finalize_kernel(double* acc) {
   const double n = acc[4];
+  acc[0] = (double)(*reinterpret_cast<unsigned long long*>(&acc[0])) * (1.0 / 1099511627776.0);   // fixed point -> double
   for (int k = 0; k < 4; ++k) acc[k] = n > 0.0 ? acc[k] / n : 0.0;   // np.mean / empty -> 0.0 (:458-461)
 }
 

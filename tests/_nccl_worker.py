@@ -43,6 +43,7 @@ def main():
     dist.all_reduce(ti_lo, op=dist.ReduceOp.MIN); dist.all_reduce(ti_hi, op=dist.ReduceOp.MAX)
     report = {"world": world, "workload": workload, "queries": nq, "gallery": G, "path": res.path,
               "ranks_agree": bool(torch.equal(lo, hi) and torch.equal(ti_lo, ti_hi)),
+              "ranks_metric_spread": (hi - lo).abs().max().item(), "ranks_top_idx_agree": bool(torch.equal(ti_lo, ti_hi)),
               "host_equals_resident": bool(all(abs(res.metrics[m] - host.metrics[m]) < 1e-9 for m in res.metrics)
                                            and torch.equal(res.top_idx, host.top_idx)),
               "flagged": res.n_flagged, "metrics": res.metrics}
