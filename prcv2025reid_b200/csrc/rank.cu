@@ -191,16 +191,16 @@ __device__ void block_bitonic_desc(float* key, int32_t* val, int n2) {
   }
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
-cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
-                   const int32_t* __restrict__ cand_count, const float* __restrict__ cand_thr, int n_chunks, int cand_cap,
-                   int kx, int n2, float* __restrict__ sel_score, int32_t* __restrict__ sel_idx, int32_t* __restrict__ sel_n,
-                   float* __restrict__ sel_cut, int32_t* __restrict__ sel_flag) {
+// one query by a whole CTA (any number of candidates up to n2): the fallback of cand_select_warp_kernel
+__device__ void cand_select_cta(int qi, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                                const int32_t* __restrict__ cand_count, const float* __restrict__ cand_thr, int n_chunks,
+                                int cand_cap, int kx, int n2, float* __restrict__ sel_score, int32_t* __restrict__ sel_idx,
+                                int32_t* __restrict__ sel_n, float* __restrict__ sel_cut, int32_t* __restrict__ sel_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* key = reinterpret_cast<float*>(smem_raw);        // [n2]
   int32_t* val = reinterpret_cast<int32_t*>(key + n2);    // [n2]
   __shared__ int s_total, s_overflow;
-  const int qi = blockIdx.x;
+  __syncthreads();                                        // (the previous query of this CTA is done with the shared state)
   if (threadIdx.x == 0) { s_total = 0; s_overflow = 0; }
   __syncthreads();
   // gather the chunk buffers (compact, order irrelevant: sorted next).  When the producer supplied a
@@ -274,8 +274,112 @@ cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restri
     // completeness cut-off: every local row whose approximate score exceeds it is among the selected rows
     // (fewer than kx candidates: the shard has no other rows to offer, -inf)
     sel_cut[qi] = (total >= kx) ? key[kx - 1] : REID_NEG_INF;
-    __syncwarp();
     sel_flag[qi] = s_overflow ? 1 : 0;                        // bit0: a candidate buffer overflowed
+  }
+}
+
+// Fallback pass: the queries cand_select_warp_kernel marked (sel_n == -1: more than CSW_MAX candidates at or above the
+// threshold), one CTA per query; the CTAs of unmarked queries leave at once.
+__global__ void __launch_bounds__(RS_THREADS)
+cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                   const int32_t* __restrict__ cand_count, const float* __restrict__ cand_thr, int64_t Q, int n_chunks,
+                   int cand_cap, int kx, int n2, float* __restrict__ sel_score, int32_t* __restrict__ sel_idx,
+                   int32_t* __restrict__ sel_n, float* __restrict__ sel_cut, int32_t* __restrict__ sel_flag) {
+  const int qi = blockIdx.x;
+  if (sel_n[qi] != -1) return;                               // (uniform over the CTA)
+  cand_select_cta(qi, cand_score, cand_idx, cand_count, cand_thr, n_chunks, cand_cap, kx, n2, sel_score, sel_idx, sel_n, sel_cut,
+                  sel_flag);
+}
+
+// The common case -- at most CSW_MAX (128) candidates at or above the query's threshold -- by ONE WARP per query, in
+// registers: the kept candidates are compacted into a per-warp staging list (ballot + popc), every 32 of them are sorted with
+// a shuffle bitonic network (score desc, index asc: the total order of ranks_before) and folded into the running best 32
+// (best(a[i], b[31 - i]) of two sorted lists is a bitonic sequence that holds the 32 best of their union; five merge stages
+// sort it).  Same outputs as the CTA form: the REID_RTOP best in order, their number, the kx-th best as the cut-off, the
+// overflow bit.  Queries with more candidates are marked (sel_n = -1) for cand_select_kernel.
+constexpr int CSW_MAX = 128;
+constexpr int CSW_WARPS = 8;
+
+__device__ __forceinline__ void warp_bitonic_merge_desc(float& s, int& gi, int lane, int jmax) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    if (j > jmax) continue;
+    const float so = __shfl_xor_sync(0xffffffffu, s, j);
+    const int io = __shfl_xor_sync(0xffffffffu, gi, j);
+    const bool other_better = ranks_before(so, io, s, gi);
+    const bool take = ((lane & j) == 0) ? other_better : !other_better;   // the lower lane keeps the better element
+    if (take) { s = so; gi = io; }
+  }
+}
+__device__ __forceinline__ void warp_bitonic_sort_desc(float& s, int& gi, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float so = __shfl_xor_sync(0xffffffffu, s, j);
+      const int io = __shfl_xor_sync(0xffffffffu, gi, j);
+      const bool lower = (lane & j) == 0;
+      const bool first_block = (lane & k) == 0 || k == 32;                // (the last level sorts the whole warp descending)
+      const bool other_better = ranks_before(so, io, s, gi);
+      const bool take = (lower == first_block) ? other_better : !other_better;
+      if (take) { s = so; gi = io; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CSW_WARPS * 32)
+cand_select_warp_kernel(const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                        const int32_t* __restrict__ cand_count, const float* __restrict__ cand_thr, int64_t Q, int n_chunks,
+                        int cand_cap, int kx, float* __restrict__ sel_score, int32_t* __restrict__ sel_idx,
+                        int32_t* __restrict__ sel_n, float* __restrict__ sel_cut, int32_t* __restrict__ sel_flag) {
+  __shared__ float s_key[CSW_WARPS][CSW_MAX];
+  __shared__ int32_t s_val[CSW_WARPS][CSW_MAX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * CSW_WARPS + warp;
+  if (q >= Q) return;
+  const float keep = cand_thr ? cand_thr[q] : REID_NEG_INF;
+  const unsigned lt = (1u << lane) - 1u;
+  int kept = 0;
+  bool overflow = false;
+  for (int c = 0; c < n_chunks; ++c) {
+    int cnt = cand_count[q * n_chunks + c];
+    if (cnt > cand_cap) { cnt = cand_cap; overflow = true; }
+    const int64_t o = (q * n_chunks + c) * (int64_t)cand_cap;
+    for (int b = 0; b < cnt; b += 64) {                       // two independent loads per lane in flight
+      const int i0 = b + lane, i1 = b + 32 + lane;
+      const float v0 = i0 < cnt ? cand_score[o + i0] : REID_NEG_INF, v1 = i1 < cnt ? cand_score[o + i1] : REID_NEG_INF;
+      const bool k0 = i0 < cnt && v0 >= keep, k1 = i1 < cnt && v1 >= keep;
+      const unsigned m0 = __ballot_sync(0xffffffffu, k0), m1 = __ballot_sync(0xffffffffu, k1);
+      if (k0) { const int pos = kept + __popc(m0 & lt); if (pos < CSW_MAX) { s_key[warp][pos] = v0; s_val[warp][pos] = cand_idx[o + i0]; } }
+      kept += __popc(m0);
+      if (k1) { const int pos = kept + __popc(m1 & lt); if (pos < CSW_MAX) { s_key[warp][pos] = v1; s_val[warp][pos] = cand_idx[o + i1]; } }
+      kept += __popc(m1);
+    }
+  }
+  if (kept > CSW_MAX) {                                       // (warp-uniform) too many for this form: the CTA pass takes the query
+    if (lane == 0) sel_n[q] = -1;
+    return;
+  }
+  __syncwarp();
+  float bs = REID_NEG_INF; int bi = 0x7fffffff;               // running best 32, sorted descending over the lanes
+  for (int c0 = 0; c0 < kept; c0 += 32) {
+    float s = c0 + lane < kept ? s_key[warp][c0 + lane] : REID_NEG_INF;
+    int gi = c0 + lane < kept ? s_val[warp][c0 + lane] : 0x7fffffff;
+    warp_bitonic_sort_desc(s, gi, lane);
+    if (c0 == 0) { bs = s; bi = gi; continue; }
+    const float so = __shfl_sync(0xffffffffu, s, 31 - lane);
+    const int io = __shfl_sync(0xffffffffu, gi, 31 - lane);
+    if (ranks_before(so, io, bs, bi)) { bs = so; bi = io; }
+    warp_bitonic_merge_desc(bs, bi, lane, 16);
+  }
+  const int R = min(kept, REID_RTOP);
+  sel_score[q * REID_RTOP + lane] = lane < R ? bs : REID_NEG_INF;
+  sel_idx[q * REID_RTOP + lane] = lane < R ? bi : -1;
+  const float cut = __shfl_sync(0xffffffffu, bs, kx - 1);
+  if (lane == 0) {
+    sel_n[q] = R;
+    sel_cut[q] = kept >= kx ? cut : REID_NEG_INF;
+    sel_flag[q] = overflow ? 1 : 0;
   }
 }
 
@@ -540,9 +644,13 @@ extern "C" int reid_cand_select(const float* cand_score, const int32_t* cand_idx
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return REID_E_CUDA;
-  cand_select_kernel<<<(unsigned)Q, RS_THREADS, smem, (cudaStream_t)stream>>>(cand_score, cand_idx, cand_count, cand_thr, n_chunks,
-                                                                            cand_cap, kx, n2, sel_score, sel_idx, sel_n, sel_cut,
-                                                                            sel_flag);
+  cudaStream_t st = (cudaStream_t)stream;
+  // one warp per query for up to 128 kept candidates; the CTA pass only does the queries the warp pass marked
+  cand_select_warp_kernel<<<(unsigned)((Q + CSW_WARPS - 1) / CSW_WARPS), CSW_WARPS * 32, 0, st>>>(
+      cand_score, cand_idx, cand_count, cand_thr, Q, n_chunks, cand_cap, kx, sel_score, sel_idx, sel_n, sel_cut, sel_flag);
+  REID_CHECK_LAUNCH();
+  cand_select_kernel<<<(unsigned)Q, RS_THREADS, smem, st>>>(cand_score, cand_idx, cand_count, cand_thr, Q, n_chunks, cand_cap, kx, n2,
+                                                     sel_score, sel_idx, sel_n, sel_cut, sel_flag);
   REID_CHECK_LAUNCH();
   return REID_OK;
 }

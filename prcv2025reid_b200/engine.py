@@ -150,6 +150,27 @@ def default_query_block(sms: int) -> int:
     return 2 * max(1, sms // 2) * WAVE_QUERIES
 
 
+def resident_query_blocks(Q: int, sms: int, G_local: int, cand_cap: int = 2048):
+    """Query blocks [(start, end)] when the queries are already on the device.  Every launch of the gallery pass ends with
+    a tail (the persistent CTA pairs of its last wave do not finish together) and carries a calibration launch of its own;
+    on a 1M-row shard a wave takes ~14 ms and two waves per launch are plenty, on a 125k-row shard (8 GPUs) a wave takes
+    ~2 ms and the tails of three launches cost ~3 % of the step: the launch grows as the shard shrinks (about 4M query x
+    kilo-rows per launch), bounded by the candidate buffers (16 KB per query and slot, at most 12 GB per block).  Blocks are
+    whole waves; a tail shorter than half a wave joins the last block."""
+    wave = max(1, sms // 2) * WAVE_QUERIES
+    waves = max(2, min(16, int(round(2.0 * 1_000_000 / max(1, G_local)))))
+    while waves > 2 and waves * wave * int(cand_cap) * 8 * 2 > (12 << 30):
+        waves -= 1
+    block = waves * wave
+    out, b0 = [], 0
+    while b0 < Q:
+        b1 = min(Q, b0 + block)
+        if 0 < Q - b1 < wave // 2:
+            b1 = Q
+        out.append((b0, b1)); b0 = b1
+    return out
+
+
 def host_query_blocks(Q: int, sms: int):
     """Query blocks [(start, end)] for HOST-resident queries.  The upload of a block overlaps the kernels of the block
     before it, but nothing hides the upload of the FIRST block: it is kept small (16 work items' worth of queries, run as
@@ -339,7 +360,7 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
     E = 0 if excl is None or excl.numel() == 0 else excl.shape[1]
     if E == 0:
         excl = None
-    ramp = query_block is None and host_queries is not None
+    auto_blocks = query_block is None
     if query_block is None:
         query_block = default_query_block(sms)
 
@@ -347,7 +368,10 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
     use_fused = (mode == "fused" and Pmax <= 2048 and d % 64 == 0 and d <= 512 and shard.G_local <= (1 << 22)
                  and (host_queries is not None or q_f16 is not None))
 
-    blocks = host_query_blocks(Q, sms) if ramp else [(b0, min(Q, b0 + query_block)) for b0 in range(0, Q, query_block)]
+    if auto_blocks:
+        blocks = host_query_blocks(Q, sms) if host_queries is not None else resident_query_blocks(Q, sms, shard.G_local, cand_cap)
+    else:
+        blocks = [(b0, min(Q, b0 + query_block)) for b0 in range(0, Q, query_block)]
     staged = {}
     kept = []                                 # (q32, pid, excl) of every block: the re-scorer and the exact re-run read them
     if host_queries is not None:

@@ -219,3 +219,18 @@ def test_host_query_blocks_partition():
             if len(sizes) > 3:
                 assert sizes[-1] >= 2 * wave // 4
     assert engine.host_query_blocks(100000, 148) == [(0, 4096), (4096, 23040), (23040, 60928), (60928, 100000)]
+
+
+def test_resident_query_blocks_partition():
+    """Blocks of device-resident queries: whole waves, larger launches on smaller shards, no short tail block."""
+    from prcv2025reid_b200 import engine
+    wave = 74 * engine.WAVE_QUERIES
+    for G in (10_000, 125_000, 250_000, 500_000, 1_000_000, 4_000_000):
+        for Q in (1, 3000, 37888, 40000, 100000, 1_000_000):
+            bl = engine.resident_query_blocks(Q, 148, G)
+            assert bl[0][0] == 0 and bl[-1][1] == Q and all(a[1] == b[0] for a, b in zip(bl, bl[1:]))
+            assert all((b - a) % wave == 0 for a, b in bl[:-1])
+            if len(bl) > 1:
+                assert bl[-1][1] - bl[-1][0] >= wave // 2
+    assert engine.resident_query_blocks(100000, 148, 1_000_000) == [(0, 37888), (37888, 75776), (75776, 100000)]
+    assert engine.resident_query_blocks(100000, 148, 125_000) == [(0, 100000)]
