@@ -91,7 +91,9 @@ int reid_pos_sort(float* pos_score, int32_t* n_pos, int64_t Q, int Pmax, void* s
  * Counting classes (shards of >= 32768 rows; a calibration pre-pass over a strided 1/32 of the shard, 2048 .. 8192
  * rows, estimates every threshold's rank inside the shard): thresholds ranked above max(1024 / n_shards, 8 calibration hits) rows are
  * counted on a 1/32 row sample, those above 32768 / n_shards rows on a 1/1024 row sample, so that a sampled count
- * rests on >= 32 sampled rows gallery-wide; all shallower thresholds on every row.
+ * rests on >= 32 sampled rows gallery-wide; all shallower thresholds on every row.  The pre-pass also seeds the running
+ * candidate threshold of (b): a positive threshold with >= REID_KLIST (16) sample rows above it has that many shard rows above it.
+ * Results are bit-identical from run to run (the classes do not depend on the order in which warps finish).
  * flags: REID_FUSED_EXACT_COUNTS = count every threshold on every row (no sampling; slow for deep positives);
  *        REID_FUSED_NO_CANDIDATES = counting only (cand_* may be NULL);
  *        REID_FUSED_KLIST16 = candidates complete down to the 16th (not the REID_KLIST-th) best score of a slot: what the

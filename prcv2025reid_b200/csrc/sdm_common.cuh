@@ -45,7 +45,7 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 
 // ---- tcgen05 path: layout of the per-pair `saved` buffer (offsets in floats unless noted) ----
 // [den_q N][den_g M][lse_r N][lse_c M][cnt_r N][cnt_c M][ce_r N][ce_c M][hdr 128][S N*M][St M*N] then, 128-byte
-// aligned, the positive masks of y as bit rows (ybits [N][16] / ybitsT [M][16] 32-bit words) and four bf16 operand images in the UMMA K-major 128B-swizzle layout (8-row x 64-element atoms of 1024 bytes,
+// aligned, the positive masks of y as bit rows (ybits [N][16] / ybitsT [M][16] 32-bit words) and four 16-bit operand images (Qn / Gn bf16; the transposed QnT / GnT fp16 unless -DREID_SDM_DS_F16=0) in the UMMA K-major 128B-swizzle layout (8-row x 64-element atoms of 1024 bytes,
 // [k block][row group]) so that an operand tile is ONE contiguous cp.async.bulk:
 //   Qn  [Np rows][d]   Gn  [Mp rows][d]   QnT [d rows][Np]   GnT [d rows][Mp]      (Np, Mp = N, M rounded up to 128)
 // hdr: [0] nR  [1] nC  [2] status bits (int)  [3] loss  [4] CTA completion counter (int)

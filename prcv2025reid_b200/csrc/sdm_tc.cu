@@ -9,7 +9,8 @@
 // Three launches per step, no host synchronisation, no cooperative grid barrier:
 //   tc_prep_kernel  normalise rows (reference bf16 rounding), write each operand twice -- row-major-K image
 //                   and transposed image -- directly in the UMMA K-major 128B-swizzle layout, so that every
-//                   operand tile is ONE contiguous cp.async.bulk (no tensor maps, any number of pairs).
+//                   operand tile is ONE contiguous cp.async.bulk (no tensor maps, any number of pairs); a third
+//                   slice of its grid turns a dense y into the positive-mask bit rows both kernels read.
 //   tc_fwd_kernel   CTA = (pair, side, 128-row block).  side 0: rows = qry, columns = gal; side 1 = the transposed
 //                   problem.  The whole row block x all columns (<= 512) accumulates in TMEM (128 lanes x 512
 //                   fp32 columns = all of it), so the epilogue thread that owns a TMEM lane owns a full row of S:
@@ -17,8 +18,8 @@
 //                   cross-thread reduction.  The last CTA of a pair (completion counter) reduces the per-row
 //                   cross-entropies to the loss and evaluates the guards (:60-68, :79-81, :89-91, :105-106, :142-147).
 //   tc_bwd_kernel   CTA = (pair, side, 128-row block).  side 0: dq^ = dS g^ (K = gal rows), side 1: dg^ = dS^T q^.
-//                   Eight producer warps form dL/dS tiles from S, the row / column LSE and y, split them into
-//                   bf16 hi + lo (16 mantissa bits) and store them in the swizzled operand layout; the MMA warp
+//                   Sixteen producer warps form dL/dS tiles from S, the row / column LSE and the mask bits as one
+//                   scaled fp16 plane (see REID_SDM_DS_F16) and store them in the swizzled operand layout; the MMA warp
 //                   multiplies them with the transposed operand image streamed by bulk copies; the accumulator
 //                   (128 rows x d columns) again gives every epilogue thread a full output row, so the
 //                   normalisation Jacobian (I - x^ x^T)/den is applied in registers and the gradient is written
