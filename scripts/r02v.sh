@@ -5,7 +5,7 @@ timeout 150 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 tail -1 gpurun_out/smoke.log
 TMO=420 bash scripts/gpu_tests_staged.sh 2>&1 | tail -14
 grep -h "AssertionError\|^E  \|^FAILED" gpurun_out/test_*.log | cut -c1-300 | sort | uniq -c | sort -rn | head -20
-for wd in 8 1; do timeout 300 python scripts/shard_probe.py $wd c4 2>&1 | tail -2; done | tee gpurun_out/r02v_shard_probe.txt
+timeout 200 python scripts/shard_probe.py 8 c4 2>&1 | tail -2 | tee gpurun_out/r02v_shard_probe.txt
 echo "=== bench default"
 timeout 900 python bench.py > gpurun_out/r02v_bench_c4.json 2> gpurun_out/bench_err.log; echo "bench rc $?"
 python - <<'PY'
