@@ -7,6 +7,7 @@ results land where the real kernels would write them).  The "fused" pass scores 
 tensor cores do, so the engine's flag -> exact re-run path is exercised for real.  Nothing here is product code, and the
 product never loads it: `prcv2025reid_b200._cabi.lib()` raises when the real library is missing.
 """
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -172,7 +173,7 @@ class FakeLib:
             sc, ix = torch.cat(sc), torch.cat(ix)
             m = sc >= keep
             sc, ix = sc[m], ix[m]
-            o = torch.argsort(sc, descending=True, stable=True)
+            o = torch.from_numpy(np.lexsort((ix.numpy(), -sc.numpy())))      # score desc, index asc (ranks_before of the kernels)
             sc, ix = sc[o], ix[o]
             total = sc.numel()
             R = min(total, RTOP)

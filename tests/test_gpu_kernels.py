@@ -725,3 +725,48 @@ def test_merge_topk_of_shard_lists(n_lists):
         items = sorted([(-float(s), int(i)) for s, i in zip(flat_s[q], flat_i[q]) if int(i) >= 0])[:k]
         assert out_i[q].tolist() == [i for _, i in items]
         assert out_s[q].tolist() == [-s for s, _ in items]
+
+
+@pytest.mark.parametrize("n_chunks,kx,with_thr", [(1, 32, True), (3, 16, True), (2, 32, False)])
+def test_cand_select_warp_and_cta_paths(n_chunks, kx, with_thr):
+    """reid_cand_select against a plain sort: queries with at most 128 kept candidates take the one-warp-per-query kernel,
+    the others the CTA fallback (marked by the warp pass) -- both must give the REID_RTOP best in (score desc, index asc)
+    order, the kx-th best as the cut-off (-inf with fewer than kx candidates) and the overflow bit; exact score ties included."""
+    from prcv2025reid_b200 import _cabi
+    from prcv2025reid_b200._cabi import check, ptr, stream_ptr
+    g = torch.Generator().manual_seed(11 + n_chunks)
+    Q, cap = 300, 512
+    counts = torch.randint(0, 200, (Q, n_chunks), generator=g).to(torch.int32)
+    counts[::7] = torch.randint(0, 12, (len(counts[::7]), n_chunks), generator=g).to(torch.int32)     # fewer than kx candidates
+    counts[3::11, 0] = cap + 5                                                                          # overflowed slot
+    counts[5::13] = torch.randint(300, cap, (len(counts[5::13]), n_chunks), generator=g).to(torch.int32)  # CTA fallback
+    score = torch.randn(Q, n_chunks, cap, generator=g)
+    score[:, :, 1::9] = score[:, :, 0:1]                                  # ties: equal scores, different rows
+    idx = torch.stack([torch.randperm(100000, generator=g)[:n_chunks * cap] for _ in range(Q)]).view(Q, n_chunks, cap).to(torch.int32)
+    thr = torch.full((Q,), float("-inf"))
+    if with_thr:
+        thr = torch.randn(Q, generator=g) * 0.5 + 0.3
+    dev = "cuda"
+    sd, idd, cd, td = score.to(dev), idx.to(dev), counts.to(dev), thr.to(dev)
+    sel_s = torch.empty(Q, _cabi.RTOP, device=dev); sel_i = torch.empty(Q, _cabi.RTOP, dtype=torch.int32, device=dev)
+    sel_n = torch.empty(Q, dtype=torch.int32, device=dev); cut = torch.empty(Q, device=dev)
+    flag = torch.empty(Q, dtype=torch.int32, device=dev)
+    check(_cabi.lib().reid_cand_select(ptr(sd), ptr(idd), ptr(cd), ptr(td) if with_thr else None, Q, n_chunks, cap, kx,
+                                       ptr(sel_s), ptr(sel_i), ptr(sel_n), ptr(cut), ptr(flag), stream_ptr()), "reid_cand_select")
+    sel_s, sel_i, sel_n, cut, flag = sel_s.cpu(), sel_i.cpu(), sel_n.cpu(), cut.cpu(), flag.cpu()
+    n_warp = n_cta = 0
+    for q in range(Q):
+        items, over = [], False
+        for c in range(n_chunks):
+            n = int(counts[q, c])
+            if n > cap:
+                n, over = cap, True
+            items += [(-float(score[q, c, i]), int(idx[q, c, i])) for i in range(n) if float(score[q, c, i]) >= float(thr[q])]
+        items.sort()
+        n_warp += len(items) <= 128; n_cta += len(items) > 128
+        R = min(len(items), _cabi.RTOP)
+        assert int(sel_n[q]) == R and int(flag[q]) == int(over)
+        assert sel_i[q, :R].tolist() == [i for _, i in items[:R]] and sel_s[q, :R].tolist() == [-s for s, _ in items[:R]]
+        assert (sel_i[q, R:] == -1).all() and torch.isinf(sel_s[q, R:]).all()
+        assert float(cut[q]) == (-items[kx - 1][0] if len(items) >= kx else float("-inf"))
+    assert n_warp > 20 and n_cta > 20                                      # both kernels were exercised
