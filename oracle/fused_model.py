@@ -28,7 +28,10 @@ built.  It follows the kernel, not the reference:
                      flags: top-k undecidable (k-th exact score < bound), CMC@10 undecidable
                      (best positive not above the bound and fewer than 10 re-scored rows above it)
 
-Not modelled: the running candidate thresholds (the model takes the candidate set as complete down to the KLIST-th best
+Not modelled: the early retirement of deep thresholds inside the calibration pre-pass (a threshold whose RUNNING rank estimate
+has passed the level-2 limit on >= 32 sample rows is classed level-2 at once; the model classes every threshold on the counts
+of the whole sample -- the two can differ for thresholds within ~18 % of the level-1 / level-2 boundary, where either class
+moves AP by < 1e-5), the seed of the candidate threshold taken from the calibration counts, the running candidate thresholds (the model takes the candidate set as complete down to the KLIST-th best
 score, which is what the kernel guarantees) and the exact re-run of flagged queries (engine.retrieve).
 """
 from typing import Dict, Optional
