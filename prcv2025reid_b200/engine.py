@@ -418,7 +418,8 @@ def retrieve(shard: GalleryShard, q_f32: Optional[torch.Tensor], q_f16: Optional
         if excl is not None:
             excl = excl.to(device=dev, dtype=torch.int32).contiguous()
         # resident queries: the positives' scores of the WHOLE batch up front (one exchange over the shards)
-        _pos_stage(shard, S, slice(0, Q), q_f32, q_pid, excl, E, group=group, world=world)
+        if Q > 0:
+            _pos_stage(shard, S, slice(0, Q), q_f32, q_pid, excl, E, group=group, world=world)
 
     for bi, (b0, b1) in enumerate(blocks):
         nb = b1 - b0
