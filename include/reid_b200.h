@@ -179,8 +179,8 @@ typedef struct {
    *   y[i][j] = row_valid[i] && col_valid[j] && row_label[i] == col_label[j]   (:605)
    * and rows of qry / gal whose valid byte is 0 (the feature masks, :570-602) are left out of the loss altogether --
    * out of the softmax denominators, the means and the guards -- and receive exact-zero gradients.  row_valid /
-   * col_valid may be NULL (all valid).  Served by the tcgen05 path only (reid_sdm_uses_tensor_cores); other shapes
-   * return REID_E_UNSUPPORTED and the caller builds y. */
+   * col_valid may be NULL (all valid).  Served by every code path (tcgen05, small-batch, general CUDA-core kernels);
+   * a pair with neither y nor both label arrays is REID_E_INVALID. */
   const int64_t* row_label; const int64_t* col_label;
   const uint8_t* row_valid; const uint8_t* col_valid;
 } reid_sdm_pair;

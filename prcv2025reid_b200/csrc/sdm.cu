@@ -31,6 +31,7 @@ using sdm::ld_elem;
 using sdm::norm_elem;
 using sdm::st_out;
 using sdm::round_dt;
+using sdm::PosMask;
 
 struct Saved {
   float *den_q, *den_g, *lse_r, *lse_c, *cnt_r, *cnt_c, *ce_r, *ce_c, *hdr, *S, *dqn, *dgn, *qn, *gn;
@@ -98,9 +99,15 @@ __device__ __forceinline__ void tile_gemm(int K, LA la, LB lb, float (&acc)[4][4
 
 // row denominators max(||x||, eps) in the reference's dtype path + non-finite detection
 template <int BF16>
-__device__ void phase_norms(const void* x, int rows, int d, float eps, float* den, float* xn, int* flags, int cta, int nctas) {
+__device__ void phase_norms(const void* x, int rows, int d, float eps, float* den, float* xn, int* flags, int cta, int nctas,
+                            const uint8_t* valid) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = cta * (TB / 32) + warp; r < rows; r += nctas * (TB / 32)) {
+    if (valid && !valid[r]) {              // label form: the row takes no part -- zero image, unit denominator, never inspected
+      for (int c = lane; c < d; c += 32) xn[(size_t)r * d + c] = 0.f;
+      if (lane == 0) den[r] = 1.f;
+      continue;
+    }
     float ss = 0.f;
     for (int c = lane; c < d; c += 32) { const float v = ld_elem<BF16>(x, (size_t)r * d + c); ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
@@ -128,12 +135,13 @@ sdm_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   const reid_sdm_pair& P = batch.p[blockIdx.y];
   const int N = P.N, M = P.M, cta = blockIdx.x, nctas = gridDim.x;
   Saved sv = carve(P.saved, N, M, d);
+  const PosMask pm(P);
   int* flags = reinterpret_cast<int*>(sv.hdr + 2);
   if (cta == 0 && threadIdx.x == 0) *flags = 0;
   sync_all(multi);
   // ---- phase 0: denominators (:31-32) ----
-  phase_norms<BF16>(P.qry, N, d, eps, sv.den_q, sv.qn, flags, cta, nctas);
-  phase_norms<BF16>(P.gal, M, d, eps, sv.den_g, sv.gn, flags, cta, nctas);
+  phase_norms<BF16>(P.qry, N, d, eps, sv.den_q, sv.qn, flags, cta, nctas, pm.rv);
+  phase_norms<BF16>(P.gal, M, d, eps, sv.den_g, sv.gn, flags, cta, nctas, pm.cv);
   sync_all(multi);
   // ---- phase 1: S = q^ g^T / tau, clamp (:86, :94) ----
   const int tiles_m = (N + TM - 1) / TM, tiles_n = (M + TN - 1) / TN;
@@ -162,37 +170,42 @@ sdm_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   // ---- phase 2: per-row and per-column log-sum-exp and cross-entropy (:34-57) ----
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // (label form: only the rows / columns that take part enter the sums; an absent row keeps cnt = 0 and is never counted)
     for (int i = cta * (TB / 32) + warp; i < N; i += nctas * (TB / 32)) {
+      const bool rin = pm.row_in(i);
       float mx = -INFINITY;
-      for (int j = lane; j < M; j += 32) mx = fmaxf(mx, sv.S[(size_t)i * M + j]);
+      for (int j = lane; j < M; j += 32) if (rin && pm.col_in(j)) mx = fmaxf(mx, sv.S[(size_t)i * M + j]);
       mx = warp_max(mx);
       float se = 0.f, ps = 0.f, pc = 0.f;
       for (int j = lane; j < M; j += 32) {
+        if (!rin || !pm.col_in(j)) continue;
         const float s = sv.S[(size_t)i * M + j];
         se += expf(s - mx);
-        if (P.y[(size_t)i * M + j] > 0.f) { ps += s; pc += 1.f; }
+        if (pm.pos(i, j)) { ps += s; pc += 1.f; }
       }
       se = warp_sum(se); ps = warp_sum(ps); pc = warp_sum(pc);
       if (lane == 0) {
-        const float lse = mx + logf(se);
+        const float lse = se > 0.f ? mx + logf(se) : 0.f;      // (se >= 1 whenever an element took part)
         sv.lse_r[i] = lse; sv.cnt_r[i] = pc;
         sv.ce_r[i] = pc > 0.f ? (lse - ps / pc) : 0.f;     // -(q * log_p).sum, q uniform over positives
       }
     }
     // columns: warp handles one column; lanes stride over rows (S is L2 resident, N*M*4 bytes)
     for (int j = cta * (TB / 32) + warp; j < M; j += nctas * (TB / 32)) {
+      const bool cin = pm.col_in(j);
       float mx = -INFINITY;
-      for (int i = lane; i < N; i += 32) mx = fmaxf(mx, sv.S[(size_t)i * M + j]);
+      for (int i = lane; i < N; i += 32) if (cin && pm.row_in(i)) mx = fmaxf(mx, sv.S[(size_t)i * M + j]);
       mx = warp_max(mx);
       float se = 0.f, ps = 0.f, pc = 0.f;
       for (int i = lane; i < N; i += 32) {
+        if (!cin || !pm.row_in(i)) continue;
         const float s = sv.S[(size_t)i * M + j];
         se += expf(s - mx);
-        if (P.y[(size_t)i * M + j] > 0.f) { ps += s; pc += 1.f; }
+        if (pm.pos(i, j)) { ps += s; pc += 1.f; }
       }
       se = warp_sum(se); ps = warp_sum(ps); pc = warp_sum(pc);
       if (lane == 0) {
-        const float lse = mx + logf(se);
+        const float lse = se > 0.f ? mx + logf(se) : 0.f;
         sv.lse_c[j] = lse; sv.cnt_c[j] = pc;
         sv.ce_c[j] = pc > 0.f ? (lse - ps / pc) : 0.f;
       }
@@ -245,6 +258,7 @@ sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   const reid_sdm_pair& P = batch.p[blockIdx.y];
   const int N = P.N, M = P.M, cta = blockIdx.x, nctas = gridDim.x;
   Saved sv = carve(P.saved, N, M, d);
+  const PosMask pm(P);
   const int st = *reinterpret_cast<const int*>(sv.hdr + 2);
   const float nR = sv.hdr[0], nC = sv.hdr[1];
   const float gscale = (st & 1) ? 0.f : (*P.grad_out) * 0.5f / tau_eff;
@@ -252,9 +266,10 @@ sdm_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   // dL/dS element (chain through clamp: zero where saturated)
   auto dS = [&](int i, int j) -> float {
     if (i >= N || j >= M) return 0.f;
+    if (!pm.row_in(i) || !pm.col_in(j)) return 0.f;          // label form: absent rows / columns
     const float s = sv.S[(size_t)i * M + j];
     if (s >= 20.f || s <= -20.f) return 0.f;
-    const float pos = P.y[(size_t)i * M + j] > 0.f ? 1.f : 0.f;
+    const float pos = pm.pos(i, j) ? 1.f : 0.f;
     float g = 0.f;
     const float cr = sv.cnt_r[i], cc = sv.cnt_c[j];
     if (cr > 0.f && isfinite(sv.ce_r[i])) g += wr * (expf(s - sv.lse_r[i]) - pos / cr);
@@ -375,6 +390,13 @@ __device__ __forceinline__ bool small_store_norm(const float (&v)[16], float dn,
   return fin;
 }
 
+__device__ __forceinline__ void small_zero_row(float* dst, int d, int lane) {
+  const int nchunk = d >> 7;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < nchunk) *reinterpret_cast<float4*>(dst + k * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 template <int BF16>
 __global__ void __launch_bounds__(TB)
 sdm_small_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
@@ -386,6 +408,7 @@ sdm_small_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   float* Ss = xs + (size_t)(N + M) * d;                // [N][M + 1]
   float* st_r = Ss + N * (M + 1);                      // cnt / ce per row, then per column
   __shared__ int s_flags;
+  const PosMask pm(P);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_flags = 0;
   __syncthreads();
@@ -394,6 +417,11 @@ sdm_small_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
     const bool isq = r < N;
     const int row = isq ? r : r - N;
     const void* x = isq ? P.qry : P.gal;
+    if (!(isq ? pm.row_in(row) : pm.col_in(row))) {     // label form: the row takes no part (zero image, never inspected)
+      small_zero_row(xs + (size_t)r * d, d, lane);
+      if (lane == 0) (isq ? sv.den_q : sv.den_g)[row] = 1.f;
+      continue;
+    }
     float v[16];
     small_load_row<BF16>(x, (size_t)row, d, lane, v);
     float ss = 0.f;
@@ -425,14 +453,15 @@ sdm_small_fwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   for (int r = warp; r < N + M; r += TB / 32) {
     const bool isrow = r < N;
     const int a = isrow ? r : r - N, len = isrow ? M : N;
-    const bool in = lane < len;
+    // (label form: only the rows / columns that take part enter the sums; an absent row keeps cnt = 0 and is never counted)
+    const bool in = lane < len && (isrow ? (pm.row_in(a) && pm.col_in(lane)) : (pm.col_in(a) && pm.row_in(lane)));
     const float s = in ? (isrow ? Ss[a * (M + 1) + lane] : Ss[lane * (M + 1) + a]) : -INFINITY;
-    const float yv = in ? (isrow ? P.y[(size_t)a * M + lane] : P.y[(size_t)lane * M + a]) : 0.f;
+    const bool yv = in && (isrow ? pm.pos(a, lane) : pm.pos(lane, a));
     const float mx = warp_max(s);
     const float se = warp_sum(in ? expf(s - mx) : 0.f);
-    const float ps = warp_sum(yv > 0.f ? s : 0.f), pc = warp_sum(yv > 0.f ? 1.f : 0.f);
+    const float ps = warp_sum(yv ? s : 0.f), pc = warp_sum(yv ? 1.f : 0.f);
     if (lane == 0) {
-      const float lse = mx + logf(se);
+      const float lse = se > 0.f ? mx + logf(se) : 0.f;        // (se >= 1 whenever an element took part)
       const float ce = pc > 0.f ? (lse - ps / pc) : 0.f;
       (isrow ? sv.lse_r : sv.lse_c)[a] = lse;
       (isrow ? sv.cnt_r : sv.cnt_c)[a] = pc;
@@ -476,6 +505,7 @@ sdm_small_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
   Saved sv = carve(P.saved, N, M, d);
   float* xs = small_smem;                              // [N + M][d] normalised rows
   float* dSs = xs + (size_t)(N + M) * d;               // [N][M + 1]
+  const PosMask pm(P);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int st = *reinterpret_cast<const int*>(sv.hdr + 2);
   if (st & 1) {                                        // the reference returned its non-differentiable zero
@@ -492,8 +522,8 @@ sdm_small_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
     const int i = idx / M, j = idx % M;
     const float s = sv.S[idx];
     float g = 0.f;
-    if (s < 20.f && s > -20.f) {
-      const float pos = P.y[idx] > 0.f ? 1.f : 0.f;
+    if (s < 20.f && s > -20.f && pm.row_in(i) && pm.col_in(j)) {
+      const float pos = pm.pos(i, j) ? 1.f : 0.f;
       const float cr = sv.cnt_r[i], cc = sv.cnt_c[j];
       if (cr > 0.f && isfinite(sv.ce_r[i])) g += wr * (expf(s - sv.lse_r[i]) - pos / cr);
       if (cc > 0.f && isfinite(sv.ce_c[j])) g += wc * (expf(s - sv.lse_c[j]) - pos / cc);
@@ -505,6 +535,7 @@ sdm_small_bwd_kernel(SdmBatch batch, int d, float tau_eff, float eps) {
     const int row = isq ? r : r - N;
     const void* x = isq ? P.qry : P.gal;
     const float dn = (isq ? sv.den_q : sv.den_g)[row];
+    if (!(isq ? pm.row_in(row) : pm.col_in(row))) { small_zero_row(xs + (size_t)r * d, d, lane); continue; }
     float v[16];
     small_load_row<BF16>(x, (size_t)row, d, lane, v);
     small_store_norm<BF16>(v, dn, xs + (size_t)r * d, d, lane);
@@ -584,17 +615,32 @@ sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
   float* Ys = st_r + 4 * (N + M);                      // [N][M]      y
   __shared__ int s_flags, s_status;
   __shared__ float s_nR, s_nC;
+  __shared__ unsigned char s_in[2 * SMALL_MAX];         // label form: does row r of [qry; gal] take part (all ones otherwise)
+  const PosMask pm(P);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float gout = *P.grad_out;
   float yreg[2];                                        // N * M <= 1024 = 2 per thread
 #pragma unroll
-  for (int u = 0; u < 2; ++u) { const int i = threadIdx.x + u * STB; yreg[u] = i < N * M ? P.y[i] : 0.f; }
+  for (int u = 0; u < 2; ++u) {
+    const int i = threadIdx.x + u * STB;
+    yreg[u] = 0.f;
+    if (i < N * M) {
+      if (pm.y) yreg[u] = pm.y[i];
+      else yreg[u] = (pm.row_in(i / M) && pm.col_in(i % M) && pm.rl[i / M] == pm.cl[i % M]) ? 1.f : 0.f;
+    }
+  }
   if (threadIdx.x == 0) s_flags = 0;
+  if (threadIdx.x < N + M) s_in[threadIdx.x] = threadIdx.x < N ? pm.row_in(threadIdx.x) : pm.col_in(threadIdx.x - N);
   __syncthreads();
   for (int r = warp; r < N + M; r += NW) {
     const bool isq = r < N;
     const int row = isq ? r : r - N;
     const void* x = isq ? P.qry : P.gal;
+    if (!s_in[r]) {                                     // label form: the row takes no part (zero image, never inspected)
+      small_zero_row(xs + (size_t)r * d, d, lane);
+      if (lane == 0) { (isq ? sv.den_q : sv.den_g)[row] = 1.f; st_r[4 * r + 3] = 1.f; }
+      continue;
+    }
     float v[16];
     small_load_row<BF16>(x, (size_t)row, d, lane, v);
     float ss = 0.f;
@@ -634,14 +680,14 @@ sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
   for (int r = warp; r < N + M; r += NW) {
     const bool isrow = r < N;
     const int a = isrow ? r : r - N, len = isrow ? M : N;
-    const bool in = lane < len;
+    const bool in = lane < len && s_in[r] && s_in[isrow ? N + lane : lane];
     const float sv_ = in ? (isrow ? Ss[a * (M + 1) + lane] : Ss[lane * (M + 1) + a]) : -INFINITY;
     const float yv = in ? (isrow ? Ys[a * M + lane] : Ys[lane * M + a]) : 0.f;
     const float mx = warp_max(sv_);
     const float se = warp_sum(in ? expf(sv_ - mx) : 0.f);
     const float ps = warp_sum(yv > 0.f ? sv_ : 0.f), pc = warp_sum(yv > 0.f ? 1.f : 0.f);
     if (lane == 0) {
-      const float lse = mx + logf(se);
+      const float lse = se > 0.f ? mx + logf(se) : 0.f;
       const float ce = pc > 0.f ? (lse - ps / pc) : 0.f;
       (isrow ? sv.lse_r : sv.lse_c)[a] = lse;
       (isrow ? sv.cnt_r : sv.cnt_c)[a] = pc;
@@ -696,7 +742,7 @@ sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
     const int i = idx / M, j = idx % M;
     const float s = Ss[i * (M + 1) + j];
     float g = 0.f;
-    if (s < 20.f && s > -20.f) {
+    if (s < 20.f && s > -20.f && s_in[i] && s_in[N + j]) {
       const float pos = Ys[idx] > 0.f ? 1.f : 0.f;
       const float cr = st_r[4 * i], cc = st_r[4 * (N + j)];
       if (cr > 0.f && isfinite(st_r[4 * i + 1])) g += wr * (expf(s - st_r[4 * i + 2]) - pos / cr);
@@ -767,8 +813,8 @@ int launch_small(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float
   size_t smem = 0;
   for (int i = 0; i < n_pairs; ++i) {
     const reid_sdm_pair& p = pairs[i];
-    if (!p.y && p.row_label && p.col_label) return REID_E_UNSUPPORTED;         // label form: tcgen05 path only
-    if (!p.qry || !p.gal || !p.y || !p.loss || !p.status || !p.saved) return REID_E_INVALID;
+    if (!p.y && !(p.row_label && p.col_label)) return REID_E_INVALID;          // dense y, or the label form
+    if (!p.qry || !p.gal || !p.loss || !p.status || !p.saved) return REID_E_INVALID;
     if (bwd && (!p.grad_out || !p.dqry || !p.dgal)) return REID_E_INVALID;
     b.p[i] = p;
     const size_t need = ((size_t)(p.N + p.M) * d + (size_t)p.N * (p.M + 1) + 4 * (size_t)(p.N + p.M) + (size_t)p.N * p.M) * sizeof(float);
@@ -790,8 +836,8 @@ int launch_sdm(K kernel, const reid_sdm_pair* pairs, int n_pairs, int d, float t
   int max_tiles = 1;
   for (int i = 0; i < n_pairs; ++i) {
     const reid_sdm_pair& p = pairs[i];
-    if (!p.y && p.row_label && p.col_label) return REID_E_UNSUPPORTED;         // label form: tcgen05 path only
-    if (!p.qry || !p.gal || !p.y || !p.loss || !p.status || !p.saved || p.N <= 0 || p.M <= 0) return REID_E_INVALID;
+    if (!p.y && !(p.row_label && p.col_label)) return REID_E_INVALID;          // dense y, or the label form
+    if (!p.qry || !p.gal || !p.loss || !p.status || !p.saved || p.N <= 0 || p.M <= 0) return REID_E_INVALID;
     if (bwd && (!p.grad_out || !p.dqry || !p.dgal)) return REID_E_INVALID;
     b.p[i] = p;
     const int tm = (p.N + TM - 1) / TM, tn = (p.M + TN - 1) / TN, td = (d + TN - 1) / TN;

@@ -43,6 +43,19 @@ __device__ __forceinline__ void st_out(void* base, size_t i, float v) {
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Positive mask of a pair as the CUDA-core kernels (sdm.cu) read it: the dense y (y[i][j] > 0), or the LABEL FORM
+// (y == NULL, include/reid_b200.h; models/model.py:570-605): y[i][j] = row_label[i] == col_label[j] between the rows
+// that take part; a row whose valid byte is 0 is absent from the problem (the reference indexes it away before the loss).
+struct PosMask {
+  const float* y; const int64_t* rl; const int64_t* cl; const uint8_t* rv; const uint8_t* cv; int M;
+  __device__ __forceinline__ explicit PosMask(const reid_sdm_pair& P)
+      : y(P.y), rl(P.row_label), cl(P.col_label), rv(P.y ? nullptr : P.row_valid), cv(P.y ? nullptr : P.col_valid), M(P.M) {}
+  __device__ __forceinline__ bool row_in(int i) const { return !rv || rv[i] != 0; }
+  __device__ __forceinline__ bool col_in(int j) const { return !cv || cv[j] != 0; }
+  // (only asked for rows / columns that take part)
+  __device__ __forceinline__ bool pos(int i, int j) const { return y ? y[(size_t)i * M + j] > 0.f : rl[i] == cl[j]; }
+};
+
 // ---- tcgen05 path: layout of the per-pair `saved` buffer (offsets in floats unless noted) ----
 // [den_q N][den_g M][lse_r N][lse_c M][cnt_r N][cnt_c M][ce_r N][ce_c M][hdr 128][S N*M][St M*N] then, 128-byte
 // aligned, the positive masks of y as bit rows (ybits [N][16] / ybitsT [M][16] 32-bit words) and four 16-bit operand images (Qn / Gn bf16; the transposed QnT / GnT fp16 unless -DREID_SDM_DS_F16=0) in the UMMA K-major 128B-swizzle layout (8-row x 64-element atoms of 1024 bytes,

@@ -242,6 +242,23 @@ def install_gallery(gallery_feats: torch.Tensor, gallery_meta: List[dict]) -> en
     return shard
 
 
+def shuffled_gallery(gallery_feats: torch.Tensor, gallery_meta: List[dict], seed: int = 0):
+    """(gallery_feats, gallery_meta) with the rows in a seeded random order (meta permuted alongside, so that image ids, the
+    same-image rule and the submission CSV are unaffected; only the order of exactly tied scores can change).
+
+    Why: beyond the exactly re-scored head, `mode="fused"` counts deep positives on row samples with a FIXED phase (local
+    rows = 5 mod 32 / mod 1024 of a shard).  The samples are unbiased unless a row's position modulo 32
+    carries information about its score -- e.g. a cache written with exactly 32 images per identity in camera order.  For
+    such a gallery pass the shuffled pair to `install_gallery` / `rank_and_metrics` / `export_submission_csv` (or evaluate
+    with `exact_ap=True`).  The reference (eval_mm_protocol.py:396-455) is invariant under gallery row order."""
+    G = gallery_feats.shape[0]
+    if len(gallery_meta) != G:
+        raise ValueError("shuffled_gallery: one meta entry per gallery row")
+    perm = torch.randperm(G, generator=torch.Generator().manual_seed(int(seed)))
+    feats = gallery_feats[perm.to(gallery_feats.device)]
+    return feats, [gallery_meta[i] for i in perm.tolist()]
+
+
 def rank_and_metrics(queries: List[dict], gallery_feats: torch.Tensor, gallery_meta: List[dict], extractor,
                      weight_cfg: Dict[str, float], ignore_same_img=True, cross_camera=False,
                      mode: str = "fused", shard: Optional[engine.GalleryShard] = None) -> Dict[str, float]:

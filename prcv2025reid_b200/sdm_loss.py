@@ -151,8 +151,12 @@ class SdmStep:
     input dtype hold the step's results after `run()`.  On the small-batch path the step is a single kernel launch;
     on the tcgen05 path three (pack, forward, backward)."""
 
-    def __init__(self, qrys, gals, ys, tau=0.2, eps=1e-8, weights=None):
+    def __init__(self, qrys, gals, ys, tau=0.2, eps=1e-8, weights=None, labels=None):
+        """`labels` (label form, `ys` = None or a list of None): per pair (row_label, col_label, row_valid or None,
+        col_valid or None) as `sdm_loss_pairs_labels` takes them; the tensors are kept (and read at every `run`)."""
         n = len(qrys)
+        if ys is None:
+            ys = [None] * n
         if not (n == len(gals) == len(ys)) or n == 0 or n > _cabi.SDM_MAX_PAIRS:
             raise ValueError("SdmStep: need equally long lists of 1..%d pairs" % _cabi.SDM_MAX_PAIRS)
         L = _cabi.lib()
@@ -160,11 +164,17 @@ class SdmStep:
         self.code = _dtype_code(qrys[0])
         self.q = [q.detach().contiguous() for q in qrys]
         self.g = [g.detach().contiguous() for g in gals]
-        self.y = [y.detach().to(torch.float32).contiguous() for y in ys]
+        self.y = [None if y is None else y.detach().to(torch.float32).contiguous() for y in ys]
+        self.labels = None
+        if any(y is None for y in self.y):
+            if labels is None or len(labels) != n or not all(y is None for y in self.y):
+                raise ValueError("SdmStep: give y for every pair, or labels for every pair")
+            self.labels = _label_tuples(self.q, self.g, [l[0] for l in labels], [l[1] for l in labels],
+                                        [l[2] for l in labels], [l[3] for l in labels])
         for q, g, y in zip(self.q, self.g, self.y):
             if q.dtype != dt or g.dtype != dt or q.shape[1] != d or g.shape[1] != d:
                 raise TypeError("sdm_loss: all features of a batch must share dtype and width")
-            if y.shape[0] != q.shape[0] or y.shape[1] != g.shape[0]:
+            if y is not None and (y.shape[0] != q.shape[0] or y.shape[1] != g.shape[0]):
                 raise ValueError("sdm_loss: y must be [N, M]")
         self.n, self.d, self.tau, self.eps = n, d, float(tau), float(eps)
         self.losses = torch.empty(n, dtype=torch.float32, device=dev)
@@ -175,7 +185,8 @@ class SdmStep:
         self.saved = torch.empty(sum(sizes), dtype=torch.float32, device=dev).split(sizes)
         self.dq = [torch.empty_like(q) for q in self.q]
         self.dg = [torch.empty_like(g) for g in self.g]
-        self.table = _pair_table(self.q, self.g, self.y, self.losses, self.status, self.saved, self.weights, self.dq, self.dg)
+        self.table = _pair_table(self.q, self.g, self.y, self.losses, self.status, self.saved, self.weights, self.dq, self.dg,
+                                 self.labels)
         self.launches = L.reid_sdm_step_launches(self.table, n, self.code, d)
 
     def run(self):
@@ -238,8 +249,25 @@ def sdm_loss_pairs(qrys: Sequence[torch.Tensor], gals: Sequence[torch.Tensor], y
 
 
 def label_form_supported(n_rows: int, d: int, dtype) -> bool:
-    """Shapes the label form of the C entry points serves (the tcgen05 path: include/reid_b200.h, reid_sdm_pair)."""
-    return dtype == torch.bfloat16 and 64 <= n_rows <= 512 and n_rows % 8 == 0 and d % 64 == 0 and 64 <= d <= 512
+    """Shapes the label form of the C entry points serves (include/reid_b200.h, reid_sdm_pair): every code path of the
+    library takes it -- the tcgen05 path (bf16, 64..512 rows), the one-CTA small-batch kernels and the general CUDA-core
+    kernels (csrc/sdm.cu; round 2: the tcgen05 path only)."""
+    return dtype in (torch.float32, torch.bfloat16, torch.float16) and n_rows >= 1 and d >= 1
+
+
+def _label_tuples(qrys, gals, row_labels, col_labels, row_valid=None, col_valid=None):
+    labs = []
+    for i in range(len(qrys)):
+        rl = row_labels[i].to(torch.int64).contiguous()
+        cl = col_labels[i].to(torch.int64).contiguous()
+        rv = None if row_valid is None or row_valid[i] is None else row_valid[i].to(torch.uint8).contiguous()
+        cv = None if col_valid is None or col_valid[i] is None else col_valid[i].to(torch.uint8).contiguous()
+        if rl.numel() != qrys[i].shape[0] or cl.numel() != gals[i].shape[0]:
+            raise ValueError("sdm_loss_pairs_labels: one label per feature row")
+        if (rv is not None and rv.numel() != rl.numel()) or (cv is not None and cv.numel() != cl.numel()):
+            raise ValueError("sdm_loss_pairs_labels: one valid byte per feature row")
+        labs.append((rl, cl, rv, cv))
+    return labs
 
 
 def sdm_loss_pairs_labels(qrys: Sequence[torch.Tensor], gals: Sequence[torch.Tensor], row_labels, col_labels,
@@ -250,15 +278,7 @@ def sdm_loss_pairs_labels(qrys: Sequence[torch.Tensor], gals: Sequence[torch.Ten
     n = len(qrys)
     if n == 0 or n > _cabi.SDM_MAX_PAIRS or not (n == len(gals) == len(row_labels) == len(col_labels)):
         raise ValueError("sdm_loss_pairs_labels: need equally long lists of 1..%d pairs" % _cabi.SDM_MAX_PAIRS)
-    labs = []
-    for i in range(n):
-        rl = row_labels[i].to(torch.int64).contiguous()
-        cl = col_labels[i].to(torch.int64).contiguous()
-        rv = None if row_valid is None or row_valid[i] is None else row_valid[i].to(torch.uint8).contiguous()
-        cv = None if col_valid is None or col_valid[i] is None else col_valid[i].to(torch.uint8).contiguous()
-        if rl.numel() != qrys[i].shape[0] or cl.numel() != gals[i].shape[0]:
-            raise ValueError("sdm_loss_pairs_labels: one label per feature row")
-        labs.append((rl, cl, rv, cv))
+    labs = _label_tuples(qrys, gals, row_labels, col_labels, row_valid, col_valid)
     return _SdmPairsFn.apply(tau, eps, n, *qrys, *gals, *([None] * n), labs)
 
 
@@ -278,9 +298,11 @@ def sdm_alignment_loss(raw_modality_features, feature_masks, labels, tau=0.2, ep
     the remaining per-modality losses are averaged (zero when none remains).
 
     The reference issues one `sdm_loss_stable` call and >= 3 host synchronisations per modality (`.sum() == 0`
-    at :572/:597/:608 plus those inside the loss); here ONE host read fetches all masks (the row filtering has
-    data-dependent shapes), all modalities go through one `sdm_loss_pairs` launch pair, and the "has a positive"
-    / finiteness selection of :608-618 is evaluated on the device."""
+    at :572/:597/:608 plus those inside the loss).  Here all modalities go through ONE launch sequence in the LABEL FORM
+    of the kernels: labels [B], masks, features [B, d] in; no y, no row filtering, NO host synchronisation, whatever the
+    batch size -- the tcgen05 path for bf16 batches of 64..512 rows, the CUDA-core kernels otherwise.  Features keep the
+    dtype the caller passes (bf16 / fp16 under the training autocast of train.py:852, fp32 otherwise): like the reference,
+    the loss normalises in that dtype (sdm_loss.py:31-32) and only then computes in fp32 (:75)."""
     vis = raw_modality_features.get("vis")
     vmask = feature_masks.get("vis")
     dev = labels.device
@@ -289,52 +311,28 @@ def sdm_alignment_loss(raw_modality_features, feature_masks, labels, tau=0.2, ep
         return zero                                                              # :566-568
     names = [m for m, f in raw_modality_features.items()
              if m != "vis" and f is not None and feature_masks.get(m) is not None]                # :586-592
-    flat = [(feature_masks[m] > 0).reshape(labels.shape[0], -1)[:, 0] for m in ["vis"] + names]
     B = labels.shape[0]
-    if names and vis.dim() == 2 and label_form_supported(B, vis.shape[1], vis.dtype) and \
-            all(raw_modality_features[m].dtype == vis.dtype and raw_modality_features[m].shape == vis.shape for m in names):
-        # large bf16 batches: the label form of the kernels -- labels [B], masks [5, B], features [5, B, d] in, no y, NO
-        # host synchronisation; masked rows are left out inside the kernels, "no positive" / finiteness (:608-618) come
-        # back as device-side status bits
-        out = []
-        for s0 in range(0, len(names), _cabi.SDM_MAX_PAIRS):
-            ms = names[s0:s0 + _cabi.SDM_MAX_PAIRS]
-            k = len(ms)
-            losses, status = sdm_loss_pairs_labels([raw_modality_features[m] for m in ms], [vis] * k, [labels] * k, [labels] * k,
-                                                   [flat[1 + names.index(m)] for m in ms], [flat[0]] * k, tau, eps)
-            out.append((losses, status))
-        losses = torch.cat([o[0] for o in out]) if len(out) > 1 else out[0][0]
-        status = torch.cat([o[1] for o in out]) if len(out) > 1 else out[0][1]
-        has_pos = ((status & 8) == 0) & torch.isfinite(losses)                   # :608-618
-        kept = torch.where(has_pos, losses, torch.zeros_like(losses))
-        return kept.sum() / has_pos.sum().clamp_min(1)                           # :621-625
-    host = torch.stack(flat).cpu()                                               # the one host read
-    vis_idx = torch.nonzero(host[0]).flatten()
-    if vis_idx.numel() == 0:
-        return zero                                                              # :572-574
-    vis_idx = vis_idx.to(dev)
-    # features keep the dtype the caller passes (bf16 / fp16 under the training autocast of train.py:852, fp32 otherwise):
-    # like the reference, the loss normalises in that dtype (sdm_loss.py:31-32) and only then computes in fp32 (:75)
-    vfeat, vlab = vis[vis_idx], labels[vis_idx]
-    groups = {}                                                                  # feature dtype -> (qs, ys)
-    order = []
-    for k, m in enumerate(names):
-        idx = torch.nonzero(host[k + 1]).flatten()
-        if idx.numel() == 0:
-            continue                                                             # :597-598
-        idx = idx.to(dev)
-        f = raw_modality_features[m][idx]
-        y = (labels[idx].view(-1, 1) == vlab.view(1, -1)).float()                 # :605
-        if f.dtype != vfeat.dtype:
-            raise TypeError("sdm_alignment_loss: %s features are %s but vis features are %s" % (m, f.dtype, vfeat.dtype))
-        qs, ys = groups.setdefault(f.dtype, ([], []))
-        qs.append(f); ys.append(y)
-        order.append(y)
-    if not order:
-        return zero
-    parts = [sdm_loss_pairs(qs, [vfeat] * len(qs), ys, tau, eps) for qs, ys in groups.values()]
-    losses = parts[0] if len(parts) == 1 else torch.cat(parts)
-    all_ys = [y for _, ys in groups.values() for y in ys]
-    has_pos = torch.stack([y.any() for y in all_ys]) & torch.isfinite(losses)     # :608-618, on the device
-    kept = torch.where(has_pos, losses, torch.zeros_like(losses))                 # (a skipped loss must not leak a NaN)
-    return kept.sum() / has_pos.sum().clamp_min(1)                                # :621-625
+    if not names or B == 0:
+        return zero                                                              # nothing to align
+    if vis.dim() != 2 or vis.shape[0] != B:
+        raise ValueError("sdm_alignment_loss: vis features must be [B, d] with one row per label")
+    for m in names:
+        f = raw_modality_features[m]
+        if f.dtype != vis.dtype:
+            raise TypeError("sdm_alignment_loss: %s features are %s but vis features are %s" % (m, f.dtype, vis.dtype))
+        if f.shape != vis.shape:
+            raise ValueError("sdm_alignment_loss: %s features are %s but vis features are %s" % (m, tuple(f.shape), tuple(vis.shape)))
+    _dtype_code(vis)                                                             # (fp32 / bf16 / fp16, else TypeError)
+    flat = [(feature_masks[m] > 0).reshape(B, -1)[:, 0] for m in ["vis"] + names]
+    # masked rows are left out inside the kernels (a modality or a vis side without a valid row ends as "no positive",
+    # :572-574 / :597-598); "no positive" / finiteness (:608-618) come back as device-side status bits
+    out = []
+    for s0 in range(0, len(names), _cabi.SDM_MAX_PAIRS):
+        k = len(names[s0:s0 + _cabi.SDM_MAX_PAIRS])
+        out.append(sdm_loss_pairs_labels([raw_modality_features[m] for m in names[s0:s0 + k]], [vis] * k, [labels] * k, [labels] * k,
+                                         flat[1 + s0:1 + s0 + k], [flat[0]] * k, tau, eps))
+    losses = torch.cat([o[0] for o in out]) if len(out) > 1 else out[0][0]
+    status = torch.cat([o[1] for o in out]) if len(out) > 1 else out[0][1]
+    has_pos = ((status & 8) == 0) & torch.isfinite(losses)                       # :608-618
+    kept = torch.where(has_pos, losses, torch.zeros_like(losses))                # (a skipped loss must not leak a NaN)
+    return kept.sum() / has_pos.sum().clamp_min(1)                               # :621-625

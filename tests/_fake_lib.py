@@ -315,7 +315,11 @@ class FakeLib:
         return 64
 
     def reid_sdm_uses_tensor_cores(self, arr, n, code, d):
-        return 1 if any(int(arr[14 * p + 2]) == 0 for p in range(n)) else 0   # (the label form is a tcgen05-path feature)
+        """bf16, 64 <= N, M <= 512 multiples of 8, d % 64 == 0, d <= 512 (include/reid_b200.h); dense y or the label form"""
+        def ok(p):
+            N, M = int(arr[14 * p + 3]) & 0xFFFFFFFF, int(arr[14 * p + 3]) >> 32
+            return all(64 <= v <= 512 and v % 8 == 0 for v in (N, M))
+        return 1 if code == 1 and d % 64 == 0 and 64 <= d <= 512 and all(ok(p) for p in range(n)) else 0
 
     def reid_sdm_step_launches(self, arr, n, code, d):
         return 1

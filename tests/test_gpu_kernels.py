@@ -524,6 +524,81 @@ def test_sdm_label_form_matches_dense_y_and_row_filtering():
     assert float(l5) == 0.0 and int(st5[0]) & 8
 
 
+@pytest.mark.parametrize("B,dtype,d", [(8, torch.float32, 512), (24, torch.bfloat16, 512), (32, torch.float16, 256),
+                                        (48, torch.float32, 512), (96, torch.float16, 512), (40, torch.bfloat16, 128),
+                                        (600, torch.bfloat16, 64), (33, torch.float32, 96)])
+def test_sdm_label_form_on_the_cuda_core_paths(B, dtype, d):
+    """The label form (y == NULL) on the CUDA-core kernels of csrc/sdm.cu -- the one-CTA small-batch kernels (B <= 32), the
+    single-launch step kernel and the general cooperative kernels -- i.e. every shape the tcgen05 path does not take:
+    (1) all rows valid: bit-identical to the dense-y form; (2) masked rows: equal to the dense form on the FILTERED rows
+    (models/model.py:570-605), exact-zero gradients for the masked rows, non-finite values in them never seen;
+    (3) no positive: status bit 3, zero loss, zero gradients; (4) SdmStep (one C call) in the label form == autograd."""
+    from prcv2025reid_b200.sdm_loss import SdmStep, sdm_loss_pairs, sdm_loss_pairs_labels
+    gen = torch.Generator().manual_seed(900 + B)
+    n_ids = max(2, B // 4)
+    labels = torch.randint(0, n_ids, (B,), generator=gen)
+    centres = torch.randn(n_ids, d, generator=gen)
+    q = (centres[labels] + 1.5 * torch.randn(B, d, generator=gen)).to(dtype).cuda()
+    v = (centres[labels] + 1.5 * torch.randn(B, d, generator=gen)).to(dtype).cuda()
+    lab = labels.cuda()
+    y = (lab[:, None] == lab[None, :]).float()
+    f32 = dtype == torch.float32
+    # (1)
+    q1, v1 = q.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    l1, st1 = sdm_loss_pairs_labels([q1], [v1], [lab], [lab], tau=0.2)
+    (2.0 * l1.sum()).backward()
+    q2, v2 = q.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    l2 = sdm_loss_pairs([q2], [v2], [y], tau=0.2)
+    (2.0 * l2.sum()).backward()
+    assert int(st1[0]) == 0 and float(l1) > 0 and torch.equal(l1, l2) and torch.equal(q1.grad, q2.grad) and torch.equal(v1.grad, v2.grad)
+    # (2)
+    nr, nc = max(1, B // 4), max(1, B // 5)
+    rv = torch.ones(B, dtype=torch.bool); rv[torch.randperm(B, generator=gen)[:nr]] = False
+    cv = torch.ones(B, dtype=torch.bool); cv[torch.randperm(B, generator=gen)[:nc]] = False
+    keep = int(torch.nonzero(rv & cv).flatten()[0])                 # (one identity present on both sides: a positive exists)
+    q3, v3 = q.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    with torch.no_grad():
+        q3[torch.nonzero(~rv).flatten()[0], 5] = float("nan"); v3[torch.nonzero(~cv).flatten()[0], 7] = float("inf")
+    l3, st3 = sdm_loss_pairs_labels([q3], [v3], [lab], [lab], [rv.cuda()], [cv.cuda()], tau=0.2)
+    l3.sum().backward()
+    ri, ci = torch.nonzero(rv).flatten().cuda(), torch.nonzero(cv).flatten().cuda()
+    q4, v4 = q[ri].clone().requires_grad_(True), v[ci].clone().requires_grad_(True)
+    l4 = sdm_loss_pairs([q4], [v4], [(lab[ri][:, None] == lab[ci][None, :]).float()], tau=0.2)
+    l4.sum().backward()
+    assert keep >= 0 and int(st3[0]) == 0 and float(l4) > 0
+    assert abs(float(l3) - float(l4)) <= (1e-5 if f32 else 1e-3) * float(l4)
+    assert not q3.grad[~rv.cuda()].float().abs().sum().item() and not v3.grad[~cv.cuda()].float().abs().sum().item()
+    for got, want in ((q3.grad[ri], q4.grad), (v3.grad[ci], v4.grad)):
+        if f32:
+            assert (got - want).abs().max() <= 1e-5 * want.abs().max()
+        else:       # (the same fp32 arithmetic up to summation order, rounded once to the 16-bit output dtype)
+            assert (got.float() - want.float()).norm() <= 1e-3 * want.float().norm()
+    # the loss of the filtered problem against the oracle (the reference's arithmetic on the rows it would keep)
+    ref = osdm.sdm_loss_oracle(q[ri].cpu(), v[ci].cpu(), (lab[ri][:, None] == lab[ci][None, :]).float().cpu(), tau=0.2)
+    assert abs(float(l3) - float(ref)) <= (1e-5 if f32 else 1e-3) * max(1.0, abs(float(ref)))
+    # (3)
+    q5, v5 = q.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    l5, st5 = sdm_loss_pairs_labels([q5], [v5], [lab], [lab + 1000], [rv.cuda()], None, tau=0.2)
+    l5.sum().backward()
+    assert float(l5) == 0.0 and int(st5[0]) & 8 and not q5.grad.float().abs().sum().item() and not v5.grad.float().abs().sum().item()
+    # a side without any valid row (:572-574 / :597-598): "no positive" as well
+    l6, st6 = sdm_loss_pairs_labels([q], [v], [lab], [lab], None, [torch.zeros(B, dtype=torch.bool).cuda()], tau=0.2)
+    assert float(l6) == 0.0 and int(st6[0]) & 8
+    # (4)
+    w = torch.tensor([0.5, 2.0], device="cuda")
+    qa = [q.clone().requires_grad_(True), q.clone().requires_grad_(True)]
+    va = [v.clone().requires_grad_(True), v.clone().requires_grad_(True)]
+    la, _ = sdm_loss_pairs_labels(qa, va, [lab, lab], [lab, lab], [rv.cuda(), None], [cv.cuda(), None], tau=0.2)
+    grads = torch.autograd.grad((la * w).sum(), qa + va)
+    step = SdmStep([q, q], [v, v], None, tau=0.2, weights=w, labels=[(lab, lab, rv.cuda(), cv.cuda()), (lab, lab, None, None)])
+    assert step.launches == (1 if B <= 32 and d % 128 == 0 else 2)
+    got = step.run()
+    torch.cuda.synchronize()
+    assert torch.equal(got, la.detach())
+    for a, b in zip(step.dq + step.dg, grads):
+        assert torch.equal(a, b)
+
+
 def test_sdm_graph_step_matches_eager():
     """The CUDA-graph replay of a whole step (both code paths) reproduces the eager losses and gradients bit for bit."""
     from prcv2025reid_b200.sdm_loss import SdmGraphStep, sdm_loss_pairs

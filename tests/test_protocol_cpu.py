@@ -142,6 +142,26 @@ def test_protocol_loop_skips_empty_mm_k(world, cpu_engine):
     assert all(v == 0.0 for v in empty["AVG(1-4)"].values()) and empty["MM-1"]["num_queries"] == 0
 
 
+@pytest.mark.parametrize("mask", [True, False])
+def test_shuffled_gallery_leaves_the_protocol_results_unchanged(world, cpu_engine, mask):
+    """`shuffled_gallery` (rows + meta in a seeded random order: the way around the fixed sampling phase of the fused path
+    for periodically laid-out caches) changes nothing the protocol reports: the same-image rule follows the image ids."""
+    index, g_feats, g_meta, ext = world
+    sf, sm = emp.shuffled_gallery(g_feats, g_meta, seed=3)
+    assert sf.shape == g_feats.shape and sorted(m["img_id"] for m in sm) == sorted(m["img_id"] for m in g_meta)
+    assert [m["img_id"] for m in sm] != [m["img_id"] for m in g_meta]
+    j = [m["img_id"] for m in g_meta].index(sm[0]["img_id"])
+    assert torch.equal(sf[0], g_feats[j]) and sm[0] is g_meta[j]
+    a = emp.run_eval_features(index, g_feats, g_meta, ext, seed=GOLDEN["run_seed"], ignore_same_img=mask)
+    b = emp.run_eval_features(index, sf, sm, ext, seed=GOLDEN["run_seed"], ignore_same_img=mask)
+    for name in a:
+        assert a[name].get("num_queries") == b[name].get("num_queries")
+        for key in ("mAP", "R@1", "R@5", "R@10"):
+            assert a[name][key] == pytest.approx(b[name][key], abs=1e-12), (name, key)
+    with pytest.raises(ValueError):
+        emp.shuffled_gallery(g_feats, g_meta[:-1])
+
+
 def test_rank_and_metrics_rejects_a_shard_of_another_gallery(world, cpu_engine):
     index, g_feats, g_meta, ext = world
     shard = emp.install_gallery(g_feats[:8], g_meta[:8])

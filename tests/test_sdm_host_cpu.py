@@ -100,14 +100,13 @@ def test_alignment_loss_host_logic_matches_compute_loss_golden(monkeypatch, name
     if abs(cs - float(z[name + "/checksum"])) > 1e-6 * abs(cs):
         pytest.skip("torch RNG stream differs from the one the fixture was generated with")
     leaves = {m: (f.clone().requires_grad_(True) if f is not None else None) for m, f in feats.items()}
-    if name == "large_bf16":
-        # 96 bf16 rows: the LABEL FORM of the C entry points -- no y, no host read of the masks
-        real_cpu = torch.Tensor.cpu
-        monkeypatch.setattr(torch.Tensor, "cpu", lambda self, *a, **k: (_ for _ in ()).throw(AssertionError("host read")))
+    # every case runs in the LABEL FORM of the C entry points (any batch size / dtype since the CUDA-core kernels take it
+    # too): no y, no row filtering, no host read of the masks
+    real_cpu = torch.Tensor.cpu
+    monkeypatch.setattr(torch.Tensor, "cpu", lambda self, *a, **k: (_ for _ in ()).throw(AssertionError("host read")))
     loss = sdm_alignment_loss(leaves, masks, labels, tau=tau)
-    if name == "large_bf16":
-        monkeypatch.setattr(torch.Tensor, "cpu", real_cpu)
-        assert fake.calls.count("reid_sdm_fwd") == 1
+    monkeypatch.setattr(torch.Tensor, "cpu", real_cpu)
+    assert fake.calls.count("reid_sdm_fwd") <= 1
     want = float(z[name + "/loss"])
     assert float(loss.detach()) == pytest.approx(want, rel=1e-6, abs=1e-7)
     if loss.requires_grad:
@@ -121,3 +120,45 @@ def test_alignment_loss_host_logic_matches_compute_loss_golden(monkeypatch, name
             assert np.allclose(t.grad.float().numpy(), z[key], rtol=1e-5 if t.dtype == torch.float32 else 2e-2, atol=1e-9 if t.dtype == torch.float32 else 1e-4), m
         elif t is not None and t.grad is not None:
             assert float(t.grad.abs().sum()) == 0.0, m
+
+
+def test_step_object_label_form_and_the_ragged_route(monkeypatch):
+    """SdmStep in the label form packs the label / valid pointers into the pair table (one reid_sdm_step call, same result as
+    the autograd label form); sdm_alignment_loss issues one label-form call and rejects mismatching modalities."""
+    from prcv2025reid_b200.sdm_loss import SdmStep, sdm_alignment_loss, sdm_loss_pairs_labels
+    fake = _fake_lib.install(monkeypatch)
+    g = torch.Generator().manual_seed(5)
+    B = 10
+    qs = [torch.randn(B, 32, generator=g) for _ in range(2)]
+    vs = [torch.randn(B, 32, generator=g) for _ in range(2)]
+    lab = torch.arange(5).repeat_interleave(2)
+    rv = torch.ones(B, dtype=torch.bool); rv[3] = False
+    cv = torch.ones(B, dtype=torch.bool); cv[[0, 7]] = False
+    w = torch.tensor([0.5, 2.0])
+    st = SdmStep(qs, vs, None, tau=0.2, weights=w, labels=[(lab, lab, rv, cv), (lab, lab, None, None)])
+    losses = st.run()
+    qa = [q.clone().requires_grad_(True) for q in qs]; va = [v.clone().requires_grad_(True) for v in vs]
+    ref, status = sdm_loss_pairs_labels(qa, va, [lab, lab], [lab, lab], [rv, None], [cv, None], tau=0.2)
+    (ref * w).sum().backward()
+    assert torch.allclose(losses, ref.detach(), rtol=1e-6) and int(status[0]) == 0
+    for p in range(2):
+        assert torch.allclose(st.dq[p], qa[p].grad, rtol=1e-5, atol=1e-9) and torch.allclose(st.dg[p], va[p].grad, rtol=1e-5, atol=1e-9)
+    assert not st.dq[0][3].any() and not st.dg[0][0].any() and not st.dg[0][7].any()       # masked rows: exact zeros
+    assert fake.calls.count("reid_sdm_step") == 1
+    with pytest.raises(ValueError):
+        SdmStep(qs, vs, None)                                           # neither y nor labels
+    with pytest.raises(ValueError):
+        sdm_loss_pairs_labels(qs, vs, [lab, lab], [lab, lab], [rv[:4], None], None)        # one valid byte per row
+    # sdm_alignment_loss: one label-form call for all modalities; mismatching modalities are rejected (the reference would
+    # fail on them too: labels[mod_valid_idx] needs one row per label, sdm_loss.py:75 one dtype)
+    feats = {"vis": vs[0], "nir": qs[0], "sk": qs[1]}
+    masks = {"vis": cv.float().view(-1, 1), "nir": rv.float().view(-1, 1), "sk": torch.ones(B, 1)}
+    n0 = fake.calls.count("reid_sdm_fwd")
+    a = sdm_alignment_loss(feats, masks, lab, tau=0.2)
+    assert fake.calls.count("reid_sdm_fwd") == n0 + 1 and float(a) > 0
+    with pytest.raises(ValueError):
+        sdm_alignment_loss(dict(feats, sk=qs[1][:6]), masks, lab, tau=0.2)
+    with pytest.raises(TypeError):
+        sdm_alignment_loss(dict(feats, sk=qs[1].to(torch.bfloat16)), masks, lab, tau=0.2)
+    with pytest.raises(TypeError):
+        sdm_alignment_loss({k: v.double() for k, v in feats.items()}, masks, lab, tau=0.2)
