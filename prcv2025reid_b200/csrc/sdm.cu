@@ -600,7 +600,9 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-template <int BF16, bool D512>                        // D512: the reference's feature width as a compile-time constant
+// LBL: some pair of the batch is in the label form (y == NULL).  The dense instantiation carries none of the validity
+// tests: at C2 the kernel is a pure latency chain and its time is what the benchmark reports.
+template <int BF16, bool D512, bool LBL>              // D512: the reference's feature width as a compile-time constant
 __global__ void __launch_bounds__(STB, 1)
 sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
   extern __shared__ __align__(16) float small_smem[];
@@ -625,18 +627,18 @@ sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
     const int i = threadIdx.x + u * STB;
     yreg[u] = 0.f;
     if (i < N * M) {
-      if (pm.y) yreg[u] = pm.y[i];
+      if (!LBL || pm.y) yreg[u] = P.y[i];
       else yreg[u] = (pm.row_in(i / M) && pm.col_in(i % M) && pm.rl[i / M] == pm.cl[i % M]) ? 1.f : 0.f;
     }
   }
   if (threadIdx.x == 0) s_flags = 0;
-  if (threadIdx.x < N + M) s_in[threadIdx.x] = threadIdx.x < N ? pm.row_in(threadIdx.x) : pm.col_in(threadIdx.x - N);
+  if (LBL && threadIdx.x < N + M) s_in[threadIdx.x] = threadIdx.x < N ? pm.row_in(threadIdx.x) : pm.col_in(threadIdx.x - N);
   __syncthreads();
   for (int r = warp; r < N + M; r += NW) {
     const bool isq = r < N;
     const int row = isq ? r : r - N;
     const void* x = isq ? P.qry : P.gal;
-    if (!s_in[r]) {                                     // label form: the row takes no part (zero image, never inspected)
+    if (LBL && !s_in[r]) {                              // label form: the row takes no part (zero image, never inspected)
       small_zero_row(xs + (size_t)r * d, d, lane);
       if (lane == 0) { (isq ? sv.den_q : sv.den_g)[row] = 1.f; st_r[4 * r + 3] = 1.f; }
       continue;
@@ -680,14 +682,14 @@ sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
   for (int r = warp; r < N + M; r += NW) {
     const bool isrow = r < N;
     const int a = isrow ? r : r - N, len = isrow ? M : N;
-    const bool in = lane < len && s_in[r] && s_in[isrow ? N + lane : lane];
+    const bool in = lane < len && (!LBL || (s_in[r] && s_in[isrow ? N + lane : lane]));
     const float sv_ = in ? (isrow ? Ss[a * (M + 1) + lane] : Ss[lane * (M + 1) + a]) : -INFINITY;
     const float yv = in ? (isrow ? Ys[a * M + lane] : Ys[lane * M + a]) : 0.f;
     const float mx = warp_max(sv_);
     const float se = warp_sum(in ? expf(sv_ - mx) : 0.f);
     const float ps = warp_sum(yv > 0.f ? sv_ : 0.f), pc = warp_sum(yv > 0.f ? 1.f : 0.f);
     if (lane == 0) {
-      const float lse = se > 0.f ? mx + logf(se) : 0.f;
+      const float lse = (!LBL || se > 0.f) ? mx + logf(se) : 0.f;
       const float ce = pc > 0.f ? (lse - ps / pc) : 0.f;
       (isrow ? sv.lse_r : sv.lse_c)[a] = lse;
       (isrow ? sv.cnt_r : sv.cnt_c)[a] = pc;
@@ -742,7 +744,7 @@ sdm_small_step_kernel(SdmBatch batch, int d_arg, float tau_eff, float eps) {
     const int i = idx / M, j = idx % M;
     const float s = Ss[i * (M + 1) + j];
     float g = 0.f;
-    if (s < 20.f && s > -20.f && s_in[i] && s_in[N + j]) {
+    if (s < 20.f && s > -20.f && (!LBL || (s_in[i] && s_in[N + j]))) {
       const float pos = Ys[idx] > 0.f ? 1.f : 0.f;
       const float cr = st_r[4 * i], cc = st_r[4 * (N + j)];
       if (cr > 0.f && isfinite(st_r[4 * i + 1])) g += wr * (expf(s - st_r[4 * i + 2]) - pos / cr);
@@ -907,20 +909,25 @@ extern "C" int reid_sdm_bwd(const reid_sdm_pair* pairs, int n_pairs, int dtype, 
   return REID_E_UNSUPPORTED;
 }
 
+template <int DT>
+static int launch_small_step(const reid_sdm_pair* pairs, int n_pairs, int d, float tau, float eps, cudaStream_t st) {
+  bool lbl = false;
+  for (int i = 0; i < n_pairs; ++i) lbl = lbl || !pairs[i].y;
+  if (d == 512)
+    return lbl ? launch_small(sdm_small_step_kernel<DT, true, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
+               : launch_small(sdm_small_step_kernel<DT, true, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
+  return lbl ? launch_small(sdm_small_step_kernel<DT, false, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
+             : launch_small(sdm_small_step_kernel<DT, false, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
+}
+
 // Forward + backward of a step in as few launches as the path allows: one for small pairs, otherwise the two calls above.
 // Every pair carries its backward slots (grad_out = the weight of loss p in the objective, dqry, dgal).
 extern "C" int reid_sdm_step(const reid_sdm_pair* pairs, int n_pairs, int dtype, int d, float tau, float eps, void* stream) {
   if (small_eligible(pairs, n_pairs, d)) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == REID_DTYPE_F32)
-      return d == 512 ? launch_small(sdm_small_step_kernel<REID_DTYPE_F32, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
-                      : launch_small(sdm_small_step_kernel<REID_DTYPE_F32, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
-    if (dtype == REID_DTYPE_BF16)
-      return d == 512 ? launch_small(sdm_small_step_kernel<REID_DTYPE_BF16, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
-                      : launch_small(sdm_small_step_kernel<REID_DTYPE_BF16, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
-    if (dtype == REID_DTYPE_F16)
-      return d == 512 ? launch_small(sdm_small_step_kernel<REID_DTYPE_F16, true>, pairs, n_pairs, d, tau, eps, true, st, STB)
-                      : launch_small(sdm_small_step_kernel<REID_DTYPE_F16, false>, pairs, n_pairs, d, tau, eps, true, st, STB);
+    if (dtype == REID_DTYPE_F32) return launch_small_step<REID_DTYPE_F32>(pairs, n_pairs, d, tau, eps, st);
+    if (dtype == REID_DTYPE_BF16) return launch_small_step<REID_DTYPE_BF16>(pairs, n_pairs, d, tau, eps, st);
+    if (dtype == REID_DTYPE_F16) return launch_small_step<REID_DTYPE_F16>(pairs, n_pairs, d, tau, eps, st);
   }
   const int rc = reid_sdm_fwd(pairs, n_pairs, dtype, d, tau, eps, stream);
   return rc != REID_OK ? rc : reid_sdm_bwd(pairs, n_pairs, dtype, d, tau, eps, stream);
