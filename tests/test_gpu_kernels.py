@@ -198,16 +198,24 @@ def test_c1_config_against_oracle(eng, mode):
                                       return_per_query=True)
     assert res.metrics["num_queries"] == o["num_queries"] == 3000
     assert abs(res.metrics["mAP"] - o["mAP"]) <= 1e-4
+    # top-10 lists: identical except where the reference's OWN fp32 scores tie within 2e-6 (summation-order noise is ~1e-7);
+    # every differing position is shown to be such a tie, and CMC may move only by the queries that have one
+    S = q32.cpu() @ shard.g_f32.cpu().T
+    ti, oi = res.top_idx.cpu().numpy(), o["_top_idx"]
+    tied = 0
+    for qi in np.nonzero((ti != oi).any(axis=1))[0]:
+        for r in np.nonzero(ti[qi] != oi[qi])[0]:
+            assert abs(float(S[qi, ti[qi, r]]) - float(S[qi, oi[qi, r]])) <= 2e-6, (qi, r)
+        tied += 1
+    assert tied <= 0.005 * 3000
     for k in ("R@1", "R@5", "R@10"):
-        assert abs(res.metrics[k] - o[k]) <= 1.0 / 3000 + 1e-12     # a fp32-order tie may move one query
+        assert abs(res.metrics[k] - o[k]) <= tied / 3000 + 1e-12, (k, tied)
     ap = res.ap.cpu().numpy()
     # per-query AP: identical except where two fp32 scores tie within summation-order noise (~1e-7),
     # which can swap two neighbours of one query
     assert np.abs(ap - o["_ap"]).max() <= 5e-3
     if mode == "exact":      # the fp16 tensor-core scores of the fused path move many deep ranks by +-1
         assert (np.abs(ap - o["_ap"]) > 1e-9).mean() <= 0.05
-    same = (res.top_idx.cpu().numpy() == o["_top_idx"]).all(axis=1).mean()
-    assert same >= 0.995
 
 
 def test_host_query_pipeline_matches_resident(eng):
