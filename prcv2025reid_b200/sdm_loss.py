@@ -81,6 +81,7 @@ class _SdmPairsFn(torch.autograd.Function):
     def forward(ctx, tau, eps, n, *tensors):
         qrys, gals, ys = tensors[:n], tensors[n:2 * n], tensors[2 * n:3 * n]
         labels = tensors[3 * n] if len(tensors) > 3 * n else None      # label form: list of (row_label, col_label, row_valid, col_valid)
+        align = len(tensors) > 3 * n + 1 and tensors[3 * n + 1] == "align"   # reduce like models/model.py:608-625 (see below)
         L = _cabi.lib()
         dev = qrys[0].device
         d = qrys[0].shape[1]
@@ -111,7 +112,16 @@ class _SdmPairsFn(torch.autograd.Function):
             words[PAIR_WORDS * i + 4] = words[PAIR_WORDS * i + 5]     # (the loss slot is not written again)
         ctx.keep = (qs, gs, yy, status, saved, words, labels)
         ctx.n_in = len(tensors)
+        ctx.align = None
         ctx.mark_non_differentiable(status)
+        if align:
+            # the tail of the compute_loss section inside the Function (no autograd nodes for it): pairs without a positive
+            # (status bit 3) or with a non-finite loss are skipped, the rest averaged (:608-625); d total / d loss[p] =
+            # has_pos[p] / count is applied in the backward
+            has_pos = ((status & 8) == 0) & torch.isfinite(losses)
+            cnt = has_pos.sum().clamp_min(1)
+            ctx.align = (has_pos, cnt)
+            return torch.where(has_pos, losses, torch.zeros_like(losses)).sum() / cnt, status
         return losses, status
 
     @staticmethod
@@ -120,6 +130,9 @@ class _SdmPairsFn(torch.autograd.Function):
         L = _cabi.lib()
         n = ctx.n
         grad = grad_losses
+        if ctx.align is not None:
+            has_pos, cnt = ctx.align
+            grad = torch.where(has_pos, grad.to(torch.float32) / cnt, torch.zeros((), dtype=torch.float32, device=grad.device))
         if grad.dtype != torch.float32 or not grad.is_contiguous():
             grad = grad.to(torch.float32).contiguous()
         q0, g0 = qs[0], gs[0]
@@ -323,16 +336,29 @@ def sdm_alignment_loss(raw_modality_features, feature_masks, labels, tau=0.2, ep
         if f.shape != vis.shape:
             raise ValueError("sdm_alignment_loss: %s features are %s but vis features are %s" % (m, tuple(f.shape), tuple(vis.shape)))
     _dtype_code(vis)                                                             # (fp32 / bf16 / fp16, else TypeError)
-    flat = [(feature_masks[m] > 0).reshape(B, -1)[:, 0] for m in ["vis"] + names]
+    # all feature masks as ONE [1 + n, B] byte tensor (three launches instead of three per modality); row i is pair i's
+    # row_valid, row 0 (vis) every pair's col_valid
+    cols = [feature_masks[m].reshape(B, -1)[:, 0] for m in ["vis"] + names]
+    if all(c.dtype == cols[0].dtype for c in cols):
+        valid = (torch.stack(cols) > 0).to(torch.uint8)
+    else:
+        valid = torch.stack([c > 0 for c in cols]).to(torch.uint8)
+    lab = labels.to(torch.int64).contiguous()
     # masked rows are left out inside the kernels (a modality or a vis side without a valid row ends as "no positive",
     # :572-574 / :597-598); "no positive" / finiteness (:608-618) come back as device-side status bits
+    n = len(names)
+    if n <= _cabi.SDM_MAX_PAIRS:
+        labs = [(lab, lab, valid[1 + i], valid[0]) for i in range(n)]
+        return _SdmPairsFn.apply(tau, eps, n, *[raw_modality_features[m] for m in names], *([vis] * n), *([None] * n),
+                                 labs, "align")[0]
     out = []
-    for s0 in range(0, len(names), _cabi.SDM_MAX_PAIRS):
+    for s0 in range(0, n, _cabi.SDM_MAX_PAIRS):
         k = len(names[s0:s0 + _cabi.SDM_MAX_PAIRS])
-        out.append(sdm_loss_pairs_labels([raw_modality_features[m] for m in names[s0:s0 + k]], [vis] * k, [labels] * k, [labels] * k,
-                                         flat[1 + s0:1 + s0 + k], [flat[0]] * k, tau, eps))
-    losses = torch.cat([o[0] for o in out]) if len(out) > 1 else out[0][0]
-    status = torch.cat([o[1] for o in out]) if len(out) > 1 else out[0][1]
+        labs = [(lab, lab, valid[1 + s0 + i], valid[0]) for i in range(k)]
+        out.append(_SdmPairsFn.apply(tau, eps, k, *[raw_modality_features[m] for m in names[s0:s0 + k]], *([vis] * k),
+                                     *([None] * k), labs))
+    losses = torch.cat([o[0] for o in out])
+    status = torch.cat([o[1] for o in out])
     has_pos = ((status & 8) == 0) & torch.isfinite(losses)                       # :608-618
     kept = torch.where(has_pos, losses, torch.zeros_like(losses))                # (a skipped loss must not leak a NaN)
     return kept.sum() / has_pos.sum().clamp_min(1)                               # :621-625
