@@ -261,8 +261,10 @@ def shuffled_gallery(gallery_feats: torch.Tensor, gallery_meta: List[dict], seed
 
 def rank_and_metrics(queries: List[dict], gallery_feats: torch.Tensor, gallery_meta: List[dict], extractor,
                      weight_cfg: Dict[str, float], ignore_same_img=True, cross_camera=False,
-                     mode: str = "fused", shard: Optional[engine.GalleryShard] = None) -> Dict[str, float]:
+                     mode: str = "fused", shard: Optional[engine.GalleryShard] = None,
+                     exact_ap: bool = False) -> Dict[str, float]:
     """eval_mm_protocol.py:369-469.  `cross_camera` is accepted and ignored like the reference (:375,392).
+    `exact_ap=True` counts every positive's rank on every gallery row (no row samples for deep positives, engine.retrieve).
 
     Returns {"mAP","R@1","R@5","R@10","num_queries"}; queries without a positive are skipped (:430-432),
     an empty result gives 0.0 metrics (:458-461).  `shard` (optional, from install_gallery on the same
@@ -279,13 +281,14 @@ def rank_and_metrics(queries: List[dict], gallery_feats: torch.Tensor, gallery_m
     by_id = getattr(shard, "img_index", None)
     g_imgid = None if by_id is not None else [m.get("img_id", None) for m in gallery_meta]    # :391
     excl = _exclusions(queries, g_imgid, ignore_same_img, dev, by_id)
-    res = engine.retrieve(shard, q32, q16, q_pid, excl, topk=10, mode=mode)
+    extra = {"exact_ap": True} if exact_ap else {}
+    res = engine.retrieve(shard, q32, q16, q_pid, excl, topk=10, mode=mode, **extra)
     return res.metrics
 
 
 def run_eval_features(index: Dict[int, Dict[str, List[dict]]], gallery_feats: torch.Tensor, gallery_meta: List[dict],
                       extractor, seed: int = 42, weight_cfg: Optional[Dict[str, float]] = None, ignore_same_img=True,
-                      cross_camera=False, mode: str = "fused") -> Dict[str, Dict[str, float]]:
+                      cross_camera=False, mode: str = "fused", exact_ap: bool = False) -> Dict[str, Dict[str, float]]:
     """The evaluation loop of run_eval (eval_mm_protocol.py:497-590) from pre-extracted features: the part of
     run_eval after the model / dataset / gallery cache have been loaded (:508-546 are out of scope: they need the
     CLIP weights and the image files).  Seeds `random.Random(seed)` (:498), default weights (:503-504), then for
@@ -304,7 +307,7 @@ def run_eval_features(index: Dict[int, Dict[str, List[dict]]], gallery_feats: to
             continue
         results["MM-%d" % k] = rank_and_metrics(queries, gallery_feats, gallery_meta, extractor, weight_cfg,
                                                 ignore_same_img=ignore_same_img, cross_camera=cross_camera,
-                                                mode=mode, shard=shard)
+                                                mode=mode, shard=shard, exact_ap=exact_ap)
     valid = [results["MM-%d" % k] for k in (1, 2, 3, 4) if results["MM-%d" % k]["num_queries"] > 0]   # :576
     results["AVG(1-4)"] = {key: (sum(r[key] for r in valid) / len(valid) if valid else 0.0)
                            for key in ("mAP", "R@1", "R@5", "R@10")}                          # :577-586

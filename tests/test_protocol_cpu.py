@@ -105,7 +105,8 @@ class _OracleEngine:
         self.installs += 1
         return types.SimpleNamespace(g_f32=orc.l2n(gallery.float()), g_pid=g_pid_all, G_total=int(g_pid_all.numel()))
 
-    def retrieve(self, shard, q32, q16, q_pid, excl, topk=10, mode="fused"):
+    def retrieve(self, shard, q32, q16, q_pid, excl, topk=10, mode="fused", exact_ap=False):
+        self.exact_ap_calls = getattr(self, "exact_ap_calls", 0) + int(bool(exact_ap))
         return types.SimpleNamespace(metrics=orc.rank_and_metrics_loop(q32, shard.g_f32, q_pid, shard.g_pid, excl))
 
 
@@ -160,6 +161,10 @@ def test_shuffled_gallery_leaves_the_protocol_results_unchanged(world, cpu_engin
             assert a[name][key] == pytest.approx(b[name][key], abs=1e-12), (name, key)
     with pytest.raises(ValueError):
         emp.shuffled_gallery(g_feats, g_meta[:-1])
+    # the other way around the fixed sampling phase: exact_ap travels from the protocol loop to engine.retrieve
+    n0 = getattr(cpu_engine, "exact_ap_calls", 0)
+    emp.run_eval_features(index, g_feats, g_meta, ext, seed=GOLDEN["run_seed"], ignore_same_img=mask, exact_ap=True)
+    assert cpu_engine.exact_ap_calls == n0 + 4 and n0 == 0
 
 
 def test_rank_and_metrics_rejects_a_shard_of_another_gallery(world, cpu_engine):
